@@ -1,0 +1,162 @@
+/*
+ * cwt_b200.h — C ABI of the B200-native CWT few-shot segmentation head.
+ *
+ * One shared object (libcwt_b200.so), plain pointers and sizes, no C++/torch types.
+ * Every entry point replaces a piece of the reference's Python/ATen hot path
+ * (TeamOfProfGuo/Few_Shot_Seg_CWT; paths below are relative to the reference checkout).
+ * The reference has no FFI of its own (it is 100 % Python), so these are the calls
+ * a maintainer would bind with ctypes — see INTEGRATION.md for the stubs.
+ *
+ * Conventions
+ *   - return 0 (CWT_OK) or a negative error code; nothing throws across the ABI;
+ *     cwt_last_error() returns a per-thread message for the last failure;
+ *   - the caller owns every buffer (inputs, outputs, workspace); the library never
+ *     allocates device memory, never frees and never keeps a pointer past the call;
+ *   - all device pointers, all work is enqueued asynchronously on `stream`
+ *     (a cudaStream_t passed as void*; 0 = legacy default stream); no hidden syncs;
+ *   - re-entrant / thread-safe for distinct streams and distinct workspaces;
+ *   - features are contiguous NCHW fp32: f[img][c][y][x]; labels are uint8 or int64
+ *     with values {0, 1, ignore_index}; any other value is counted as "invalid"
+ *     (torch's CrossEntropyLoss would raise on it) and treated as ignored;
+ *   - geometry: the bilinear maps are align_corners=True with H = 8*(h-1)+1 and
+ *     W = 8*(w-1)+1 (473 <-> 60, 417 <-> 53: the PSPNet zoom-8 head), which makes the
+ *     scale exactly 1/8; other ratios return CWT_ERR_UNSUPPORTED.
+ */
+#ifndef CWT_B200_H_
+#define CWT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CWT_OK                 0
+#define CWT_ERR_INVALID_ARG   -1
+#define CWT_ERR_UNSUPPORTED   -2
+#define CWT_ERR_WORKSPACE     -3
+#define CWT_ERR_CUDA          -4
+
+#define CWT_LABEL_U8   0
+#define CWT_LABEL_I64  1
+
+/* fit algorithms */
+#define CWT_FIT_AUTO       0
+#define CWT_FIT_STREAM     1   /* features streamed from HBM/L2 every step (any S)            */
+#define CWT_FIT_RESIDENT   2   /* features staged once into shared memory, persistent kernel  */
+
+/* transformer score algorithms */
+#define CWT_ATTN_REASSOC   0   /* scores = (Q_h A_h) X^T : skinny contraction on CUDA cores   */
+#define CWT_ATTN_TCGEN05   1   /* K = X A_h^T as a tcgen05/TMEM GEMM (3xbf16 split), scores in the epilogue */
+
+int         cwt_version(void);
+const char* cwt_last_error(void);
+/* number of kernels this library has launched from the calling process (bench bookkeeping) */
+long long   cwt_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * (a-2) label statistics.  Replaces the per-episode D2H copy + numpy `where` of
+ * src/test.py:169-171 / src/train.py:211-213,237-239 and model_util.py:27-31.
+ *   labels  [n_img, npix] uint8 or int64
+ *   packed  [n_img, npix] uint8 out (0, 1, 2 = ignored, 3 = invalid) or NULL
+ *   counts  [n_img, 4] int32 out: n0, n1, n_ignored, n_invalid  (zeroed by the call)
+ * ------------------------------------------------------------------------------------- */
+int cwt_prep_labels(const void* labels, int label_kind, int n_img, long long npix, int ignore_index,
+                    uint8_t* packed_or_null, int32_t* counts, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (a-1..a-3) support-classifier fit.  Replaces the inline loop of src/test.py:164-187
+ * (= src/train.py:206-231) and PSPNet.inner_loop, src/model/pspnet.py:189-205:
+ * n_iter x { 1x1 conv 2xC, bilinear up to HxW, class-weighted CE (ignore), backward, SGD }.
+ *   f_s     [E,S,C,h,w] fp32        s_label [E,S,H,W]
+ *   w0      [E,2,C] initial weights (the reference draws them with kaiming-uniform, a-1)
+ *   class_weight_or_null [E,2]; NULL => [1, n0/n1] counted on the device over all S shots
+ *   w_out   [E,2,C]
+ *   loss_trace_or_null [n_iter,E]: the CE value of every step (slower kernels when given)
+ *   label_counts_or_null [E,4] int32 out: n0,n1,n_ignored,n_invalid per episode; n1 == 0 is
+ *       the reference's ZeroDivisionError — the caller checks it (the Python layer raises)
+ * ------------------------------------------------------------------------------------- */
+size_t cwt_fit_workspace_bytes(int E, int S, int C, int h, int w, int H, int W);
+int cwt_fit_classifier_f32(const float* f_s, const void* s_label, int label_kind, const float* w0,
+                           const float* class_weight_or_null, float* w_out,
+                           float* loss_trace_or_null, int32_t* label_counts_or_null,
+                           int E, int S, int C, int h, int w, int H, int W,
+                           int n_iter, float lr, int ignore_index, int algo,
+                           void* workspace, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (a-5, a-6) MultiHeadAttentionOne forward.  Replaces src/model/transformer.py:54-83
+ * (+ ScaledDotProductAttention :23-30) for the call transformer(W, f_q, f_q) of
+ * src/test.py:197 / src/train.py:257 (k is v, one shared projection w_qkvs).
+ *   q        [E,Lq,C]  (the classifier weights; Lq = 2 on the path, <= 4 supported)
+ *   k        [E,C,HW]  query features; normalize_k != 0 fuses F.normalize(dim=1) (src/test.py:194)
+ *   w_qkvs   [nH*C, C]   fc_w [C, nH*C]   fc_b, ln_g, ln_b [C]     (d_model = d_k = d_v = C)
+ *   keep_attn_or_null [nH,E,Lq,HW] uint8 keep-mask of the attention dropout (scaled 1/(1-p_attn))
+ *   keep_out_or_null  [E,Lq,C]     uint8 keep-mask of the output dropout   (scaled 1/(1-p_out))
+ *   out      [E,Lq,C]
+ *   saved_or_null: activations kept for cwt_transformer_bwd_f32 (size: cwt_transformer_saved_bytes)
+ * ------------------------------------------------------------------------------------- */
+size_t cwt_transformer_workspace_bytes(int E, int Lq, int nH, int C, int HW, int algo);
+size_t cwt_transformer_saved_bytes(int E, int Lq, int nH, int C, int HW);
+int cwt_transformer_fwd_f32(const float* q, const float* k, int normalize_k,
+                            const float* w_qkvs, const float* fc_w, const float* fc_b,
+                            const float* ln_g, const float* ln_b,
+                            const uint8_t* keep_attn_or_null, const uint8_t* keep_out_or_null,
+                            float p_attn, float p_out, float* out, void* saved_or_null,
+                            int E, int Lq, int nH, int C, int HW, int algo,
+                            void* workspace, size_t ws_bytes, void* stream);
+
+/* (a-13) backward of the block w.r.t. its five parameters, given dL/d(out) [E,Lq,C].
+ * Gradients are SUMMED over the E episodes of the batch into d_* (which the call overwrites).
+ * No gradient w.r.t. q or k (src/train.py:246-253: .data / no_grad). */
+int cwt_transformer_bwd_f32(const float* d_out, const float* q, const float* k, int normalize_k,
+                            const float* w_qkvs, const float* fc_w, const float* ln_g,
+                            const uint8_t* keep_attn_or_null, const uint8_t* keep_out_or_null,
+                            float p_attn, float p_out, const void* saved,
+                            float* d_w_qkvs, float* d_fc_w, float* d_fc_b, float* d_ln_g, float* d_ln_b,
+                            int E, int Lq, int nH, int C, int HW,
+                            void* workspace, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (a-4, a-7..a-12) query logits -> bilinear up to HxW -> argmax -> intersection/union (+CE).
+ * Replaces src/test.py:192,200-204,214-223 and batch_intersectionAndUnionGPU /
+ * intersectionAndUnionGPU, src/util.py:237-308.
+ *   w        [E,V,2,C]  V weight sets per episode (e.g. adapted and baseline classifier)
+ *   f_q      [E,C,h,w]
+ *   normalize_mask: bit v set => variant v scores the L2-normalised features (src/test.py:194,204)
+ *   iu_counts  [E,V,2,3] int64 out: per class I, U, T   (U = O + T - I as util.py:306)
+ *   logits60_or_null [E,V,2,h,w] fp32 out
+ *   ce_or_null [E,V,2] double out: sum of -log p[y] over valid pixels, number of valid pixels
+ *   weighted CE for training (a-13): see cwt_query_loss_grad below.
+ * ------------------------------------------------------------------------------------- */
+size_t cwt_logits_iou_workspace_bytes(int E, int V, int C, int h, int w, int H, int W);
+int cwt_logits_iou(const float* w, const float* f_q, const void* q_label, int label_kind,
+                   int normalize_mask, long long* iu_counts, float* logits60_or_null,
+                   double* ce_or_null, int E, int V, int C, int h, int w, int H, int W,
+                   int ignore_index, void* workspace, size_t ws_bytes, void* stream);
+
+/* Same tail on ready-made low-resolution logits: the drop-in for
+ * batch_intersectionAndUnionGPU(logits[n,2,h,w] -> counts[n,2,3]).  (src/util.py:237-277) */
+int cwt_upsample_argmax_iou(const float* logits60, const void* label, int label_kind,
+                            long long* iu_counts, double* ce_or_null,
+                            int n, int h, int w, int H, int W, int ignore_index, void* stream);
+
+/* intersectionAndUnionGPU on ready-made integer predictions (src/util.py:280-308), 2 classes+.
+ *   preds, target [n, npix] (same label_kind), counts [n, num_classes, 3] int64 */
+int cwt_intersection_union(const void* preds, const void* target, int label_kind, long long* counts,
+                           int n, long long npix, int num_classes, int ignore_index, void* stream);
+
+/* (a-13) training loss on the query: weighted CE at HxW of up(logits60) and its gradient
+ * w.r.t. logits60 (the adjoint bilinear map), class weight [1, n0/(n1+1e-12)] counted on
+ * the device (src/train.py:237-243,262-264).
+ *   logits60 [E,2,h,w]; label [E,H,W]; loss [E] fp32 out; d_logits60 [E,2,h,w] out */
+size_t cwt_query_loss_workspace_bytes(int E, int h, int w, int H, int W);
+int cwt_query_loss_grad(const float* logits60, const void* label, int label_kind,
+                        float* loss, float* d_logits60, int E, int h, int w, int H, int W,
+                        int ignore_index, void* workspace, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CWT_B200_H_ */

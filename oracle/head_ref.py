@@ -1,0 +1,289 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY. Never imported by the product package.
+
+CPU restatement (PyTorch fp32/fp64, the same ATen ops the reference executes) of the
+per-episode few-shot segmentation head of TeamOfProfGuo/Few_Shot_Seg_CWT:
+
+    support-classifier fit  ->  Classifier Weight Transformer  ->  query logits /
+    473x473 upsample / argmax / intersection-union
+
+Every function cites the reference ``file:line`` it follows (paths relative to the
+reference checkout). Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
+``cpu_baseline`` / ``--impl reference`` legs may import this module, and only as the
+checker or as the timed CPU baseline — never as a product code path.
+
+Parity pin: the reference repository has **no tests, fixtures or golden vectors** of its
+own, so this restatement is pinned against the *live reference code*
+imported from ``/root/reference`` (``oracle/pin_against_reference.py`` — the reference's
+own ``MultiHeadAttentionOne``, ``batch_intersectionAndUnionGPU``, ``intersectionAndUnionGPU``
+objects and a literal transcription of the ``src/test.py:162-234`` episode body that
+calls them) and the outputs are committed under ``tests/golden/``. All arithmetic on
+the path is third-party ATen (torch; the reference pins torch==1.6.0 in README prose
+only, README.md:11-15; this container has torch 2.11.0).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+IGNORE = 255
+
+
+# --------------------------------------------------------------------------------------
+# (a-2) class weight                                              src/test.py:169-175
+# --------------------------------------------------------------------------------------
+def class_weight_ref(s_label: torch.Tensor) -> torch.Tensor:
+    """``[1.0, n0 / n1]`` with n0/n1 counted over all shots jointly; python float division
+    (raises ZeroDivisionError when the support mask is empty), stored as fp32."""
+    arr = s_label.cpu().numpy()
+    n0 = int((arr == 0).sum())
+    n1 = int((arr == 1).sum())
+    return torch.tensor([1.0, n0 / n1])
+
+
+# --------------------------------------------------------------------------------------
+# (a-1, a-3) support classifier fit                               src/test.py:164-187
+#            (= src/train.py:206-231, src/model/pspnet.py:189-205 inner_loop)
+# --------------------------------------------------------------------------------------
+def fit_classifier_ref(f_s: torch.Tensor, s_label: torch.Tensor, w0: torch.Tensor, lr: float,
+                       n_iter: int, class_weight: Optional[torch.Tensor] = None,
+                       return_losses: bool = False, dtype: torch.dtype = torch.float32):
+    """Literal loop: 1x1 conv -> bilinear upsample (align_corners) to the label size ->
+    class-weighted CE (ignore 255) -> backward -> plain SGD step.
+
+    f_s [S,C,h,w]; s_label [S,H,W] (any integer dtype); w0 [2,C]. Returns W_fit [2,C]
+    (and the per-step losses)."""
+    S, C = f_s.shape[:2]
+    f_s = f_s.to(dtype)
+    tgt = s_label.long()
+    clf = nn.Conv2d(C, 2, kernel_size=1, bias=False).to(dtype)
+    with torch.no_grad():
+        clf.weight.copy_(w0.reshape(2, C, 1, 1).to(dtype))
+    opt = torch.optim.SGD(clf.parameters(), lr=lr)
+    wt = class_weight_ref(s_label) if class_weight is None else class_weight
+    crit = nn.CrossEntropyLoss(weight=wt.to(dtype), ignore_index=IGNORE)
+    losses = []
+    for _ in range(n_iter):
+        out = clf(f_s)
+        out = F.interpolate(out, size=tgt.shape[-2:], mode="bilinear", align_corners=True)
+        loss = crit(out, tgt)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        if return_losses:
+            losses.append(float(loss))
+    w = clf.weight.detach().reshape(2, C).clone()
+    return (w, losses) if return_losses else w
+
+
+def bilinear_matrix(n_in: int, n_out: int, dtype=torch.float64) -> torch.Tensor:
+    """Dense [n_out, n_in] align_corners=True interpolation matrix (2 non-zeros per row).
+    ATen: scale = (n_in-1)/(n_out-1); src = scale*dst; i0 = floor(src); l1 = src - i0."""
+    B = torch.zeros(n_out, n_in, dtype=dtype)
+    scale = (n_in - 1) / (n_out - 1) if n_out > 1 else 0.0
+    for o in range(n_out):
+        src = scale * o
+        i0 = min(int(math.floor(src)), n_in - 1)
+        i1 = min(i0 + 1, n_in - 1)
+        l1 = src - i0
+        B[o, i0] += 1.0 - l1
+        B[o, i1] += l1
+    return B
+
+
+def fit_classifier_closed_form(f_s, s_label, w0, lr, n_iter, class_weight=None,
+                               dtype=torch.float64):
+    """Independent restatement of the same loop with explicit matrices — no autograd,
+    no F.interpolate, no nn.CrossEntropyLoss (SURVEY.md §8 a-3 formula):
+        L60 = W F ; U = Bh L60 Bw^T ; p = softmax_c(U) ; G = w_y (p - 1_y) / sum w_y
+        G60 = Bh^T G Bw ; dW = G60 F^T ; W <- W - lr dW
+    Used to cross-check fit_classifier_ref and to study fp32 vs fp64 drift."""
+    S, C, h, w = f_s.shape
+    H, W = s_label.shape[-2:]
+    Fm = f_s.to(dtype).reshape(S, C, h * w)
+    y = s_label.long()
+    wt = (class_weight_ref(s_label) if class_weight is None else class_weight).to(dtype)
+    Bh = bilinear_matrix(h, H, dtype)
+    Bw = bilinear_matrix(w, W, dtype)
+    valid = (y != IGNORE)
+    ys = torch.where(valid, y, torch.zeros_like(y))
+    wy = wt[ys] * valid.to(dtype)                       # [S,H,W]
+    denom = wy.sum()
+    onehot = torch.stack([(ys == 0), (ys == 1)], 1).to(dtype)  # [S,2,H,W]
+    Wc = w0.to(dtype).clone()
+    for _ in range(n_iter):
+        L60 = torch.einsum("kc,scp->skp", Wc, Fm).reshape(S, 2, h, w)
+        U = torch.einsum("Yy,skyx,Xx->skYX", Bh, L60, Bw)
+        p = torch.softmax(U, dim=1)
+        G = (p - onehot) * (wy / denom).unsqueeze(1)
+        G60 = torch.einsum("Yy,skYX,Xx->skyx", Bh, G, Bw).reshape(S, 2, h * w)
+        dW = torch.einsum("skp,scp->kc", G60, Fm)
+        Wc = Wc - lr * dW
+    return Wc
+
+
+# --------------------------------------------------------------------------------------
+# (a-6) MultiHeadAttentionOne                         src/model/transformer.py:12-83
+# --------------------------------------------------------------------------------------
+def mha_one_forward_ref(q: torch.Tensor, k: torch.Tensor, params: Dict[str, torch.Tensor],
+                        n_head: int, keep_attn: Optional[torch.Tensor] = None,
+                        keep_out: Optional[torch.Tensor] = None,
+                        p_attn: float = 0.1, p_out: float = 0.5) -> torch.Tensor:
+    """Functional restatement of ``MultiHeadAttentionOne.forward(q, k, v)`` with ``v is k``.
+
+    q [B,Lq,C] (the classifier weights, Lq=2); k [B,C,h,w] (normalised query features).
+    params: reference state-dict names. Eval mode when both keep masks are None; otherwise
+    inverted dropout with explicit uint8/bool keep-masks: ``keep_attn [nH*B, Lq, HW]``
+    (head-major, as the reference's permute(2,0,1,3) lays heads out; transformer.py:71-75)
+    scaled by 1/(1-p_attn) and ``keep_out [B,Lq,C]`` scaled by 1/(1-p_out)
+    (transformer.py:17-20,28,52,80)."""
+    A = params["w_qkvs.weight"]
+    B_, Lq, C = q.shape
+    d_k = A.shape[0] // n_head
+    X = k.reshape(B_, k.shape[1], -1).permute(0, 2, 1)           # [B,HW,C]   :55-59
+    HW = X.shape[1]
+    Q = (q @ A.t()).view(B_, Lq, n_head, d_k)                     # :67
+    K = (X @ A.t()).view(B_, HW, n_head, d_k)                     # :68-69 (k is v, one weight)
+    Qh = Q.permute(2, 0, 1, 3).reshape(-1, Lq, d_k)               # [(nH*B),Lq,dk]  :71
+    Kh = K.permute(2, 0, 1, 3).reshape(-1, HW, d_k)               # :72-73
+    attn = torch.bmm(Qh, Kh.transpose(1, 2)) / float(np.power(d_k, 0.5))   # :24-25,47
+    attn = torch.softmax(attn, dim=2)                             # :27
+    if keep_attn is not None:
+        attn = attn * keep_attn.to(attn.dtype) / (1.0 - p_attn)   # :28
+    out = torch.bmm(attn, Kh)                                     # :29
+    out = out.view(n_head, B_, Lq, d_k).permute(1, 2, 0, 3).reshape(B_, Lq, -1)  # :77-78
+    out = out @ params["fc.weight"].t() + params["fc.bias"]       # :80
+    if keep_out is not None:
+        out = out * keep_out.to(out.dtype) / (1.0 - p_out)        # :80
+    return F.layer_norm(out + q, (C,), params["layer_norm.weight"],
+                        params["layer_norm.bias"], 1e-5)          # :81
+
+
+# --------------------------------------------------------------------------------------
+# (a-9, a-10) intersection / union                                src/util.py:237-308
+# --------------------------------------------------------------------------------------
+def intersection_and_union_ref(preds: torch.Tensor, target: torch.Tensor, num_classes: int,
+                               ignore_index: int = IGNORE):
+    """preds, target integer tensors of identical shape. Returns float32 (I, U, T) [num_classes]
+    computed with histc exactly as src/util.py:297-307 (ignored pixels fall outside the
+    histc range). Unlike the reference it does not mutate the caller's ``preds``."""
+    assert preds.dim() in [1, 2, 3]
+    assert preds.shape == target.shape
+    preds = preds.reshape(-1).clone()
+    target = target.reshape(-1)
+    preds[target == ignore_index] = ignore_index
+    inter = preds[preds == target]
+    a_i = torch.histc(inter.float(), bins=num_classes, min=0, max=num_classes - 1)
+    a_o = torch.histc(preds.float(), bins=num_classes, min=0, max=num_classes - 1)
+    a_t = torch.histc(target.float(), bins=num_classes, min=0, max=num_classes - 1)
+    return a_i, a_o + a_t - a_i, a_t
+
+
+def batch_intersection_and_union_ref(logits: torch.Tensor, target: torch.Tensor, num_classes: int,
+                                     ignore_index: int = IGNORE):
+    """logits [n_task,shot,C,h,w]; target [n_task,shot,H,W] -> (I,U,T) float32 [n_task,shot,C]
+    (src/util.py:237-277: bilinear align_corners upsample, argmax over classes, per-item histc)."""
+    n_task, shots, ncls, h, w = logits.shape
+    H, W = target.shape[-2:]
+    up = F.interpolate(logits.reshape(n_task * shots, ncls, h, w), size=(H, W), mode="bilinear",
+                       align_corners=True).view(n_task, shots, ncls, H, W)
+    preds = up.argmax(2)
+    I = torch.zeros(n_task, shots, ncls)
+    U = torch.zeros(n_task, shots, ncls)
+    T = torch.zeros(n_task, shots, ncls)
+    for t in range(n_task):
+        for s in range(shots):
+            i, u, tt = intersection_and_union_ref(preds[t][s], target[t][s].long(), ncls, ignore_index)
+            I[t, s], U[t, s], T[t, s] = i, u, tt
+    return I, U, T
+
+
+# --------------------------------------------------------------------------------------
+# the whole episode body                                          src/test.py:162-234
+# --------------------------------------------------------------------------------------
+def episode_ref(f_s, s_label, f_q, q_label, w0, params, n_head: int, lr: float, n_iter: int,
+                dtype: torch.dtype = torch.float32) -> Dict[str, torch.Tensor]:
+    """One evaluation episode on pre-computed features (the frozen backbone is outside
+    the path). f_s [S,C,h,w]; s_label [S,H,W]; f_q [C,h,w]; q_label [H,W]; w0 [2,C].
+
+    Returns W_fit, W_adapted [2,C]; logits60 / logits60_0 [2,h,w] (adapted / baseline);
+    counts / counts0 int64 [2 classes, 3 = I,U,T]; loss (unweighted CE of the upsampled
+    adapted logits, src/test.py:222-223); tie_margin [H,W] = |up(l1) - up(l0)| of the adapted
+    logits (for the stated argmax-tie set)."""
+    C, h, w = f_q.shape
+    H, W = q_label.shape
+    w_fit = fit_classifier_ref(f_s, s_label, w0, lr, n_iter, dtype=dtype)          # :164-187
+    with torch.no_grad():
+        fq = f_q.to(dtype).unsqueeze(0)
+        pred_q0 = F.conv2d(fq, w_fit.view(2, C, 1, 1))                              # :192
+        fqn = F.normalize(fq, dim=1)                                                # :194
+        pd = {k: v.to(dtype) for k, v in params.items()}
+        w_ad = mha_one_forward_ref(w_fit.view(1, 2, C), fqn, pd, n_head)            # :195-197
+        pred_q = F.conv2d(fqn, w_ad.view(2, C, 1, 1))                               # :200-204
+        tgt = q_label.long().view(1, 1, H, W)
+        up = F.interpolate(pred_q.float(), size=(H, W), mode="bilinear", align_corners=True)   # :214
+        up0 = F.interpolate(pred_q0.float(), size=(H, W), mode="bilinear", align_corners=True)  # :215
+        I, U, T = batch_intersection_and_union_ref(up.unsqueeze(1), tgt, 2)         # :216
+        I0, U0, T0 = batch_intersection_and_union_ref(up0.unsqueeze(1), tgt, 2)     # :218
+        loss = F.cross_entropy(up, tgt.view(1, H, W), ignore_index=IGNORE)          # :222-223
+    counts = torch.stack([I[0, 0], U[0, 0], T[0, 0]], 1).round().long()
+    counts0 = torch.stack([I0[0, 0], U0[0, 0], T0[0, 0]], 1).round().long()
+    return {
+        "W_fit": w_fit, "W_adapted": w_ad[0], "logits60": pred_q[0], "logits60_0": pred_q0[0],
+        "counts": counts, "counts0": counts0, "loss": loss,
+        "tie_margin": (up[0, 1] - up[0, 0]).abs(), "tie_margin0": (up0[0, 1] - up0[0, 0]).abs(),
+    }
+
+
+def miou_from_counts(cls_I: Dict[int, float], cls_U: Dict[int, float]) -> float:
+    """src/test.py:232-243: IoU_c = I_c / (U_c + 1e-10), mean over classes seen."""
+    return float(np.mean([cls_I[c] / (cls_U[c] + 1e-10) for c in cls_U]))
+
+
+# --------------------------------------------------------------------------------------
+# (a-13) meta-training step of the transformer                    src/train.py:233-267
+# --------------------------------------------------------------------------------------
+def query_class_weight_ref(q_label: torch.Tensor) -> torch.Tensor:
+    """src/train.py:237-243: [1, n0 / (n1 + 1e-12)]."""
+    arr = q_label.cpu().numpy()
+    n0 = int((arr == 0).sum())
+    n1 = int((arr == 1).sum())
+    return torch.tensor([1.0, n0 / (n1 + 1e-12)])
+
+
+def meta_train_step_ref(w_fit, f_q, q_label, params, n_head, keep_attn=None, keep_out=None,
+                        p_attn=0.1, p_out=0.5, dtype=torch.float32):
+    """Forward a-5..a-7 in train mode, weighted CE at full resolution, backward to the five
+    transformer parameters (autograd). No gradient flows to w_fit (it enters as ``.data``,
+    src/train.py:253) nor to f_q (``no_grad``, :246-250).
+
+    Returns dict(loss, W_adapted, grads{name: tensor})."""
+    C, h, w = f_q.shape
+    H, W = q_label.shape
+    pd = {k: v.detach().clone().to(dtype).requires_grad_(True) for k, v in params.items()}
+    with torch.no_grad():
+        fqn = F.normalize(f_q.to(dtype).unsqueeze(0), dim=1)                        # :250
+    q = w_fit.detach().to(dtype).view(1, 2, C)
+    w_ad = mha_one_forward_ref(q, fqn, pd, n_head, keep_attn, keep_out, p_attn, p_out)   # :257
+    pred = torch.matmul(w_ad, fqn.view(1, C, -1)).view(1, 2, h, w)                  # :259-261
+    pred = F.interpolate(pred, size=(H, W), mode="bilinear", align_corners=True)    # :262
+    wt = query_class_weight_ref(q_label).to(dtype)
+    loss = F.cross_entropy(pred, q_label.long().view(1, H, W), weight=wt, ignore_index=IGNORE)  # :264
+    loss.backward()                                                                  # :266
+    return {"loss": loss.detach(), "W_adapted": w_ad.detach()[0],
+            "grads": {k: v.grad.detach() for k, v in pd.items()}}
+
+
+def sgd_nesterov_step_ref(params, grads, bufs, lr, momentum=0.9, weight_decay=1e-4):
+    """torch.optim.SGD(momentum, nesterov=True, weight_decay) update (src/optimizer.py:11-15)."""
+    new_p, new_b = {}, {}
+    for k in params:
+        g = grads[k] + weight_decay * params[k]
+        b = g.clone() if bufs is None or k not in bufs else momentum * bufs[k] + g
+        new_b[k] = b
+        new_p[k] = params[k] - lr * (g + momentum * b)
+    return new_p, new_b

@@ -1,0 +1,312 @@
+"""ORACLE PIN — TEST INFRASTRUCTURE ONLY (run in the build container, where /root/reference exists).
+
+    python -m oracle.pin_against_reference [--write]
+
+1. Imports the *live reference code* (``/root/reference/src``) and checks the restatement in
+   ``oracle/head_ref.py`` against it on seeded inputs:
+     * ``MultiHeadAttentionOne`` (src/model/transformer.py:33-83) in eval mode, and in train
+       mode with the dropout keep-masks captured from the reference's own ``nn.Dropout``
+       modules by forward hooks (so the explicit-mask convention is pinned too), forward
+       and parameter gradients;
+     * ``batch_intersectionAndUnionGPU`` / ``intersectionAndUnionGPU`` (src/util.py:237-308).
+2. Runs the episode body of ``src/test.py:162-234`` with the reference's own module objects
+   doing the work (``episode_via_reference``) and the meta-training step of
+   ``src/train.py:233-267``, and with ``--write`` stores the outputs as golden vectors under
+   ``tests/golden/`` (inputs are regenerated from the episode seed by
+   ``few_shot_seg_cwt_b200.synthetic``; an input checksum is stored beside the outputs).
+
+The reference ships no tests or fixtures of its own, so these files *are* the pin.
+"""
+from __future__ import annotations
+
+import argparse
+import hashlib
+import json
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+REF = os.environ.get("CWT_REFERENCE", "/root/reference")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import head_ref as O  # noqa: E402
+from few_shot_seg_cwt_b200 import synthetic as syn  # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+# name -> generator / hyper-parameter settings.  "full" = BASELINE.json shapes.
+CASES = {
+    # small shapes (CPU suite, seconds)
+    "small_1shot_h1":  dict(idx=3, shot=1, C=64, h=12, w=12, H=89, W=89, style="unit", n_head=1, lr=0.0025, n_iter=200),
+    "small_1shot_h4":  dict(idx=4, shot=1, C=64, h=12, w=12, H=89, W=89, style="unit", n_head=4, lr=0.1, n_iter=200),
+    "small_5shot_h4":  dict(idx=5, shot=5, C=64, h=12, w=12, H=89, W=89, style="unit", n_head=4, lr=0.1, n_iter=50),
+    "small_rect":      dict(idx=6, shot=2, C=128, h=9, w=14, H=65, W=105, style="backbone", n_head=2, lr=0.01, n_iter=30),
+    # BASELINE.json configs[0] (pascal.yaml defaults) and the scripts/test.sh overrides
+    "full_1shot_h1_yaml":    dict(idx=0, shot=1, C=512, h=60, w=60, H=473, W=473, style="unit", n_head=1, lr=0.0025, n_iter=200),
+    "full_1shot_h4_script":  dict(idx=1, shot=1, C=512, h=60, w=60, H=473, W=473, style="unit", n_head=4, lr=0.1, n_iter=200),
+    "full_1shot_h4_backbone": dict(idx=2, shot=1, C=512, h=60, w=60, H=473, W=473, style="backbone", n_head=4, lr=0.1, n_iter=200),
+    # configs[1]: 5-shot, pooled class weight and pooled mean
+    "full_5shot_h4":         dict(idx=7, shot=5, C=512, h=60, w=60, H=473, W=473, style="unit", n_head=4, lr=0.1, n_iter=200),
+}
+TRAIN_CASES = {
+    "train_small_h2": dict(idx=11, shot=1, C=64, h=12, w=12, H=89, W=89, style="unit", n_head=2, lr=0.1, n_iter=20, p_attn=0.1, p_out=0.5),
+    "train_full_h1":  dict(idx=12, shot=1, C=512, h=60, w=60, H=473, W=473, style="unit", n_head=1, lr=0.1, n_iter=20, p_attn=0.1, p_out=0.5),
+}
+
+
+def _import_reference():
+    sys.path.insert(0, REF)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from src.model.transformer import MultiHeadAttentionOne
+        from src.util import batch_intersectionAndUnionGPU, intersectionAndUnionGPU
+    return MultiHeadAttentionOne, batch_intersectionAndUnionGPU, intersectionAndUnionGPU
+
+
+def input_checksum(ep: syn.Episode) -> str:
+    hsh = hashlib.sha256()
+    for t in (ep.f_s, ep.s_label, ep.f_q, ep.q_label, ep.w0):
+        hsh.update(t.contiguous().numpy().tobytes())
+    return hsh.hexdigest()
+
+
+def gen_kwargs(case):
+    return {k: case[k] for k in ("shot", "C", "h", "w", "H", "W", "style")}
+
+
+def build_reference_transformer(MHA, params, n_head, C, dropout=0.5):
+    m = MHA(n_head, C, C, C, dropout=dropout)       # ctor as src/test.py:57 / src/train.py:96
+    m.load_state_dict(params)                        # names pinned by SURVEY.md §5
+    return m
+
+
+def episode_via_reference(ep, params, n_head, lr, n_iter, MHA, batch_iou):
+    """src/test.py:162-234 with the reference's own objects on the path (CPU, fp32)."""
+    C, h, w = ep.f_q.shape
+    H, W = ep.q_label.shape
+    transformer = build_reference_transformer(MHA, params, n_head, C).eval()
+    s_label = ep.s_label.long().unsqueeze(0)                                   # [1,S,H,W]
+    binary_classifier = nn.Conv2d(C, 2, kernel_size=1, bias=False)
+    with torch.no_grad():
+        binary_classifier.weight.copy_(ep.w0.view(2, C, 1, 1))                # explicit W0 (a-1)
+    optimizer = torch.optim.SGD(binary_classifier.parameters(), lr=lr)
+    arr = s_label.numpy().copy()
+    back_pix, target_pix = np.where(arr == 0), np.where(arr == 1)
+    criterion = nn.CrossEntropyLoss(weight=torch.tensor([1.0, len(back_pix[0]) / len(target_pix[0])]),
+                                    ignore_index=255)
+    f_s = ep.f_s
+    for _ in range(n_iter):
+        out = binary_classifier(f_s)
+        out = F.interpolate(out, size=s_label.size()[2:], mode="bilinear", align_corners=True)
+        loss = criterion(out, s_label.squeeze(0))
+        optimizer.zero_grad()
+        loss.backward()
+        optimizer.step()
+    with torch.no_grad():
+        f_q = ep.f_q.unsqueeze(0)
+        pred_q0 = binary_classifier(f_q)
+        f_q = F.normalize(f_q, dim=1)
+        weights_cls = binary_classifier.weight.data
+        wr = weights_cls.squeeze().unsqueeze(0).expand(f_q.shape[0], 2, C)
+        updated = transformer(wr, f_q, f_q)
+        pseudo = nn.Conv2d(C, 2, kernel_size=1, bias=False)
+        pseudo.weight.data = torch.as_tensor(updated.squeeze(0).unsqueeze(2).unsqueeze(3))
+        pred_q = pseudo(f_q)
+    logits_q = pred_q.detach().unsqueeze(0)          # [1,1,2,h,w]
+    logits_q0 = pred_q0.detach().unsqueeze(0)
+    gt_q = ep.q_label.long().view(1, 1, H, W)
+    logits = F.interpolate(logits_q.squeeze(1), size=(H, W), mode="bilinear", align_corners=True).detach()
+    logits0 = F.interpolate(logits_q0.squeeze(1), size=(H, W), mode="bilinear", align_corners=True).detach()
+    I, U, T = batch_iou(logits.unsqueeze(1), gt_q.clone(), 2)
+    I0, U0, T0 = batch_iou(logits0.unsqueeze(1), gt_q.clone(), 2)
+    loss = nn.CrossEntropyLoss(ignore_index=255)(logits, gt_q.squeeze(1))
+    return {
+        "W_fit": weights_cls.view(2, C).clone(), "W_adapted": updated[0].clone(),
+        "logits60": pred_q[0].clone(), "logits60_0": pred_q0[0].clone(),
+        "counts": torch.stack([I[0, 0], U[0, 0], T[0, 0]], 1).round().long(),
+        "counts0": torch.stack([I0[0, 0], U0[0, 0], T0[0, 0]], 1).round().long(),
+        "loss": loss,
+        "tie_margin": (logits[0, 1] - logits[0, 0]).abs(),
+        "tie_margin0": (logits0[0, 1] - logits0[0, 0]).abs(),
+    }
+
+
+def relerr(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def check_transformer(MHA):
+    """Eval + train-mode (captured masks) forward and parameter grads vs the reference module."""
+    worst = 0.0
+    for n_head, C, hw in ((1, 64, (12, 12)), (4, 64, (12, 12)), (2, 128, (9, 14))):
+        params = syn.make_transformer_params(n_head, C)
+        g = torch.Generator().manual_seed(n_head * 100 + C)
+        q = torch.randn(1, 2, C, generator=g) * 0.3
+        k = F.normalize(torch.relu(torch.randn(1, C, *hw, generator=g)), dim=1)
+        m = build_reference_transformer(MHA, params, n_head, C, dropout=0.5)
+        m.eval()
+        with torch.no_grad():
+            y_ref = m(q, k, k)
+        y = O.mha_one_forward_ref(q, k, params, n_head)
+        worst = max(worst, relerr(y, y_ref))
+        # train mode: capture the keep masks the reference drew
+        m.train()
+        cap = {}
+        h1 = m.attention.dropout.register_forward_hook(
+            lambda mod, inp, out: cap.__setitem__("attn", ((out != 0) | (inp[0] == 0))))
+        h2 = m.dropout.register_forward_hook(
+            lambda mod, inp, out: cap.__setitem__("out", ((out != 0) | (inp[0] == 0))))
+        torch.manual_seed(1234 + n_head)
+        y_ref = m(q, k, k)
+        tgt = torch.randn(y_ref.shape, generator=g)
+        (y_ref * tgt).sum().backward()
+        h1.remove(); h2.remove()
+        pd = {kk: v.clone().requires_grad_(True) for kk, v in params.items()}
+        y = O.mha_one_forward_ref(q, k, pd, n_head, cap["attn"], cap["out"],
+                                  p_attn=m.attention.dropout.p, p_out=m.dropout.p)
+        (y * tgt).sum().backward()
+        worst = max(worst, relerr(y.detach(), y_ref.detach()))
+        for name, prm in m.named_parameters():
+            worst = max(worst, relerr(pd[name].grad, prm.grad))
+    return worst
+
+
+def check_iou(batch_iou, single_iou):
+    g = torch.Generator().manual_seed(7)
+    ok = True
+    for (h, w, H, W) in ((12, 12, 89, 89), (60, 60, 473, 473), (9, 14, 65, 105)):
+        logits = torch.randn(3, 1, 2, h, w, generator=g)
+        tgt = torch.randint(0, 3, (3, 1, H, W), generator=g)
+        tgt[tgt == 2] = 255
+        a = batch_iou(logits, tgt.clone(), 2)
+        b = O.batch_intersection_and_union_ref(logits, tgt, 2)
+        ok &= all(torch.equal(x, y) for x, y in zip(a, b))
+        p = torch.randint(0, 2, (H, W), generator=g)
+        a = single_iou(p.clone(), tgt[0, 0].clone(), 2)
+        b = O.intersection_and_union_ref(p, tgt[0, 0], 2)
+        ok &= all(torch.equal(x, y) for x, y in zip(a, b))
+    return ok
+
+
+def train_step_via_reference(ep, params, case, MHA):
+    """src/train.py:233-267 with the reference module in train mode; returns outputs and the
+    keep masks it drew (so CUDA / oracle can be fed the same masks)."""
+    C, h, w = ep.f_q.shape
+    H, W = ep.q_label.shape
+    n_head = case["n_head"]
+    w_fit = O.fit_classifier_ref(ep.f_s, ep.s_label, ep.w0, case["lr"], case["n_iter"])
+    m = build_reference_transformer(MHA, params, n_head, C, dropout=case["p_out"]).train()
+    cap = {}
+    h1 = m.attention.dropout.register_forward_hook(
+        lambda mod, inp, out: cap.__setitem__("attn", ((out != 0) | (inp[0] == 0))))
+    h2 = m.dropout.register_forward_hook(
+        lambda mod, inp, out: cap.__setitem__("out", ((out != 0) | (inp[0] == 0))))
+    torch.manual_seed(2021 + ep.idx)
+    q_label = ep.q_label.long().unsqueeze(0)
+    arr = q_label.numpy().copy()
+    q_back, q_tgt = np.where(arr == 0), np.where(arr == 1)
+    criterion = nn.CrossEntropyLoss(weight=torch.tensor([1.0, len(q_back[0]) / (len(q_tgt[0]) + 1e-12)]),
+                                    ignore_index=255)
+    with torch.no_grad():
+        f_q = F.normalize(ep.f_q.unsqueeze(0), dim=1)
+    wr = w_fit.view(2, C, 1, 1).squeeze().unsqueeze(0).expand(1, 2, C)
+    updated = m(wr, f_q, f_q)
+    pred_q = torch.matmul(updated, f_q.view(1, C, -1)).view(1, 2, h, w)
+    pred_q = F.interpolate(pred_q, size=q_label.shape[1:], mode="bilinear", align_corners=True)
+    loss_q = criterion(pred_q, q_label)
+    loss_q.backward()
+    h1.remove(); h2.remove()
+    grads = {n: p.grad.detach().clone() for n, p in m.named_parameters()}
+    return {"W_fit": w_fit, "W_adapted": updated.detach()[0], "loss": loss_q.detach(),
+            "grads": grads, "keep_attn": cap["attn"].to(torch.uint8), "keep_out": cap["out"].to(torch.uint8)}
+
+
+SUB = 5  # stride of the stored sub-sample of large gradient tensors
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--write", action="store_true", help="write tests/golden/*.npz")
+    ap.add_argument("--only", default=None)
+    a = ap.parse_args()
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    MHA, batch_iou, single_iou = _import_reference()
+    report = {"torch": torch.__version__, "numpy": np.__version__, "cases": {}}
+
+    e = check_transformer(MHA)
+    print(f"[pin] MultiHeadAttentionOne restatement vs reference module (fwd+grads, eval+train masks): max rel {e:.2e}")
+    assert e < 2e-6, e
+    ok = check_iou(batch_iou, single_iou)
+    print(f"[pin] intersection/union restatement vs reference functions: bit-exact={ok}")
+    assert ok
+    report["transformer_max_rel"] = e
+
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    for name, case in CASES.items():
+        if a.only and a.only not in name:
+            continue
+        ep = syn.make_episode(case["idx"], **gen_kwargs(case))
+        params = syn.make_transformer_params(case["n_head"], case["C"])
+        ref = episode_via_reference(ep, params, case["n_head"], case["lr"], case["n_iter"], MHA, batch_iou)
+        ora = O.episode_ref(ep.f_s, ep.s_label, ep.f_q, ep.q_label, ep.w0, params,
+                            case["n_head"], case["lr"], case["n_iter"])
+        errs = {k: relerr(ora[k], ref[k]) for k in ("W_fit", "W_adapted", "logits60", "logits60_0")}
+        cnt_ok = bool(torch.equal(ora["counts"], ref["counts"]) and torch.equal(ora["counts0"], ref["counts0"]))
+        print(f"[pin] {name}: oracle vs reference rel {errs} counts_equal={cnt_ok} "
+              f"loss {float(ref['loss']):.6f} counts {ref['counts'].tolist()}")
+        assert max(errs.values()) < 1e-6 and cnt_ok
+        report["cases"][name] = {"errs": errs, "loss": float(ref["loss"])}
+        if a.write:
+            tm, tm0 = ref["tie_margin"], ref["tie_margin0"]
+            np.savez_compressed(
+                os.path.join(GOLDEN_DIR, name + ".npz"),
+                case=json.dumps(case), checksum=input_checksum(ep), torch_version=torch.__version__,
+                W_fit=ref["W_fit"].numpy(), W_adapted=ref["W_adapted"].numpy(),
+                logits60=ref["logits60"].numpy(), logits60_0=ref["logits60_0"].numpy(),
+                counts=ref["counts"].numpy(), counts0=ref["counts0"].numpy(), loss=float(ref["loss"]),
+                # size of the stated argmax-tie set at a few thresholds (adapted / baseline)
+                tie_thresholds=np.array([1e-6, 1e-5, 1e-4]),
+                tie_counts=np.array([[int((tm <= t).sum()) for t in (1e-6, 1e-5, 1e-4)],
+                                     [int((tm0 <= t).sum()) for t in (1e-6, 1e-5, 1e-4)]]))
+
+    for name, case in TRAIN_CASES.items():
+        if a.only and a.only not in name:
+            continue
+        ep = syn.make_episode(case["idx"], **gen_kwargs(case))
+        params = syn.make_transformer_params(case["n_head"], case["C"])
+        ref = train_step_via_reference(ep, params, case, MHA)
+        ora = O.meta_train_step_ref(ref["W_fit"], ep.f_q, ep.q_label, params, case["n_head"],
+                                    ref["keep_attn"], ref["keep_out"], case["p_attn"], case["p_out"])
+        errs = {k: relerr(ora["grads"][k], ref["grads"][k]) for k in ref["grads"] if k != "layer_norm.bias"}
+        errs["loss"] = abs(float(ora["loss"]) - float(ref["loss"])) / abs(float(ref["loss"]))
+        errs["W_adapted"] = relerr(ora["W_adapted"], ref["W_adapted"])
+        print(f"[pin] {name}: oracle vs reference train step rel {errs}")
+        assert max(errs.values()) < 5e-5, errs
+        report["cases"][name] = {"errs": errs, "loss": float(ref["loss"])}
+        if a.write:
+            out = dict(case=json.dumps(case), checksum=input_checksum(ep), torch_version=torch.__version__,
+                       W_fit=ref["W_fit"].numpy(), W_adapted=ref["W_adapted"].numpy(), loss=float(ref["loss"]),
+                       keep_attn=np.packbits(ref["keep_attn"].numpy().reshape(-1)),
+                       keep_attn_shape=np.array(ref["keep_attn"].shape),
+                       keep_out=ref["keep_out"].numpy(), sub=SUB)
+            for k, gten in ref["grads"].items():
+                flat = gten.reshape(-1)
+                out["grad_" + k] = (flat if flat.numel() <= 70000 else flat[::SUB]).numpy()
+                out["gradnorm_" + k] = float(gten.double().norm())
+            np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **out)
+
+    if a.write:
+        with open(os.path.join(GOLDEN_DIR, "PIN_REPORT.json"), "w") as f:
+            json.dump(report, f, indent=1)
+    print("[pin] done")
+
+
+if __name__ == "__main__":
+    main()
