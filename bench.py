@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""Benchmark of the CWT per-episode head (BASELINE.json metric: episodes/sec, PASCAL 1-shot, 60x60x512).
+
+    python bench.py --gpus N --steps K --warmup W                 # our CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W  # reference algorithm on the host CPU
+
+A "step" is one pass of the head (fit 200 SGD steps -> transformer -> logits/upsample/argmax/IoU) over one
+batch of E synthetic episodes per GPU. N > 1: one process per GPU under torchrun, episodes sharded across ranks
+(weak scaling: E per rank fixed), the only collective is the int64 all-reduce of the IoU table each step.
+
+One JSON line on stdout (rank 0). `value` = device-resident throughput; `e2e` = the same through the public API
+with pinned host buffers (H2D of every input + D2H of the counts inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "episodes_per_sec_head_pascal_1shot_60x60x512"
+UNIT = "episodes/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--episodes", type=int, default=64, help="episodes per GPU per step")
+    ap.add_argument("--shot", type=int, default=1)
+    ap.add_argument("--heads", type=int, default=4)          # scripts/test.sh:16
+    ap.add_argument("--cls-lr", type=float, default=0.1)     # scripts/test.sh:15
+    ap.add_argument("--adapt-iter", type=int, default=200)   # config_files/pascal.yaml:43
+    ap.add_argument("--style", default="unit", choices=["unit", "backbone"])
+    ap.add_argument("--fit-algo", type=int, default=0)
+    ap.add_argument("--attn-algo", type=int, default=0)
+    ap.add_argument("--cpu-baseline-episodes", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic episodes generated per rank (tiled to E)")
+    return ap.parse_args()
+
+
+GEOM = dict(C=512, h=60, w=60, H=473, W=473)
+
+
+def workload_name(a):
+    return (f"PASCAL-5i {a.shot}-shot head, synthetic 473x473 episodes, f[{a.shot},512,60,60] fp32, heads={a.heads}, "
+            f"cls_lr={a.cls_lr}, adapt_iter={a.adapt_iter} (config_files/pascal.yaml + scripts/test.sh overrides)")
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_rate(a, n_episodes: int, warm: int = 1):
+    """The reference algorithm (oracle port, torch CPU, all host threads) on the same workload."""
+    from few_shot_seg_cwt_b200 import synthetic as syn
+    from oracle import head_ref as O
+    params = syn.make_transformer_params(a.heads, 512)
+    eps = [syn.make_episode(i, shot=a.shot, style=a.style, **GEOM) for i in range(warm + n_episodes)]
+    for ep in eps[:warm]:
+        O.episode_ref(ep.f_s, ep.s_label, ep.f_q, ep.q_label, ep.w0, params, a.heads, a.cls_lr, a.adapt_iter)
+    t0 = time.perf_counter()
+    for ep in eps[warm:]:
+        O.episode_ref(ep.f_s, ep.s_label, ep.f_q, ep.q_label, ep.w0, params, a.heads, a.cls_lr, a.adapt_iter)
+    dt = time.perf_counter() - t0
+    return n_episodes / dt, dt
+
+
+def run_reference(a, rank):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference is pure
+    Python and cannot travel to the GPU box). Rank 0 only."""
+    if rank != 0:
+        return
+    per_step = 2
+    from few_shot_seg_cwt_b200 import synthetic as syn
+    from oracle import head_ref as O
+    params = syn.make_transformer_params(a.heads, 512)
+    eps = [syn.make_episode(i, shot=a.shot, style=a.style, **GEOM) for i in range(per_step)]
+    run = lambda: [O.episode_ref(ep.f_s, ep.s_label, ep.f_q, ep.q_label, ep.w0, params, a.heads, a.cls_lr, a.adapt_iter) for ep in eps]
+    for _ in range(a.warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        run()
+    dt = time.perf_counter() - t0
+    v = per_step * a.steps / dt
+    cores = torch.get_num_threads()
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "episodes_per_step": per_step},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{per_step} episodes/step x {a.steps} steps, torch {torch.__version__} CPU fp32, "
+                                   f"oracle/head_ref.episode_ref (restatement of src/test.py:162-234)"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.impl == "reference":
+        run_reference(a, rank)
+        return
+
+    import torch.distributed as dist
+    import few_shot_seg_cwt_b200 as cwt
+    from few_shot_seg_cwt_b200 import synthetic as syn
+    from few_shot_seg_cwt_b200 import _lib as L
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback). Use --impl reference for the CPU arm.")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L.load()
+
+    E = a.episodes
+    F_bytes = 3600 * 512 * 4
+    P = 473 * 473
+    params = {k: v.to(dev) for k, v in syn.make_transformer_params(a.heads, 512).items()}
+
+    # synthetic episodes: rank r owns indices r, r+world, ... ; `distinct` generated, tiled up to E
+    nd = min(a.distinct, E)
+    idx = syn.shard_indices(nd * world, rank, world)
+    host = syn.make_batch(idx, shot=a.shot, style=a.style, **GEOM)
+    rep = (E + nd - 1) // nd
+    tile = lambda t: t.repeat(rep, *([1] * (t.dim() - 1)))[:E].contiguous()
+    host = syn.EpisodeBatch(*(tile(t) for t in (host.f_s, host.s_label, host.f_q, host.q_label, host.w0, host.subcls, host.idx)))
+    host = host.pin_memory()
+    devb = host.to(dev)
+    table = cwt.IoUTable(5, dev)
+    torch.cuda.synchronize()
+
+    def step_resident():
+        out = cwt.episode_head(devb.f_s, devb.s_label, devb.f_q, devb.q_label, devb.w0, params, a.heads, a.cls_lr,
+                               a.adapt_iter, fit_algo=a.fit_algo, attn_algo=a.attn_algo)
+        table.update(out.counts, devb.subcls, out.ce)
+        table.all_reduce()                      # the one collective (int64 counts), no-op at world 1
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput ("value") ----
+    for _ in range(a.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    n0 = L.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(a.steps):
+        step_resident()
+    ev1.record()
+    barrier()
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = L.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * E * a.steps / (ms / 1e3)
+
+    # ---- per-stage timing on the launching stream (roofline) ----
+    def timed(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps, r
+
+    fit_ms, w_fit = timed(lambda: cwt.fit_classifier(devb.f_s, devb.s_label, devb.w0, a.cls_lr, a.adapt_iter, check=False,
+                                                     algo=a.fit_algo))
+    tr_ms, w_ad = timed(lambda: cwt.transformer_forward(w_fit, devb.f_q, params["w_qkvs.weight"], params["fc.weight"],
+                                                        params["fc.bias"], params["layer_norm.weight"],
+                                                        params["layer_norm.bias"], a.heads, normalize_k=True, algo=a.attn_algo))
+    wts = torch.stack([w_ad, w_fit], 1)
+    iou_ms, _ = timed(lambda: cwt.logits_iou(wts, devb.f_q, devb.q_label, 0b01, return_logits=False))
+    label_bytes = devb.s_label.element_size()
+    bytes_fit = E * ((2 * a.adapt_iter + 1) * a.shot * F_bytes + a.shot * P * label_bytes + 2 * (2 * 512 * 4))
+    bytes_iou = E * (F_bytes + P * label_bytes + 2 * 6 * 8)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    fit_gbs = bytes_fit / (fit_ms / 1e3) / 1e9
+    roofline = {
+        "kernel": "fit_classifier: 200 x {rows_times_feat<1>, fit_hires, feat_times_cols<1>+SGD}",
+        "bound": "hbm", "achieved": fit_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": fit_gbs / hbm_peak,
+        "traffic": None, "peak_source": peak_src,
+        "algorithmic_bytes_per_call": bytes_fit, "ms_per_call": fit_ms,
+        "stages_ms": {"fit": fit_ms, "transformer": tr_ms, "logits_iou": iou_ms},
+        "logits_iou": {"achieved": bytes_iou / (iou_ms / 1e3) / 1e9, "frac": bytes_iou / (iou_ms / 1e3) / 1e9 / hbm_peak},
+    }
+
+    # ---- end to end through the public API with host buffers ("e2e") ----
+    e2e = None
+    if not a.no_e2e:
+        h2d = host.nbytes()
+        d2h_holder = {}
+
+        def step_e2e():
+            b = host.to(dev, non_blocking=True)
+            out = cwt.episode_head(b.f_s, b.s_label, b.f_q, b.q_label, b.w0, params, a.heads, a.cls_lr, a.adapt_iter,
+                                   fit_algo=a.fit_algo, attn_algo=a.attn_algo)
+            table.update(out.counts, b.subcls.to(dev), out.ce)
+            table.all_reduce()
+            c = out.counts.cpu()                # D2H read of the step's result (syncs the stream)
+            d2h_holder["n"] = c.numel() * c.element_size()
+            return c
+
+        for _ in range(max(1, a.warmup)):
+            step_e2e()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.steps):
+            step_e2e()
+        e1.record()
+        barrier()
+        ms_e = max_over_ranks(e0.elapsed_time(e1))
+        e2e = {"value": world * E * a.steps / (ms_e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h_holder.get("n", 0), "ms_per_step": ms_e / a.steps}
+
+    # ---- CPU baseline on the box's host cores (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        rate, dt = cpu_reference_rate(a, a.cpu_baseline_episodes)
+        cpu = {"value": rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{a.cpu_baseline_episodes} episodes of the same workload after 1 warm-up ({dt:.1f} s), "
+                         f"oracle/head_ref.episode_ref, torch {torch.__version__} CPU fp32"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "episodes_per_gpu_per_step": E, "global_episodes_per_step": E * world,
+                       "parallelism": f"episodes sharded over {world} GPU(s), int64 IoU all-reduce",
+                       "l2_policy": f"inputs larger than L2 ({host.nbytes() / 1e6:.0f} MB per step per GPU, streamed every SGD step)",
+                       "fit_algo": a.fit_algo, "attn_algo": a.attn_algo},
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "miou_adapted": table.miou(0), "miou_baseline": table.miou(1),
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,1 +1,40 @@
-"""placeholder — filled in below"""
+"""few_shot_seg_cwt_b200 — B200-native per-episode few-shot segmentation head of CWT.
+
+Hand-written sm_100a CUDA kernels behind a C ABI (include/cwt_b200.h, lib/libcwt_b200.so),
+wrapped with the reference's own Python call surface:
+
+    MultiHeadAttentionOne          src/model/transformer.py:33-83
+    fit_classifier / inner_loop    src/test.py:164-187, src/model/pspnet.py:189-205
+    batch_intersectionAndUnionGPU  src/util.py:237-277
+    intersectionAndUnionGPU        src/util.py:280-308
+    validate_transformer           src/test.py:103-254
+    meta_train_step                src/train.py:233-267
+
+Importing the package never needs a GPU; calling an op without the built library or without a CUDA
+tensor raises (there is no CPU fallback).
+"""
+from . import _lib, synthetic  # noqa: F401
+from .classifier import draw_initial_weights, get_classifier, inner_loop  # noqa: F401
+from .episodic import (HeadOutput, IoUTable, episode_head, meta_train_step, query_loss, run_sweep,  # noqa: F401
+                       transformer_params, validate_transformer)
+from .metrics import (batch_intersection_union_int, batch_intersectionAndUnionGPU,  # noqa: F401
+                      intersection_union_int, intersectionAndUnionGPU)
+from .ops import (feat_times_rows, fit_classifier, intersection_union, label_counts, logits_iou,  # noqa: F401
+                  query_loss_grad, rows_times_feat, transformer_backward, transformer_forward,
+                  upsample_argmax_iou)
+from .transformer import MultiHeadAttentionOne  # noqa: F401
+
+__all__ = [
+    "MultiHeadAttentionOne", "fit_classifier", "inner_loop", "get_classifier", "draw_initial_weights",
+    "batch_intersectionAndUnionGPU", "intersectionAndUnionGPU", "batch_intersection_union_int",
+    "intersection_union_int", "validate_transformer", "episode_head", "run_sweep", "IoUTable",
+    "meta_train_step", "query_loss", "transformer_forward", "transformer_backward", "logits_iou",
+    "upsample_argmax_iou", "intersection_union", "label_counts", "query_loss_grad",
+    "rows_times_feat", "feat_times_rows", "synthetic",
+]
+
+
+def register_torch_ops() -> None:
+    """Register ``torch.ops.cwt_b200.*`` custom ops in front of the C ABI."""
+    from .ops import _register_custom_ops
+    _register_custom_ops()

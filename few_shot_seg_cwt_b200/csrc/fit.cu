@@ -1,0 +1,134 @@
+// (a-1..a-3) Support-classifier fit — replaces the 200-step autograd loop of the reference
+// (src/test.py:164-187 = src/train.py:206-231 = PSPNet.inner_loop, src/model/pspnet.py:189-205).
+//
+// Math per SGD step, for every episode of the batch:
+//     zd   = (W1 - W0) . F                       logit difference, [S, h*w]          (RTF<1>)
+//     d    = up(zd)   bilinear, align_corners, scale exactly 1/8, at H x W
+//     p    = sigmoid(d) = softmax(U)[1]          2-class softmax == sigmoid of the difference
+//     g    = w[y] (p - y) / sum_i w[y_i]         (0 on ignored pixels)
+//     g60  = up^T(g)                             adjoint as a deterministic gather   (k_fit_hires)
+//     dW1  = g60 . F^T ;  dW0 = -dW1             (the two softmax gradients cancel)   (FTC<1>)
+//     W1  -= lr dW1 ; W0 += lr dW1               plain SGD, no momentum / weight decay
+//
+// CWT_FIT_STREAM: three launches per step; the feature map is streamed twice per step
+// from HBM/L2 (bytes_fit = (2T+1) S F per episode) — any S, any batch size.
+#include "common.cuh"
+#include "skinny.cuh"
+#include "hires.cuh"
+
+namespace cwt {
+
+int prep_labels(const void* labels, int label_kind, int n_img, long long npix, int ignore_index,
+                uint8_t* packed, int32_t* counts, cudaStream_t st);
+
+// one CTA per episode: W <- W0, Wd = W1 - W0
+__global__ void __launch_bounds__(256)
+k_fit_init_weights(const float* __restrict__ w0, float* __restrict__ w_out, float* __restrict__ wd, int C) {
+    const int e = blockIdx.x;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = w0[(size_t)(e * 2) * C + c], b = w0[(size_t)(e * 2 + 1) * C + c];
+        w_out[(size_t)(e * 2) * C + c] = a;
+        w_out[(size_t)(e * 2 + 1) * C + c] = b;
+        wd[(size_t)e * C + c] = b - a;
+    }
+}
+
+// pass-2 epilogue: complete dW1[c] -> SGD update of both rows and the next step's difference
+struct FitUpdateEpilogue {
+    float* W; float* wd; float lr; int C;
+    __device__ __forceinline__ void operator()(int e, int r, int c, float dw) const {
+        if (r != 0) return;
+        float* p0 = W + (size_t)(e * 2) * C + c;
+        float* p1 = W + (size_t)(e * 2 + 1) * C + c;
+        const float n0 = fmaf(lr, dw, *p0);       // dW0 = -dW1
+        const float n1 = fmaf(-lr, dw, *p1);
+        *p0 = n0; *p1 = n1;
+        wd[(size_t)e * C + c] = n1 - n0;
+    }
+};
+
+struct FitWs {
+    uint8_t* lab; int32_t* counts_img; float2* cw; float* wd; float* zd; float* g60; float* loss_part;
+    int nblk;
+};
+
+static size_t carve_fit(Carver& cv, FitWs& ws, int E, int S, int C, int h, int w, int H, int W) {
+    ws.nblk = (h + HIRES_RROWS - 1) / HIRES_RROWS;
+    ws.lab = cv.take<uint8_t>((size_t)E * S * H * W);
+    ws.counts_img = cv.take<int32_t>((size_t)E * S * 4);
+    ws.cw = cv.take<float2>((size_t)E);
+    ws.wd = cv.take<float>((size_t)E * C);
+    ws.zd = cv.take<float>((size_t)E * S * h * w);
+    ws.g60 = cv.take<float>((size_t)E * S * h * w);
+    ws.loss_part = cv.take<float>((size_t)E * S * ws.nblk);
+    return align_up(cv.off);
+}
+
+}  // namespace cwt
+
+using namespace cwt;
+
+extern "C" size_t cwt_fit_workspace_bytes(int E, int S, int C, int h, int w, int H, int W) {
+    Carver cv(nullptr, 0);
+    FitWs ws;
+    return carve_fit(cv, ws, E, S, C, h, w, H, W);
+}
+
+extern "C" int cwt_fit_classifier_f32(const float* f_s, const void* s_label, int label_kind, const float* w0,
+                                      const float* class_weight_or_null, float* w_out,
+                                      float* loss_trace_or_null, int32_t* label_counts_or_null,
+                                      int E, int S, int C, int h, int w, int H, int W,
+                                      int n_iter, float lr, int ignore_index, int algo,
+                                      void* workspace, size_t ws_bytes, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CWT_REQUIRE(E >= 0 && S >= 1 && C >= 1 && h >= 1 && w >= 1 && n_iter >= 0, CWT_ERR_INVALID_ARG,
+                "fit: bad sizes E=%d S=%d C=%d h=%d w=%d n_iter=%d", E, S, C, h, w, n_iter);
+    if (E == 0) return CWT_OK;
+    CWT_REQUIRE(f_s && s_label && w0 && w_out, CWT_ERR_INVALID_ARG, "fit: null pointer");
+    CWT_REQUIRE(H == 8 * (h - 1) + 1 && W == 8 * (w - 1) + 1, CWT_ERR_UNSUPPORTED,
+                "fit: label size %dx%d is not 8*(%dx%d - 1) + 1 (align_corners scale must be 1/8)", H, W, h, w);
+    CWT_REQUIRE(w <= HIRES_MAXW && W <= HIRES_THREADS * HIRES_MAXCOL, CWT_ERR_UNSUPPORTED,
+                "fit: w=%d / W=%d exceeds the supported width (128 / 1024)", w, W);
+    CWT_REQUIRE(label_kind == CWT_LABEL_U8 || label_kind == CWT_LABEL_I64, CWT_ERR_INVALID_ARG,
+                "fit: label_kind %d", label_kind);
+    CWT_REQUIRE(algo == CWT_FIT_AUTO || algo == CWT_FIT_STREAM || algo == CWT_FIT_RESIDENT, CWT_ERR_INVALID_ARG,
+                "fit: algo %d", algo);
+    Carver cv(workspace, ws_bytes);
+    FitWs ws;
+    size_t need = carve_fit(cv, ws, E, S, C, h, w, H, W);
+    CWT_REQUIRE(workspace && ws_bytes >= need, CWT_ERR_WORKSPACE, "fit: workspace %zu < %zu bytes", ws_bytes, need);
+
+    const int HWl = h * w;
+    int rc = prep_labels(s_label, label_kind, E * S, (long long)H * W, ignore_index, ws.lab, ws.counts_img, st);
+    if (rc != CWT_OK) return rc;
+    k_class_consts<<<(E + 127) / 128, 128, 0, st>>>(ws.counts_img, class_weight_or_null, 0.0, ws.cw,
+                                                    label_counts_or_null, E, S);
+    CWT_LAUNCHED("class_consts");
+    k_fit_init_weights<<<E, 256, 0, st>>>(w0, w_out, ws.wd, C);
+    CWT_LAUNCHED("fit_init_weights");
+
+    if (algo == CWT_FIT_RESIDENT) {
+        CWT_REQUIRE(false, CWT_ERR_UNSUPPORTED, "fit: CWT_FIT_RESIDENT is not available in this build");
+    }
+
+    dim3 hgrid(ws.nblk, E * S);
+    FitUpdateEpilogue epi{w_out, ws.wd, lr, C};
+    for (int it = 0; it < n_iter; ++it) {
+        rc = launch_rows_times_feat(f_s, ws.wd, ws.zd, nullptr, E * S, C, HWl, S, 1, st);
+        if (rc != CWT_OK) return rc;
+        if (loss_trace_or_null) {
+            k_fit_hires<HIRES_RROWS, true><<<hgrid, HIRES_THREADS, 0, st>>>(ws.zd, ws.lab, ws.cw, ws.g60,
+                                                                             ws.loss_part, h, w, H, W, S);
+            CWT_LAUNCHED("fit_hires");
+            k_reduce_loss<<<E, 32, 0, st>>>(ws.loss_part, loss_trace_or_null + (size_t)it * E, S * ws.nblk);
+            CWT_LAUNCHED("reduce_loss");
+        } else {
+            k_fit_hires<HIRES_RROWS, false><<<hgrid, HIRES_THREADS, 0, st>>>(ws.zd, ws.lab, ws.cw, ws.g60,
+                                                                              nullptr, h, w, H, W, S);
+            CWT_LAUNCHED("fit_hires");
+        }
+        rc = launch_ftc_t<1, 4>(f_s, ws.g60, E, S, C, HWl, 1, epi, st);
+        if (rc != CWT_OK) return rc;
+    }
+    return CWT_OK;
+}

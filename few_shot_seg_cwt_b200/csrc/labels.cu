@@ -1,0 +1,59 @@
+// (a-2) label statistics on the device: replaces the per-episode D2H copy + numpy `where`
+// of the reference (src/test.py:169-171, src/train.py:211-213,237-239, model_util.py:27-31).
+#include "common.cuh"
+
+namespace cwt {
+
+template <bool I64>
+__global__ void __launch_bounds__(256)
+k_prep_labels(const void* __restrict__ labels, long long npix, int ignore_index,
+              uint8_t* __restrict__ packed, int32_t* __restrict__ counts) {
+    const int img = blockIdx.y;
+    const size_t base = (size_t)img * (size_t)npix;
+    int c[4] = {0, 0, 0, 0};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix;
+         i += (long long)gridDim.x * blockDim.x) {
+        int code = load_label_code<I64>(labels, base + (size_t)i, ignore_index);
+        if (packed) packed[base + (size_t)i] = (uint8_t)code;
+        c[0] += (code == 0); c[1] += (code == 1); c[2] += (code == 2); c[3] += (code == 3);
+    }
+    __shared__ int sm[4];
+    if (threadIdx.x < 4) sm[threadIdx.x] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int v = __reduce_add_sync(0xffffffffu, c[k]);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&sm[k], v);
+    }
+    __syncthreads();
+    if (threadIdx.x < 4 && sm[threadIdx.x]) atomicAdd(&counts[img * 4 + threadIdx.x], sm[threadIdx.x]);
+}
+
+int prep_labels(const void* labels, int label_kind, int n_img, long long npix, int ignore_index,
+                uint8_t* packed, int32_t* counts, cudaStream_t st) {
+    CWT_REQUIRE(labels && counts, CWT_ERR_INVALID_ARG, "prep_labels: null pointer");
+    CWT_REQUIRE(label_kind == CWT_LABEL_U8 || label_kind == CWT_LABEL_I64, CWT_ERR_INVALID_ARG,
+                "prep_labels: label_kind %d", label_kind);
+    CWT_REQUIRE(n_img >= 0 && npix >= 0, CWT_ERR_INVALID_ARG, "prep_labels: negative size");
+    if (n_img == 0) return CWT_OK;
+    CWT_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * 4 * (size_t)n_img, st));
+    if (npix == 0) return CWT_OK;
+    int bx = (int)((npix + 256 * 8 - 1) / (256 * 8));
+    if (bx < 1) bx = 1;
+    if (bx > 64) bx = 64;
+    dim3 grid(bx, n_img);
+    if (label_kind == CWT_LABEL_I64)
+        k_prep_labels<true><<<grid, 256, 0, st>>>(labels, npix, ignore_index, packed, counts);
+    else
+        k_prep_labels<false><<<grid, 256, 0, st>>>(labels, npix, ignore_index, packed, counts);
+    CWT_LAUNCHED("prep_labels");
+    return CWT_OK;
+}
+
+}  // namespace cwt
+
+extern "C" int cwt_prep_labels(const void* labels, int label_kind, int n_img, long long npix, int ignore_index,
+                               uint8_t* packed_or_null, int32_t* counts, void* stream) {
+    return cwt::prep_labels(labels, label_kind, n_img, npix, ignore_index, packed_or_null, counts,
+                            static_cast<cudaStream_t>(stream));
+}

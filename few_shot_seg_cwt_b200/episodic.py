@@ -1,0 +1,279 @@
+"""Episodic drivers: the batched per-episode head, the reference's ``validate_transformer`` loop
+(src/test.py:103-254), the sharded multi-GPU sweep and the meta-training step
+(src/train.py:233-267).
+
+Episodes are independent (fresh classifier per episode, frozen backbone and transformer), so a
+sweep is sharded by episode index — rank r of G takes episodes r, r+G, ... — with no data-path
+collective; the only exchange is one integer all-reduce of the per-class intersection / union
+table at the end (NCCL on GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import time
+from collections import defaultdict
+from dataclasses import dataclass
+from typing import Dict, Iterable, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib as L
+from . import ops
+from .synthetic import EpisodeBatch, make_batch, shard_indices
+
+IGNORE = 255
+
+
+def transformer_params(transformer) -> Dict[str, torch.Tensor]:
+    """The five tensors of the block, by the reference's state-dict names (module or dict)."""
+    sd = transformer if isinstance(transformer, dict) else {
+        "w_qkvs.weight": transformer.w_qkvs.weight, "fc.weight": transformer.fc.weight,
+        "fc.bias": transformer.fc.bias, "layer_norm.weight": transformer.layer_norm.weight,
+        "layer_norm.bias": transformer.layer_norm.bias}
+    return {k: v.detach() for k, v in sd.items()}
+
+
+@dataclass
+class HeadOutput:
+    w_fit: torch.Tensor        # [E,2,C]
+    w_adapted: torch.Tensor    # [E,2,C]
+    counts: torch.Tensor       # int64 [E,2,2,3]  variant (0 adapted / 1 baseline) x class x (I,U,T)
+    ce: torch.Tensor           # float64 [E,2,2]  variant x (sum -log p[y], #valid)
+    logits60: Optional[torch.Tensor]   # [E,2,2,h,w] variant x class
+
+
+def episode_head(f_s, s_label, f_q, q_label, w0, params: Dict[str, torch.Tensor], n_head: int, lr: float,
+                 n_iter: int, return_logits: bool = False, fit_algo: int = L.FIT_AUTO,
+                 attn_algo: int = L.ATTN_REASSOC) -> HeadOutput:
+    """The head of E evaluation episodes (src/test.py:162-234), fully on the device, no host sync.
+
+    f_s [E,S,C,h,w]; s_label [E,S,H,W]; f_q [E,C,h,w] (un-normalised backbone features);
+    q_label [E,H,W]; w0 [E,2,C]."""
+    w_fit = ops.fit_classifier(f_s, s_label, w0, lr, n_iter, check=False, algo=fit_algo)       # :164-187
+    w_ad = ops.transformer_forward(w_fit, f_q, params["w_qkvs.weight"], params["fc.weight"], params["fc.bias"],
+                                   params["layer_norm.weight"], params["layer_norm.bias"], n_head,
+                                   normalize_k=True, algo=attn_algo)                            # :194-197
+    weights = torch.stack([w_ad, w_fit], dim=1)                                                 # [E,2,2,C]
+    counts, ce, logits = ops.logits_iou(weights, f_q, q_label, normalize_mask=0b01,
+                                        return_logits=return_logits)                            # :192,200-223
+    return HeadOutput(w_fit, w_ad, counts, ce, logits)
+
+
+class IoUTable:
+    """Device-resident int64 accumulator of the sweep metrics:
+    ``cls[c, v, 0/1]`` = foreground intersection / union of class c (1..num_classes) for variant v
+    (0 adapted, 1 baseline) — what src/test.py:225-230 keeps in dicts of float32 tensors — and
+    ``fb[v, k, 0/1]`` = class-agnostic background / foreground I, U for FB-IoU."""
+
+    def __init__(self, num_classes: int, device, n_variants: int = 2):
+        self.num_classes = num_classes
+        self.cls = torch.zeros(num_classes + 1, n_variants, 2, dtype=torch.int64, device=device)
+        self.fb = torch.zeros(n_variants, 2, 2, dtype=torch.int64, device=device)
+        self.ce = torch.zeros(n_variants, 2, dtype=torch.float64, device=device)
+        self.n_episodes = torch.zeros(1, dtype=torch.int64, device=device)
+
+    def update(self, counts: torch.Tensor, subcls: torch.Tensor, ce: Optional[torch.Tensor] = None) -> None:
+        """counts int64 [E,V,2,3]; subcls int64 [E] in 1..num_classes."""
+        fg = counts[:, :, 1, :2]                                   # [E,V,(I,U)]  "do not count background"
+        self.cls.index_add_(0, subcls.to(self.cls.device), fg)
+        self.fb += counts[:, :, :, :2].sum(0)
+        if ce is not None:
+            self.ce += ce.sum(0)
+        self.n_episodes += counts.shape[0]
+
+    def all_reduce(self) -> None:
+        """The one collective of a sharded sweep: integer sum over ranks (NVLink / NVSwitch via NCCL)."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            flat = torch.cat([self.cls.reshape(-1), self.fb.reshape(-1), self.n_episodes])
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            a, b = self.cls.numel(), self.fb.numel()
+            self.cls.copy_(flat[:a].view_as(self.cls))
+            self.fb.copy_(flat[a:a + b].view_as(self.fb))
+            self.n_episodes.copy_(flat[a + b:])
+            dist.all_reduce(self.ce, op=dist.ReduceOp.SUM)
+
+    def miou(self, variant: int = 0) -> float:
+        """mean over classes seen of I_c / (U_c + 1e-10)   (src/test.py:232-243)."""
+        c = self.cls[1:, variant].cpu().double()
+        seen = c[:, 1] > 0
+        if not bool(seen.any()):
+            return 0.0
+        return float((c[seen, 0] / (c[seen, 1] + 1e-10)).mean())
+
+    def class_iou(self, variant: int = 0) -> Dict[int, float]:
+        c = self.cls[:, variant].cpu().double()
+        return {i: float(c[i, 0] / (c[i, 1] + 1e-10)) for i in range(1, self.num_classes + 1) if c[i, 1] > 0}
+
+    def fb_iou(self, variant: int = 0) -> float:
+        """Standard FB-IoU: mean of the global background and foreground IoU."""
+        f = self.fb[variant].cpu().double()
+        return float((f[:, 0] / (f[:, 1] + 1e-10)).mean())
+
+    def mean_loss(self, variant: int = 0) -> float:
+        c = self.ce[variant].cpu()
+        return float(c[0] / c[1].clamp_min(1.0))
+
+
+# ----------------------------------------------------------------------------------------
+# synthetic sharded sweep (BASELINE.json configs[3])
+# ----------------------------------------------------------------------------------------
+def run_sweep(n_episodes: int, params: Dict[str, torch.Tensor], n_head: int, lr: float, n_iter: int,
+              device, rank: int = 0, world: int = 1, batch: int = 16, num_classes_val: int = 5,
+              gen_kwargs: Optional[dict] = None, reduce: bool = True) -> IoUTable:
+    """Evaluate synthetic episodes ``start..start+n_episodes`` sharded as i -> rank i mod world."""
+    gen_kwargs = dict(gen_kwargs or {})
+    gen_kwargs.setdefault("num_classes_val", num_classes_val)
+    table = IoUTable(num_classes_val, device)
+    mine = shard_indices(n_episodes, rank, world)
+    p = {k: v.to(device) for k, v in params.items()}
+    for i in range(0, len(mine), batch):
+        b = make_batch(mine[i:i + batch], **gen_kwargs).to(device)
+        out = episode_head(b.f_s, b.s_label, b.f_q, b.q_label, b.w0, p, n_head, lr, n_iter)
+        table.update(out.counts, b.subcls, out.ce)
+    if reduce:
+        table.all_reduce()
+    return table
+
+
+# ----------------------------------------------------------------------------------------
+# validate_transformer drop-in (src/test.py:103-254)
+# ----------------------------------------------------------------------------------------
+def validate_transformer(args, val_loader, model, transformer, verbose: bool = True) -> Tuple[float, float]:
+    """Same arguments and return value as the reference: ``(mean mIoU over runs, mean loss over runs)``.
+
+    ``args`` needs test_num, batch_size_val, image_size, n_runs, bottleneck_dim, num_classes_tr, cls_lr,
+    adapt_iter (and optionally heads). Loader items are the reference's 7-tuples
+    ``(qry_img, q_label, spprt_imgs, s_label, subcls, spprt_oris, qry_oris)`` with a leading batch
+    dimension of 1 (src/dataset/dataset.py:326-327). The backbone ``model.extract_features`` stays the
+    caller's PyTorch module; everything after it runs in the fused kernels, batch_size_val episodes
+    per launch."""
+    if verbose:
+        print('==> Start testing')
+    model.eval()
+    transformer.eval()
+    device = next(transformer.parameters()).device
+    if device.type != "cuda":
+        raise RuntimeError("validate_transformer (cwt_b200): the transformer must live on a CUDA device")
+    nb_episodes = int(args.test_num / args.batch_size_val)
+    params = transformer_params(transformer)
+    n_head = transformer.n_head
+    C = args.bottleneck_dim
+    num_classes_val = int(getattr(args, "num_classes_val", 0) or 0)
+
+    runtimes = torch.zeros(args.n_runs)
+    val_IoUs = np.zeros(args.n_runs)
+    val_losses = np.zeros(args.n_runs)
+    iter_loader = iter(val_loader)
+    for run in range(args.n_runs):
+        cls_I: Dict[int, int] = defaultdict(int)
+        cls_U: Dict[int, int] = defaultdict(int)
+        cls_I0: Dict[int, int] = defaultdict(int)
+        cls_U0: Dict[int, int] = defaultdict(int)
+        IoU: Dict[int, float] = {}
+        IoU0: Dict[int, float] = {}
+        loss_sum, loss_cnt, iter_num, runtime = 0.0, 0, 0, 0.0
+        for e in range(nb_episodes):
+            t0 = time.time()
+            fs_l, sl_l, fq_l, ql_l, w0_l, classes = [], [], [], [], [], []
+            for i in range(args.batch_size_val):
+                try:
+                    item = next(iter_loader)
+                except StopIteration:
+                    iter_loader = iter(val_loader)
+                    item = next(iter_loader)
+                qry_img, q_label, spprt_imgs, s_label, subcls = item[:5]
+                iter_num += 1
+                spprt_imgs, s_label = spprt_imgs.to(device), s_label.to(device)
+                q_label, qry_img = q_label.to(device), qry_img.to(device)
+                # fresh classifier init, drawn like the reference's nn.Conv2d(...) (a-1)
+                w0_l.append(nn.Conv2d(C, args.num_classes_tr, kernel_size=1, bias=False).weight.detach().view(2, C))
+                with torch.no_grad():
+                    f_s, _ = model.extract_features(spprt_imgs.squeeze(0))
+                    f_q, _ = model.extract_features(qry_img)
+                fs_l.append(f_s.float()); fq_l.append(f_q[0].float())
+                sl_l.append(s_label.squeeze(0)); ql_l.append(q_label.squeeze(0))
+                classes.append([int(c.item()) if torch.is_tensor(c) else int(c) for c in subcls])
+            out = episode_head(torch.stack(fs_l), torch.stack(sl_l), torch.stack(fq_l), torch.stack(ql_l),
+                               torch.stack(w0_l).to(device), params, n_head, args.cls_lr, args.adapt_iter)
+            counts = out.counts.cpu()
+            ce = out.ce.cpu()
+            runtime += time.time() - t0
+            loss = float(ce[:, 0, 0].sum() / ce[:, 0, 1].sum().clamp_min(1.0))     # CE over the batch's valid pixels
+            loss_sum += loss; loss_cnt += 1
+            for i, task_classes in enumerate(classes):
+                for j, class_ in enumerate(task_classes):
+                    cls_I[class_] += int(counts[i, 0, j + 1, 0]); cls_U[class_] += int(counts[i, 0, j + 1, 1])
+                    cls_I0[class_] += int(counts[i, 1, j + 1, 0]); cls_U0[class_] += int(counts[i, 1, j + 1, 1])
+            for class_ in cls_U:
+                IoU[class_] = cls_I[class_] / (cls_U[class_] + 1e-10)
+                IoU0[class_] = cls_I0[class_] / (cls_U0[class_] + 1e-10)
+            if verbose and iter_num % 200 == 0:
+                print('Test: [{}/{}] mIoU {:.4f} mIoU0 {:.4f} Loss {:.4f} ({:.4f}) '.format(
+                    iter_num, args.test_num, np.mean(list(IoU.values())), np.mean(list(IoU0.values())),
+                    loss, loss_sum / loss_cnt))
+        runtimes[run] = runtime
+        mIoU = float(np.mean(list(IoU.values()))) if IoU else 0.0
+        if verbose:
+            print('mIoU---Val result: mIoU {:.4f}.'.format(mIoU))
+            for class_ in cls_U:
+                print("Class {} : {:.4f}".format(class_, IoU[class_]))
+        val_IoUs[run] = mIoU
+        val_losses[run] = loss_sum / max(loss_cnt, 1)
+    if verbose:
+        print('Average mIoU over {} runs --- {:.4f}.'.format(args.n_runs, val_IoUs.mean()))
+        print('Average runtime / run --- {:.4f}.'.format(runtimes.mean()))
+    return val_IoUs.mean(), val_losses.mean()
+
+
+# ----------------------------------------------------------------------------------------
+# meta-training step (src/train.py:233-267)
+# ----------------------------------------------------------------------------------------
+class _QueryLoss(torch.autograd.Function):
+    """loss(W') = weighted CE( up( W' . normalize(f_q) ), q_label ), mean over the batch's episodes
+    (the reference trains with batch_size 1: config_files/pascal.yaml:25)."""
+
+    @staticmethod
+    def forward(ctx, w_ad, f_q, q_label):
+        E, Lq, C = w_ad.shape
+        h, w = f_q.shape[-2:]
+        logits = ops.rows_times_feat(w_ad.detach(), f_q, normalize=True).view(E, 2, h, w)
+        loss, dl = ops.query_loss_grad(logits, q_label)
+        ctx.save_for_backward(dl, f_q)
+        ctx.mark_non_differentiable(logits)
+        return loss.sum(), logits
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_logits):
+        dl, f_q = ctx.saved_tensors
+        E = dl.shape[0]
+        d_w = ops.feat_times_rows(dl.view(E, 2, -1), f_q, normalize=True)
+        return d_w * g_loss, None, None
+
+
+def query_loss(w_adapted: torch.Tensor, f_q: torch.Tensor, q_label: torch.Tensor):
+    """Returns (loss, logits60 [E,2,h,w]); differentiable w.r.t. ``w_adapted``."""
+    return _QueryLoss.apply(w_adapted, f_q, q_label)
+
+
+def meta_train_step(transformer, optimizer, f_s, s_label, f_q, q_label, w0, cls_lr: float, adapt_iter: int,
+                    keep_attn=None, keep_out=None):
+    """One iteration of src/train.py:do_epoch on pre-computed features (batch of E episodes; E = 1 in the
+    reference). Fits the classifier, adapts it with the transformer in train mode, takes the weighted
+    query CE and steps ``optimizer`` (SGD momentum .9, nesterov, wd 1e-4: src/optimizer.py:11-15).
+    Returns dict(loss, w_fit, w_adapted, logits60)."""
+    w_fit = ops.fit_classifier(f_s, s_label, w0, cls_lr, adapt_iter, check=False)
+    transformer.train()
+    prev = transformer.normalize_k
+    transformer.normalize_k = True
+    try:
+        updated = transformer(w_fit.detach(), f_q, f_q, keep_attn=keep_attn, keep_out=keep_out)
+    finally:
+        transformer.normalize_k = prev
+    loss, logits = query_loss(updated, f_q, q_label)
+    optimizer.zero_grad()
+    loss.backward()
+    optimizer.step()
+    return {"loss": loss.detach(), "w_fit": w_fit, "w_adapted": updated.detach(), "logits60": logits}

@@ -1,0 +1,343 @@
+"""Functional API over the C ABI — batched over E episodes, CUDA tensors in / CUDA tensors out.
+
+Each function is also registered as a PyTorch custom op (``torch.ops.cwt_b200.*``, see
+``_register_custom_ops``) so the head can sit inside torch graphs / profilers like any ATen op.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+IGNORE = 255
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    return t.contiguous()
+
+
+# ----------------------------------------------------------------------------------------
+# (a-2) label statistics
+# ----------------------------------------------------------------------------------------
+def label_counts(labels: torch.Tensor, ignore_index: int = IGNORE) -> torch.Tensor:
+    """labels [..., H, W] uint8/int64 -> int32 [..., 4] = (#0, #1, #ignored, #invalid) per image.
+    Device-side replacement of the ``np.where`` counting in src/test.py:169-171."""
+    dev = L.require_cuda(labels)
+    lab = labels.contiguous()
+    lead = lab.shape[:-2]
+    n_img = int(torch.Size(lead).numel()) if len(lead) else 1
+    npix = lab.shape[-2] * lab.shape[-1]
+    counts = torch.empty(n_img, 4, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.load().cwt_prep_labels(L.ptr(lab), L.label_kind(lab), n_img, npix, ignore_index, None,
+                                      L.ptr(counts), L.stream_ptr(dev))
+    L.check(rc, "cwt_prep_labels")
+    return counts.view(*lead, 4)
+
+
+# ----------------------------------------------------------------------------------------
+# (a-1..a-3) classifier fit
+# ----------------------------------------------------------------------------------------
+def fit_classifier(f_s: torch.Tensor, s_label: torch.Tensor, w0: torch.Tensor, lr: float, n_iter: int,
+                   class_weight: Optional[torch.Tensor] = None, ignore_index: int = IGNORE,
+                   return_losses: bool = False, check: bool = True, algo: int = L.FIT_AUTO):
+    """Fit a fresh 2-class 1x1-conv classifier per episode with ``n_iter`` plain-SGD steps
+    (reference: src/test.py:164-187, src/train.py:206-231, PSPNet.inner_loop pspnet.py:189-205).
+
+    f_s      [E,S,C,h,w] (or [S,C,h,w] for one episode) float32 support features
+    s_label  [E,S,H,W]   (or [S,H,W]) uint8 / int64 in {0,1,ignore_index}; H = 8(h-1)+1
+    w0       [E,2,C]     (or [2,C] / [2,C,1,1]) initial weights
+    class_weight [E,2] or [2] or None (None => [1, n0/n1] counted on the device, all shots pooled)
+    check    True: one host sync to raise ZeroDivisionError when an episode has no foreground
+             pixel (what the reference's python division does) and ValueError on labels outside
+             {0,1,ignore}. False: fully asynchronous.
+
+    Returns W [E,2,C] (same leading shape as given), and losses [n_iter,E] if requested."""
+    dev = L.require_cuda(f_s, s_label, w0)
+    single = f_s.dim() == 4
+    if single:
+        f_s, s_label = f_s.unsqueeze(0), s_label.unsqueeze(0)
+    if f_s.dim() != 5 or s_label.dim() != 4:
+        raise ValueError(f"f_s must be [E,S,C,h,w] and s_label [E,S,H,W]; got {tuple(f_s.shape)}, {tuple(s_label.shape)}")
+    E, S, Cc, h, w = f_s.shape
+    H, W = s_label.shape[-2:]
+    if s_label.shape[0] != E or s_label.shape[1] != S:
+        raise ValueError("f_s and s_label disagree on E or S")
+    w0_shape = w0.shape
+    w0v = _f32c(w0, "w0").reshape(E, 2, Cc)
+    f_s = _f32c(f_s, "f_s")
+    lab = s_label.contiguous()
+    cw = None
+    if class_weight is not None:
+        cw = _f32c(class_weight.to(dev), "class_weight").reshape(-1, 2)
+        if cw.shape[0] == 1 and E > 1:
+            cw = cw.expand(E, 2).contiguous()
+        if cw.shape[0] != E:
+            raise ValueError("class_weight must be [2] or [E,2]")
+    w_out = torch.empty(E, 2, Cc, dtype=torch.float32, device=dev)
+    losses = torch.empty(n_iter, E, dtype=torch.float32, device=dev) if return_losses else None
+    counts = torch.empty(E, 4, dtype=torch.int32, device=dev)
+    lib = L.load()
+    nbytes = lib.cwt_fit_workspace_bytes(E, S, Cc, h, w, H, W)
+    ws = L.WORKSPACE.get(nbytes, dev, "fit")
+    with torch.cuda.device(dev):
+        rc = lib.cwt_fit_classifier_f32(L.ptr(f_s), L.ptr(lab), L.label_kind(lab), L.ptr(w0v), L.ptr(cw),
+                                        L.ptr(w_out), L.ptr(losses), L.ptr(counts), E, S, Cc, h, w, H, W,
+                                        int(n_iter), float(lr), int(ignore_index), int(algo),
+                                        L.ptr(ws), ws.numel(), L.stream_ptr(dev))
+    L.check(rc, "cwt_fit_classifier_f32")
+    if check:
+        c = counts.cpu()
+        if int(c[:, 3].sum()) > 0:
+            raise ValueError("s_label holds values outside {0, 1, ignore_index}")
+        if class_weight is None and bool((c[:, 1] == 0).any()):
+            raise ZeroDivisionError("division by zero: an episode's support mask has no foreground pixel "
+                                    "(reference: len(back_pix[0]) / len(target_pix[0]), src/test.py:174)")
+    out = w_out.reshape(w0_shape)          # same leading shape as the w0 that was given
+    return (out, losses) if return_losses else out
+
+
+# ----------------------------------------------------------------------------------------
+# (a-5, a-6, a-13) transformer forward / backward
+# ----------------------------------------------------------------------------------------
+def _tdims(q, k):
+    if q.dim() != 3:
+        raise ValueError(f"q must be [B,Lq,C], got {tuple(q.shape)}")
+    B, Lq, Cc = q.shape
+    if k.dim() == 4:
+        HW = k.shape[2] * k.shape[3]
+    elif k.dim() == 3:
+        HW = k.shape[2]
+    else:
+        raise ValueError(f"k must be [B,C,h,w] or [B,C,HW], got {tuple(k.shape)}")
+    if k.shape[0] != B or k.shape[1] != Cc:
+        raise ValueError("q and k disagree on batch or channel size")
+    return B, Lq, Cc, HW
+
+
+def transformer_forward(q, k, w_qkvs, fc_w, fc_b, ln_g, ln_b, n_head: int, normalize_k: bool = False,
+                        keep_attn=None, keep_out=None, p_attn: float = 0.1, p_out: float = 0.5,
+                        need_saved: bool = False, algo: int = L.ATTN_REASSOC):
+    """MultiHeadAttentionOne.forward(q, k, k) (src/model/transformer.py:54-83), batched.
+    Returns out [B,Lq,C] (and the opaque saved-activation buffer when ``need_saved``)."""
+    dev = L.require_cuda(q, k, w_qkvs, fc_w, fc_b, ln_g, ln_b)
+    B, Lq, Cc, HW = _tdims(q, k)
+    if tuple(w_qkvs.shape) != (n_head * Cc, Cc) or tuple(fc_w.shape) != (Cc, n_head * Cc):
+        raise ValueError("only d_model == d_k == d_v is supported (the reference constructs 512/512/512): "
+                         f"w_qkvs {tuple(w_qkvs.shape)}, fc {tuple(fc_w.shape)}, n_head {n_head}, C {Cc}")
+    q_, k_ = _f32c(q, "q"), _f32c(k, "k")
+    ka = ko = None
+    if keep_attn is not None:
+        ka = keep_attn.to(torch.uint8).contiguous()
+        if ka.numel() != n_head * B * Lq * HW:
+            raise ValueError("keep_attn must be [n_head*B, Lq, HW]")
+    if keep_out is not None:
+        ko = keep_out.to(torch.uint8).contiguous()
+        if ko.numel() != B * Lq * Cc:
+            raise ValueError("keep_out must be [B, Lq, C]")
+    out = torch.empty(B, Lq, Cc, dtype=torch.float32, device=dev)
+    lib = L.load()
+    saved = None
+    if need_saved:
+        saved = torch.empty(lib.cwt_transformer_saved_bytes(B, Lq, n_head, Cc, HW), dtype=torch.uint8, device=dev)
+    ws = L.WORKSPACE.get(lib.cwt_transformer_workspace_bytes(B, Lq, n_head, Cc, HW, algo), dev, "tr")
+    with torch.cuda.device(dev):
+        rc = lib.cwt_transformer_fwd_f32(L.ptr(q_), L.ptr(k_), int(bool(normalize_k)), L.ptr(_f32c(w_qkvs, "w_qkvs")),
+                                         L.ptr(_f32c(fc_w, "fc_w")), L.ptr(_f32c(fc_b, "fc_b")),
+                                         L.ptr(_f32c(ln_g, "ln_g")), L.ptr(_f32c(ln_b, "ln_b")),
+                                         L.ptr(ka), L.ptr(ko), float(p_attn), float(p_out), L.ptr(out), L.ptr(saved),
+                                         B, Lq, n_head, Cc, HW, int(algo), L.ptr(ws), ws.numel(), L.stream_ptr(dev))
+    L.check(rc, "cwt_transformer_fwd_f32")
+    return (out, saved) if need_saved else out
+
+
+def transformer_backward(d_out, q, k, w_qkvs, fc_w, ln_g, n_head: int, saved, normalize_k: bool = False,
+                         keep_attn=None, keep_out=None, p_attn: float = 0.1, p_out: float = 0.5):
+    """Gradients of the block w.r.t. (w_qkvs, fc.weight, fc.bias, ln.weight, ln.bias), summed over the batch."""
+    dev = L.require_cuda(d_out, q, k, w_qkvs, fc_w, ln_g, saved)
+    B, Lq, Cc, HW = _tdims(q, k)
+    ka = None if keep_attn is None else keep_attn.to(torch.uint8).contiguous()
+    ko = None if keep_out is None else keep_out.to(torch.uint8).contiguous()
+    d_wqkvs = torch.empty_like(w_qkvs, dtype=torch.float32).contiguous()
+    d_fcw = torch.empty_like(fc_w, dtype=torch.float32).contiguous()
+    d_fcb = torch.empty(Cc, dtype=torch.float32, device=dev)
+    d_g = torch.empty(Cc, dtype=torch.float32, device=dev)
+    d_b = torch.empty(Cc, dtype=torch.float32, device=dev)
+    lib = L.load()
+    ws = L.WORKSPACE.get(lib.cwt_transformer_workspace_bytes(B, Lq, n_head, Cc, HW, L.ATTN_REASSOC), dev, "tr")
+    with torch.cuda.device(dev):
+        rc = lib.cwt_transformer_bwd_f32(L.ptr(_f32c(d_out, "d_out")), L.ptr(_f32c(q, "q")), L.ptr(_f32c(k, "k")),
+                                         int(bool(normalize_k)), L.ptr(_f32c(w_qkvs, "w_qkvs")), L.ptr(_f32c(fc_w, "fc_w")),
+                                         L.ptr(_f32c(ln_g, "ln_g")), L.ptr(ka), L.ptr(ko), float(p_attn), float(p_out),
+                                         L.ptr(saved), L.ptr(d_wqkvs), L.ptr(d_fcw), L.ptr(d_fcb), L.ptr(d_g), L.ptr(d_b),
+                                         B, Lq, n_head, Cc, HW, L.ptr(ws), ws.numel(), L.stream_ptr(dev))
+    L.check(rc, "cwt_transformer_bwd_f32")
+    return d_wqkvs, d_fcw, d_fcb, d_g, d_b
+
+
+# ----------------------------------------------------------------------------------------
+# (a-4, a-7..a-12) logits / upsample / argmax / IoU
+# ----------------------------------------------------------------------------------------
+def logits_iou(weights: torch.Tensor, f_q: torch.Tensor, q_label: torch.Tensor, normalize_mask: int = 0,
+               ignore_index: int = IGNORE, return_logits: bool = True):
+    """weights [E,V,2,C]; f_q [E,C,h,w]; q_label [E,H,W].
+    Returns counts int64 [E,V,2,3] (class x (I,U,T)), ce float64 [E,V,2] (sum of -log p[y], #valid),
+    logits60 float32 [E,V,2,h,w] or None."""
+    dev = L.require_cuda(weights, f_q, q_label)
+    E, V, two, Cc = weights.shape
+    if two != 2:
+        raise ValueError("weights must be [E,V,2,C]")
+    _, C2, h, w = f_q.shape
+    H, W = q_label.shape[-2:]
+    if C2 != Cc or f_q.shape[0] != E or q_label.shape[0] != E:
+        raise ValueError("shape mismatch between weights, f_q and q_label")
+    wt, fq, lab = _f32c(weights, "weights"), _f32c(f_q, "f_q"), q_label.contiguous()
+    counts = torch.empty(E, V, 2, 3, dtype=torch.int64, device=dev)
+    ce = torch.empty(E, V, 2, dtype=torch.float64, device=dev)
+    logits = torch.empty(E, V, 2, h, w, dtype=torch.float32, device=dev) if return_logits else None
+    lib = L.load()
+    ws = L.WORKSPACE.get(lib.cwt_logits_iou_workspace_bytes(E, V, Cc, h, w, H, W), dev, "iou")
+    with torch.cuda.device(dev):
+        rc = lib.cwt_logits_iou(L.ptr(wt), L.ptr(fq), L.ptr(lab), L.label_kind(lab), int(normalize_mask), L.ptr(counts),
+                                L.ptr(logits), L.ptr(ce), E, V, Cc, h, w, H, W, int(ignore_index),
+                                L.ptr(ws), ws.numel(), L.stream_ptr(dev))
+    L.check(rc, "cwt_logits_iou")
+    return counts, ce, logits
+
+
+def upsample_argmax_iou(logits: torch.Tensor, target: torch.Tensor, ignore_index: int = IGNORE):
+    """logits [n,2,h,w] float32; target [n,H,W] -> counts int64 [n,2,3], ce float64 [n,2]."""
+    dev = L.require_cuda(logits, target)
+    n, two, h, w = logits.shape
+    if two != 2:
+        raise NotImplementedError("the fused upsample/argmax/IoU kernel handles the head's 2 classes "
+                                  f"(num_classes_tr = 2); got {two}")
+    H, W = target.shape[-2:]
+    lg, tg = _f32c(logits, "logits"), target.contiguous()
+    counts = torch.empty(n, 2, 3, dtype=torch.int64, device=dev)
+    ce = torch.empty(n, 2, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.load().cwt_upsample_argmax_iou(L.ptr(lg), L.ptr(tg), L.label_kind(tg), L.ptr(counts), L.ptr(ce),
+                                              n, h, w, H, W, int(ignore_index), L.stream_ptr(dev))
+    L.check(rc, "cwt_upsample_argmax_iou")
+    return counts, ce
+
+
+def intersection_union(preds: torch.Tensor, target: torch.Tensor, num_classes: int, ignore_index: int = IGNORE):
+    """preds, target [n, ...] same shape and dtype (uint8 / int64) -> counts int64 [n, num_classes, 3] (I,U,T)."""
+    dev = L.require_cuda(preds, target)
+    if preds.shape != target.shape:
+        raise AssertionError("preds.shape == target.shape")          # src/util.py:298
+    if preds.dtype != target.dtype:
+        target = target.to(preds.dtype)
+    n = preds.shape[0]
+    npix = preds[0].numel() if n else 0
+    p, t = preds.contiguous(), target.contiguous()
+    counts = torch.empty(n, num_classes, 3, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.load().cwt_intersection_union(L.ptr(p), L.ptr(t), L.label_kind(p), L.ptr(counts), n, npix,
+                                             int(num_classes), int(ignore_index), L.stream_ptr(dev))
+    L.check(rc, "cwt_intersection_union")
+    return counts
+
+
+def query_loss_grad(logits60: torch.Tensor, q_label: torch.Tensor, ignore_index: int = IGNORE):
+    """Weighted CE at full resolution of up(logits60) with weight [1, n0/(n1+1e-12)]
+    (src/train.py:237-243,262-264). logits60 [E,2,h,w]; q_label [E,H,W].
+    Returns loss [E] and d loss / d logits60 [E,2,h,w]."""
+    dev = L.require_cuda(logits60, q_label)
+    E, two, h, w = logits60.shape
+    H, W = q_label.shape[-2:]
+    lg, lab = _f32c(logits60, "logits60"), q_label.contiguous()
+    loss = torch.empty(E, dtype=torch.float32, device=dev)
+    dl = torch.empty_like(lg)
+    lib = L.load()
+    ws = L.WORKSPACE.get(lib.cwt_query_loss_workspace_bytes(E, h, w, H, W), dev, "ql")
+    with torch.cuda.device(dev):
+        rc = lib.cwt_query_loss_grad(L.ptr(lg), L.ptr(lab), L.label_kind(lab), L.ptr(loss), L.ptr(dl), E, h, w, H, W,
+                                     int(ignore_index), L.ptr(ws), ws.numel(), L.stream_ptr(dev))
+    L.check(rc, "cwt_query_loss_grad")
+    return loss, dl
+
+
+
+def rows_times_feat(M: torch.Tensor, f: torch.Tensor, normalize: bool = False) -> torch.Tensor:
+    """out[e,r,p] = sum_c M[e,r,c] * fn[e,c,p] with fn = f or F.normalize(f, dim=1).
+    M [E,R,C]; f [E,C,h,w] or [E,C,HW] -> [E,R,HW]  (logits = W' X^T, src/train.py:259-261)."""
+    dev = L.require_cuda(M, f)
+    E, R, Cc = M.shape
+    HW = f[0, 0].numel()
+    out = torch.empty(E, R, HW, dtype=torch.float32, device=dev)
+    lib = L.load()
+    ws = L.WORKSPACE.get(lib.cwt_skinny_workspace_bytes(E, R, Cc, HW), dev, "sk")
+    with torch.cuda.device(dev):
+        rc = lib.cwt_rows_times_feat(L.ptr(_f32c(M, "M")), L.ptr(_f32c(f, "f")), int(bool(normalize)), L.ptr(out),
+                                     E, R, Cc, HW, L.ptr(ws), ws.numel(), L.stream_ptr(dev))
+    L.check(rc, "cwt_rows_times_feat")
+    return out
+
+
+def feat_times_rows(P: torch.Tensor, f: torch.Tensor, normalize: bool = False) -> torch.Tensor:
+    """out[e,r,c] = sum_p P[e,r,p] * fn[e,c,p].  P [E,R,HW]; f [E,C,h,w] -> [E,R,C]."""
+    dev = L.require_cuda(P, f)
+    E, R, HW = P.shape
+    Cc = f.shape[1]
+    out = torch.empty(E, R, Cc, dtype=torch.float32, device=dev)
+    lib = L.load()
+    ws = L.WORKSPACE.get(lib.cwt_skinny_workspace_bytes(E, R, Cc, HW), dev, "sk")
+    with torch.cuda.device(dev):
+        rc = lib.cwt_feat_times_rows(L.ptr(_f32c(P, "P")), L.ptr(_f32c(f, "f")), int(bool(normalize)), L.ptr(out),
+                                     E, R, Cc, HW, L.ptr(ws), ws.numel(), L.stream_ptr(dev))
+    L.check(rc, "cwt_feat_times_rows")
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# torch.ops.cwt_b200.* registration (PyTorch custom ops in front of the C ABI)
+# ----------------------------------------------------------------------------------------
+_registered = False
+
+
+def _register_custom_ops() -> None:
+    global _registered
+    if _registered:
+        return
+    _registered = True
+    from torch.library import custom_op
+
+    @custom_op("cwt_b200::fit_classifier", mutates_args=(), device_types="cuda")
+    def _fit(f_s: torch.Tensor, s_label: torch.Tensor, w0: torch.Tensor, lr: float, n_iter: int) -> torch.Tensor:
+        return fit_classifier(f_s, s_label, w0, lr, n_iter, check=False)
+
+    @_fit.register_fake
+    def _(f_s, s_label, w0, lr, n_iter):
+        return torch.empty_like(w0)
+
+    @custom_op("cwt_b200::transformer_forward", mutates_args=(), device_types="cuda")
+    def _tf(q: torch.Tensor, k: torch.Tensor, w_qkvs: torch.Tensor, fc_w: torch.Tensor, fc_b: torch.Tensor,
+            ln_g: torch.Tensor, ln_b: torch.Tensor, n_head: int, normalize_k: bool) -> torch.Tensor:
+        return transformer_forward(q, k, w_qkvs, fc_w, fc_b, ln_g, ln_b, n_head, normalize_k)
+
+    @_tf.register_fake
+    def _(q, k, w_qkvs, fc_w, fc_b, ln_g, ln_b, n_head, normalize_k):
+        return torch.empty_like(q)
+
+    @custom_op("cwt_b200::logits_iou", mutates_args=(), device_types="cuda")
+    def _li(weights: torch.Tensor, f_q: torch.Tensor, q_label: torch.Tensor, normalize_mask: int) -> torch.Tensor:
+        return logits_iou(weights, f_q, q_label, normalize_mask, return_logits=False)[0]
+
+    @_li.register_fake
+    def _(weights, f_q, q_label, normalize_mask):
+        return weights.new_empty(weights.shape[0], weights.shape[1], 2, 3, dtype=torch.int64)
+
+    @custom_op("cwt_b200::upsample_argmax_iou", mutates_args=(), device_types="cuda")
+    def _ui(logits: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        return upsample_argmax_iou(logits, target)[0]
+
+    @_ui.register_fake
+    def _(logits, target):
+        return logits.new_empty(logits.shape[0], 2, 3, dtype=torch.int64)

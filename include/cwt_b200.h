@@ -122,7 +122,7 @@ int cwt_transformer_bwd_f32(const float* d_out, const float* q, const float* k, 
  * (a-4, a-7..a-12) query logits -> bilinear up to HxW -> argmax -> intersection/union (+CE).
  * Replaces src/test.py:192,200-204,214-223 and batch_intersectionAndUnionGPU /
  * intersectionAndUnionGPU, src/util.py:237-308.
- *   w        [E,V,2,C]  V weight sets per episode (e.g. adapted and baseline classifier)
+ *   wts      [E,V,2,C]  V weight sets per episode (e.g. adapted and baseline classifier)
  *   f_q      [E,C,h,w]
  *   normalize_mask: bit v set => variant v scores the L2-normalised features (src/test.py:194,204)
  *   iu_counts  [E,V,2,3] int64 out: per class I, U, T   (U = O + T - I as util.py:306)
@@ -131,7 +131,7 @@ int cwt_transformer_bwd_f32(const float* d_out, const float* q, const float* k, 
  *   weighted CE for training (a-13): see cwt_query_loss_grad below.
  * ------------------------------------------------------------------------------------- */
 size_t cwt_logits_iou_workspace_bytes(int E, int V, int C, int h, int w, int H, int W);
-int cwt_logits_iou(const float* w, const float* f_q, const void* q_label, int label_kind,
+int cwt_logits_iou(const float* wts, const float* f_q, const void* q_label, int label_kind,
                    int normalize_mask, long long* iu_counts, float* logits60_or_null,
                    double* ce_or_null, int E, int V, int C, int h, int w, int H, int W,
                    int ignore_index, void* workspace, size_t ws_bytes, void* stream);
@@ -155,6 +155,18 @@ size_t cwt_query_loss_workspace_bytes(int E, int h, int w, int H, int W);
 int cwt_query_loss_grad(const float* logits60, const void* label, int label_kind,
                         float* loss, float* d_logits60, int E, int h, int w, int H, int W,
                         int ignore_index, void* workspace, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * The two skinny contractions behind everything above, exposed for the training step (a-13):
+ *   cwt_rows_times_feat : out[e][r][p] = sum_c M[e][r][c] * fn[e][c][p]   (logits = W' X^T, src/train.py:259-261)
+ *   cwt_feat_times_rows : out[e][r][c] = sum_p P[e][r][p] * fn[e][c][p]   (its adjoint: dW' = dlogits X)
+ * fn = f, or F.normalize(f, dim=1) when normalize != 0.  R <= 16.
+ * ------------------------------------------------------------------------------------- */
+size_t cwt_skinny_workspace_bytes(int E, int R, int C, int HW);
+int cwt_rows_times_feat(const float* M, const float* f, int normalize, float* out,
+                        int E, int R, int C, int HW, void* workspace, size_t ws_bytes, void* stream);
+int cwt_feat_times_rows(const float* P, const float* f, int normalize, float* out,
+                        int E, int R, int C, int HW, void* workspace, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

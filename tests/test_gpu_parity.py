@@ -1,0 +1,418 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI, against the oracle on identical seeded
+inputs and against the golden vectors recorded from the live reference.
+
+Tolerances (BASELINE.json north_star): weights / logits within 1e-4 relative (fp32 accumulate) —
+measured drift is ~1e-6, so most asserts use a tighter bound; IoU counts bit-exact except at
+stated argmax near-tie pixels (|up(l1) - up(l0)| <= TIE_TAU * max|logit|, listed by the oracle);
+mIoU / FB-IoU within 0.05 points.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import gen_kwargs, golden_names, load_golden, rel_err
+import few_shot_seg_cwt_b200 as cwt
+from few_shot_seg_cwt_b200 import _lib as L, ops, synthetic as syn
+from oracle import head_ref as O
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-4          # north-star tolerance
+TIGHT = 2e-5        # what fp32 re-association actually needs
+TIE_TAU = 1e-5
+
+SMALL = dict(shot=1, C=64, h=12, w=12, H=89, W=89, style="unit")
+
+
+def dev_params(params, dev):
+    return {k: v.to(dev) for k, v in params.items()}
+
+
+def assert_counts_match(got, ref, tie_margin, scale, what=""):
+    """bit-exact outside the stated tie set: every count may differ by at most the number of pixels
+    whose up-sampled logit margin is within TIE_TAU * scale."""
+    allowed = int((tie_margin <= TIE_TAU * max(scale, 1.0)).sum())
+    diff = (torch.as_tensor(got).cpu().long() - torch.as_tensor(ref).cpu().long()).abs().max().item()
+    assert diff <= allowed, f"{what}: counts differ by {diff} with a tie set of {allowed} pixels"
+
+
+# ---------------------------------------------------------------------------- primitives
+def test_loaded_native_library(cuda_device):
+    assert L.load().cwt_version() >= 100
+    n0 = L.launch_count()
+    ops.label_counts(torch.zeros(2, 9, 9, dtype=torch.uint8, device=cuda_device))
+    assert L.launch_count() > n0
+
+
+@pytest.mark.parametrize("dtype", [torch.uint8, torch.int64])
+def test_label_counts(cuda_device, dtype):
+    g = torch.Generator().manual_seed(0)
+    lab = torch.randint(0, 4, (3, 2, 89, 89), generator=g)
+    lab[lab == 2] = 255
+    lab[lab == 3] = 7                      # invalid value
+    lab = lab.to(dtype)
+    c = ops.label_counts(lab.to(cuda_device)).cpu()
+    for i in range(3):
+        for s in range(2):
+            l = lab[i, s]
+            assert c[i, s].tolist() == [int((l == 0).sum()), int((l == 1).sum()), int((l == 255).sum()), int((l == 7).sum())]
+
+
+@pytest.mark.parametrize("shape", [(3, 2, 64, 12, 12), (2, 5, 40, 9, 14), (1, 10, 512, 60, 60), (2, 16, 96, 7, 5)])
+@pytest.mark.parametrize("normalize", [False, True])
+def test_skinny_contractions(cuda_device, shape, normalize):
+    E, R, C, h, w = shape
+    g = torch.Generator().manual_seed(R)
+    f = torch.relu(torch.randn(E, C, h, w, generator=g))
+    f[0, :, 0, 0] = 0.0                    # an all-zero pixel: F.normalize clamps the norm at 1e-12
+    M = torch.randn(E, R, C, generator=g)
+    P = torch.randn(E, R, h * w, generator=g)
+    fn = F.normalize(f, dim=1) if normalize else f
+    ref1 = torch.einsum("erc,ecp->erp", M.double(), fn.reshape(E, C, -1).double())
+    ref2 = torch.einsum("erp,ecp->erc", P.double(), fn.reshape(E, C, -1).double())
+    out1 = ops.rows_times_feat(M.to(cuda_device), f.to(cuda_device), normalize)
+    out2 = ops.feat_times_rows(P.to(cuda_device), f.to(cuda_device), normalize)
+    assert rel_err(out1, ref1) < 2e-6
+    assert rel_err(out2, ref2) < 2e-6
+
+
+# ---------------------------------------------------------------------------- (a) fit
+@pytest.mark.parametrize("name", ["small_1shot_h1", "small_1shot_h4", "small_5shot_h4", "small_rect"])
+def test_fit_small_vs_oracle_and_golden(cuda_device, name):
+    g = load_golden(name)
+    case = g["case"]
+    ep = syn.make_episode(case["idx"], **gen_kwargs(case))
+    w_ref, losses_ref = O.fit_classifier_ref(ep.f_s, ep.s_label, ep.w0, case["lr"], case["n_iter"], return_losses=True)
+    w, losses = cwt.fit_classifier(ep.f_s.to(cuda_device), ep.s_label.to(cuda_device), ep.w0.to(cuda_device),
+                                   case["lr"], case["n_iter"], return_losses=True)
+    assert rel_err(w, w_ref) < TIGHT
+    assert rel_err(w, g["W_fit"]) < TIGHT
+    assert rel_err(losses[:, 0], torch.tensor(losses_ref)) < TIGHT
+    # without the loss trace (the fast kernels) the result is identical
+    w2 = cwt.fit_classifier(ep.f_s.to(cuda_device), ep.s_label.to(cuda_device), ep.w0.to(cuda_device),
+                            case["lr"], case["n_iter"])
+    assert torch.equal(w2, w)
+
+
+@pytest.mark.parametrize("name", ["full_1shot_h1_yaml", "full_1shot_h4_script", "full_1shot_h4_backbone", "full_5shot_h4"])
+def test_fit_full_size_vs_golden(cuda_device, name):
+    """BASELINE.json shapes (60x60x512 -> 473x473, 200 steps) against the reference's recorded output."""
+    g = load_golden(name)
+    case = g["case"]
+    ep = syn.make_episode(case["idx"], **gen_kwargs(case))
+    w = cwt.fit_classifier(ep.f_s.to(cuda_device), ep.s_label.to(cuda_device), ep.w0.to(cuda_device),
+                           case["lr"], case["n_iter"])
+    assert rel_err(w, g["W_fit"]) < REL
+
+
+def test_fit_batch_equals_single_and_label_dtypes(cuda_device):
+    b = syn.make_batch([20, 21, 22], **SMALL)
+    d = b.to(cuda_device)
+    w = cwt.fit_classifier(d.f_s, d.s_label, d.w0, 0.1, 40)
+    for i in range(3):
+        wi = cwt.fit_classifier(d.f_s[i], d.s_label[i], d.w0[i], 0.1, 40)
+        assert torch.equal(wi, w[i])
+    w64 = cwt.fit_classifier(d.f_s, d.s_label.long(), d.w0, 0.1, 40)
+    assert torch.equal(w64, w)
+    # 4-d conv-style initial weights keep their shape (nn.Conv2d.weight)
+    w4 = cwt.fit_classifier(d.f_s[0], d.s_label[0], d.w0[0].view(2, -1, 1, 1), 0.1, 40)
+    assert w4.shape == (2, 64, 1, 1) and torch.equal(w4.view(2, 64), w[0])
+
+
+def test_fit_explicit_class_weight_and_errors(cuda_device):
+    ep = syn.make_episode(30, **SMALL)
+    cw = torch.tensor([1.0, 3.5])
+    w_ref = O.fit_classifier_ref(ep.f_s, ep.s_label, ep.w0, 0.05, 30, class_weight=cw)
+    w = cwt.fit_classifier(ep.f_s.to(cuda_device), ep.s_label.to(cuda_device), ep.w0.to(cuda_device), 0.05, 30,
+                           class_weight=cw.to(cuda_device))
+    assert rel_err(w, w_ref) < TIGHT
+    no_fg = ep.s_label.clone()
+    no_fg[no_fg == 1] = 0
+    with pytest.raises(ZeroDivisionError):           # the reference's python division, src/test.py:174
+        cwt.fit_classifier(ep.f_s.to(cuda_device), no_fg.to(cuda_device), ep.w0.to(cuda_device), 0.05, 2)
+    bad = ep.s_label.clone()
+    bad[0, 0, 0] = 9
+    with pytest.raises(ValueError):
+        cwt.fit_classifier(ep.f_s.to(cuda_device), bad.to(cuda_device), ep.w0.to(cuda_device), 0.05, 2)
+    with pytest.raises(NotImplementedError):         # geometry the fused kernels do not cover
+        cwt.fit_classifier(ep.f_s.to(cuda_device), ep.s_label[:, :80, :80].contiguous().to(cuda_device),
+                           ep.w0.to(cuda_device), 0.05, 2)
+    # zero iterations: the initial weights come back
+    w0 = cwt.fit_classifier(ep.f_s.to(cuda_device), ep.s_label.to(cuda_device), ep.w0.to(cuda_device), 0.05, 0)
+    assert torch.equal(w0.cpu(), ep.w0)
+
+
+def test_inner_loop_dropin(cuda_device):
+    """PSPNet.inner_loop form (src/model/pspnet.py:189-205): mutates classifier.weight in place."""
+    ep = syn.make_episode(31, **SMALL)
+    clf = cwt.get_classifier(64, 2, cuda_device)
+    torch.manual_seed(3)
+    clf.reset_parameters()
+    w0 = clf.weight.detach().clone().view(2, 64).cpu()
+    cwt.inner_loop(clf, ep.f_s.to(cuda_device), ep.s_label.to(cuda_device), 0.1, 25, reset=False)
+    w_ref = O.fit_classifier_ref(ep.f_s, ep.s_label, w0, 0.1, 25)
+    assert clf.weight.shape == (2, 64, 1, 1)
+    assert rel_err(clf.weight.detach().view(2, 64), w_ref) < TIGHT
+
+
+# ---------------------------------------------------------------------------- (b) transformer
+@pytest.mark.parametrize("n_head,C,hw", [(1, 64, (12, 12)), (4, 64, (12, 12)), (2, 128, (9, 14)), (4, 512, (60, 60))])
+def test_transformer_forward_eval(cuda_device, n_head, C, hw):
+    params = syn.make_transformer_params(n_head, C)
+    g = torch.Generator().manual_seed(n_head + C)
+    B = 3
+    q = torch.randn(B, 2, C, generator=g) * 0.3
+    kraw = torch.relu(torch.randn(B, C, *hw, generator=g)) * 3.0
+    k = F.normalize(kraw, dim=1)
+    ref = O.mha_one_forward_ref(q, k, params, n_head)
+    m = cwt.MultiHeadAttentionOne(n_head, C, C, C, dropout=0.5).to(cuda_device).eval()
+    m.load_state_dict(params)
+    with torch.no_grad():
+        out = m(q.to(cuda_device), k.to(cuda_device), k.to(cuda_device))
+        m.normalize_k = True                         # fused F.normalize on the raw features
+        out_fused = m(q.to(cuda_device), kraw.to(cuda_device), kraw.to(cuda_device))
+    assert out.shape == (B, 2, C)
+    assert rel_err(out, ref) < TIGHT
+    assert rel_err(out_fused, ref) < TIGHT
+
+
+@pytest.mark.parametrize("n_head,C,hw,B", [(2, 64, (12, 12), 1), (4, 64, (12, 12), 2), (1, 128, (9, 14), 3)])
+def test_transformer_train_mode_forward_backward(cuda_device, n_head, C, hw, B):
+    """Explicit keep-masks, forward and the five parameter gradients against autograd of the oracle."""
+    params = syn.make_transformer_params(n_head, C)
+    g = torch.Generator().manual_seed(7 * n_head + C)
+    HW = hw[0] * hw[1]
+    q = torch.randn(B, 2, C, generator=g) * 0.3
+    k = F.normalize(torch.relu(torch.randn(B, C, *hw, generator=g)), dim=1)
+    ka = (torch.rand(n_head * B, 2, HW, generator=g) >= 0.1).to(torch.uint8)
+    ko = (torch.rand(B, 2, C, generator=g) >= 0.5).to(torch.uint8)
+    tgt = torch.randn(B, 2, C, generator=g)
+    pd = {kk: v.clone().requires_grad_(True) for kk, v in params.items()}
+    y_ref = O.mha_one_forward_ref(q, k, pd, n_head, ka, ko, 0.1, 0.5)
+    (y_ref * tgt).sum().backward()
+    m = cwt.MultiHeadAttentionOne(n_head, C, C, C, dropout=0.5).to(cuda_device).train()
+    m.load_state_dict(params)
+    kd = k.to(cuda_device)
+    y = m(q.to(cuda_device), kd, kd, keep_attn=ka.to(cuda_device), keep_out=ko.to(cuda_device))
+    (y * tgt.to(cuda_device)).sum().backward()
+    assert rel_err(y.detach(), y_ref.detach()) < TIGHT
+    for name, prm in m.named_parameters():
+        assert prm.grad is not None, name
+        assert rel_err(prm.grad, pd[name].grad) < 5e-5, name
+
+
+def test_transformer_train_mode_draws_masks(cuda_device):
+    m = cwt.MultiHeadAttentionOne(2, 64, 64, 64, dropout=0.5).to(cuda_device)
+    q = torch.randn(1, 2, 64, device=cuda_device)
+    k = F.normalize(torch.rand(1, 64, 12, 12, device=cuda_device), dim=1)
+    m.train()
+    a, b = m(q, k, k), m(q, k, k)
+    assert not torch.equal(a, b)                     # dropout active
+    m.eval()
+    with torch.no_grad():
+        assert torch.equal(m(q, k, k), m(q, k, k))
+    with pytest.raises(NotImplementedError):         # v must be k
+        m(q, k, k.clone() * 2.0)
+
+
+# ---------------------------------------------------------------------------- (c) logits / IoU
+@pytest.mark.parametrize("geom", [(12, 12, 89, 89), (60, 60, 473, 473), (9, 14, 65, 105)])
+@pytest.mark.parametrize("dtype", [torch.uint8, torch.int64])
+def test_batch_intersection_and_union_dropin(cuda_device, geom, dtype):
+    h, w, H, W = geom
+    g = torch.Generator().manual_seed(h)
+    logits = torch.randn(3, 2, 2, h, w, generator=g)
+    tgt = torch.randint(0, 3, (3, 2, H, W), generator=g)
+    tgt[tgt == 2] = 255
+    tgt[2] = 255                                       # a fully ignored task
+    I, U, T = O.batch_intersection_and_union_ref(logits, tgt, 2)
+    I2, U2, T2 = cwt.batch_intersectionAndUnionGPU(logits.to(cuda_device), tgt.to(dtype).to(cuda_device), 2)
+    assert I2.dtype == torch.float32 and I2.shape == (3, 2, 2)
+    # identical logits in, ATen rounding order reproduced -> bit-exact counts
+    assert torch.equal(I2.cpu(), I) and torch.equal(U2.cpu(), U) and torch.equal(T2.cpu(), T)
+    counts, ce = cwt.batch_intersection_union_int(logits.to(cuda_device), tgt.to(dtype).to(cuda_device))
+    up = F.interpolate(logits.view(6, 2, h, w), size=(H, W), mode="bilinear", align_corners=True)
+    ce_ref = F.cross_entropy(up[:4], tgt.view(6, H, W)[:4], ignore_index=255)
+    got = ce[:2, :, 0].sum() / ce[:2, :, 1].sum()
+    assert abs(float(got) - float(ce_ref)) < 1e-5 * max(1.0, float(ce_ref))
+
+
+def test_argmax_ties_and_empty(cuda_device):
+    lg = torch.zeros(1, 1, 2, 3, 3, device=cuda_device)                      # exact tie everywhere
+    tgt = torch.zeros(1, 1, 17, 17, dtype=torch.long, device=cuda_device)
+    I, U, T = cwt.batch_intersectionAndUnionGPU(lg, tgt, 2)
+    assert I[0, 0].tolist() == [289.0, 0.0] and U[0, 0].tolist() == [289.0, 0.0] and T[0, 0].tolist() == [289.0, 0.0]
+    I, U, T = cwt.batch_intersectionAndUnionGPU(lg, torch.full_like(tgt, 255), 2)
+    assert float(I.sum() + U.sum() + T.sum()) == 0.0
+    e = cwt.batch_intersectionAndUnionGPU(lg[:0], tgt[:0], 2)                  # empty batch
+    assert e[0].shape == (0, 1, 2)
+
+
+@pytest.mark.parametrize("dtype", [torch.uint8, torch.int64])
+def test_intersection_and_union_dropin(cuda_device, dtype):
+    g = torch.Generator().manual_seed(11)
+    p = torch.randint(0, 2, (89, 89), generator=g)
+    t = torch.randint(0, 3, (89, 89), generator=g)
+    t[t == 2] = 255
+    ref = O.intersection_and_union_ref(p, t, 2)
+    pd = p.to(dtype).to(cuda_device)
+    got = cwt.intersectionAndUnionGPU(pd, t.to(dtype).to(cuda_device), 2)
+    for a, b in zip(got, ref):
+        assert torch.equal(a.cpu(), b)
+    assert bool((pd.cpu()[t == 255] == 255).all())      # the reference's in-place side effect (util.py:301)
+    # more classes (histc semantics: values outside [0, C-1] are dropped)
+    p5 = torch.randint(0, 7, (500,), generator=g)
+    t5 = torch.randint(0, 7, (500,), generator=g)
+    ref5 = O.intersection_and_union_ref(p5, t5, 5, ignore_index=6)
+    got5 = cwt.intersectionAndUnionGPU(p5.to(cuda_device), t5.to(cuda_device), 5, ignore_index=6)
+    for a, b in zip(got5, ref5):
+        assert torch.equal(a.cpu(), b)
+    with pytest.raises(AssertionError):
+        cwt.intersectionAndUnionGPU(pd, pd[:10], 2)
+
+
+# ---------------------------------------------------------------------------- whole episode
+@pytest.mark.parametrize("name", [n for n in golden_names() if not n.startswith("train_")])
+def test_episode_head_vs_golden(cuda_device, name):
+    g = load_golden(name)
+    case = g["case"]
+    ep = syn.make_episode(case["idx"], **gen_kwargs(case))
+    params = syn.make_transformer_params(case["n_head"], case["C"])
+    b = syn.make_batch([case["idx"]], **gen_kwargs(case)).to(cuda_device)
+    out = cwt.episode_head(b.f_s, b.s_label, b.f_q, b.q_label, b.w0, dev_params(params, cuda_device),
+                           case["n_head"], case["lr"], case["n_iter"], return_logits=True)
+    assert rel_err(out.w_fit[0], g["W_fit"]) < REL
+    assert rel_err(out.w_adapted[0], g["W_adapted"]) < REL
+    assert rel_err(out.logits60[0, 0], g["logits60"]) < REL
+    assert rel_err(out.logits60[0, 1], g["logits60_0"]) < REL
+    # tie set from the oracle run on the same inputs (needs the full-resolution margins)
+    ora = O.episode_ref(ep.f_s, ep.s_label, ep.f_q, ep.q_label, ep.w0, params, case["n_head"], case["lr"], case["n_iter"])
+    assert np.array_equal(ora["counts"].numpy(), g["counts"])
+    assert_counts_match(out.counts[0, 0], g["counts"], ora["tie_margin"], float(ora["logits60"].abs().max()), "adapted")
+    assert_counts_match(out.counts[0, 1], g["counts0"], ora["tie_margin0"], float(ora["logits60_0"].abs().max()), "baseline")
+    loss = float(out.ce[0, 0, 0] / out.ce[0, 0, 1])
+    assert abs(loss - float(g["loss"])) < 1e-4 * max(1.0, abs(float(g["loss"])))
+
+
+def test_sweep_miou_matches_oracle(cuda_device):
+    """A short sharded-style sweep: per-class accumulation, mIoU / FB-IoU within 0.05 points."""
+    kw = dict(shot=1, C=64, h=12, w=12, H=89, W=89, style="unit")
+    n, n_head, lr, n_iter = 10, 2, 0.1, 60
+    params = syn.make_transformer_params(n_head, 64)
+    table = cwt.run_sweep(n, dev_params(params, cuda_device), n_head, lr, n_iter, cuda_device, batch=4, gen_kwargs=kw)
+    cI, cU, fb = {}, {}, torch.zeros(2, 2, dtype=torch.float64)
+    for i in range(n):
+        ep = syn.make_episode(i, **kw)
+        o = O.episode_ref(ep.f_s, ep.s_label, ep.f_q, ep.q_label, ep.w0, params, n_head, lr, n_iter)
+        cI[ep.subcls] = cI.get(ep.subcls, 0) + int(o["counts"][1, 0])
+        cU[ep.subcls] = cU.get(ep.subcls, 0) + int(o["counts"][1, 1])
+        fb += o["counts"][:, :2].double()
+    miou_ref = O.miou_from_counts(cI, cU)
+    fb_ref = float((fb[:, 0] / (fb[:, 1] + 1e-10)).mean())
+    assert int(table.n_episodes) == n
+    assert abs(table.miou(0) - miou_ref) * 100 < 0.05
+    assert abs(table.fb_iou(0) - fb_ref) * 100 < 0.05
+
+
+class _FakeBackbone(torch.nn.Module):
+    """Stands in for PSPNet.extract_features: looks the pre-computed features up by image id."""
+    def __init__(self, feats):
+        super().__init__()
+        self.feats = feats
+        self.dummy = torch.nn.Parameter(torch.zeros(1))
+
+    def extract_features(self, x):
+        ids = x[:, 0, 0, 0].long().tolist()
+        return torch.stack([self.feats[i] for i in ids]).to(x.device), None
+
+
+class _Args:
+    pass
+
+
+def test_validate_transformer_dropin(cuda_device):
+    """The reference loop signature (src/test.py:103-106) on a fake loader/backbone; mIoU / loss against
+    the oracle run episode by episode with the same initial classifier weights."""
+    kw = dict(shot=1, C=64, h=12, w=12, H=89, W=89, style="unit")
+    n = 6
+    eps = [syn.make_episode(100 + i, label_dtype=torch.int64, **kw) for i in range(n)]
+    feats, items = {}, []
+    for i, ep in enumerate(eps):
+        feats[2 * i], feats[2 * i + 1] = ep.f_s[0], ep.f_q
+        simg = torch.full((1, 1, 3, 89, 89), float(2 * i))
+        qimg = torch.full((1, 3, 89, 89), float(2 * i + 1))
+        items.append((qimg, ep.q_label.unsqueeze(0), simg, ep.s_label.unsqueeze(0), [torch.tensor([ep.subcls])], None, None))
+    args = _Args()
+    args.test_num, args.batch_size_val, args.image_size, args.n_runs = n, 3, 89, 1
+    args.bottleneck_dim, args.num_classes_tr, args.cls_lr, args.adapt_iter = 64, 2, 0.1, 50
+    n_head = 2
+    params = syn.make_transformer_params(n_head, 64)
+    tr = cwt.MultiHeadAttentionOne(n_head, 64, 64, 64, dropout=0.5).to(cuda_device)
+    tr.load_state_dict(params)
+    torch.manual_seed(5)
+    miou, loss = cwt.validate_transformer(args, items, _FakeBackbone(feats), tr, verbose=False)
+    # oracle with the same RNG stream for the per-episode nn.Conv2d init
+    torch.manual_seed(5)
+    cI, cU, losses = {}, {}, []
+    batch_ce = []
+    for i, ep in enumerate(eps):
+        w0 = torch.nn.Conv2d(64, 2, 1, bias=False).weight.detach().view(2, 64)
+        o = O.episode_ref(ep.f_s, ep.s_label, ep.f_q, ep.q_label, w0, params, n_head, 0.1, 50)
+        cI[ep.subcls] = cI.get(ep.subcls, 0) + int(o["counts"][1, 0])
+        cU[ep.subcls] = cU.get(ep.subcls, 0) + int(o["counts"][1, 1])
+        nvalid = int((ep.q_label != 255).sum())
+        batch_ce.append((float(o["loss"]) * nvalid, nvalid))
+        if len(batch_ce) == 3:
+            losses.append(sum(a for a, _ in batch_ce) / sum(b for _, b in batch_ce))
+            batch_ce = []
+    assert abs(miou - O.miou_from_counts(cI, cU)) * 100 < 0.05
+    assert abs(loss - float(np.mean(losses))) < 1e-4
+
+
+# ---------------------------------------------------------------------------- (a-13) training step
+@pytest.mark.parametrize("name", ["train_small_h2", "train_full_h1"])
+def test_meta_train_step_vs_golden(cuda_device, name):
+    g = load_golden(name)
+    case = g["case"]
+    ep = syn.make_episode(case["idx"], **gen_kwargs(case))
+    params = syn.make_transformer_params(case["n_head"], case["C"])
+    shape = tuple(int(x) for x in g["keep_attn_shape"])
+    ka = torch.from_numpy(np.unpackbits(g["keep_attn"])[: int(np.prod(shape))].reshape(shape))
+    ko = torch.from_numpy(g["keep_out"])
+    tr = cwt.MultiHeadAttentionOne(case["n_head"], case["C"], case["C"], case["C"], dropout=case["p_out"]).to(cuda_device)
+    tr.load_state_dict(params)
+    lr_t, mom, wd = 0.0025, 0.9, 1e-4
+    opt = torch.optim.SGD(tr.parameters(), lr=lr_t, momentum=mom, weight_decay=wd, nesterov=True)   # src/optimizer.py:11-15
+    b = syn.make_batch([case["idx"]], **gen_kwargs(case)).to(cuda_device)
+    before = {k: v.detach().clone() for k, v in tr.named_parameters()}
+    out = cwt.meta_train_step(tr, opt, b.f_s, b.s_label, b.f_q, b.q_label, b.w0, case["lr"], case["n_iter"],
+                              keep_attn=ka.to(cuda_device), keep_out=ko.to(cuda_device))
+    assert rel_err(out["w_fit"][0], g["W_fit"]) < REL
+    assert rel_err(out["w_adapted"][0], g["W_adapted"]) < REL
+    assert abs(float(out["loss"]) - float(g["loss"])) < 1e-4 * max(1.0, float(g["loss"]))
+    sub = int(g["sub"])
+    grads = {}
+    for k, p in tr.named_parameters():
+        ref = g["grad_" + k]
+        flat = p.grad.detach().reshape(-1).cpu()
+        got = flat if flat.numel() == ref.size else flat[::sub]
+        if k == "layer_norm.bias":                     # analytically zero (the two logit-gradient rows cancel)
+            assert float(got.abs().max()) < 1e-4 * float(g["gradnorm_layer_norm.weight"])
+        else:
+            assert rel_err(got, ref) < 2e-4, k
+        grads[k] = p.grad.detach().cpu()
+    # the optimiser step itself (first step: momentum buffer = g)
+    new_ref, _ = O.sgd_nesterov_step_ref({k: v.cpu() for k, v in before.items()}, grads, None, lr_t, mom, wd)
+    for k, p in tr.named_parameters():
+        assert torch.allclose(p.detach().cpu(), new_ref[k], rtol=1e-5, atol=1e-7), k
+
+
+def test_torch_custom_ops_registered(cuda_device):
+    cwt.register_torch_ops()
+    ep = syn.make_batch([40], **SMALL).to(cuda_device)
+    w = torch.ops.cwt_b200.fit_classifier(ep.f_s, ep.s_label, ep.w0, 0.1, 10)
+    assert torch.equal(w, cwt.fit_classifier(ep.f_s, ep.s_label, ep.w0, 0.1, 10))
+    lg = torch.randn(2, 2, 12, 12, device=cuda_device)
+    tg = torch.zeros(2, 89, 89, dtype=torch.uint8, device=cuda_device)
+    assert torch.equal(torch.ops.cwt_b200.upsample_argmax_iou(lg, tg), ops.upsample_argmax_iou(lg, tg)[0])

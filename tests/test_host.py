@@ -1,0 +1,166 @@
+"""CPU suite, part 2: host-side logic — the C-ABI library loads and exports every symbol the header
+declares, the drop-in modules keep the reference's names/shapes, the synthetic generator is
+deterministic, the metric table and the world-size-2 sharding + all-reduce (gloo) agree with a single
+process, and ops refuse to run without CUDA (no silent CPU fallback)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+import few_shot_seg_cwt_b200 as cwt
+from few_shot_seg_cwt_b200 import _lib, synthetic as syn
+from few_shot_seg_cwt_b200.episodic import IoUTable
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "cwt_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cwt_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_header_symbol():
+    names = _header_functions()
+    assert len(names) >= 15
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/cwt_b200.h but not exported"
+    assert set(names) == set(_lib.SIGNATURES), "ctypes binding table and header disagree"
+    assert _lib.load().cwt_version() >= 100
+
+
+def test_library_is_blackwell_native():
+    """sm_100a cubin only (no PTX-JIT for other arches, no multi-backend dispatch)."""
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump not available")
+    arches = set(re.findall(r"sm_\d+a?", out.stdout))
+    assert arches == {"sm_100a"}, arches
+
+
+def test_workspace_size_queries_need_no_gpu():
+    lib = _lib.load()
+    assert lib.cwt_fit_workspace_bytes(4, 1, 512, 60, 60, 473, 473) > 4 * 473 * 473
+    assert lib.cwt_transformer_workspace_bytes(4, 2, 4, 512, 3600, 0) > 0
+    assert lib.cwt_logits_iou_workspace_bytes(4, 2, 512, 60, 60, 473, 473) > 0
+
+
+def test_no_cpu_fallback():
+    f = torch.zeros(1, 1, 8, 2, 2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        cwt.fit_classifier(f, torch.zeros(1, 1, 9, 9, dtype=torch.uint8), torch.zeros(1, 2, 8), 0.1, 1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        cwt.batch_intersectionAndUnionGPU(torch.zeros(1, 1, 2, 2, 2), torch.zeros(1, 1, 9, 9, dtype=torch.long), 2)
+    m = cwt.MultiHeadAttentionOne(1, 8, 8, 8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        k = torch.zeros(1, 8, 2, 2)
+        m.eval()(torch.zeros(1, 2, 8), k, k)
+
+
+def test_module_state_dict_matches_reference_names_and_shapes():
+    m = cwt.MultiHeadAttentionOne(4, 512, 512, 512, dropout=0.5)
+    sd = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert sd == {"w_qkvs.weight": (2048, 512), "layer_norm.weight": (512,), "layer_norm.bias": (512,),
+                  "fc.weight": (512, 2048), "fc.bias": (512,)}
+    assert len(list(m.parameters())) == 5
+    m.load_state_dict(syn.make_transformer_params(4, 512))
+    m.train(); assert m.training
+    m.eval(); assert not m.training
+    # init statistics of src/model/transformer.py:44-51
+    assert abs(float(m.w_qkvs.weight.std()) - np.sqrt(2.0 / 1024)) < 2e-3
+    with pytest.raises(NotImplementedError):
+        cwt.MultiHeadAttentionOne(1, 512, 256, 256)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference checkout not present")
+def test_module_loads_reference_checkpoint_format():
+    sys.path.insert(0, "/root/reference")
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from src.model.transformer import MultiHeadAttentionOne as RefMHA
+    ref = RefMHA(4, 512, 512, 512, dropout=0.5)
+    ckpt = {"epoch": 1, "state_dict": ref.state_dict()}          # src/train.py:138-163
+    m = cwt.MultiHeadAttentionOne(4, 512, 512, 512, dropout=0.5)
+    m.load_state_dict(ckpt["state_dict"])
+    assert torch.equal(m.fc.weight, ref.fc.weight)
+
+
+def test_synthetic_generator_deterministic_and_well_formed():
+    a = syn.make_episode(5, shot=2, C=32, h=12, w=12, H=89, W=89)
+    b = syn.make_episode(5, shot=2, C=32, h=12, w=12, H=89, W=89)
+    assert torch.equal(a.f_s, b.f_s) and torch.equal(a.q_label, b.q_label) and torch.equal(a.w0, b.w0)
+    assert a.f_s.shape == (2, 32, 12, 12) and a.s_label.shape == (2, 89, 89) and a.s_label.dtype == torch.uint8
+    assert set(torch.unique(a.s_label).tolist()) <= {0, 1, 255}
+    assert (a.s_label == 1).sum() > 0 and (a.q_label == 1).sum() > 0
+    assert float(a.f_s.min()) >= 0.0 and 0.2 < float((a.f_s == 0).float().mean()) < 0.8
+    assert float(a.w0.abs().max()) <= 1 / np.sqrt(32) + 1e-7
+    assert a.subcls == 5 % 5 + 1
+    assert syn.shard_indices(10, 1, 4) == [1, 5, 9]
+    batch = syn.make_batch([0, 1, 2], shot=1, C=32, h=12, w=12, H=89, W=89)
+    assert batch.f_s.shape == (3, 1, 32, 12, 12) and batch.n_episodes == 3
+
+
+def _fake_counts(idx):
+    g = torch.Generator().manual_seed(idx)
+    I = torch.randint(0, 1000, (2, 2), generator=g)
+    U = I + torch.randint(1, 1000, (2, 2), generator=g)
+    T = I + torch.randint(0, 500, (2, 2), generator=g)
+    return torch.stack([I, U, T], -1)          # [V=2, class=2, 3]
+
+
+def _table_for(indices, num_classes=5):
+    t = IoUTable(num_classes, "cpu")
+    if indices:
+        counts = torch.stack([_fake_counts(i) for i in indices])
+        sub = torch.tensor([i % num_classes + 1 for i in indices])
+        t.update(counts, sub, torch.ones(len(indices), 2, 2, dtype=torch.float64))
+    return t
+
+
+def test_iou_table_matches_reference_accumulation():
+    idx = list(range(23))
+    t = _table_for(idx)
+    # reference arithmetic: dict of per-class sums, IoU = I/(U+1e-10), mean over classes seen
+    cI, cU = {}, {}
+    for i in idx:
+        c = i % 5 + 1
+        k = _fake_counts(i)
+        cI[c] = cI.get(c, 0) + int(k[0, 1, 0]); cU[c] = cU.get(c, 0) + int(k[0, 1, 1])
+    ref = np.mean([cI[c] / (cU[c] + 1e-10) for c in cU])
+    assert abs(t.miou(0) - ref) < 1e-12
+    assert 0.0 < t.fb_iou(0) < 1.0 and int(t.n_episodes) == 23
+
+
+def _worker(rank, world, port, n, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    t = _table_for(syn.shard_indices(n, rank, world))
+    t.all_reduce()
+    q.put((rank, t.cls.clone(), t.fb.clone(), int(t.n_episodes), t.miou(0), t.miou(1)))
+    dist.destroy_process_group()
+
+
+def test_sharded_sweep_all_reduce_world2_gloo():
+    """episodes i -> rank i mod 2, one integer all-reduce: identical table on both ranks, equal to the
+    single-process table."""
+    n, world = 17, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=120) for _ in range(world)]
+    [p.join(60) for p in procs]
+    single = _table_for(list(range(n)))
+    for rank, cls, fb, ne, m0, m1 in res:
+        assert torch.equal(cls, single.cls) and torch.equal(fb, single.fb) and ne == n
+        assert m0 == single.miou(0) and m1 == single.miou(1)

@@ -1,0 +1,105 @@
+"""CPU suite, part 1: the oracle against the golden vectors recorded from the live reference
+(tests/golden/*.npz, written by oracle/pin_against_reference.py), and against an independent
+closed-form restatement."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import gen_kwargs, golden_names, load_golden, rel_err
+from few_shot_seg_cwt_b200 import synthetic as syn
+from oracle import head_ref as O
+
+
+def _checksum(ep):
+    h = hashlib.sha256()
+    for t in (ep.f_s, ep.s_label, ep.f_q, ep.q_label, ep.w0):
+        h.update(t.contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+EVAL_CASES = [n for n in golden_names() if not n.startswith("train_")]
+FAST = [n for n in EVAL_CASES if n.startswith("small")] + ["full_1shot_h1_yaml"]
+
+
+@pytest.mark.parametrize("name", FAST)
+def test_oracle_reproduces_reference_golden(name):
+    g = load_golden(name)
+    case = g["case"]
+    ep = syn.make_episode(case["idx"], **gen_kwargs(case))
+    assert _checksum(ep) == str(g["checksum"]), "synthetic generator drifted from the pinned inputs"
+    params = syn.make_transformer_params(case["n_head"], case["C"])
+    out = O.episode_ref(ep.f_s, ep.s_label, ep.f_q, ep.q_label, ep.w0, params, case["n_head"], case["lr"], case["n_iter"])
+    for k in ("W_fit", "W_adapted", "logits60", "logits60_0"):
+        assert rel_err(out[k], g[k]) < 1e-6, k
+    assert np.array_equal(out["counts"].numpy(), g["counts"])
+    assert np.array_equal(out["counts0"].numpy(), g["counts0"])
+    assert abs(float(out["loss"]) - float(g["loss"])) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["small_1shot_h4", "small_5shot_h4", "small_rect"])
+def test_closed_form_fit_matches_literal_loop(name):
+    """The explicit-matrix restatement (fp64) agrees with the autograd loop (fp32) far inside the
+    1e-4 tolerance of the north-star: this bounds fp32 drift of the 200-step recursion."""
+    case = load_golden(name)["case"]
+    ep = syn.make_episode(case["idx"], **gen_kwargs(case))
+    w_lit = O.fit_classifier_ref(ep.f_s, ep.s_label, ep.w0, case["lr"], case["n_iter"])
+    w_cf = O.fit_classifier_closed_form(ep.f_s, ep.s_label, ep.w0, case["lr"], case["n_iter"])
+    assert rel_err(w_lit, w_cf) < 2e-5
+    # the two softmax-gradient rows cancel: W0 + W1 is invariant under the fit
+    assert torch.allclose((w_cf[0] + w_cf[1]).float(), ep.w0[0] + ep.w0[1], atol=1e-5)
+
+
+def test_train_step_golden_small():
+    g = load_golden("train_small_h2")
+    case = g["case"]
+    ep = syn.make_episode(case["idx"], **gen_kwargs(case))
+    params = syn.make_transformer_params(case["n_head"], case["C"])
+    ka = torch.from_numpy(np.unpackbits(g["keep_attn"])[: int(np.prod(g["keep_attn_shape"]))].reshape(tuple(g["keep_attn_shape"])))
+    ko = torch.from_numpy(g["keep_out"])
+    out = O.meta_train_step_ref(torch.from_numpy(g["W_fit"]), ep.f_q, ep.q_label, params, case["n_head"], ka, ko,
+                                case["p_attn"], case["p_out"])
+    assert abs(float(out["loss"]) - float(g["loss"])) < 1e-5
+    assert rel_err(out["W_adapted"], g["W_adapted"]) < 1e-5
+    for k, v in out["grads"].items():
+        ref = g["grad_" + k]
+        flat = v.reshape(-1)
+        got = flat if flat.numel() == ref.size else flat[:: int(g["sub"])]
+        if k == "layer_norm.bias":      # analytically zero: absolute tolerance (SURVEY.md §8 math block)
+            assert float(got.abs().max()) < 1e-5
+        else:
+            assert rel_err(got, ref) < 5e-5, k
+
+
+def test_iou_edge_cases():
+    # all ignored -> all zero; ties -> class 0
+    tgt = torch.full((1, 1, 17, 17), 255)
+    lg = torch.zeros(1, 1, 2, 3, 3)
+    I, U, T = O.batch_intersection_and_union_ref(lg, tgt, 2)
+    assert I.sum() == 0 and U.sum() == 0 and T.sum() == 0
+    tgt = torch.zeros(1, 1, 17, 17, dtype=torch.long)
+    I, U, T = O.batch_intersection_and_union_ref(lg, tgt, 2)      # exact tie everywhere -> pred 0
+    assert I[0, 0].tolist() == [289.0, 0.0] and U[0, 0].tolist() == [289.0, 0.0]
+
+
+def test_class_weight_zero_foreground_raises():
+    with pytest.raises(ZeroDivisionError):
+        O.class_weight_ref(torch.zeros(1, 9, 9, dtype=torch.long))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference checkout not present (GPU box)")
+def test_pin_against_live_reference_small():
+    """Where the reference is mounted: the restatement still matches the reference's own objects."""
+    from oracle import pin_against_reference as P
+    MHA, biou, siou = P._import_reference()
+    assert P.check_transformer(MHA) < 2e-6
+    assert P.check_iou(biou, siou)
+    case = P.CASES["small_1shot_h4"]
+    ep = syn.make_episode(case["idx"], **P.gen_kwargs(case))
+    params = syn.make_transformer_params(case["n_head"], case["C"])
+    ref = P.episode_via_reference(ep, params, case["n_head"], case["lr"], case["n_iter"], MHA, biou)
+    g = load_golden("small_1shot_h4")
+    assert rel_err(ref["W_adapted"], g["W_adapted"]) < 1e-6
+    assert np.array_equal(ref["counts"].numpy(), g["counts"])
