@@ -80,8 +80,10 @@ class MultiHeadAttentionOne(nn.Module):
         """q [B,Lq,C]; k, v [B,C,h,w] -> [B,Lq,C].  ``v`` must be ``k`` (the only call pattern on the
         reference path: transformer(W, f_q, f_q))."""
         if v is not None and v is not k and not (v.data_ptr() == k.data_ptr() and v.shape == k.shape):
-            raise NotImplementedError("cwt_b200 MultiHeadAttentionOne requires v is k (shared K/V projection); "
-                                      "the reference only ever calls transformer(W, f_q, f_q)")
+            # distinct storage: accept only equal values (costs one comparison pass + a host sync)
+            if v.shape != k.shape or not torch.equal(v, k):
+                raise NotImplementedError("cwt_b200 MultiHeadAttentionOne requires v == k (shared K/V projection); "
+                                          "the reference only ever calls transformer(W, f_q, f_q)")
         if self.training and keep_attn is None and keep_out is None:
             B, Lq, C = q.shape
             HW = k.shape[2] * (k.shape[3] if k.dim() == 4 else 1)

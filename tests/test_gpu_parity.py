@@ -169,9 +169,11 @@ def test_transformer_forward_eval(cuda_device, n_head, C, hw):
     m = cwt.MultiHeadAttentionOne(n_head, C, C, C, dropout=0.5).to(cuda_device).eval()
     m.load_state_dict(params)
     with torch.no_grad():
-        out = m(q.to(cuda_device), k.to(cuda_device), k.to(cuda_device))
+        kd, krd = k.to(cuda_device), kraw.to(cuda_device)
+        out = m(q.to(cuda_device), kd, kd)
+        assert torch.equal(m(q.to(cuda_device), kd, kd.clone()), out)      # equal-valued v in distinct storage
         m.normalize_k = True                         # fused F.normalize on the raw features
-        out_fused = m(q.to(cuda_device), kraw.to(cuda_device), kraw.to(cuda_device))
+        out_fused = m(q.to(cuda_device), krd, krd)
     assert out.shape == (B, 2, C)
     assert rel_err(out, ref) < TIGHT
     assert rel_err(out_fused, ref) < TIGHT
@@ -354,10 +356,12 @@ def test_validate_transformer_dropin(cuda_device):
     miou, loss = cwt.validate_transformer(args, items, _FakeBackbone(feats), tr, verbose=False)
     # oracle with the same RNG stream for the per-episode nn.Conv2d init
     torch.manual_seed(5)
+    # (drawn up front: the oracle's own nn.Conv2d construction would otherwise advance the RNG in between)
+    w0s = [torch.nn.Conv2d(64, 2, 1, bias=False).weight.detach().view(2, 64).clone() for _ in eps]
     cI, cU, losses = {}, {}, []
     batch_ce = []
     for i, ep in enumerate(eps):
-        w0 = torch.nn.Conv2d(64, 2, 1, bias=False).weight.detach().view(2, 64)
+        w0 = w0s[i]
         o = O.episode_ref(ep.f_s, ep.s_label, ep.f_q, ep.q_label, w0, params, n_head, 0.1, 50)
         cI[ep.subcls] = cI.get(ep.subcls, 0) + int(o["counts"][1, 0])
         cU[ep.subcls] = cU.get(ep.subcls, 0) + int(o["counts"][1, 1])
