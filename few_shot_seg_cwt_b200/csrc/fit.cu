@@ -18,8 +18,8 @@
 
 namespace cwt {
 
-int prep_labels(const void* labels, int label_kind, int n_img, long long npix, int ignore_index,
-                uint8_t* packed, int32_t* counts, cudaStream_t st);
+int pack_label_cells(const void* labels, int label_kind, int n_img, int h, int w, int H, int W, int ignore_index,
+                     uint4* cells, int32_t* counts, cudaStream_t st);
 
 // one CTA per episode: W <- W0, Wd = W1 - W0
 __global__ void __launch_bounds__(256)
@@ -48,13 +48,13 @@ struct FitUpdateEpilogue {
 };
 
 struct FitWs {
-    uint8_t* lab; int32_t* counts_img; float2* cw; float* wd; float* zd; float* g60; float* loss_part;
+    uint4* cells; int32_t* counts_img; float2* cw; float* wd; float* zd; float* g60; float* loss_part;
     int nblk;
 };
 
 static size_t carve_fit(Carver& cv, FitWs& ws, int E, int S, int C, int h, int w, int H, int W) {
-    ws.nblk = (h + HIRES_RROWS - 1) / HIRES_RROWS;
-    ws.lab = cv.take<uint8_t>((size_t)E * S * H * W);
+    ws.nblk = hires_bands(h);
+    ws.cells = cv.take<uint4>((size_t)E * S * h * w);
     ws.counts_img = cv.take<int32_t>((size_t)E * S * 4);
     ws.cw = cv.take<float2>((size_t)E);
     ws.wd = cv.take<float>((size_t)E * C);
@@ -87,8 +87,7 @@ extern "C" int cwt_fit_classifier_f32(const float* f_s, const void* s_label, int
     CWT_REQUIRE(f_s && s_label && w0 && w_out, CWT_ERR_INVALID_ARG, "fit: null pointer");
     CWT_REQUIRE(H == 8 * (h - 1) + 1 && W == 8 * (w - 1) + 1, CWT_ERR_UNSUPPORTED,
                 "fit: label size %dx%d is not 8*(%dx%d - 1) + 1 (align_corners scale must be 1/8)", H, W, h, w);
-    CWT_REQUIRE(w <= HIRES_MAXW && W <= HIRES_THREADS * HIRES_MAXCOL, CWT_ERR_UNSUPPORTED,
-                "fit: w=%d / W=%d exceeds the supported width (128 / 1024)", w, W);
+    CWT_REQUIRE(w <= HIRES_MAXW, CWT_ERR_UNSUPPORTED, "fit: w=%d exceeds the supported width (%d)", w, HIRES_MAXW);
     CWT_REQUIRE(label_kind == CWT_LABEL_U8 || label_kind == CWT_LABEL_I64, CWT_ERR_INVALID_ARG,
                 "fit: label_kind %d", label_kind);
     CWT_REQUIRE(algo == CWT_FIT_AUTO || algo == CWT_FIT_STREAM || algo == CWT_FIT_RESIDENT, CWT_ERR_INVALID_ARG,
@@ -99,7 +98,7 @@ extern "C" int cwt_fit_classifier_f32(const float* f_s, const void* s_label, int
     CWT_REQUIRE(workspace && ws_bytes >= need, CWT_ERR_WORKSPACE, "fit: workspace %zu < %zu bytes", ws_bytes, need);
 
     const int HWl = h * w;
-    int rc = prep_labels(s_label, label_kind, E * S, (long long)H * W, ignore_index, ws.lab, ws.counts_img, st);
+    int rc = pack_label_cells(s_label, label_kind, E * S, h, w, H, W, ignore_index, ws.cells, ws.counts_img, st);
     if (rc != CWT_OK) return rc;
     k_class_consts<<<(E + 127) / 128, 128, 0, st>>>(ws.counts_img, class_weight_or_null, 0.0, ws.cw,
                                                     label_counts_or_null, E, S);
@@ -111,21 +110,18 @@ extern "C" int cwt_fit_classifier_f32(const float* f_s, const void* s_label, int
         CWT_REQUIRE(false, CWT_ERR_UNSUPPORTED, "fit: CWT_FIT_RESIDENT is not available in this build");
     }
 
-    dim3 hgrid(ws.nblk, E * S);
     FitUpdateEpilogue epi{w_out, ws.wd, lr, C};
     for (int it = 0; it < n_iter; ++it) {
         rc = launch_rows_times_feat(f_s, ws.wd, ws.zd, nullptr, E * S, C, HWl, S, 1, st);
         if (rc != CWT_OK) return rc;
         if (loss_trace_or_null) {
-            k_fit_hires<HIRES_RROWS, true><<<hgrid, HIRES_THREADS, 0, st>>>(ws.zd, ws.lab, ws.cw, ws.g60,
-                                                                             ws.loss_part, h, w, H, W, S);
-            CWT_LAUNCHED("fit_hires");
+            rc = launch_fit_hires<true>(ws.zd, ws.cells, ws.cw, ws.g60, ws.loss_part, E * S, h, w, S, st);
+            if (rc != CWT_OK) return rc;
             k_reduce_loss<<<E, 32, 0, st>>>(ws.loss_part, loss_trace_or_null + (size_t)it * E, S * ws.nblk);
             CWT_LAUNCHED("reduce_loss");
         } else {
-            k_fit_hires<HIRES_RROWS, false><<<hgrid, HIRES_THREADS, 0, st>>>(ws.zd, ws.lab, ws.cw, ws.g60,
-                                                                              nullptr, h, w, H, W, S);
-            CWT_LAUNCHED("fit_hires");
+            rc = launch_fit_hires<false>(ws.zd, ws.cells, ws.cw, ws.g60, nullptr, E * S, h, w, S, st);
+            if (rc != CWT_OK) return rc;
         }
         rc = launch_ftc_t<1, 4>(f_s, ws.g60, E, S, C, HWl, 1, epi, st);
         if (rc != CWT_OK) return rc;

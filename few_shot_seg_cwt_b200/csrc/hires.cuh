@@ -1,7 +1,13 @@
-// Full-resolution (H x W) stage shared by the support fit (a-3) and the query training
-// loss (a-13): bilinear up (scale exactly 1/8) of a logit difference, 2-class softmax as a
-// sigmoid, class-weighted CE gradient, and the adjoint bilinear map as a deterministic
-// gather (the reference's upsample_bilinear2d_backward uses float atomics on CUDA).
+// Full-resolution (H x W) stage shared by the support fit (a-3) and the query training loss (a-13):
+// bilinear up (align_corners, scale exactly 1/8) of a 2-class logit difference, softmax as a
+// sigmoid, class-weighted CE gradient, and the adjoint bilinear map.
+//
+// Work unit = one CELL of the align_corners grid: cell (a,b) covers pixels [8a,8a+8) x [8b,8b+8),
+// is interpolated from the four low-res corners z(a,b) z(a,b+1) z(a+1,b) z(a+1,b+1) and sends its
+// gradient back to exactly those four corners. A thread evaluates one cell (64 sigmoids, all in
+// registers, labels as 8 x uint16 = one 128-bit load); the four corner contributions are then
+// combined by a deterministic gather (the reference's upsample_bilinear2d_backward uses float
+// atomics on CUDA and is run-to-run non-deterministic).
 #pragma once
 #include "common.cuh"
 
@@ -29,92 +35,99 @@ k_class_consts(const int32_t* __restrict__ counts_img, const float* __restrict__
         for (int k = 0; k < 4; ++k) counts_ep[e * 4 + k] = (int32_t)n[k];
 }
 
-// Full-resolution stage: CTA = (band of RROWS low-res rows, image). Recomputes the sigmoid of
-// the hi-res rows it gathers from (8 halo rows per band: (RROWS+1)/RROWS redundancy).
-constexpr int HIRES_THREADS = 256;
-constexpr int HIRES_MAXCOL = 4;      // W <= 1024
+// One cell: 64 pixels. bits = 8 rows x 16 bit (2 bit label code per pixel, see k_pack_label_cells).
+// c0 / c1 = w[0]/sum_w, w[1]/sum_w. Outputs the gradient mass sent to the four corners.
+template <bool LOSS>
+__device__ __forceinline__ void hires_cell(float z00, float z01, float z10, float z11, uint4 bits,
+                                           float c0, float c1, float& o00, float& o01, float& o10, float& o11,
+                                           float& loss) {
+    const uint32_t words[4] = {bits.x, bits.y, bits.z, bits.w};
+    const float dl = (z10 - z00) * 0.125f, dr = (z11 - z01) * 0.125f;
+    float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const uint32_t rb = (words[r >> 1] >> ((r & 1) * 16)) & 0xffffu;
+        const float left = fmaf((float)r, dl, z00), right = fmaf((float)r, dr, z01);
+        const float slope = (right - left) * 0.125f;
+        float gs = 0.f, gr = 0.f;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const uint32_t code = (rb >> (2 * s)) & 3u;
+            const float d = fmaf((float)s, slope, left);
+            const float p = __fdividef(1.f, 1.f + __expf(-d));
+            const float coef = (code == 0u) ? c0 : ((code == 1u) ? c1 : 0.f);
+            const float g = coef * (p - (float)(code & 1u));
+            gs += g;
+            gr = fmaf((float)s, g, gr);
+            if (LOSS) {
+                if (code < 2u) {
+                    const float t = (code == 1u) ? -d : d;                 // -log p_y = softplus(t)
+                    loss = fmaf(coef, fmaxf(t, 0.f) + log1pf(expf(-fabsf(t))), loss);
+                }
+            }
+        }
+        gr *= 0.125f;                         // mass sent to the right column
+        const float gl = gs - gr;             // ... and to the left one
+        const float h1 = (float)r * 0.125f, h0 = 1.f - h1;
+        a00 = fmaf(h0, gl, a00); a01 = fmaf(h0, gr, a01);
+        a10 = fmaf(h1, gl, a10); a11 = fmaf(h1, gr, a11);
+    }
+    o00 = a00; o01 = a01; o10 = a10; o11 = a11;
+}
+
+// Streaming form: CTA = (band of RROWS low-res rows, image); one thread per cell of the band plus the
+// cell row above it (the halo row is recomputed: (RROWS+1)/RROWS redundancy, no cross-CTA traffic).
 constexpr int HIRES_MAXW = 128;      // w <= 128
+constexpr int HIRES_RROWS = 4;
 
 template <int RROWS, bool LOSS>
-__global__ void __launch_bounds__(HIRES_THREADS)
-k_fit_hires(const float* __restrict__ zd, const uint8_t* __restrict__ lab, const float2* __restrict__ cw,
-            float* __restrict__ g60, float* __restrict__ loss_part, int h, int w, int H, int W, int S) {
-    __shared__ float zs[(RROWS + 2) * HIRES_MAXW];
-    __shared__ float colbuf[HIRES_THREADS * HIRES_MAXCOL];
-    __shared__ float lred[HIRES_THREADS / 32];
+__global__ void __launch_bounds__((RROWS + 1) * HIRES_MAXW > 1024 ? 1024 : 512)
+k_fit_hires(const float* __restrict__ zd, const uint4* __restrict__ cells, const float2* __restrict__ cw,
+            float* __restrict__ g60, float* __restrict__ loss_part, int h, int w, int S) {
+    extern __shared__ float hsm[];
+    float* zs = hsm;                                  // [(RROWS+2)][w]   rows a_first-1 .. a_last+1
+    float* cc = zs + (RROWS + 2) * w;                 // [4][(RROWS+1)][w] corner contributions
+    __shared__ float lred[32];
     const int img = blockIdx.y, e = img / S;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, nthr = blockDim.x;
     const int a_first = blockIdx.x * RROWS;
     const int a_last = min(a_first + RROWS - 1, h - 1);
     const float2 c01 = cw[e];
     const float* zimg = zd + (size_t)img * h * w;
-    for (int i = tid; i < (RROWS + 2) * w; i += HIRES_THREADS) {
-        int ar = i / w, b = i - ar * w;
-        int a = a_first - 1 + ar;
-        zs[ar * w + b] = (a >= 0 && a < h) ? zimg[a * w + b] : 0.f;
+    for (int i = tid; i < (RROWS + 2) * w; i += nthr) {
+        const int ar = i / w, b = i - ar * w;
+        const int a = min(max(a_first - 1 + ar, 0), h - 1);       // clamped (out-of-range rows carry zero weight)
+        zs[i] = zimg[a * w + b];
     }
     __syncthreads();
-
-    const uint8_t* limg = lab + (size_t)img * H * W;
-    float acc_cur[HIRES_MAXCOL], acc_next[HIRES_MAXCOL];
-#pragma unroll
-    for (int j = 0; j < HIRES_MAXCOL; ++j) { acc_cur[j] = 0.f; acc_next[j] = 0.f; }
     float loss = 0.f;
-    const int ncol = (W + HIRES_THREADS - 1) / HIRES_THREADS;
-
-    for (int a0 = a_first - 1; a0 <= a_last; ++a0) {
-        if (a0 >= 0) {
-            const int a1 = min(a0 + 1, h - 1);
-            const float* z0 = zs + (a0 - a_first + 1) * w;
-            const float* z1 = zs + (a1 - a_first + 1) * w;
-            const bool need_cur = (a0 >= a_first);
-            for (int r = 0; r < 8; ++r) {
-                const int Y = 8 * a0 + r;
-                if (Y >= H) break;
-                const bool need_next = (r > 0) && (a0 + 1 <= a_last);
-                if (!need_cur && !need_next) continue;
-                const float h1 = r * 0.125f, h0 = 1.f - h1;
-#pragma unroll
-                for (int j = 0; j < HIRES_MAXCOL; ++j) {
-                    const int X = tid + j * HIRES_THREADS;
-                    if (j < ncol && X < W) {
-                        const int b0 = X >> 3, b1 = min(b0 + 1, w - 1);
-                        const float w1 = (X & 7) * 0.125f, w0 = 1.f - w1;
-                        const float d = bilerp8(z0[b0], z0[b1], z1[b0], z1[b1], w0, w1, h0, h1);
-                        const int code = limg[(size_t)Y * W + X];
-                        const float p = __fdividef(1.f, 1.f + __expf(-d));
-                        const float g = (code == 0) ? c01.x * p : ((code == 1) ? c01.y * (p - 1.f) : 0.f);
-                        acc_cur[j] = fmaf(h0, g, acc_cur[j]);
-                        acc_next[j] = fmaf(h1, g, acc_next[j]);
-                        if (LOSS && need_cur && code < 2) {
-                            const float t = (code == 1) ? -d : d;          // -log p_y = softplus(t)
-                            const float sp = fmaxf(t, 0.f) + log1pf(expf(-fabsf(t)));
-                            loss = fmaf((code == 1) ? c01.y : c01.x, sp, loss);
-                        }
-                    }
-                }
-            }
+    const uint4* cimg = cells + (size_t)img * h * w;
+    for (int i = tid; i < (RROWS + 1) * w; i += nthr) {
+        const int ar = i / w, b = i - ar * w;
+        const int a = a_first - 1 + ar;
+        float o00 = 0.f, o01 = 0.f, o10 = 0.f, o11 = 0.f;
+        if (a >= 0 && a <= a_last) {
+            const int b1 = min(b + 1, w - 1);
+            const float* z0 = zs + ar * w;
+            const float* z1 = zs + (ar + 1) * w;
+            float l = 0.f;
+            hires_cell<LOSS>(z0[b], z0[b1], z1[b], z1[b1], cimg[a * w + b], c01.x, c01.y, o00, o01, o10, o11, l);
+            if (LOSS && ar >= 1) loss += l;                       // each cell is owned by exactly one band
         }
-        if (a0 >= a_first) {
-#pragma unroll
-            for (int j = 0; j < HIRES_MAXCOL; ++j) {
-                const int X = tid + j * HIRES_THREADS;
-                if (j < ncol && X < W) colbuf[X] = acc_cur[j];
-            }
-            __syncthreads();
-            for (int b = tid; b < w; b += HIRES_THREADS) {
-                float s = 0.f;
-#pragma unroll
-                for (int k = -7; k <= 7; ++k) {
-                    const int X = 8 * b + k;
-                    if (X >= 0 && X < W) s = fmaf(1.f - fabsf((float)k) * 0.125f, colbuf[X], s);
-                }
-                g60[(size_t)img * h * w + a0 * w + b] = s;
-            }
-            __syncthreads();
-        }
-#pragma unroll
-        for (int j = 0; j < HIRES_MAXCOL; ++j) { acc_cur[j] = acc_next[j]; acc_next[j] = 0.f; }
+        cc[(0 * (RROWS + 1) + ar) * w + b] = o00;
+        cc[(1 * (RROWS + 1) + ar) * w + b] = o01;
+        cc[(2 * (RROWS + 1) + ar) * w + b] = o10;
+        cc[(3 * (RROWS + 1) + ar) * w + b] = o11;
+    }
+    __syncthreads();
+    // g60(a,b) = c00(a,b) + c01(a,b-1) + c10(a-1,b) + c11(a-1,b-1)
+    for (int i = tid; i < RROWS * w; i += nthr) {
+        const int ar = 1 + i / w, b = i - (ar - 1) * w;
+        const int a = a_first - 1 + ar;
+        if (a > a_last) break;
+        float s = cc[(0 * (RROWS + 1) + ar) * w + b] + cc[(2 * (RROWS + 1) + ar - 1) * w + b];
+        if (b > 0) s += cc[(1 * (RROWS + 1) + ar) * w + b - 1] + cc[(3 * (RROWS + 1) + ar - 1) * w + b - 1];
+        g60[(size_t)img * h * w + a * w + b] = s;
     }
     if (LOSS) {
         loss = warp_sum(loss);
@@ -122,10 +135,27 @@ k_fit_hires(const float* __restrict__ zd, const uint8_t* __restrict__ lab, const
         __syncthreads();
         if (tid == 0) {
             float s = 0.f;
-            for (int k = 0; k < HIRES_THREADS / 32; ++k) s += lred[k];
+            for (int k = 0; k < (nthr + 31) / 32; ++k) s += lred[k];
             loss_part[(size_t)e * (S * gridDim.x) + (img - e * S) * gridDim.x + blockIdx.x] = s;
         }
     }
+}
+
+static inline int hires_threads(int w) {
+    int t = (HIRES_RROWS + 1) * w;
+    t = (t + 31) / 32 * 32;
+    return t > 512 ? 512 : t;
+}
+static inline size_t hires_smem(int w) { return sizeof(float) * ((HIRES_RROWS + 2) * w + 4 * (HIRES_RROWS + 1) * w); }
+static inline int hires_bands(int h) { return (h + HIRES_RROWS - 1) / HIRES_RROWS; }
+
+template <bool LOSS>
+static int launch_fit_hires(const float* zd, const uint4* cells, const float2* cw, float* g60, float* loss_part,
+                            int n_img, int h, int w, int S, cudaStream_t st) {
+    dim3 grid(hires_bands(h), n_img);
+    k_fit_hires<HIRES_RROWS, LOSS><<<grid, hires_threads(w), hires_smem(w), st>>>(zd, cells, cw, g60, loss_part, h, w, S);
+    CWT_LAUNCHED("fit_hires");
+    return CWT_OK;
 }
 
 static __global__ void k_reduce_loss(const float* __restrict__ part, float* __restrict__ out, int n_per_ep) {
@@ -135,8 +165,5 @@ static __global__ void k_reduce_loss(const float* __restrict__ part, float* __re
     s = warp_sum(s);
     if (threadIdx.x == 0) out[e] = s;
 }
-
-
-constexpr int HIRES_RROWS = 4;
 
 }  // namespace cwt

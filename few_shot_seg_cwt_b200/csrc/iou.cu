@@ -12,8 +12,8 @@
 
 namespace cwt {
 
-int prep_labels(const void* labels, int label_kind, int n_img, long long npix, int ignore_index,
-                uint8_t* packed, int32_t* counts, cudaStream_t st);
+int pack_label_cells(const void* labels, int label_kind, int n_img, int h, int w, int H, int W, int ignore_index,
+                     uint4* cells, int32_t* counts, cudaStream_t st);
 
 constexpr int IOU_THREADS = 256;
 constexpr int IOU_MAXW = 128;
@@ -170,10 +170,10 @@ static size_t carve_logits_iou(Carver& cv, LogitsIouWs& ws, int E, int V, int HW
     return align_up(cv.off);
 }
 
-struct QueryLossWs { uint8_t* lab; int32_t* counts; float2* cw; float* zd; float* g60; float* part; int nblk; };
+struct QueryLossWs { uint4* cells; int32_t* counts; float2* cw; float* zd; float* g60; float* part; int nblk; };
 static size_t carve_query_loss(Carver& cv, QueryLossWs& ws, int E, int h, int w, int H, int W) {
-    ws.nblk = (h + HIRES_RROWS - 1) / HIRES_RROWS;
-    ws.lab = cv.take<uint8_t>((size_t)E * H * W);
+    ws.nblk = hires_bands(h);
+    ws.cells = cv.take<uint4>((size_t)E * h * w);
     ws.counts = cv.take<int32_t>((size_t)E * 4);
     ws.cw = cv.take<float2>((size_t)E);
     ws.zd = cv.take<float>((size_t)E * h * w);
@@ -266,23 +266,22 @@ extern "C" int cwt_query_loss_grad(const float* logits60, const void* label, int
     CWT_REQUIRE(logits60 && label && loss && d_logits60 && E > 0, CWT_ERR_INVALID_ARG, "query_loss_grad: bad argument");
     CWT_REQUIRE(H == 8 * (h - 1) + 1 && W == 8 * (w - 1) + 1, CWT_ERR_UNSUPPORTED,
                 "query_loss_grad: label size %dx%d is not 8*(%dx%d - 1) + 1", H, W, h, w);
-    CWT_REQUIRE(w <= HIRES_MAXW && W <= HIRES_THREADS * HIRES_MAXCOL, CWT_ERR_UNSUPPORTED, "query_loss_grad: width");
+    CWT_REQUIRE(w <= HIRES_MAXW, CWT_ERR_UNSUPPORTED, "query_loss_grad: w=%d > %d", w, HIRES_MAXW);
     CWT_REQUIRE(label_kind == CWT_LABEL_U8 || label_kind == CWT_LABEL_I64, CWT_ERR_INVALID_ARG, "label_kind %d", label_kind);
     Carver cv(workspace, ws_bytes);
     QueryLossWs ws;
     size_t need = carve_query_loss(cv, ws, E, h, w, H, W);
     CWT_REQUIRE(workspace && ws_bytes >= need, CWT_ERR_WORKSPACE, "query_loss_grad: workspace %zu < %zu", ws_bytes, need);
     const int HWl = h * w;
-    int rc = prep_labels(label, label_kind, E, (long long)H * W, ignore_index, ws.lab, ws.counts, st);
+    int rc = pack_label_cells(label, label_kind, E, h, w, H, W, ignore_index, ws.cells, ws.counts, st);
     if (rc != CWT_OK) return rc;
     k_class_consts<<<(E + 127) / 128, 128, 0, st>>>(ws.counts, nullptr, 1e-12, ws.cw, nullptr, E, 1);
     CWT_LAUNCHED("class_consts");
     size_t total = (size_t)E * HWl;
     k_logit_diff<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(logits60, ws.zd, HWl, total);
     CWT_LAUNCHED("logit_diff");
-    dim3 hgrid(ws.nblk, E);
-    k_fit_hires<HIRES_RROWS, true><<<hgrid, HIRES_THREADS, 0, st>>>(ws.zd, ws.lab, ws.cw, ws.g60, ws.part, h, w, H, W, 1);
-    CWT_LAUNCHED("query_hires");
+    rc = launch_fit_hires<true>(ws.zd, ws.cells, ws.cw, ws.g60, ws.part, E, h, w, 1, st);
+    if (rc != CWT_OK) return rc;
     k_reduce_loss<<<E, 32, 0, st>>>(ws.part, loss, ws.nblk);
     CWT_LAUNCHED("reduce_loss");
     k_spread_grad<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws.g60, d_logits60, HWl, total);
