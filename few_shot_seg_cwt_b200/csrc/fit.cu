@@ -20,6 +20,10 @@ namespace cwt {
 
 int pack_label_cells(const void* labels, int label_kind, int n_img, int h, int w, int H, int W, int ignore_index,
                      uint4* cells, int32_t* counts, cudaStream_t st);
+size_t fit_resident_workspace_bytes(int C, int h, int w);
+int fit_resident(const float* f_s, const uint4* cells, const float2* cw, float* w_io, int E, int C, int h, int w,
+                 int n_iter, float lr, void* ws, size_t ws_bytes, long long* prof_out, cudaStream_t st);
+static long long* g_prof_buffer = nullptr;   // debug: per-CTA phase cycle counters of the resident kernel
 
 // one CTA per episode: W <- W0, Wd = W1 - W0
 __global__ void __launch_bounds__(256)
@@ -49,6 +53,7 @@ struct FitUpdateEpilogue {
 
 struct FitWs {
     uint4* cells; int32_t* counts_img; float2* cw; float* wd; float* zd; float* g60; float* loss_part;
+    void* resident; size_t resident_bytes;
     int nblk;
 };
 
@@ -61,6 +66,8 @@ static size_t carve_fit(Carver& cv, FitWs& ws, int E, int S, int C, int h, int w
     ws.zd = cv.take<float>((size_t)E * S * h * w);
     ws.g60 = cv.take<float>((size_t)E * S * h * w);
     ws.loss_part = cv.take<float>((size_t)E * S * ws.nblk);
+    ws.resident_bytes = (S == 1) ? fit_resident_workspace_bytes(C, h, w) : 0;
+    ws.resident = cv.take<char>(ws.resident_bytes);
     return align_up(cv.off);
 }
 
@@ -106,8 +113,17 @@ extern "C" int cwt_fit_classifier_f32(const float* f_s, const void* s_label, int
     k_fit_init_weights<<<E, 256, 0, st>>>(w0, w_out, ws.wd, C);
     CWT_LAUNCHED("fit_init_weights");
 
-    if (algo == CWT_FIT_RESIDENT) {
-        CWT_REQUIRE(false, CWT_ERR_UNSUPPORTED, "fit: CWT_FIT_RESIDENT is not available in this build");
+    // resident (shared-memory) algorithm: 1-shot, no loss trace, shape must fit on chip
+    if (algo != CWT_FIT_STREAM && n_iter > 0) {
+        if (S == 1 && !loss_trace_or_null && HWl % 4 == 0) {
+            rc = fit_resident(f_s, ws.cells, ws.cw, w_out, E, C, h, w, n_iter, lr, ws.resident, ws.resident_bytes,
+                              g_prof_buffer, st);
+            if (rc == CWT_OK) return CWT_OK;
+            if (rc != CWT_ERR_UNSUPPORTED || algo == CWT_FIT_RESIDENT) return rc;
+        } else if (algo == CWT_FIT_RESIDENT) {
+            CWT_REQUIRE(false, CWT_ERR_UNSUPPORTED,
+                        "fit: CWT_FIT_RESIDENT needs shot == 1, h*w %% 4 == 0 and no loss trace (S=%d, h*w=%d)", S, HWl);
+        }
     }
 
     FitUpdateEpilogue epi{w_out, ws.wd, lr, C};
@@ -128,3 +144,6 @@ extern "C" int cwt_fit_classifier_f32(const float* f_s, const void* s_label, int
     }
     return CWT_OK;
 }
+
+// debug hook: device buffer [grid][8] int64 receiving the resident kernel's per-phase cycle counters
+extern "C" void cwt_debug_set_prof_buffer(void* dev_buffer) { cwt::g_prof_buffer = static_cast<long long*>(dev_buffer); }

@@ -54,6 +54,9 @@ int         cwt_version(void);
 const char* cwt_last_error(void);
 /* number of kernels this library has launched from the calling process (bench bookkeeping) */
 long long   cwt_launch_count(void);
+/* debug: device buffer [grid][8] int64 that receives the resident fit kernel's per-phase cycle
+ * counters (P1, X1, HR, P3, X2) on its next launches; NULL switches the instrumented build off */
+void        cwt_debug_set_prof_buffer(void* dev_buffer);
 
 /* ---------------------------------------------------------------------------------------
  * (a-2) label statistics.  Replaces the per-episode D2H copy + numpy `where` of

@@ -89,34 +89,65 @@ def test_fit_small_vs_oracle_and_golden(cuda_device, name):
     assert rel_err(w, w_ref) < TIGHT
     assert rel_err(w, g["W_fit"]) < TIGHT
     assert rel_err(losses[:, 0], torch.tensor(losses_ref)) < TIGHT
-    # without the loss trace (the fast kernels) the result is identical
-    w2 = cwt.fit_classifier(ep.f_s.to(cuda_device), ep.s_label.to(cuda_device), ep.w0.to(cuda_device),
-                            case["lr"], case["n_iter"])
+    # without the loss trace the streaming kernels give the identical result ...
+    args = (ep.f_s.to(cuda_device), ep.s_label.to(cuda_device), ep.w0.to(cuda_device), case["lr"], case["n_iter"])
+    w2 = cwt.fit_classifier(*args, algo=L.FIT_STREAM)
     assert torch.equal(w2, w)
+    # ... and the shared-memory-resident kernel (1-shot, h*w % 4 == 0) agrees to rounding
+    if case["shot"] == 1 and (case["h"] * case["w"]) % 4 == 0:
+        w3 = cwt.fit_classifier(*args, algo=L.FIT_RESIDENT)
+        assert rel_err(w3, w_ref) < TIGHT
+        assert rel_err(cwt.fit_classifier(*args), w_ref) < TIGHT          # CWT_FIT_AUTO
+    else:
+        with pytest.raises(NotImplementedError):
+            cwt.fit_classifier(*args, algo=L.FIT_RESIDENT)
+        assert torch.equal(cwt.fit_classifier(*args), w)                   # AUTO falls back to streaming
 
 
+@pytest.mark.parametrize("algo", [L.FIT_STREAM, L.FIT_RESIDENT])
 @pytest.mark.parametrize("name", ["full_1shot_h1_yaml", "full_1shot_h4_script", "full_1shot_h4_backbone", "full_5shot_h4"])
-def test_fit_full_size_vs_golden(cuda_device, name):
+def test_fit_full_size_vs_golden(cuda_device, name, algo):
     """BASELINE.json shapes (60x60x512 -> 473x473, 200 steps) against the reference's recorded output."""
     g = load_golden(name)
     case = g["case"]
+    if algo == L.FIT_RESIDENT and case["shot"] != 1:
+        pytest.skip("the resident kernel holds one shot on chip; multi-shot streams")
     ep = syn.make_episode(case["idx"], **gen_kwargs(case))
     w = cwt.fit_classifier(ep.f_s.to(cuda_device), ep.s_label.to(cuda_device), ep.w0.to(cuda_device),
-                           case["lr"], case["n_iter"])
+                           case["lr"], case["n_iter"], algo=algo)
     assert rel_err(w, g["W_fit"]) < REL
+
+
+def test_fit_resident_many_episodes_per_group(cuda_device):
+    """More episodes than groups: every group loops over several episodes (flags / accumulators are
+    monotonic across episodes), result equals the streaming kernels to rounding."""
+    b = syn.make_batch(list(range(50, 61)), **SMALL).to(cuda_device)       # 11 episodes
+    ws = cwt.fit_classifier(b.f_s, b.s_label, b.w0, 0.1, 30, algo=L.FIT_STREAM)
+    wr = cwt.fit_classifier(b.f_s, b.s_label, b.w0, 0.1, 30, algo=L.FIT_RESIDENT)
+    assert torch.isfinite(wr).all()
+    for i in range(11):
+        assert rel_err(wr[i], ws[i]) < 1e-5, i
+    big = syn.make_batch(list(range(70, 76)), shot=1, C=512, h=60, w=60, H=473, W=473).to(cuda_device)   # 6 episodes on 4 groups
+    ws = cwt.fit_classifier(big.f_s, big.s_label, big.w0, 0.1, 25, algo=L.FIT_STREAM)
+    wr = cwt.fit_classifier(big.f_s, big.s_label, big.w0, 0.1, 25, algo=L.FIT_RESIDENT)
+    for i in range(6):
+        assert rel_err(wr[i], ws[i]) < 1e-5, i
 
 
 def test_fit_batch_equals_single_and_label_dtypes(cuda_device):
     b = syn.make_batch([20, 21, 22], **SMALL)
     d = b.to(cuda_device)
-    w = cwt.fit_classifier(d.f_s, d.s_label, d.w0, 0.1, 40)
+    S = L.FIT_STREAM                       # deterministic summation order: bit-identical results
+    w = cwt.fit_classifier(d.f_s, d.s_label, d.w0, 0.1, 40, algo=S)
     for i in range(3):
-        wi = cwt.fit_classifier(d.f_s[i], d.s_label[i], d.w0[i], 0.1, 40)
+        wi = cwt.fit_classifier(d.f_s[i], d.s_label[i], d.w0[i], 0.1, 40, algo=S)
         assert torch.equal(wi, w[i])
-    w64 = cwt.fit_classifier(d.f_s, d.s_label.long(), d.w0, 0.1, 40)
+        wr = cwt.fit_classifier(d.f_s[i], d.s_label[i], d.w0[i], 0.1, 40, algo=L.FIT_RESIDENT)
+        assert rel_err(wr, w[i]) < 1e-5
+    w64 = cwt.fit_classifier(d.f_s, d.s_label.long(), d.w0, 0.1, 40, algo=S)
     assert torch.equal(w64, w)
     # 4-d conv-style initial weights keep their shape (nn.Conv2d.weight)
-    w4 = cwt.fit_classifier(d.f_s[0], d.s_label[0], d.w0[0].view(2, -1, 1, 1), 0.1, 40)
+    w4 = cwt.fit_classifier(d.f_s[0], d.s_label[0], d.w0[0].view(2, -1, 1, 1), 0.1, 40, algo=S)
     assert w4.shape == (2, 64, 1, 1) and torch.equal(w4.view(2, 64), w[0])
 
 
@@ -416,7 +447,7 @@ def test_torch_custom_ops_registered(cuda_device):
     cwt.register_torch_ops()
     ep = syn.make_batch([40], **SMALL).to(cuda_device)
     w = torch.ops.cwt_b200.fit_classifier(ep.f_s, ep.s_label, ep.w0, 0.1, 10)
-    assert torch.equal(w, cwt.fit_classifier(ep.f_s, ep.s_label, ep.w0, 0.1, 10))
+    assert rel_err(w, cwt.fit_classifier(ep.f_s, ep.s_label, ep.w0, 0.1, 10)) < 1e-5
     lg = torch.randn(2, 2, 12, 12, device=cuda_device)
     tg = torch.zeros(2, 89, 89, dtype=torch.uint8, device=cuda_device)
     assert torch.equal(torch.ops.cwt_b200.upsample_argmax_iou(lg, tg), ops.upsample_argmax_iou(lg, tg)[0])

@@ -1,0 +1,45 @@
+"""Time the resident fit kernel and dump its per-phase cycle counters (P1, X1, HR, P3, X2)."""
+import argparse, ctypes, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import few_shot_seg_cwt_b200 as cwt
+from few_shot_seg_cwt_b200 import _lib as L, synthetic as syn
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--episodes", type=int, default=16)
+ap.add_argument("--iters", type=int, default=200)
+ap.add_argument("--prof", type=int, default=1)
+a = ap.parse_args()
+dev = torch.device("cuda:0")
+g = torch.Generator(device=dev).manual_seed(0)
+E = a.episodes
+f_s = torch.relu(torch.randn(E, 1, 512, 60, 60, device=dev, generator=g))
+b = syn.make_batch([0]).to(dev)
+s_label = b.s_label[:1].expand(E, 1, 473, 473).contiguous()
+w0 = (torch.rand(E, 2, 512, device=dev, generator=g) * 2 - 1) / 512 ** 0.5
+lib = L.load()
+def run(algo):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    w = cwt.fit_classifier(f_s, s_label, w0, 0.1, a.iters, check=False, algo=algo)
+    e1.record(); torch.cuda.synchronize()
+    return w, e0.elapsed_time(e1)
+ws, ts = run(L.FIT_STREAM); ws, ts = run(L.FIT_STREAM)
+wr, tr = run(L.FIT_RESIDENT); wr, tr = run(L.FIT_RESIDENT)
+err = float((wr - ws).norm() / ws.norm())
+print(f"E={E} iters={a.iters}: stream {ts:.2f} ms ({E/ts*1e3:.0f} ep/s)  resident {tr:.2f} ms ({E/tr*1e3:.0f} ep/s)  rel diff {err:.2e} finite={bool(torch.isfinite(wr).all())}")
+if a.prof:
+    buf = torch.zeros(160, 8, dtype=torch.int64, device=dev)
+    lib.cwt_debug_set_prof_buffer(ctypes.c_void_p(buf.data_ptr()))
+    wr, tp = run(L.FIT_RESIDENT)
+    lib.cwt_debug_set_prof_buffer(None)
+    c = buf.cpu().double()
+    used = c[:, 0] > 0
+    n_steps = a.iters * ((E + 3) // 4)
+    names = ["P1", "X1", "HR", "P3", "X2"]
+    print(f"instrumented run {tp:.2f} ms; per-step cycles (mean over {int(used.sum())} CTAs, ~{n_steps} steps each; min/max over CTAs):")
+    for i, n in enumerate(names):
+        col = c[used, i] / n_steps
+        print(f"  {n}: mean {col.mean():8.0f}  min {col.min():8.0f}  max {col.max():8.0f}")
+    print(f"  total/step {c[used, :5].sum(1).mean() / n_steps:8.0f} cycles")
