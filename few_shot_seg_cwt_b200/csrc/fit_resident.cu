@@ -7,68 +7,58 @@
 // then runs every step out of shared memory:
 //
 //   P1  z[p]   = sum_c Wd[c] F[c][p]          linear conflict-free sweep of the strip, own NP pixels
-//   X1  publish z strip, read the (w+1)-pixel halos of strips k-1 / k+1        (neighbour flags)
-//   HR  full-resolution stage on the NP + w + 1 cells that touch the strip      (hires_cell, gather form)
-//   P3  dW[c]  = sum_p g[p] F[c][p]           thread = channel, second sweep of the strip
-//   X2  group all-reduce of dW (fp32 reductions at L2 + one group barrier), SGD update of W0/W1/Wd
+//   X1  halo exchange of z with strips k-1 / k+1 (w+1 pixels each side)
+//   HR  full-resolution stage on the NP + w + 1 cells that touch the strip (one task = one cell row)
+//   P3  dW[c]  = sum_p g[p] F[c][p]           second sweep of the strip, 4 threads per channel
+//   AR  group all-reduce of dW, SGD update of W0 / W1 / Wd
+//
+// All cross-CTA traffic uses SEQUENCE-TAGGED 8-byte words {fp32 value, step number}: 64-bit stores are
+// single-copy atomic, so a reader simply polls the data word until its tag matches — no fences, no
+// atomics, no barriers, and a stale value can never be consumed. The all-reduce is two such hops,
+// pipelined in RES_KCH channel chunks underneath P3 / P1: every CTA owns a slice of the channels; its
+// REDUCER WARP (warp 16, never computes) collects the CPG partials of the slice, adds them in a fixed
+// order (deterministic), and republishes the sums, which the compute threads pick up right before the
+// P1 chunk that needs them.
 //
 // HBM traffic per episode drops from (2T+1) F to F (+ labels); the per-step bound becomes the shared
-// memory sweep (2 x C*NP*4 B at 128 B/clk/SM) plus two group synchronisations. floor(#SM / CPG) groups
-// run concurrently (4 x 36 = 144 of 148 SMs for 60x60x512), each looping over its share of the batch.
+// memory sweep (2 x C*NP*4 B at 128 B/clk/SM). floor(#SM / CPG) groups run concurrently
+// (4 x 36 = 144 of 148 SMs for 60x60x512), each looping over its share of the batch.
 //
-// Launch: cooperative (all CTAs must be co-resident: the groups spin on each other's flags).
-// Every spin loop has a watchdog: on timeout the kernel raises an abort flag, stops waiting and
-// writes NaN results rather than hanging the GPU.
+// The kernel is compiled twice: specialised for the PSPNet head geometry (C=512, 60x60, NP=100: all
+// loop bounds, divisions and predicates become compile-time) and generic (run-time shapes).
+//
+// Launch: cooperative (all CTAs must be co-resident: they poll each other's words). Every poll loop
+// has a watchdog: on timeout the kernel raises an abort flag, stops waiting and writes NaN results
+// rather than hanging the GPU.
 #include "common.cuh"
 #include "hires.cuh"
 #include <cstdlib>
 
 namespace cwt {
 
-constexpr int RES_THREADS = 512;
+constexpr int RES_CTHREADS = 512;               // 16 compute warps
+constexpr int RES_THREADS = RES_CTHREADS + 32;  // + the reducer warp
 constexpr unsigned RES_SPIN_LIMIT = 1u << 24;
+constexpr int RES_KCH = 4;        // channel chunks of the pipelined all-reduce
+constexpr int RES_MAXQ = 8;       // float4 pixel-quads per P3 thread (NP <= 128)
+constexpr int RES_RW = 5;         // tagged words a reducer lane keeps in flight per chunk
+constexpr int RES_MAXTASK = 4;    // HR row-tasks per compute thread (8*(NP+w+1) <= 4*512)
 
 struct ResidentParams {
-    const float* f_s;        // [E][C][HW]
-    const uint4* cells;      // [E][HW]
-    const float2* cw;        // [E]
-    float* w;                // [E][2][C]  in: W0, out: fitted
-    float* zbuf;             // [G][2][HW]
-    float* acc;              // [G][3][C]
-    unsigned* zflag;         // [G][CPG]
-    unsigned* bar;           // [G][32]   (one counter per 128 B)
-    unsigned* abort_flag;    // [1]
-    long long* prof;         // [grid][8] or null
-    int E, C, HW, h, w_lo, NP, CPG, G, T;
+    const float* f_s;          // [E][C][HW]
+    const uint4* cells;        // [E][HW]
+    const float2* cw;          // [E]
+    float* w;                  // [E][2][C]  in: W0, out: fitted
+    unsigned long long* zll;   // [G][2][HW]                            {z, step} words of the halo exchange
+    unsigned long long* inbox; // [G][2][KCH][CPG owner][CPG src][SLS]  {partial dW, step} words (hop 1)
+    unsigned long long* sums;  // [G][2][C]                             {all-reduced dW, step} words (hop 2)
+    unsigned* abort_flag;      // [1]
+    long long* prof;           // [grid][8] or null
+    int E, C, HW, h, w_lo, NP, CPG, G, T, SLS;
     float lr;
 };
 
-__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
-    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ void red_add_f32(float* p, float v) {
-    asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
-}
-// spin until *p >= target; returns false on watchdog / abort
-__device__ __forceinline__ bool spin_until(const unsigned* p, unsigned target, unsigned* abort_flag) {
-    unsigned it = 0;
-    while (ld_acquire(p) < target) {
-        if ((++it & 0x3ffu) == 0u) {
-            if (*reinterpret_cast<volatile unsigned*>(abort_flag) != 0u) return false;
-            if (it > RES_SPIN_LIMIT) { atomicExch(abort_flag, 1u); return false; }
-        }
-    }
-    return true;
-}
-
+// ---- small PTX helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -87,67 +77,77 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// compute warps only (the reducer warp never joins): named barrier 1
+__device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(RES_CTHREADS) : "memory"); }
 
-// half a cell (4 of its 8 rows): same arithmetic as hires_cell, used to spread the NP+w+1 cells of a
-// strip over twice as many threads
-__device__ __forceinline__ void hires_half_cell(float z00, float z01, float z10, float z11, uint32_t w0, uint32_t w1,
-                                                int r0, float c0, float c1, float& o00, float& o01, float& o10,
-                                                float& o11) {
-    const uint32_t words[2] = {w0, w1};
-    const float dl = (z10 - z00) * 0.125f, dr = (z11 - z01) * 0.125f;
-    float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
-#pragma unroll
-    for (int rr = 0; rr < 4; ++rr) {
-        const float r = (float)(r0 + rr);
-        const uint32_t rb = (words[rr >> 1] >> ((rr & 1) * 16)) & 0xffffu;
-        const float left = fmaf(r, dl, z00), right = fmaf(r, dr, z01);
-        const float slope = (right - left) * 0.125f;
-        float gs = 0.f, gr = 0.f;
-#pragma unroll
-        for (int s = 0; s < 8; ++s) {
-            const uint32_t code = (rb >> (2 * s)) & 3u;
-            const float d = fmaf((float)s, slope, left);
-            const float p = __fdividef(1.f, 1.f + __expf(-d));
-            const float coef = (code == 0u) ? c0 : ((code == 1u) ? c1 : 0.f);
-            const float g = coef * (p - (float)(code & 1u));
-            gs += g;
-            gr = fmaf((float)s, g, gr);
+// tagged words: {payload bits, step number} in one 64-bit access (single-copy atomic)
+__device__ __forceinline__ void st_tagged(unsigned long long* p, float v, unsigned seq) {
+    asm volatile("{\n .reg .b64 t;\n mov.b64 t, {%1, %2};\n st.relaxed.gpu.global.u64 [%0], t;\n}"
+                 ::"l"(p), "r"(__float_as_uint(v)), "r"(seq) : "memory");
+}
+__device__ __forceinline__ void ld_tagged(const unsigned long long* p, unsigned& bits, unsigned& seq) {
+    asm volatile("{\n .reg .b64 t;\n ld.relaxed.gpu.global.u64 t, [%2];\n mov.b64 {%0, %1}, t;\n}"
+                 : "=r"(bits), "=r"(seq) : "l"(p) : "memory");
+}
+// poll a tagged word until it carries step number `seq`; returns the payload (0 on abort)
+__device__ __noinline__ float poll_word(const unsigned long long* src, unsigned seq, unsigned* abort_flag) {
+    unsigned bits, tag, it = 0;
+    ld_tagged(src, bits, tag);
+    while (tag != seq) {
+        if ((++it & 0x3ffu) == 0u) {
+            if (*reinterpret_cast<volatile unsigned*>(abort_flag) != 0u) return 0.f;
+            if (it > RES_SPIN_LIMIT) { atomicExch(abort_flag, 1u); return 0.f; }
         }
-        gr *= 0.125f;
-        const float gl = gs - gr;
-        const float h1 = r * 0.125f, h0 = 1.f - h1;
-        a00 = fmaf(h0, gl, a00); a01 = fmaf(h0, gr, a01);
-        a10 = fmaf(h1, gl, a10); a11 = fmaf(h1, gr, a11);
+        ld_tagged(src, bits, tag);
     }
-    o00 = a00; o01 = a01; o10 = a10; o11 = a11;
+    return __uint_as_float(bits);
+}
+
+// one row (8 pixels) of a cell: gradient mass sent to the left / right low-res column of that row
+__device__ __forceinline__ void hires_row(float left, float right, uint32_t rb, float c0, float c1,
+                                          float& gl_out, float& gr_out) {
+    const float nleft = NEG_LOG2E * left, nslope = NEG_LOG2E * (right - left) * 0.125f;
+    float gs = 0.f, gr = 0.f;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+        const float g = ce_grad_pixel(fmaf((float)s, nslope, nleft), rb & (3u << (2 * s)), 1u << (2 * s), c0, c1);
+        gs += g;
+        gr = fmaf((float)s, g, gr);
+    }
+    gr *= 0.125f;
+    gl_out = gs - gr;
+    gr_out = gr;
 }
 
 struct ResSmem {
-    size_t F, W0, W1, Wd, zfull, g, scratch, cellbits, mbar, total;
+    size_t F, W0, W1, Wd, zfull, g, scratch, mbar, total;
 };
 static __host__ __device__ inline ResSmem res_smem_layout(int C, int NP, int w_lo) {
     ResSmem s;
-    const int NQ = NP / 4, NG = RES_THREADS / NQ, NCELL = NP + w_lo + 1;
+    const int NQ = NP / 4, NG = RES_CTHREADS / NQ, NCELL = NP + w_lo + 1;
     size_t o = 0;
-    auto take = [&](size_t bytes) { size_t r = o; o = (o + bytes + 127) / 128 * 128; return r; };
-    s.F = take((size_t)C * NP * 4);
-    s.W0 = take((size_t)C * 4);
-    s.W1 = take((size_t)C * 4);
-    s.Wd = take((size_t)C * 4);
-    s.zfull = take((size_t)(NP + 2 * (w_lo + 1)) * 4);
-    s.g = take((size_t)NP * 4);
-    const size_t sc1 = (size_t)NG * NP * 4, sc2 = (size_t)8 * NCELL * 4;
-    s.scratch = take(sc1 > sc2 ? sc1 : sc2);
-    s.cellbits = take((size_t)NCELL * 16);
-    s.mbar = take(8);
-    s.total = o;
+    size_t sz[8];
+    sz[0] = (size_t)C * NP * 4; sz[1] = sz[2] = sz[3] = (size_t)C * 4;
+    sz[4] = (size_t)(NP + 2 * (w_lo + 1)) * 4; sz[5] = (size_t)NP * 4;
+    const size_t sc1 = (size_t)NG * NP * 4, sc2 = (size_t)4 * NCELL * 4;
+    sz[6] = sc1 > sc2 ? sc1 : sc2; sz[7] = 8;
+    size_t off[8];
+    for (int i = 0; i < 8; ++i) { off[i] = o; o = (o + sz[i] + 127) / 128 * 128; }
+    s.F = off[0]; s.W0 = off[1]; s.W1 = off[2]; s.Wd = off[3]; s.zfull = off[4]; s.g = off[5];
+    s.scratch = off[6]; s.mbar = off[7]; s.total = o;
     return s;
 }
 
-template <bool PROF>
+// TC/TNP/TWL/THL > 0: compile-time shape (C, strip pixels, low-res width / height); 0: run-time shape.
+template <int TC, int TNP, int TWL, int THL, bool PROF>
 __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int C = p.C, NP = p.NP, HW = p.HW, wl = p.w_lo, h = p.h;
+    const int C = TC ? TC : p.C, NP = TNP ? TNP : p.NP, wl = TWL ? TWL : p.w_lo, h = THL ? THL : p.h;
+    const int HW = (TWL && THL) ? TWL * THL : p.HW;
+    const int CPG = (TNP && TWL && THL) ? (TWL * THL) / (TNP ? TNP : 1) : p.CPG;
+    const int CCH = C / RES_KCH;                     // channels per chunk (C % RES_KCH == 0)
+    const int SLS = (CCH + CPG - 1) / CPG;           // channels of a chunk owned by one CTA
+    const int NQ = NP / 4, NG = RES_CTHREADS / NQ, NCELL = NP + wl + 1, HALO = wl + 1;
     const ResSmem L = res_smem_layout(C, NP, wl);
     float* F = reinterpret_cast<float*>(smem_raw + L.F);
     float* W0 = reinterpret_cast<float*>(smem_raw + L.W0);
@@ -156,21 +156,21 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
     float* zfull = reinterpret_cast<float*>(smem_raw + L.zfull);
     float* gsm = reinterpret_cast<float*>(smem_raw + L.g);
     float* scratch = reinterpret_cast<float*>(smem_raw + L.scratch);
-    uint4* cellbits = reinterpret_cast<uint4*>(smem_raw + L.cellbits);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + L.mbar);
 
-    const int tid = threadIdx.x;
-    const int group = blockIdx.x / p.CPG, k = blockIdx.x - group * p.CPG;
-    const int NQ = NP / 4, NG = RES_THREADS / NQ, NCELL = NP + wl + 1, HALO = wl + 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool is_reducer = warp == RES_CTHREADS / 32;
+    const int group = blockIdx.x / CPG, k = blockIdx.x - group * CPG;
     const bool p1_active = tid < NQ * NG;
     const int v = tid % NQ, grp = tid / NQ;
     const int strip0 = k * NP;                       // first own pixel
     const int cell0 = strip0 - HALO;                 // pixel / cell index of zfull[0] / cell 0
 
-    float* zbuf = p.zbuf + (size_t)group * 2 * HW;
-    float* acc = p.acc + (size_t)group * 3 * C;
-    unsigned* zflag = p.zflag + (size_t)group * p.CPG;
-    unsigned* bar = p.bar + (size_t)group * 32;
+    // group-private exchange areas (all words are {value, step}; step numbers start at 1)
+    unsigned long long* zll = p.zll + (size_t)group * 2 * HW;
+    unsigned long long* inbox = p.inbox + (size_t)group * 2 * RES_KCH * CPG * CPG * SLS;
+    unsigned long long* sums = p.sums + (size_t)group * 2 * C;
+    const unsigned inbox_chunk = (unsigned)(CPG * CPG * SLS);          // words per (parity, chunk)
 
     if (tid == 0) mbar_init(mbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -180,8 +180,37 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
     bool ok = true;
     long long t_acc[6] = {0, 0, 0, 0, 0, 0};
 
+    // P3 thread mapping: 4 threads per channel (adjacent lanes), interleaved pixel-quads -> conflict-free LDS.128
+    const int p3_cl = tid >> 2, p3_part = tid & 3;
+    // where this thread's partial of a chunk goes: owner CTA's inbox row of this CTA, slot of the channel
+    const unsigned p3_inbox_off = (unsigned)(((p3_cl / SLS) * CPG + k) * SLS + (p3_cl % SLS));
+
+    // Pick up the all-reduced dW of chunk j of global step gs and apply the SGD update (thread i <-> channel
+    // j*CCH + i). The word is requested one phase ahead so its L2 round trip overlaps compute.
+    unsigned sum_bits = 0u, sum_tag = 0u;
+    auto request_chunk = [&](int j, unsigned gs) {
+        if (tid < CCH) ld_tagged(&sums[(gs & 1u) * (unsigned)C + j * CCH + tid], sum_bits, sum_tag);
+    };
+    auto apply_chunk = [&](int j, unsigned gs) {
+        if (tid < CCH) {
+            const int c = j * CCH + tid;
+            float dw = __uint_as_float(sum_bits);
+            if (sum_tag != gs + 1u) dw = poll_word(&sums[(gs & 1u) * (unsigned)C + c], gs + 1u, p.abort_flag);
+            const float n0 = fmaf(p.lr, dw, W0[c]), n1 = fmaf(-p.lr, dw, W1[c]);
+            W0[c] = n0; W1[c] = n1; Wd[c] = n1 - n0;
+        }
+        for (int i = tid + RES_CTHREADS; i < CCH; i += RES_CTHREADS) {       // C / RES_KCH > 512 (not the usual case)
+            const int c = j * CCH + i;
+            const float dw = poll_word(&sums[(gs & 1u) * (unsigned)C + c], gs + 1u, p.abort_flag);
+            const float n0 = fmaf(p.lr, dw, W0[c]), n1 = fmaf(-p.lr, dw, W1[c]);
+            W0[c] = n0; W1[c] = n1; Wd[c] = n1 - n0;
+        }
+        compute_sync();                                  // Wd of chunk j visible to every P1 thread
+        if (j + 1 < RES_KCH) request_chunk(j + 1, gs);
+    };
+
     for (int e = group; e < p.E; e += p.G) {
-        // ---------------- stage the episode: strip of F via bulk-TMA, weights, label cells ----------------
+        // ---------------- stage the episode: strip of F via bulk-TMA, weights, HR task descriptors ----------------
         __syncthreads();                                           // previous episode is done with shared memory
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads before async-proxy writes
         if (tid == 0) mbar_expect_tx(mbar, (unsigned)(C * NP * 4));
@@ -191,9 +220,33 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
             const float a = p.w[((size_t)e * 2) * C + c], b = p.w[((size_t)e * 2 + 1) * C + c];
             W0[c] = a; W1[c] = b; Wd[c] = b - a;
         }
-        for (int ci = tid; ci < NCELL; ci += RES_THREADS) {
-            const int q = cell0 + ci;
-            cellbits[ci] = (q >= 0) ? p.cells[(size_t)e * HW + q] : make_uint4(0xAAAAAAAAu, 0xAAAAAAAAu, 0xAAAAAAAAu, 0xAAAAAAAAu);
+        // HR task descriptors (static for the episode): task = (cell ci, row r); 8 adjacent lanes = one cell.
+        // desc = row label bits | dx << 16 | dy_flag << 17 | live << 18
+        unsigned hr_desc[RES_MAXTASK];
+#pragma unroll
+        for (int m = 0; m < RES_MAXTASK; ++m) {
+            const int task = m * RES_CTHREADS + tid;
+            const int ci = task >> 3, r = task & 7;
+            unsigned d = 0u;
+            if (tid < RES_CTHREADS && ci < NCELL) {
+                const int q = cell0 + ci;
+                if (q >= 0) {
+                    const uint4 bits = p.cells[(size_t)e * HW + q];
+                    const uint32_t wsel = (r < 4) ? ((r < 2) ? bits.x : bits.y) : ((r < 6) ? bits.z : bits.w);
+                    const uint32_t rb = (wsel >> ((r & 1) * 16)) & 0xffffu;
+                    const int a = q / wl, b = q - a * wl;
+                    if (rb != 0xAAAAu)                              // rows with only ignored pixels send nothing
+                        d = rb | ((b + 1 < wl) ? (1u << 16) : 0u) | ((a + 1 < h) ? (1u << 17) : 0u) | (1u << 18);
+                }
+            }
+            hr_desc[m] = d;
+        }
+        // own pixel -> which neighbouring cells feed it (static): bit0 left column exists, bit1 upper row exists
+        unsigned own_flags = 0u;
+        if (tid < NP) {
+            const int q = strip0 + tid;
+            const int a = q / wl, b = q - a * wl;
+            own_flags = (b > 0 ? 1u : 0u) | (a > 0 ? 2u : 0u);
         }
         const float2 c01 = p.cw[e];
         {
@@ -203,125 +256,190 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
         }
         __syncthreads();
 
-        for (int t = 0; t < p.T; ++t, ++gstep) {
-            long long tk0 = 0;
-            if (PROF && tid == 0) tk0 = clock64();
-            // ---------------- P1: z = Wd . F over the own strip ----------------
-            {
-                float4 za = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p1_active) {
+        if (is_reducer) {
+            // ================= reducer warp: hop 1 (collect + add the CPG partials of the own slice), hop 2 (republish) =================
+            const int n_own = max(0, min(SLS, CCH - k * SLS));       // channels of every chunk owned by this CTA
+            int slp = 1;
+            while (slp < n_own) slp <<= 1;                            // lanes per source-CTA row (power of two)
+            const int sl = lane % slp, kg = lane / slp, nkg = 32 / slp;
+            for (int t = 0; t < p.T; ++t) {
+                const unsigned gs = gstep + (unsigned)t;
+                if (n_own > 0) {
+                    for (int j = 0; j < RES_KCH; ++j) {
+                        const unsigned long long* ib = inbox + ((gs & 1u) * RES_KCH + j) * inbox_chunk + (unsigned)(k * CPG * SLS);
+                        float acc = 0.f;
+                        if (sl < n_own) {
+                            // every load of this lane is issued before any tag is looked at (independent L2 round
+                            // trips); words that are not there yet are re-requested together, again as one batch
+                            unsigned wb[RES_RW], wt[RES_RW];
+                            unsigned pending = 0u, it = 0u;
+#pragma unroll
+                            for (int m = 0; m < RES_RW; ++m) { wb[m] = 0u; if (kg + m * nkg < CPG) pending |= 1u << m; }
+                            while (pending) {
+#pragma unroll
+                                for (int m = 0; m < RES_RW; ++m)
+                                    if (pending & (1u << m)) ld_tagged(&ib[(kg + m * nkg) * SLS + sl], wb[m], wt[m]);
+#pragma unroll
+                                for (int m = 0; m < RES_RW; ++m)
+                                    if ((pending & (1u << m)) && wt[m] == gs + 1u) pending &= ~(1u << m);
+                                if (pending && (++it & 0xffu) == 0u) {
+                                    if (*reinterpret_cast<volatile unsigned*>(p.abort_flag) != 0u) break;
+                                    if (it > (RES_SPIN_LIMIT >> 2)) { atomicExch(p.abort_flag, 1u); break; }
+                                }
+                            }
+#pragma unroll
+                            for (int m = 0; m < RES_RW; ++m) acc += __uint_as_float(wb[m]);       // fixed order: deterministic
+                            for (int kk = kg + RES_RW * nkg; kk < CPG; kk += nkg)                  // (unusual shapes only)
+                                acc += poll_word(&ib[kk * SLS + sl], gs + 1u, p.abort_flag);
+                        }
+                        for (int o = slp; o < 32; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                        if (lane < n_own) st_tagged(&sums[(gs & 1u) * (unsigned)C + j * CCH + k * SLS + lane], acc, gs + 1u);
+                    }
+                }
+            }
+            gstep += (unsigned)p.T;
+        } else {
+            // ================= compute warps =================
+            for (int t = 0; t < p.T; ++t, ++gstep) {
+                long long tk0 = 0;
+                if (PROF && tid == 0) tk0 = clock64();
+                // ------------ P1 (each chunk first picks up the previous step's all-reduced dW) ------------
+                {
+                    float4 za = make_float4(0.f, 0.f, 0.f, 0.f);
                     const float4* F4 = reinterpret_cast<const float4*>(F) + tid;
                     const int stride = NQ * NG;
-#pragma unroll 4
-                    for (int c = grp; c < C; c += NG) {
-                        const float4 f = *F4;
-                        F4 += stride;
-                        const float wd = Wd[c];
-                        za.x = fmaf(wd, f.x, za.x); za.y = fmaf(wd, f.y, za.y);
-                        za.z = fmaf(wd, f.z, za.z); za.w = fmaf(wd, f.w, za.w);
-                    }
-                    *reinterpret_cast<float4*>(scratch + grp * NP + 4 * v) = za;
-                }
-                __syncthreads();
-                if (tid < NP) {
-                    float z = 0.f;
-                    for (int g2 = 0; g2 < NG; ++g2) z += scratch[g2 * NP + tid];
-                    zfull[HALO + tid] = z;
-                    zbuf[(size_t)(gstep & 1u) * HW + strip0 + tid] = z;
-                }
-            }
-            if (PROF && tid == 0) { long long n = clock64(); t_acc[0] += n - tk0; tk0 = n; }
-            // ---------------- X1: publish the strip, fetch both halos ----------------
-            __threadfence();
-            __syncthreads();
-            if (tid == 0) {
-                st_release(&zflag[k], gstep + 1u);
-                if (k > 0 && ok) ok = spin_until(&zflag[k - 1], gstep + 1u, p.abort_flag);
-            } else if (tid == 32) {
-                if (k + 1 < p.CPG && ok) ok = spin_until(&zflag[k + 1], gstep + 1u, p.abort_flag);
-            }
-            __syncthreads();
-            if (tid < 2 * HALO) {
-                const bool before = tid < HALO;
-                const int j = before ? tid : tid - HALO;
-                const int q = before ? cell0 + j : strip0 + NP + j;
-                float z = 0.f;
-                if (q >= 0 && q < HW) z = __ldcg(&zbuf[(size_t)(gstep & 1u) * HW + q]);
-                zfull[before ? j : HALO + NP + j] = z;
-            }
-            __syncthreads();
-            if (PROF && tid == 0) { long long n = clock64(); t_acc[1] += n - tk0; tk0 = n; }
-            // ---------------- HR: full-resolution stage on the cells touching the strip ----------------
-            for (int task = tid; task < 2 * NCELL; task += RES_THREADS) {
-                const int ci = task >> 1, half = task & 1;
-                const int q = cell0 + ci;
-                float o00 = 0.f, o01 = 0.f, o10 = 0.f, o11 = 0.f;
-                if (q >= 0) {
-                    const int a = q / wl, b = q - a * wl;
-                    const int dx = (b + 1 < wl) ? 1 : 0, dy = (a + 1 < h) ? wl : 0;
-                    const uint4 bits = cellbits[ci];
-                    hires_half_cell(zfull[ci], zfull[ci + dx], zfull[ci + dy], zfull[ci + dy + dx],
-                                    half ? bits.z : bits.x, half ? bits.w : bits.y, half * 4, c01.x, c01.y,
-                                    o00, o01, o10, o11);
-                }
-                float* cc = scratch + (size_t)half * 4 * NCELL;
-                cc[0 * NCELL + ci] = o00; cc[1 * NCELL + ci] = o01;
-                cc[2 * NCELL + ci] = o10; cc[3 * NCELL + ci] = o11;
-            }
-            __syncthreads();
-            if (tid < NP) {
-                const int q = strip0 + tid, ci = HALO + tid;
-                const int a = q / wl, b = q - a * wl;
-                float s = 0.f;
+                    int c = grp;
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const float* cc = scratch + (size_t)half * 4 * NCELL;
-                    s += cc[0 * NCELL + ci];
-                    if (b > 0) s += cc[1 * NCELL + ci - 1];
-                    if (a > 0) s += cc[2 * NCELL + ci - wl];
-                    if (a > 0 && b > 0) s += cc[3 * NCELL + ci - wl - 1];
-                }
-                gsm[tid] = s;
-            }
-            __syncthreads();
-            if (PROF && tid == 0) { long long n = clock64(); t_acc[2] += n - tk0; tk0 = n; }
-            // ---------------- P3: dW = g . F^T (thread = channel), L2 reductions into the group accumulator ----------------
-            {
-                float* acc_cur = acc + (size_t)(gstep % 3u) * C;
-                float* acc_nxt = acc + (size_t)((gstep + 1u) % 3u) * C;
-                for (int c = tid; c < C; c += RES_THREADS) {
-                    const float4* row = reinterpret_cast<const float4*>(F + (size_t)c * NP);
-                    const float4* g4 = reinterpret_cast<const float4*>(gsm);
-                    float d0 = 0.f, d1 = 0.f;
-#pragma unroll 5
-                    for (int j = 0; j < NQ; ++j) {
-                        const float4 f = row[j];
-                        const float4 gg = g4[j];
-                        d0 = fmaf(gg.x, f.x, d0); d1 = fmaf(gg.y, f.y, d1);
-                        d0 = fmaf(gg.z, f.z, d0); d1 = fmaf(gg.w, f.w, d1);
+                    for (int j = 0; j < RES_KCH; ++j) {
+                        if (t > 0) apply_chunk(j, gstep - 1u);
+                        if (p1_active) {
+                            const int cend = (j + 1) * CCH;
+#pragma unroll 8
+                            for (; c < cend; c += NG) {
+                                const float4 f = *F4;
+                                F4 += stride;
+                                const float wd = Wd[c];
+                                za.x = fmaf(wd, f.x, za.x); za.y = fmaf(wd, f.y, za.y);
+                                za.z = fmaf(wd, f.z, za.z); za.w = fmaf(wd, f.w, za.w);
+                            }
+                        }
                     }
-                    red_add_f32(&acc_cur[c], d0 + d1);
-                    if (c % p.CPG == k) acc_nxt[c] = 0.f;          // recycled two barriers from now
+                    if (p1_active) *reinterpret_cast<float4*>(scratch + grp * NP + 4 * v) = za;
+                    compute_sync();
+                    if (tid < NP) {
+                        float z = 0.f;
+#pragma unroll 4
+                        for (int g2 = 0; g2 < NG; ++g2) z += scratch[g2 * NP + tid];
+                        zfull[HALO + tid] = z;
+                        st_tagged(&zll[(gstep & 1u) * (unsigned)HW + strip0 + tid], z, gstep + 1u);
+                    }
                 }
+                if (PROF && tid == 0) { long long n = clock64(); t_acc[0] += n - tk0; tk0 = n; }
+                // ------------ X1: fetch both halos from the neighbouring strips ------------
+                if (tid < 2 * HALO) {
+                    const bool before = tid < HALO;
+                    const int j = before ? tid : tid - HALO;
+                    const int q = before ? cell0 + j : strip0 + NP + j;
+                    float z = 0.f;
+                    if (q >= 0 && q < HW) z = poll_word(&zll[(gstep & 1u) * (unsigned)HW + q], gstep + 1u, p.abort_flag);
+                    zfull[before ? j : HALO + NP + j] = z;
+                }
+                compute_sync();
+                if (PROF && tid == 0) { long long n = clock64(); t_acc[1] += n - tk0; tk0 = n; }
+                // ------------ HR: one task = one row of one cell; 8 adjacent lanes = one cell ------------
+#pragma unroll
+                for (int m = 0; m < RES_MAXTASK; ++m) {
+                    if (m * RES_CTHREADS < 8 * NCELL) {                     // uniform: does this round have tasks at all
+                        const int ci = (m * RES_CTHREADS + tid) >> 3, r = tid & 7;
+                        const unsigned d = hr_desc[m];
+                        float o00 = 0.f, o01 = 0.f, o10 = 0.f, o11 = 0.f;
+                        if (d & (1u << 18)) {
+                            const int dx = (d >> 16) & 1, dy = (d & (1u << 17)) ? wl : 0;
+                            const float z00 = zfull[ci], z01 = zfull[ci + dx], z10 = zfull[ci + dy], z11 = zfull[ci + dy + dx];
+                            const float fr = (float)r * 0.125f;
+                            float gl, gr;
+                            hires_row(fmaf(fr, z10 - z00, z00), fmaf(fr, z11 - z01, z01), d & 0xffffu, c01.x, c01.y, gl, gr);
+                            o10 = fr * gl; o11 = fr * gr; o00 = gl - o10; o01 = gr - o11;
+                        }
+#pragma unroll
+                        for (int o = 1; o < 8; o <<= 1) {
+                            o00 += __shfl_xor_sync(0xffffffffu, o00, o); o01 += __shfl_xor_sync(0xffffffffu, o01, o);
+                            o10 += __shfl_xor_sync(0xffffffffu, o10, o); o11 += __shfl_xor_sync(0xffffffffu, o11, o);
+                        }
+                        if (r == 0 && ci < NCELL) {
+                            scratch[0 * NCELL + ci] = o00; scratch[1 * NCELL + ci] = o01;
+                            scratch[2 * NCELL + ci] = o10; scratch[3 * NCELL + ci] = o11;
+                        }
+                    }
+                }
+                compute_sync();
+                if (tid < NP) {
+                    const int ci = HALO + tid;
+                    float s2 = scratch[0 * NCELL + ci];
+                    if (own_flags & 1u) s2 += scratch[1 * NCELL + ci - 1];
+                    if (own_flags & 2u) s2 += scratch[2 * NCELL + ci - wl];
+                    if (own_flags == 3u) s2 += scratch[3 * NCELL + ci - wl - 1];
+                    gsm[tid] = s2;
+                }
+                compute_sync();
+                if (PROF && tid == 0) { long long n = clock64(); t_acc[2] += n - tk0; tk0 = n; }
+                // ------------ P3: dW = g . F^T chunk by chunk; every partial goes straight to its owner's inbox ------------
+                {
+                    // this thread's pixel-quads of g are the same for every channel: keep them in registers
+                    float4 gq[RES_MAXQ];
+#pragma unroll
+                    for (int i = 0; i < RES_MAXQ / 2; ++i) {
+                        const int q0 = 2 * p3_part + 8 * i;
+                        gq[2 * i] = (q0 < NQ) ? reinterpret_cast<const float4*>(gsm)[q0] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        gq[2 * i + 1] = (q0 + 1 < NQ) ? reinterpret_cast<const float4*>(gsm)[q0 + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    unsigned long long* ibw = inbox + (gstep & 1u) * RES_KCH * inbox_chunk + p3_inbox_off;
+#pragma unroll
+                    for (int j = 0; j < RES_KCH; ++j) {
+                        // the first chunk of THIS step was handed to the reducers three chunks ago: ask for its sum now
+                        if (j == RES_KCH - 1) request_chunk(0, gstep);
+                        for (int cb = 0; cb < CCH; cb += RES_CTHREADS / 4) {
+                            const int cl = cb + p3_cl;
+                            float d0 = 0.f, d1 = 0.f;
+                            if (cl < CCH) {
+                                const float4* row = reinterpret_cast<const float4*>(F + (size_t)(j * CCH + cl) * NP) + 2 * p3_part;
+#pragma unroll
+                                for (int i = 0; i < RES_MAXQ / 2; ++i) {
+                                    const int q0 = 2 * p3_part + 8 * i;
+                                    if (q0 < NQ) {
+                                        const float4 f = row[8 * i];
+                                        d0 = fmaf(gq[2 * i].x, f.x, d0); d1 = fmaf(gq[2 * i].y, f.y, d1);
+                                        d0 = fmaf(gq[2 * i].z, f.z, d0); d1 = fmaf(gq[2 * i].w, f.w, d1);
+                                    }
+                                    if (q0 + 1 < NQ) {
+                                        const float4 f = row[8 * i + 1];
+                                        d0 = fmaf(gq[2 * i + 1].x, f.x, d0); d1 = fmaf(gq[2 * i + 1].y, f.y, d1);
+                                        d0 = fmaf(gq[2 * i + 1].z, f.z, d0); d1 = fmaf(gq[2 * i + 1].w, f.w, d1);
+                                    }
+                                }
+                            }
+                            float d = d0 + d1;
+                            d += __shfl_xor_sync(0xffffffffu, d, 1);
+                            d += __shfl_xor_sync(0xffffffffu, d, 2);
+                            if (cl < CCH && p3_part == 0) {
+                                const int off = (cb == 0) ? 0 : (((cl / SLS) * CPG + k) * SLS + (cl % SLS)) - (int)p3_inbox_off;
+                                st_tagged(ibw + (int)(j * inbox_chunk) + off, d, gstep + 1u);
+                            }
+                        }
+                    }
+                }
+                if (PROF && tid == 0) { long long n = clock64(); t_acc[3] += n - tk0; tk0 = n; }
             }
-            if (PROF && tid == 0) { long long n = clock64(); t_acc[3] += n - tk0; tk0 = n; }
-            // ---------------- X2: group barrier, then everyone applies the same SGD update ----------------
-            __threadfence();
-            __syncthreads();
-            if (tid == 0) {
-                red_release_add(bar, 1u);
-                if (ok) ok = spin_until(bar, (gstep + 1u) * (unsigned)p.CPG, p.abort_flag);
+            // ------------ drain the last step's all-reduce ------------
+            if (p.T > 0) {
+                long long tk0 = 0;
+                if (PROF && tid == 0) tk0 = clock64();
+#pragma unroll
+                for (int j = 0; j < RES_KCH; ++j) apply_chunk(j, gstep - 1u);
+                if (PROF && tid == 0) t_acc[4] += clock64() - tk0;
             }
-            __syncthreads();
-            for (int c = tid; c < C; c += RES_THREADS) {
-                const float dw = __ldcg(&acc[(size_t)(gstep % 3u) * C + c]);
-                const float n0 = fmaf(p.lr, dw, W0[c]), n1 = fmaf(-p.lr, dw, W1[c]);
-                W0[c] = n0; W1[c] = n1; Wd[c] = n1 - n0;
-            }
-            __syncthreads();
-            if (PROF && tid == 0) { long long n = clock64(); t_acc[4] += n - tk0; tk0 = n; }
         }
-        // ---------------- result ----------------
+        __syncthreads();
         if (k == 0) {
             const bool bad = *reinterpret_cast<volatile unsigned*>(p.abort_flag) != 0u;
             for (int c = tid; c < C; c += RES_THREADS) {
@@ -337,10 +455,10 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
 }
 
 // ---- host side ---------------------------------------------------------------------------------
-struct ResidentPlan { int NP, CPG, G; size_t smem; bool ok; };
+struct ResidentPlan { int NP, CPG, G; size_t smem; bool ok; int SLS; size_t inbox_words; };
 
 static ResidentPlan plan_resident(int E, int C, int h, int w, int n_sm, size_t smem_cap) {
-    ResidentPlan best{0, 0, 0, 0, false};
+    ResidentPlan best{0, 0, 0, 0, false, 0, 0};
     const int HW = h * w;
     int forced = 0;
     if (const char* s = getenv("CWT_RESIDENT_NP")) forced = atoi(s);
@@ -349,7 +467,9 @@ static ResidentPlan plan_resident(int E, int C, int h, int w, int n_sm, size_t s
         if (HW % NP) continue;
         if (forced && NP != forced) continue;
         if (NP < w + 1 && HW != NP) continue;          // halos must come from the adjacent strips only
-        if (NP / 4 > RES_THREADS) continue;
+        if (NP > 16 * RES_MAXQ) continue;              // P3 register tiling
+        if (8 * (NP + w + 1) > RES_MAXTASK * RES_CTHREADS) continue;   // HR task descriptors
+        if (C % RES_KCH) continue;
         const size_t sm = res_smem_layout(C, NP, w).total;
         if (sm > smem_cap) continue;
         const int CPG = HW / NP;
@@ -357,7 +477,8 @@ static ResidentPlan plan_resident(int E, int C, int h, int w, int n_sm, size_t s
         int G = n_sm / CPG;
         if (G > E) G = E;
         const double score = (double)G / NP + 1e-9 * NP;
-        if (score > best_score) { best_score = score; best = ResidentPlan{NP, CPG, G, sm, true}; }
+        const int CCH = C / RES_KCH, SLS = (CCH + CPG - 1) / CPG;
+        if (score > best_score) { best_score = score; best = ResidentPlan{NP, CPG, G, sm, true, SLS, (size_t)2 * RES_KCH * CPG * CPG * SLS}; }
     }
     return best;
 }
@@ -365,12 +486,25 @@ static ResidentPlan plan_resident(int E, int C, int h, int w, int n_sm, size_t s
 size_t fit_resident_workspace_bytes(int C, int h, int w) {
     const int HW = h * w;
     const int maxG = 148;
-    return align_up(sizeof(float) * 2 * HW * maxG) + align_up(sizeof(float) * 3 * C * maxG) +
-           align_up(sizeof(unsigned) * (size_t)maxG * 160) + align_up(sizeof(unsigned) * 32 * maxG) + 256 +
-           align_up(sizeof(long long) * 8 * 160);
+    // zll: 2*HW words per group; inbox: 2*KCH*CPG*CPG*SLS words per group (CPG*SLS < C/KCH + CPG, G*CPG <= 148);
+    // sums: 2*C words per group; abort flag; profile counters
+    const size_t inbox_words_all = (size_t)2 * RES_KCH * 148 * ((size_t)C / RES_KCH + 148);
+    return align_up(sizeof(unsigned long long) * 2 * HW * maxG) + align_up(sizeof(unsigned long long) * inbox_words_all) +
+           align_up(sizeof(unsigned long long) * 2 * (size_t)C * maxG) + 512 + align_up(sizeof(long long) * 8 * 160);
 }
 
-// returns CWT_ERR_UNSUPPORTED (without error text side effects mattering) when the shape does not fit
+template <int TC, int TNP, int TWL, int THL>
+static int launch_resident(const ResidentParams& p, const ResidentPlan& pl, bool prof, cudaStream_t st) {
+    void* args[] = {const_cast<ResidentParams*>(&p)};
+    dim3 grid(pl.G * pl.CPG), block(RES_THREADS);
+    const void* fn = prof ? (const void*)k_fit_resident<TC, TNP, TWL, THL, true> : (const void*)k_fit_resident<TC, TNP, TWL, THL, false>;
+    CWT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    CWT_CUDA(cudaLaunchCooperativeKernel(fn, grid, block, args, pl.smem, st));
+    count_launch();
+    return CWT_OK;
+}
+
+// returns CWT_ERR_UNSUPPORTED when the shape does not fit on chip
 int fit_resident(const float* f_s, const uint4* cells, const float2* cw, float* w_io, int E, int C, int h, int w,
                  int n_iter, float lr, void* ws, size_t ws_bytes, long long* prof_out, cudaStream_t st) {
     int dev = 0, n_sm = 0, smem_cap = 0, coop = 0;
@@ -379,37 +513,29 @@ int fit_resident(const float* f_s, const uint4* cells, const float2* cw, float* 
     CWT_CUDA(cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     CWT_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
     CWT_REQUIRE(coop, CWT_ERR_UNSUPPORTED, "fit_resident: device lacks cooperative launch");
-    CWT_REQUIRE(C <= RES_THREADS * 4, CWT_ERR_UNSUPPORTED, "fit_resident: C=%d too large", C);
+    CWT_REQUIRE(C <= RES_CTHREADS * RES_KCH, CWT_ERR_UNSUPPORTED, "fit_resident: C=%d too large", C);
     if (n_sm > 148) n_sm = 148;
     const ResidentPlan pl = plan_resident(E, C, h, w, n_sm, (size_t)smem_cap);
     CWT_REQUIRE(pl.ok, CWT_ERR_UNSUPPORTED, "fit_resident: no strip size fits C=%d, %dx%d in %d B of shared memory", C, h, w, smem_cap);
     const int HW = h * w;
     Carver cv(ws, ws_bytes);
     ResidentParams p{};
-    p.zbuf = cv.take<float>((size_t)2 * HW * pl.G);
-    p.acc = cv.take<float>((size_t)3 * C * pl.G);
-    p.zflag = cv.take<unsigned>((size_t)pl.G * pl.CPG);
-    p.bar = cv.take<unsigned>((size_t)32 * pl.G);
+    p.zll = cv.take<unsigned long long>((size_t)2 * HW * pl.G);
+    p.inbox = cv.take<unsigned long long>(pl.inbox_words * pl.G);
+    p.sums = cv.take<unsigned long long>((size_t)2 * C * pl.G);
     p.abort_flag = cv.take<unsigned>(64);
     p.prof = prof_out ? cv.take<long long>((size_t)8 * pl.G * pl.CPG) : nullptr;
     CWT_REQUIRE(ws && cv.ok(), CWT_ERR_WORKSPACE, "fit_resident: workspace too small");
-    // the sync area (accumulators, flags, counters) must start at zero
-    const size_t sync_bytes = (size_t)(reinterpret_cast<char*>(p.abort_flag + 64) - reinterpret_cast<char*>(p.acc));
-    CWT_CUDA(cudaMemsetAsync(p.acc, 0, sync_bytes, st));
+    // every tagged word and the abort flag start at zero (step numbers start at 1)
+    const size_t sync_bytes = (size_t)(reinterpret_cast<char*>(p.abort_flag + 64) - reinterpret_cast<char*>(p.zll));
+    CWT_CUDA(cudaMemsetAsync(p.zll, 0, sync_bytes, st));
     p.f_s = f_s; p.cells = cells; p.cw = cw; p.w = w_io;
-    p.E = E; p.C = C; p.HW = HW; p.h = h; p.w_lo = w; p.NP = pl.NP; p.CPG = pl.CPG; p.G = pl.G; p.T = n_iter; p.lr = lr;
-    void* args[] = {&p};
-    dim3 grid(pl.G * pl.CPG), block(RES_THREADS);
-    if (prof_out) {
-        CWT_CUDA(cudaFuncSetAttribute(k_fit_resident<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-        CWT_CUDA(cudaLaunchCooperativeKernel((void*)k_fit_resident<true>, grid, block, args, pl.smem, st));
-        count_launch();
-        CWT_CUDA(cudaMemcpyAsync(prof_out, p.prof, sizeof(long long) * 8 * pl.G * pl.CPG, cudaMemcpyDeviceToDevice, st));
-    } else {
-        CWT_CUDA(cudaFuncSetAttribute(k_fit_resident<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-        CWT_CUDA(cudaLaunchCooperativeKernel((void*)k_fit_resident<false>, grid, block, args, pl.smem, st));
-        count_launch();
-    }
+    p.E = E; p.C = C; p.HW = HW; p.h = h; p.w_lo = w; p.NP = pl.NP; p.CPG = pl.CPG; p.G = pl.G; p.T = n_iter; p.lr = lr; p.SLS = pl.SLS;
+    int rc;
+    if (C == 512 && h == 60 && w == 60 && pl.NP == 100) rc = launch_resident<512, 100, 60, 60>(p, pl, prof_out != nullptr, st);
+    else rc = launch_resident<0, 0, 0, 0>(p, pl, prof_out != nullptr, st);
+    if (rc != CWT_OK) return rc;
+    if (prof_out) CWT_CUDA(cudaMemcpyAsync(prof_out, p.prof, sizeof(long long) * 8 * pl.G * pl.CPG, cudaMemcpyDeviceToDevice, st));
     return CWT_OK;
 }
 

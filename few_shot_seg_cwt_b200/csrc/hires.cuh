@@ -35,6 +35,24 @@ k_class_consts(const int32_t* __restrict__ counts_img, const float* __restrict__
         for (int k = 0; k < 4; ++k) counts_ep[e * 4 + k] = (int32_t)n[k];
 }
 
+
+// sigmoid pieces as single MUFU ops (no denormal fix-up code, no branches)
+__device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// One pixel of the CE gradient, branch-free. nd = -log2(e) * d (pre-scaled logit difference);
+// sel = the row's label bits masked to this pixel's 2-bit field, one = 1 << field, c0/c1 = w/sum_w.
+//   code 0: g = c0 * p ; code 1: g = c1 * (p - 1) ; ignored / invalid: 0        (p = sigmoid(d))
+__device__ __forceinline__ float ce_grad_pixel(float nd, uint32_t sel, uint32_t one, float c0, float c1) {
+    const float p = fast_rcp(1.f + fast_ex2(nd));
+    // selects on integer masks (kept branch-free: label codes differ from lane to lane)
+    const uint32_t bB = (sel == one) ? __float_as_uint(c1) : 0u;
+    const uint32_t bA = (sel == 0u) ? __float_as_uint(c0) : bB;
+    const float A = __uint_as_float(bA), B = __uint_as_float(bB);
+    return fmaf(A, p, -B);
+}
+constexpr float NEG_LOG2E = -1.4426950408889634f;
+
 // One cell: 64 pixels. bits = 8 rows x 16 bit (2 bit label code per pixel, see k_pack_label_cells).
 // c0 / c1 = w[0]/sum_w, w[1]/sum_w. Outputs the gradient mass sent to the four corners.
 template <bool LOSS>
@@ -50,19 +68,18 @@ __device__ __forceinline__ void hires_cell(float z00, float z01, float z10, floa
         const float left = fmaf((float)r, dl, z00), right = fmaf((float)r, dr, z01);
         const float slope = (right - left) * 0.125f;
         float gs = 0.f, gr = 0.f;
+        const float nleft = NEG_LOG2E * left, nslope = NEG_LOG2E * slope;
 #pragma unroll
         for (int s = 0; s < 8; ++s) {
-            const uint32_t code = (rb >> (2 * s)) & 3u;
-            const float d = fmaf((float)s, slope, left);
-            const float p = __fdividef(1.f, 1.f + __expf(-d));
-            const float coef = (code == 0u) ? c0 : ((code == 1u) ? c1 : 0.f);
-            const float g = coef * (p - (float)(code & 1u));
+            const float g = ce_grad_pixel(fmaf((float)s, nslope, nleft), rb & (3u << (2 * s)), 1u << (2 * s), c0, c1);
             gs += g;
             gr = fmaf((float)s, g, gr);
             if (LOSS) {
+                const uint32_t code = (rb >> (2 * s)) & 3u;
                 if (code < 2u) {
+                    const float d = fmaf((float)s, slope, left);
                     const float t = (code == 1u) ? -d : d;                 // -log p_y = softplus(t)
-                    loss = fmaf(coef, fmaxf(t, 0.f) + log1pf(expf(-fabsf(t))), loss);
+                    loss = fmaf((code == 1u) ? c1 : c0, fmaxf(t, 0.f) + log1pf(expf(-fabsf(t))), loss);
                 }
             }
         }
