@@ -17,8 +17,9 @@
 // atomics, no barriers, and a stale value can never be consumed. The all-reduce is two such hops,
 // pipelined in RES_KCH channel chunks underneath P3 / P1: every CTA owns a slice of the channels; its
 // REDUCER WARP (warp 16, never computes) collects the CPG partials of the slice, adds them in a fixed
-// order (deterministic), and republishes the sums, which the compute threads pick up right before the
-// P1 chunk that needs them.
+// order (deterministic), and republishes the sums; the APPLIER WARP (warp 17) picks the sums up, applies
+// the SGD update to W0 / W1 / Wd in shared memory and releases the compute warps chunk by chunk through a
+// shared-memory mbarrier. The compute warps never wait on global memory for the all-reduce.
 //
 // HBM traffic per episode drops from (2T+1) F to F (+ labels); the per-step bound becomes the shared
 // memory sweep (2 x C*NP*4 B at 128 B/clk/SM). floor(#SM / CPG) groups run concurrently
@@ -37,11 +38,12 @@
 namespace cwt {
 
 constexpr int RES_CTHREADS = 512;               // 16 compute warps
-constexpr int RES_THREADS = RES_CTHREADS + 32;  // + the reducer warp
+constexpr int RES_THREADS = RES_CTHREADS + 64;  // + the reducer warp (16) and the applier warp (17)
 constexpr unsigned RES_SPIN_LIMIT = 1u << 24;
 constexpr int RES_KCH = 4;        // channel chunks of the pipelined all-reduce
 constexpr int RES_MAXQ = 8;       // float4 pixel-quads per P3 thread (NP <= 128)
 constexpr int RES_RW = 5;         // tagged words a reducer lane keeps in flight per chunk
+constexpr int RES_AW = 4;         // tagged words an applier lane keeps in flight
 constexpr int RES_MAXTASK = 4;    // HR row-tasks per compute thread (8*(NP+w+1) <= 4*512)
 
 struct ResidentParams {
@@ -77,7 +79,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-// compute warps only (the reducer warp never joins): named barrier 1
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// compute warps only (the helper warps never join): named barrier 1
 __device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(RES_CTHREADS) : "memory"); }
 
 // tagged words: {payload bits, step number} in one 64-bit access (single-copy atomic)
@@ -129,8 +134,8 @@ static __host__ __device__ inline ResSmem res_smem_layout(int C, int NP, int w_l
     size_t sz[8];
     sz[0] = (size_t)C * NP * 4; sz[1] = sz[2] = sz[3] = (size_t)C * 4;
     sz[4] = (size_t)(NP + 2 * (w_lo + 1)) * 4; sz[5] = (size_t)NP * 4;
-    const size_t sc1 = (size_t)NG * NP * 4, sc2 = (size_t)4 * NCELL * 4;
-    sz[6] = sc1 > sc2 ? sc1 : sc2; sz[7] = 8;
+    const size_t sc1 = (size_t)NG * NP * 4, sc2 = (size_t)16 * NCELL * 4;
+    sz[6] = sc1 > sc2 ? sc1 : sc2; sz[7] = 8 * (1 + RES_KCH);
     size_t off[8];
     for (int i = 0; i < 8; ++i) { off[i] = o; o = (o + sz[i] + 127) / 128 * 128; }
     s.F = off[0]; s.W0 = off[1]; s.W1 = off[2]; s.Wd = off[3]; s.zfull = off[4]; s.g = off[5];
@@ -159,7 +164,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + L.mbar);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool is_reducer = warp == RES_CTHREADS / 32;
+    const bool is_reducer = warp == RES_CTHREADS / 32, is_applier = warp == RES_CTHREADS / 32 + 1;
     const int group = blockIdx.x / CPG, k = blockIdx.x - group * CPG;
     const bool p1_active = tid < NQ * NG;
     const int v = tid % NQ, grp = tid / NQ;
@@ -172,7 +177,8 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
     unsigned long long* sums = p.sums + (size_t)group * 2 * C;
     const unsigned inbox_chunk = (unsigned)(CPG * CPG * SLS);          // words per (parity, chunk)
 
-    if (tid == 0) mbar_init(mbar, 1);
+    uint64_t* applied = mbar + 1;                     // [RES_KCH] chunk j of the previous step has been applied to Wd
+    if (tid == 0) { mbar_init(mbar, 1); for (int j = 0; j < RES_KCH; ++j) mbar_init(&applied[j], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
@@ -185,28 +191,15 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
     // where this thread's partial of a chunk goes: owner CTA's inbox row of this CTA, slot of the channel
     const unsigned p3_inbox_off = (unsigned)(((p3_cl / SLS) * CPG + k) * SLS + (p3_cl % SLS));
 
-    // Pick up the all-reduced dW of chunk j of global step gs and apply the SGD update (thread i <-> channel
-    // j*CCH + i). The word is requested one phase ahead so its L2 round trip overlaps compute.
-    unsigned sum_bits = 0u, sum_tag = 0u;
-    auto request_chunk = [&](int j, unsigned gs) {
-        if (tid < CCH) ld_tagged(&sums[(gs & 1u) * (unsigned)C + j * CCH + tid], sum_bits, sum_tag);
-    };
-    auto apply_chunk = [&](int j, unsigned gs) {
-        if (tid < CCH) {
-            const int c = j * CCH + tid;
-            float dw = __uint_as_float(sum_bits);
-            if (sum_tag != gs + 1u) dw = poll_word(&sums[(gs & 1u) * (unsigned)C + c], gs + 1u, p.abort_flag);
-            const float n0 = fmaf(p.lr, dw, W0[c]), n1 = fmaf(-p.lr, dw, W1[c]);
-            W0[c] = n0; W1[c] = n1; Wd[c] = n1 - n0;
+    // compute warps: chunk j of global step gs has been folded into W0 / W1 / Wd by the applier warp
+    auto wait_applied = [&](int j, unsigned gs) {
+        unsigned it = 0;
+        while (!mbar_try_wait(&applied[j], gs & 1u)) {
+            if ((++it & 0xfffu) == 0u) {
+                if (*reinterpret_cast<volatile unsigned*>(p.abort_flag) != 0u) break;
+                if (it > RES_SPIN_LIMIT) { atomicExch(p.abort_flag, 1u); break; }
+            }
         }
-        for (int i = tid + RES_CTHREADS; i < CCH; i += RES_CTHREADS) {       // C / RES_KCH > 512 (not the usual case)
-            const int c = j * CCH + i;
-            const float dw = poll_word(&sums[(gs & 1u) * (unsigned)C + c], gs + 1u, p.abort_flag);
-            const float n0 = fmaf(p.lr, dw, W0[c]), n1 = fmaf(-p.lr, dw, W1[c]);
-            W0[c] = n0; W1[c] = n1; Wd[c] = n1 - n0;
-        }
-        compute_sync();                                  // Wd of chunk j visible to every P1 thread
-        if (j + 1 < RES_KCH) request_chunk(j + 1, gs);
     };
 
     for (int e = group; e < p.E; e += p.G) {
@@ -240,13 +233,6 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
                 }
             }
             hr_desc[m] = d;
-        }
-        // own pixel -> which neighbouring cells feed it (static): bit0 left column exists, bit1 upper row exists
-        unsigned own_flags = 0u;
-        if (tid < NP) {
-            const int q = strip0 + tid;
-            const int a = q / wl, b = q - a * wl;
-            own_flags = (b > 0 ? 1u : 0u) | (a > 0 ? 2u : 0u);
         }
         const float2 c01 = p.cw[e];
         {
@@ -298,6 +284,45 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
                 }
             }
             gstep += (unsigned)p.T;
+        } else if (is_applier) {
+            // ================= applier warp: sums -> SGD update in shared memory -> release the compute warps =================
+            for (int t = 0; t < p.T; ++t) {
+                const unsigned gs = gstep + (unsigned)t;
+                for (int j = 0; j < RES_KCH; ++j) {
+                    const unsigned long long* sw = sums + (gs & 1u) * (unsigned)C + j * CCH;
+                    for (int c0 = 0; c0 < CCH; c0 += 32 * RES_AW) {
+                        unsigned wb[RES_AW], wt[RES_AW];
+                        unsigned pending = 0u, it = 0u;
+#pragma unroll
+                        for (int m = 0; m < RES_AW; ++m) { wb[m] = 0u; if (c0 + m * 32 + lane < CCH) pending |= 1u << m; }
+                        while (pending) {
+#pragma unroll
+                            for (int m = 0; m < RES_AW; ++m)
+                                if (pending & (1u << m)) ld_tagged(&sw[c0 + m * 32 + lane], wb[m], wt[m]);
+#pragma unroll
+                            for (int m = 0; m < RES_AW; ++m)
+                                if ((pending & (1u << m)) && wt[m] == gs + 1u) pending &= ~(1u << m);
+                            if (pending && (++it & 0xffu) == 0u) {
+                                if (*reinterpret_cast<volatile unsigned*>(p.abort_flag) != 0u) break;
+                                if (it > (RES_SPIN_LIMIT >> 2)) { atomicExch(p.abort_flag, 1u); break; }
+                            }
+                        }
+#pragma unroll
+                        for (int m = 0; m < RES_AW; ++m) {
+                            const int cl = c0 + m * 32 + lane;
+                            if (cl < CCH) {
+                                const int c = j * CCH + cl;
+                                const float dw = __uint_as_float(wb[m]);
+                                const float n0 = fmaf(p.lr, dw, W0[c]), n1 = fmaf(-p.lr, dw, W1[c]);
+                                W0[c] = n0; W1[c] = n1; Wd[c] = n1 - n0;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&applied[j]);          // release.cta: the Wd stores above are visible to the waiters
+                }
+            }
+            gstep += (unsigned)p.T;
         } else {
             // ================= compute warps =================
             for (int t = 0; t < p.T; ++t, ++gstep) {
@@ -311,7 +336,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
                     int c = grp;
 #pragma unroll
                     for (int j = 0; j < RES_KCH; ++j) {
-                        if (t > 0) apply_chunk(j, gstep - 1u);
+                        if (t > 0) wait_applied(j, gstep - 1u);
                         if (p1_active) {
                             const int cend = (j + 1) * CCH;
 #pragma unroll 8
@@ -346,40 +371,49 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
                 }
                 compute_sync();
                 if (PROF && tid == 0) { long long n = clock64(); t_acc[1] += n - tk0; tk0 = n; }
-                // ------------ HR: one task = one row of one cell; 8 adjacent lanes = one cell ------------
+                // ------------ HR: one task = one row of one cell -> (gl, gr) of that row in shared memory ------------
 #pragma unroll
                 for (int m = 0; m < RES_MAXTASK; ++m) {
                     if (m * RES_CTHREADS < 8 * NCELL) {                     // uniform: does this round have tasks at all
-                        const int ci = (m * RES_CTHREADS + tid) >> 3, r = tid & 7;
+                        const int task = m * RES_CTHREADS + tid;
+                        const int ci = task >> 3, r = tid & 7;
                         const unsigned d = hr_desc[m];
-                        float o00 = 0.f, o01 = 0.f, o10 = 0.f, o11 = 0.f;
+                        float gl = 0.f, gr = 0.f;
                         if (d & (1u << 18)) {
                             const int dx = (d >> 16) & 1, dy = (d & (1u << 17)) ? wl : 0;
                             const float z00 = zfull[ci], z01 = zfull[ci + dx], z10 = zfull[ci + dy], z11 = zfull[ci + dy + dx];
                             const float fr = (float)r * 0.125f;
-                            float gl, gr;
                             hires_row(fmaf(fr, z10 - z00, z00), fmaf(fr, z11 - z01, z01), d & 0xffffu, c01.x, c01.y, gl, gr);
-                            o10 = fr * gl; o11 = fr * gr; o00 = gl - o10; o01 = gr - o11;
                         }
-#pragma unroll
-                        for (int o = 1; o < 8; o <<= 1) {
-                            o00 += __shfl_xor_sync(0xffffffffu, o00, o); o01 += __shfl_xor_sync(0xffffffffu, o01, o);
-                            o10 += __shfl_xor_sync(0xffffffffu, o10, o); o11 += __shfl_xor_sync(0xffffffffu, o11, o);
-                        }
-                        if (r == 0 && ci < NCELL) {
-                            scratch[0 * NCELL + ci] = o00; scratch[1 * NCELL + ci] = o01;
-                            scratch[2 * NCELL + ci] = o10; scratch[3 * NCELL + ci] = o11;
-                        }
+                        if (ci < NCELL) *reinterpret_cast<float2*>(scratch + 2 * task) = make_float2(gl, gr);   // [cell][row][gl,gr]
                     }
                 }
                 compute_sync();
-                if (tid < NP) {
-                    const int ci = HALO + tid;
-                    float s2 = scratch[0 * NCELL + ci];
-                    if (own_flags & 1u) s2 += scratch[1 * NCELL + ci - 1];
-                    if (own_flags & 2u) s2 += scratch[2 * NCELL + ci - wl];
-                    if (own_flags == 3u) s2 += scratch[3 * NCELL + ci - wl - 1];
-                    gsm[tid] = s2;
+                // g(q) = sum_r (1-r/8) [gl(q,r) + gr(q-1,r)] + (r/8) [gl(q-w,r) + gr(q-w-1,r)]; 4 threads per own pixel, 2 rows each
+                {
+                    const int pl = tid >> 2, rq = tid & 3;
+                    float s2 = 0.f;
+                    if (pl < NP) {
+                        const int ci = HALO + pl;
+                        const int q = strip0 + pl;
+                        const int a = q / wl, b = q - a * wl;
+#pragma unroll
+                        for (int rr = 0; rr < 2; ++rr) {
+                            const int r = 2 * rq + rr;
+                            const float h1 = (float)r * 0.125f, h0 = 1.f - h1;
+                            float top = scratch[(ci * 8 + r) * 2];                               // gl(q, r)
+                            if (b > 0) top += scratch[((ci - 1) * 8 + r) * 2 + 1];               // gr(q-1, r)
+                            float bot = 0.f;
+                            if (a > 0) {
+                                bot = scratch[((ci - wl) * 8 + r) * 2];                          // gl(q-w, r)
+                                if (b > 0) bot += scratch[((ci - wl - 1) * 8 + r) * 2 + 1];      // gr(q-w-1, r)
+                            }
+                            s2 = fmaf(h0, top, fmaf(h1, bot, s2));
+                        }
+                    }
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+                    if (pl < NP && rq == 0) gsm[pl] = s2;
                 }
                 compute_sync();
                 if (PROF && tid == 0) { long long n = clock64(); t_acc[2] += n - tk0; tk0 = n; }
@@ -396,8 +430,6 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
                     unsigned long long* ibw = inbox + (gstep & 1u) * RES_KCH * inbox_chunk + p3_inbox_off;
 #pragma unroll
                     for (int j = 0; j < RES_KCH; ++j) {
-                        // the first chunk of THIS step was handed to the reducers three chunks ago: ask for its sum now
-                        if (j == RES_KCH - 1) request_chunk(0, gstep);
                         for (int cb = 0; cb < CCH; cb += RES_CTHREADS / 4) {
                             const int cl = cb + p3_cl;
                             float d0 = 0.f, d1 = 0.f;
@@ -435,7 +467,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
                 long long tk0 = 0;
                 if (PROF && tid == 0) tk0 = clock64();
 #pragma unroll
-                for (int j = 0; j < RES_KCH; ++j) apply_chunk(j, gstep - 1u);
+                for (int j = 0; j < RES_KCH; ++j) wait_applied(j, gstep - 1u);
                 if (PROF && tid == 0) t_acc[4] += clock64() - tk0;
             }
         }
@@ -449,7 +481,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
         }
     }
     if (PROF && tid == 0 && p.prof) {
-        for (int i = 0; i < 5; ++i) p.prof[(size_t)blockIdx.x * 8 + i] = t_acc[i];
+        for (int i = 0; i < 6; ++i) p.prof[(size_t)blockIdx.x * 8 + i] = t_acc[i];
     }
     if (tid == 0 && !ok) atomicExch(p.abort_flag, 1u);
 }

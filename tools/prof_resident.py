@@ -37,7 +37,7 @@ if a.prof:
     c = buf.cpu().double()
     used = c[:, 0] > 0
     n_steps = a.iters * ((E + 3) // 4)
-    names = ["P1", "X1", "HR", "P3", "X2"]
+    names = ["P1", "X1", "HR", "P3", "drain", "apply(in P1)"]
     print(f"instrumented run {tp:.2f} ms; per-step cycles (mean over {int(used.sum())} CTAs, ~{n_steps} steps each; min/max over CTAs):")
     for i, n in enumerate(names):
         col = c[used, i] / n_steps
