@@ -33,7 +33,7 @@ UNIT = "episodes/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--episodes", type=int, default=64, help="episodes per GPU per step")
@@ -67,25 +67,31 @@ class ClockSampler:
 
     def __init__(self, gpu_index: int):
         self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.t0 = self.t1 = None
+
+    def window(self, t0, t1):
+        """only samples taken inside [t0, t1] (time.time()) count: the timed region"""
+        self.t0, self.t1 = t0, t1
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        rows = [r for t, r in self.rows if self.t0 is None or (self.t0 <= t <= self.t1)] or [r for _, r in self.rows[-3:]]
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx = float(r[2])
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
@@ -204,13 +210,14 @@ def main():
         return float(t.item())
 
     # ---- device-resident throughput ("value") ----
-    for _ in range(a.warmup):
-        step_resident()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(a.warmup):
+        step_resident()
+    barrier()
     n0 = L.launch_count()
+    t_wall0 = time.time()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(a.steps):
@@ -219,6 +226,7 @@ def main():
     barrier()
     ms = max_over_ranks(ev0.elapsed_time(ev1))
     launches = L.launch_count() - n0
+    sampler.window(t_wall0, time.time())
     clocks = sampler.stop() if rank == 0 else None
     value = world * E * a.steps / (ms / 1e3)
 
@@ -252,43 +260,45 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     fit_gbs = bytes_fit / (fit_ms / 1e3) / 1e9
+    resident = (a.fit_algo != 1 and a.shot == 1)
+    # measured DRAM traffic of the dominant kernel per launch at E=64 (ncu --set full, profiles/r1_resident_E64_ncu.txt)
+    traffic = {True: 483.9e6, False: None}[resident and E == 64]
+    sm_clk = (clocks or {}).get("sm_mhz") or 1965.0
+    steps_per_group = a.adapt_iter * ((E + 3) // 4)
+    smem_B_per_clk = (2 * 512 * 100 * 4) / (fit_ms * 1e-3 * sm_clk * 1e6 / max(steps_per_group, 1)) if resident else None
     roofline = {
-        "kernel": "fit_classifier: 200 x {rows_times_feat<1>, fit_hires, feat_times_cols<1>+SGD}",
+        "kernel": ("k_fit_resident<512,100,60,60> (one cooperative launch: features staged once into shared memory, "
+                   "200 SGD steps on chip)") if resident else
+                  "fit_classifier streaming: 200 x {rows_times_feat<1>, fit_hires, feat_times_cols<1>+SGD}",
         "bound": "hbm", "achieved": fit_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": fit_gbs / hbm_peak,
-        "traffic": None, "peak_source": peak_src,
+        "traffic": traffic, "peak_source": peak_src,
+        "note": ("achieved = ALGORITHMIC bytes (2T+1)*S*F per episode / time; > 1 x HBM peak because the resident kernel "
+                 "reads the features from HBM once (see traffic) and sweeps them 2T times from shared memory") if resident else
+                "achieved = algorithmic bytes (2T+1)*S*F per episode / time, features streamed from HBM every step",
         "algorithmic_bytes_per_call": bytes_fit, "ms_per_call": fit_ms,
+        "smem_sweep": ({"achieved_B_per_clk_per_SM": smem_B_per_clk, "peak": 128.0, "frac": smem_B_per_clk / 128.0}
+                       if resident else None),
         "stages_ms": {"fit": fit_ms, "transformer": tr_ms, "logits_iou": iou_ms},
         "logits_iou": {"achieved": bytes_iou / (iou_ms / 1e3) / 1e9, "frac": bytes_iou / (iou_ms / 1e3) / 1e9 / hbm_peak},
     }
 
     # ---- end to end through the public API with host buffers ("e2e") ----
+    # few_shot_seg_cwt_b200.HostPipeline: every step copies its inputs from pinned host memory (side stream, overlapping
+    # the previous step's head) and reads the step's int64 counts back to the host.
     e2e = None
     if not a.no_e2e:
-        h2d = host.nbytes()
-        d2h_holder = {}
-
-        def step_e2e():
-            b = host.to(dev, non_blocking=True)
-            out = cwt.episode_head(b.f_s, b.s_label, b.f_q, b.q_label, b.w0, params, a.heads, a.cls_lr, a.adapt_iter,
-                                   fit_algo=a.fit_algo, attn_algo=a.attn_algo)
-            table.update(out.counts, b.subcls.to(dev), out.ce)
-            table.all_reduce()
-            c = out.counts.cpu()                # D2H read of the step's result (syncs the stream)
-            d2h_holder["n"] = c.numel() * c.element_size()
-            return c
-
-        for _ in range(max(1, a.warmup)):
-            step_e2e()
+        pipe = cwt.HostPipeline(dev, params, a.heads, a.cls_lr, a.adapt_iter, fit_algo=a.fit_algo, attn_algo=a.attn_algo)
+        pipe.run([host] * max(1, a.warmup))
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(a.steps):
-            step_e2e()
+        res = pipe.run([host] * a.steps)
         e1.record()
         barrier()
         ms_e = max_over_ranks(e0.elapsed_time(e1))
-        e2e = {"value": world * E * a.steps / (ms_e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h_holder.get("n", 0), "ms_per_step": ms_e / a.steps}
+        e2e = {"value": world * E * a.steps / (ms_e / 1e3), "unit": UNIT, "h2d_bytes_per_step": host.nbytes() + host.subcls.numel() * 8,
+               "d2h_bytes_per_step": res[0].numel() * res[0].element_size(), "ms_per_step": ms_e / a.steps,
+               "api": "few_shot_seg_cwt_b200.HostPipeline.run (double-buffered H2D, async D2H of the counts)"}
 
     # ---- CPU baseline on the box's host cores (rank 0, N = 1 only) ----
     cpu = None
