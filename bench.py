@@ -104,8 +104,19 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def use_all_host_threads() -> int:
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every core this process may run on."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def cpu_reference_rate(a, n_episodes: int, warm: int = 1):
     """The reference algorithm (oracle port, torch CPU, all host threads) on the same workload."""
+    use_all_host_threads()
     from few_shot_seg_cwt_b200 import synthetic as syn
     from oracle import head_ref as O
     params = syn.make_transformer_params(a.heads, 512)
@@ -125,6 +136,7 @@ def run_reference(a, rank):
     if rank != 0:
         return
     per_step = 2
+    use_all_host_threads()
     from few_shot_seg_cwt_b200 import synthetic as syn
     from oracle import head_ref as O
     params = syn.make_transformer_params(a.heads, 512)

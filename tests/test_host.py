@@ -145,7 +145,8 @@ def _worker(rank, world, port, n, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     t = _table_for(syn.shard_indices(n, rank, world))
     t.all_reduce()
-    q.put((rank, t.cls.clone(), t.fb.clone(), int(t.n_episodes), t.miou(0), t.miou(1)))
+    # plain lists: torch tensors in an mp.Queue travel through shared-memory files that vanish when the child exits
+    q.put((rank, t.cls.tolist(), t.fb.tolist(), int(t.n_episodes), t.miou(0), t.miou(1)))
     dist.destroy_process_group()
 
 
@@ -162,5 +163,5 @@ def test_sharded_sweep_all_reduce_world2_gloo():
     [p.join(60) for p in procs]
     single = _table_for(list(range(n)))
     for rank, cls, fb, ne, m0, m1 in res:
-        assert torch.equal(cls, single.cls) and torch.equal(fb, single.fb) and ne == n
+        assert cls == single.cls.tolist() and fb == single.fb.tolist() and ne == n
         assert m0 == single.miou(0) and m1 == single.miou(1)
