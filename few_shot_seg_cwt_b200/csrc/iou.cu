@@ -17,72 +17,134 @@ int pack_label_cells(const void* labels, int label_kind, int n_img, int h, int w
 
 constexpr int IOU_THREADS = 256;
 constexpr int IOU_MAXW = 128;
+constexpr int IOU_MAXV = 8;           // weight sets (variants) per episode
+constexpr int IOU_R = 4;              // low-res cell rows per CTA band
 
-// grid (h, n_maps): CTA a0 owns hi-res rows [8 a0, 8 a0 + 8) of one 2-channel logit map
+// ------------------------------------------------------------------------------------------------
+// Column-threaded upsample / argmax / confusion counting of one band of low-res rows.
+//   lsm[v][ch][row][w]  low-res logits of the band (rows a0 .. a0+nlo-1) in shared memory
+//   thread <-> hi-res column X: the horizontal lerp t(row) = fma(l[b0], w0, l[b1]*w1) is computed once per
+//   low-res row and reused by the 8 hi-res rows below it; vertically u = fma(t0, h0, t1*h1) — exactly ATen's
+//   CPU rounding order (verified bit-exact against F.interpolate), 2 FP ops per channel per pixel.
+//   cnt[v][pred][code] (code in {0,1}) per thread -> I = n[c][c], T = n[0][c]+n[1][c], U = row_c + col_c - I.
+// ------------------------------------------------------------------------------------------------
+template <bool I64, int V>
+__device__ __forceinline__ void iou_band(const float* __restrict__ lsm, int lrows, const void* __restrict__ lab, size_t lbase,
+                                         int a0, int nlo, int h, int w, int H, int W, int ignore_index, unsigned ce_mask,
+                                         int (&cnt)[V][4], float (&loss)[V], int& nvalid) {
+    const int tid = threadIdx.x;
+    for (int X = tid; X < W; X += IOU_THREADS) {
+        const int b0 = X >> 3, b1 = min(b0 + 1, w - 1);
+        const float w1 = (X & 7) * 0.125f, w0 = 1.f - w1;
+        float t0[V][2], t1[V][2];
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                const float* row = lsm + ((v * 2 + ch) * lrows) * w;
+                t1[v][ch] = __fmaf_rn(row[b0], w0, __fmul_rn(row[b1], w1));
+            }
+        for (int ar = 0; ar < nlo; ++ar) {                 // cell row a0+ar: hi-res rows 8(a0+ar) .. +7
+            const int a = a0 + ar;
+            const int an = min(ar + 1, lrows - 1);         // next low-res row inside the band buffer
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch) {
+                    t0[v][ch] = t1[v][ch];
+                    const float* row = lsm + ((v * 2 + ch) * lrows + an) * w;
+                    t1[v][ch] = (a + 1 < h) ? __fmaf_rn(row[b0], w0, __fmul_rn(row[b1], w1)) : t0[v][ch];
+                }
+            const int nr = min(8, H - 8 * a);
+#pragma unroll 2
+            for (int r = 0; r < nr; ++r) {
+                const int Y = 8 * a + r;
+                const float h1 = r * 0.125f, h0 = 1.f - h1;
+                const int code = load_label_code<I64>(lab, lbase + (size_t)Y * W + X, ignore_index);
+                const bool valid = code < 2;
+                nvalid += valid;
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const float u0 = __fmaf_rn(t0[v][0], h0, __fmul_rn(t1[v][0], h1));
+                    const float u1 = __fmaf_rn(t0[v][1], h0, __fmul_rn(t1[v][1], h1));
+                    const int pred = (u1 > u0) ? 1 : 0;    // torch.argmax: first index wins ties
+                    if (valid) {
+                        cnt[v][pred * 2 + code] += 1;
+                        if ((ce_mask >> v) & 1u) {
+                            const float t = (code == 1) ? (u0 - u1) : (u1 - u0);   // -log softmax(u)[y] = softplus(t)
+                            loss[v] += fmaxf(t, 0.f) + __logf(1.f + __expf(-fabsf(t)));
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// block-level reduction of the per-thread counters into counts[n][class][I,U,T] / ce[n][sum,count]
+template <int V>
+__device__ __forceinline__ void iou_flush(int (&cnt)[V][4], float (&loss)[V], int nvalid, size_t map0,
+                                          unsigned long long* __restrict__ counts, double* __restrict__ ce, int* sred,
+                                          float* fred) {
+    const int tid = threadIdx.x;
+    for (int i = tid; i < V * 4 + 1; i += IOU_THREADS) sred[i] = 0;
+    for (int i = tid; i < V; i += IOU_THREADS) fred[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int s = __reduce_add_sync(0xffffffffu, cnt[v][k]);
+            if ((tid & 31) == 0 && s) atomicAdd(&sred[v * 4 + k], s);
+        }
+        const float l = warp_sum(loss[v]);
+        if ((tid & 31) == 0 && l != 0.f) atomicAdd(&fred[v], l);      // (CE is a logged metric: order-insensitive to ~1e-7)
+    }
+    const int nv = __reduce_add_sync(0xffffffffu, nvalid);
+    if ((tid & 31) == 0 && nv) atomicAdd(&sred[V * 4], nv);
+    __syncthreads();
+    if (tid < V) {
+        const int v = tid;
+        const int n00 = sred[v * 4 + 0], n01 = sred[v * 4 + 1], n10 = sred[v * 4 + 2], n11 = sred[v * 4 + 3];   // [pred][code]
+        unsigned long long* c = counts + (map0 + v) * 6;
+        const int I0 = n00, I1 = n11, T0 = n00 + n10, T1 = n01 + n11;
+        const int U0 = n00 + n01 + n10, U1 = n11 + n10 + n01;
+        if (I0) atomicAdd(&c[0], (unsigned long long)I0);
+        if (U0) atomicAdd(&c[1], (unsigned long long)U0);
+        if (T0) atomicAdd(&c[2], (unsigned long long)T0);
+        if (I1) atomicAdd(&c[3], (unsigned long long)I1);
+        if (U1) atomicAdd(&c[4], (unsigned long long)U1);
+        if (T1) atomicAdd(&c[5], (unsigned long long)T1);
+        if (ce) {
+            atomicAdd(&ce[(map0 + v) * 2], (double)fred[v]);
+            atomicAdd(&ce[(map0 + v) * 2 + 1], (double)sred[V * 4]);
+        }
+    }
+}
+
+// ready-made low-res logits: grid (bands, n_maps); one 2-channel map per blockIdx.y
 template <bool I64>
-__global__ void __launch_bounds__(IOU_THREADS)
+__global__ void __launch_bounds__(IOU_THREADS, 4)
 k_upsample_argmax_iou(const float* __restrict__ l60, const void* __restrict__ lab, int maps_per_label,
                       unsigned long long* __restrict__ counts, double* __restrict__ ce,
                       int h, int w, int H, int W, int ignore_index) {
-    __shared__ float ls[2][2][IOU_MAXW];
-    __shared__ int scnt[6];
-    __shared__ float sloss[IOU_THREADS / 32];
-    const int n = blockIdx.y, a0 = blockIdx.x, a1 = min(a0 + 1, h - 1);
-    const int tid = threadIdx.x;
+    __shared__ float lsm[2 * (IOU_R + 1) * IOU_MAXW];
+    __shared__ int sred[8];
+    __shared__ float fred[1];
+    const int n = blockIdx.y, a0 = blockIdx.x * IOU_R;
+    const int nlo = min(IOU_R, h - a0), lrows = min(IOU_R + 1, h - a0);
     const float* lm = l60 + (size_t)n * 2 * h * w;
-    for (int i = tid; i < 4 * w; i += IOU_THREADS) {
-        int ch = i / (2 * w), rem = i - ch * 2 * w, rr = rem / w, b = rem - rr * w;
-        ls[ch][rr][b] = lm[(size_t)ch * h * w + (rr ? a1 : a0) * w + b];
+    for (int i = threadIdx.x; i < 2 * lrows * w; i += IOU_THREADS) {
+        const int ch = i / (lrows * w), rem = i - ch * lrows * w;
+        lsm[i] = lm[(size_t)ch * h * w + a0 * w + rem];
     }
-    if (tid < 6) scnt[tid] = 0;
     __syncthreads();
-    const size_t lbase = (size_t)(n / maps_per_label) * H * W;
-    const int rows = min(8, H - 8 * a0);
-    int cI0 = 0, cI1 = 0, cU0 = 0, cU1 = 0, cT0 = 0, cT1 = 0, nvalid = 0;
-    float loss = 0.f;
-    for (int idx = tid; idx < rows * W; idx += IOU_THREADS) {
-        const int r = idx / W, X = idx - r * W, Y = 8 * a0 + r;
-        const float h1 = r * 0.125f, h0 = 1.f - h1;
-        const int b0 = X >> 3, b1 = min(b0 + 1, w - 1);
-        const float w1 = (X & 7) * 0.125f, w0 = 1.f - w1;
-        const float u0 = bilerp8(ls[0][0][b0], ls[0][0][b1], ls[0][1][b0], ls[0][1][b1], w0, w1, h0, h1);
-        const float u1 = bilerp8(ls[1][0][b0], ls[1][0][b1], ls[1][1][b0], ls[1][1][b1], w0, w1, h0, h1);
-        const int pred = (u1 > u0) ? 1 : 0;                       // torch.argmax: first index wins ties
-        const int code = load_label_code<I64>(lab, lbase + (size_t)Y * W + X, ignore_index);
-        const bool valid = code < 2;
-        cI0 += (valid && code == 0 && pred == 0);
-        cI1 += (valid && code == 1 && pred == 1);
-        cU0 += (valid && (code == 0 || pred == 0));
-        cU1 += (valid && (code == 1 || pred == 1));
-        cT0 += (code == 0);
-        cT1 += (code == 1);
-        if (valid) {
-            nvalid += 1;
-            const float t = (code == 1) ? (u0 - u1) : (u1 - u0);   // -log softmax(u)[y] = softplus(t)
-            loss += fmaxf(t, 0.f) + log1pf(expf(-fabsf(t)));
-        }
-    }
-    int v[6] = {cI0, cU0, cT0, cI1, cU1, cT1};                    // layout [class][I,U,T]
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        int s = __reduce_add_sync(0xffffffffu, v[k]);
-        if ((tid & 31) == 0 && s) atomicAdd(&scnt[k], s);
-    }
-    loss = warp_sum(loss);
-    nvalid = __reduce_add_sync(0xffffffffu, nvalid);
-    if ((tid & 31) == 0) sloss[tid >> 5] = loss;
-    __shared__ int svalid;
-    if (tid == 0) svalid = 0;
-    __syncthreads();
-    if ((tid & 31) == 0 && nvalid) atomicAdd(&svalid, nvalid);
-    __syncthreads();
-    if (tid < 6 && scnt[tid]) atomicAdd(&counts[(size_t)n * 6 + tid], (unsigned long long)scnt[tid]);
-    if (tid == 0 && ce) {
-        double s = 0.0;
-        for (int k = 0; k < IOU_THREADS / 32; ++k) s += (double)sloss[k];
-        atomicAdd(&ce[(size_t)n * 2], s);
-        atomicAdd(&ce[(size_t)n * 2 + 1], (double)svalid);
-    }
+    int cnt[1][4] = {{0, 0, 0, 0}};
+    float loss[1] = {0.f};
+    int nvalid = 0;
+    iou_band<I64, 1>(lsm, lrows, lab, (size_t)(n / maps_per_label) * H * W, a0, nlo, h, w, H, W, ignore_index, ce ? 1u : 0u,
+                     cnt, loss, nvalid);
+    iou_flush<1>(cnt, loss, nvalid, (size_t)n, counts, ce, sred, fred);
 }
 
 static int launch_upsample_iou(const float* l60, const void* lab, int label_kind, int maps_per_label,
@@ -93,13 +155,124 @@ static int launch_upsample_iou(const float* l60, const void* lab, int label_kind
     CWT_REQUIRE(w <= IOU_MAXW, CWT_ERR_UNSUPPORTED, "iou: w=%d > %d", w, IOU_MAXW);
     CWT_CUDA(cudaMemsetAsync(counts, 0, sizeof(long long) * 6 * (size_t)n, st));
     if (ce) CWT_CUDA(cudaMemsetAsync(ce, 0, sizeof(double) * 2 * (size_t)n, st));
-    dim3 grid(h, n);
+    dim3 grid((h + IOU_R - 1) / IOU_R, n);
     auto* cnt = reinterpret_cast<unsigned long long*>(counts);
     if (label_kind == CWT_LABEL_I64)
         k_upsample_argmax_iou<true><<<grid, IOU_THREADS, 0, st>>>(l60, lab, maps_per_label, cnt, ce, h, w, H, W, ignore_index);
     else
         k_upsample_argmax_iou<false><<<grid, IOU_THREADS, 0, st>>>(l60, lab, maps_per_label, cnt, ce, h, w, H, W, ignore_index);
     CWT_LAUNCHED("upsample_argmax_iou");
+    return CWT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// (c) fused: query logits of V weight sets -> up to H x W -> argmax -> I/U/T (+CE), ONE pass over f_q.
+// CTA = (band of IOU_R cell rows, episode). Phase 1 streams the (IOU_R+1) low-res rows x C channels of f_q
+// that the band's cells interpolate from (the shared halo row is re-read from L2 by the next band) and keeps
+// the 2V logit rows (+ |f_p|^2 for F.normalize) in shared memory; phase 2 is iou_band.
+// ------------------------------------------------------------------------------------------------
+template <bool I64, int V>
+__global__ void __launch_bounds__(IOU_THREADS, 3)
+k_logits_iou_fused(const float* __restrict__ wts, const float* __restrict__ f_q, const void* __restrict__ lab,
+                   int normalize_mask, unsigned ce_mask, unsigned long long* __restrict__ counts, float* __restrict__ logits_out,
+                   double* __restrict__ ce, int C, int h, int w, int H, int W, int ignore_index) {
+    extern __shared__ __align__(16) float fsm[];
+    constexpr int R2 = 2 * V;                          // logit rows
+    const int e = blockIdx.y, a0 = blockIdx.x * IOU_R, tid = threadIdx.x;
+    const int nlo = min(IOU_R, h - a0), lrows = min(IOU_R + 1, h - a0);
+    const int HW = h * w, npx = lrows * w, nq = (npx + 3) >> 2;          // band pixels, float4 quads (HW % 4 == 0)
+    const int ng = IOU_THREADS / nq;                   // channel groups
+    float* Ms = fsm;                                   // [C][R2]
+    float* red = Ms + (size_t)C * R2;                  // [ng][R2+1][nq*4]
+    float* lsm = red + (size_t)IOU_THREADS * (R2 + 1) * 4; // [R2][lrows][w]   (ng * nq <= IOU_THREADS)
+    __shared__ int sred[IOU_MAXV * 4 + 1];
+    __shared__ float fred[IOU_MAXV];
+    const float* Mg = wts + (size_t)e * R2 * C;
+    for (int i = tid; i < C * R2; i += IOU_THREADS) { const int c = i / R2, r = i - c * R2; Ms[i] = Mg[(size_t)r * C + c]; }
+    __syncthreads();
+    // ---- phase 1: logits of the band
+    const int q = tid % nq, grp = tid / nq;
+    if (grp < ng) {
+        float acc[R2][4], n2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < R2; ++r) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f; }
+        const float* fp = f_q + ((size_t)e * C) * HW + (size_t)a0 * w + 4 * q;
+        const bool inb = 4 * q < npx;
+        if (inb) {
+            // 8 independent 16-byte loads in flight per thread before the first use (memory-level parallelism)
+            int c = grp;
+            for (; c + 7 * ng < C; c += 8 * ng) {
+                float4 t[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) t[u] = ldg_stream4(fp + (size_t)(c + u * ng) * HW);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float v[4] = {t[u].x, t[u].y, t[u].z, t[u].w};
+                    const float* m = Ms + (c + u * ng) * R2;
+#pragma unroll
+                    for (int r = 0; r < R2; ++r)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) acc[r][k] = fmaf(m[r], v[k], acc[r][k]);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) n2[k] = fmaf(v[k], v[k], n2[k]);
+                }
+            }
+            for (; c < C; c += ng) {
+                const float4 t = ldg_stream4(fp + (size_t)c * HW);
+                const float v[4] = {t.x, t.y, t.z, t.w};
+                const float* m = Ms + c * R2;
+#pragma unroll
+                for (int r = 0; r < R2; ++r)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) acc[r][k] = fmaf(m[r], v[k], acc[r][k]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) n2[k] = fmaf(v[k], v[k], n2[k]);
+            }
+        }
+        float* rg = red + (size_t)grp * (R2 + 1) * nq * 4;
+#pragma unroll
+        for (int r = 0; r < R2; ++r)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) rg[r * nq * 4 + 4 * q + k] = acc[r][k];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rg[R2 * nq * 4 + 4 * q + k] = n2[k];
+    }
+    __syncthreads();
+    for (int i = tid; i < R2 * npx; i += IOU_THREADS) {
+        const int r = i / npx, pp = i - r * npx;
+        float s = 0.f, nn = 0.f;
+        for (int g2 = 0; g2 < ng; ++g2) {
+            s += red[((size_t)g2 * (R2 + 1) + r) * nq * 4 + pp];
+            nn += red[((size_t)g2 * (R2 + 1) + R2) * nq * 4 + pp];
+        }
+        const int v = r >> 1;
+        if ((normalize_mask >> v) & 1) s = s / fmaxf(sqrtf(nn), 1e-12f);          // F.normalize(f_q, dim=1)
+        lsm[r * npx + pp] = s;
+        if (logits_out && pp < nlo * w) logits_out[((size_t)e * R2 + r) * HW + (size_t)a0 * w + pp] = s;   // own rows only
+    }
+    __syncthreads();
+    // ---- phase 2: up-sample, argmax, count
+    int cnt[V][4];
+    float loss[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) { cnt[v][0] = cnt[v][1] = cnt[v][2] = cnt[v][3] = 0; loss[v] = 0.f; }
+    int nvalid = 0;
+    iou_band<I64, V>(lsm, lrows, lab, (size_t)e * H * W, a0, nlo, h, w, H, W, ignore_index, ce ? ce_mask : 0u, cnt, loss, nvalid);
+    iou_flush<V>(cnt, loss, nvalid, (size_t)e * V, counts, ce, sred, fred);
+}
+
+template <bool I64, int V>
+static int launch_fused_t(const float* wts, const float* f_q, const void* lab, int normalize_mask, unsigned ce_mask,
+                          unsigned long long* counts, float* logits_out, double* ce, int E, int C, int h, int w, int H, int W,
+                          int ignore_index, cudaStream_t st) {
+    const int npx = (IOU_R + 1) * w;
+    const size_t sm = sizeof(float) * ((size_t)C * 2 * V + (size_t)IOU_THREADS * (2 * V + 1) * 4 + (size_t)2 * V * npx);
+    CWT_REQUIRE(sm <= 200 * 1024, CWT_ERR_UNSUPPORTED, "logits_iou: C=%d too large for the fused kernel", C);
+    auto kern = k_logits_iou_fused<I64, V>;
+    if (sm > 48 * 1024) CWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    dim3 grid((h + IOU_R - 1) / IOU_R, E);
+    kern<<<grid, IOU_THREADS, sm, st>>>(wts, f_q, lab, normalize_mask, ce_mask, counts, logits_out, ce, C, h, w, H, W, ignore_index);
+    CWT_LAUNCHED("logits_iou_fused");
     return CWT_OK;
 }
 
@@ -216,6 +389,27 @@ extern "C" int cwt_logits_iou(const float* wts, const float* f_q, const void* q_
     LogitsIouWs ws;
     size_t need = carve_logits_iou(cv, ws, E, V, HWl);
     CWT_REQUIRE(workspace && ws_bytes >= need, CWT_ERR_WORKSPACE, "logits_iou: workspace %zu < %zu", ws_bytes, need);
+    // fused single pass (north-star (c)) whenever the band loads can be vectorised; otherwise logits pass + histogram pass
+    if (HWl % 4 == 0 && V <= 4 && w <= IOU_MAXW && H == 8 * (h - 1) + 1 && W == 8 * (w - 1) + 1 &&
+        (size_t)C * 2 * V * 4 <= 96 * 1024) {
+        CWT_CUDA(cudaMemsetAsync(iu_counts, 0, sizeof(long long) * 6 * (size_t)E * V, st));
+        if (ce_or_null) CWT_CUDA(cudaMemsetAsync(ce_or_null, 0, sizeof(double) * 2 * (size_t)E * V, st));
+        auto* cnt = reinterpret_cast<unsigned long long*>(iu_counts);
+        const unsigned ce_mask = (1u << V) - 1u;
+        const bool i64 = label_kind == CWT_LABEL_I64;
+#define CWT_FUSED(VV)                                                                                                       \
+        return i64 ? launch_fused_t<true, VV>(wts, f_q, q_label, normalize_mask, ce_mask, cnt, logits60_or_null, ce_or_null, \
+                                              E, C, h, w, H, W, ignore_index, st)                                          \
+                   : launch_fused_t<false, VV>(wts, f_q, q_label, normalize_mask, ce_mask, cnt, logits60_or_null, ce_or_null, \
+                                               E, C, h, w, H, W, ignore_index, st)
+        switch (V) {
+            case 1: CWT_FUSED(1);
+            case 2: CWT_FUSED(2);
+            case 3: CWT_FUSED(3);
+            default: CWT_FUSED(4);
+        }
+#undef CWT_FUSED
+    }
     float* l60 = logits60_or_null ? logits60_or_null : ws.l60;
     int rc = launch_rows_times_feat(f_q, wts, l60, normalize_mask ? ws.n2 : nullptr, E, C, HWl, 1, V * 2, st);
     if (rc != CWT_OK) return rc;
