@@ -152,7 +152,8 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
     const int CPG = (TNP && TWL && THL) ? (TWL * THL) / (TNP ? TNP : 1) : p.CPG;
     const int CCH = C / RES_KCH;                     // channels per chunk (C % RES_KCH == 0)
     const int SLS = (CCH + CPG - 1) / CPG;           // channels of a chunk owned by one CTA
-    const int NQ = NP / 4, NG = RES_CTHREADS / NQ, NCELL = NP + wl + 1, HALO = wl + 1;
+    constexpr bool kStatic = (TC == 512 && TNP == 100);          // PSPNet head geometry: fully unrolled sweeps
+    const int NQ = NP / 4, NG = kStatic ? 16 : RES_CTHREADS / NQ, NCELL = NP + wl + 1, HALO = wl + 1;
     const ResSmem L = res_smem_layout(C, NP, wl);
     float* F = reinterpret_cast<float*>(smem_raw + L.F);
     float* W0 = reinterpret_cast<float*>(smem_raw + L.W0);
@@ -192,8 +193,15 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
     const unsigned p3_inbox_off = (unsigned)(((p3_cl / SLS) * CPG + k) * SLS + (p3_cl % SLS));
 
     // compute warps: chunk j of global step gs has been folded into W0 / W1 / Wd by the applier warp
+    long long t_store[RES_KCH] = {0, 0, 0, 0};        // PROF: when chunk j's partials left this CTA
     auto wait_applied = [&](int j, unsigned gs) {
         unsigned it = 0;
+        if (PROF && tid == 0 && !mbar_try_wait(&applied[j], gs & 1u)) {      // had to wait: latency = now - store time
+            while (!mbar_try_wait(&applied[j], gs & 1u)) { if (++it > RES_SPIN_LIMIT) break; }
+            t_acc[5] += clock64() - t_store[j];
+            t_acc[4] += 1;
+            return;
+        }
         while (!mbar_try_wait(&applied[j], gs & 1u)) {
             if ((++it & 0xfffu) == 0u) {
                 if (*reinterpret_cast<volatile unsigned*>(p.abort_flag) != 0u) break;
@@ -338,14 +346,29 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
                     for (int j = 0; j < RES_KCH; ++j) {
                         if (t > 0) wait_applied(j, gstep - 1u);
                         if (p1_active) {
-                            const int cend = (j + 1) * CCH;
+                            if constexpr (kStatic) {
+                                // chunk j = channels grp + 16*(8j .. 8j+7): 8 independent LDS.128 + 8 broadcast LDS.32, immediate offsets
+                                const float4* Fj = reinterpret_cast<const float4*>(F) + tid + j * (8 * 400);
+                                const float* Wj = Wd + grp + j * 128;
+                                float4 f[8];
+                                float wd[8];
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) { f[u] = Fj[u * 400]; wd[u] = Wj[u * 16]; }
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) {
+                                    za.x = fmaf(wd[u], f[u].x, za.x); za.y = fmaf(wd[u], f[u].y, za.y);
+                                    za.z = fmaf(wd[u], f[u].z, za.z); za.w = fmaf(wd[u], f[u].w, za.w);
+                                }
+                            } else {
+                                const int cend = (j + 1) * CCH;
 #pragma unroll 8
-                            for (; c < cend; c += NG) {
-                                const float4 f = *F4;
-                                F4 += stride;
-                                const float wd = Wd[c];
-                                za.x = fmaf(wd, f.x, za.x); za.y = fmaf(wd, f.y, za.y);
-                                za.z = fmaf(wd, f.z, za.z); za.w = fmaf(wd, f.w, za.w);
+                                for (; c < cend; c += NG) {
+                                    const float4 f = *F4;
+                                    F4 += stride;
+                                    const float wd = Wd[c];
+                                    za.x = fmaf(wd, f.x, za.x); za.y = fmaf(wd, f.y, za.y);
+                                    za.z = fmaf(wd, f.z, za.z); za.w = fmaf(wd, f.w, za.w);
+                                }
                             }
                         }
                     }
@@ -435,18 +458,34 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
                             float d0 = 0.f, d1 = 0.f;
                             if (cl < CCH) {
                                 const float4* row = reinterpret_cast<const float4*>(F + (size_t)(j * CCH + cl) * NP) + 2 * p3_part;
+                                if constexpr (kStatic) {
+                                    // 25 quads per channel row: parts own quads {2p, 2p+1} + 8i for i = 0..2; quad 24 belongs to part 0
+                                    float4 f[6];
 #pragma unroll
-                                for (int i = 0; i < RES_MAXQ / 2; ++i) {
-                                    const int q0 = 2 * p3_part + 8 * i;
-                                    if (q0 < NQ) {
-                                        const float4 f = row[8 * i];
-                                        d0 = fmaf(gq[2 * i].x, f.x, d0); d1 = fmaf(gq[2 * i].y, f.y, d1);
-                                        d0 = fmaf(gq[2 * i].z, f.z, d0); d1 = fmaf(gq[2 * i].w, f.w, d1);
+                                    for (int i = 0; i < 3; ++i) { f[2 * i] = row[8 * i]; f[2 * i + 1] = row[8 * i + 1]; }
+                                    float4 f6 = make_float4(0.f, 0.f, 0.f, 0.f);
+                                    if (p3_part == 0) f6 = row[24];
+#pragma unroll
+                                    for (int i = 0; i < 6; ++i) {
+                                        d0 = fmaf(gq[i].x, f[i].x, d0); d1 = fmaf(gq[i].y, f[i].y, d1);
+                                        d0 = fmaf(gq[i].z, f[i].z, d0); d1 = fmaf(gq[i].w, f[i].w, d1);
                                     }
-                                    if (q0 + 1 < NQ) {
-                                        const float4 f = row[8 * i + 1];
-                                        d0 = fmaf(gq[2 * i + 1].x, f.x, d0); d1 = fmaf(gq[2 * i + 1].y, f.y, d1);
-                                        d0 = fmaf(gq[2 * i + 1].z, f.z, d0); d1 = fmaf(gq[2 * i + 1].w, f.w, d1);
+                                    d0 = fmaf(gq[6].x, f6.x, d0); d1 = fmaf(gq[6].y, f6.y, d1);
+                                    d0 = fmaf(gq[6].z, f6.z, d0); d1 = fmaf(gq[6].w, f6.w, d1);
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < RES_MAXQ / 2; ++i) {
+                                        const int q0 = 2 * p3_part + 8 * i;
+                                        if (q0 < NQ) {
+                                            const float4 f = row[8 * i];
+                                            d0 = fmaf(gq[2 * i].x, f.x, d0); d1 = fmaf(gq[2 * i].y, f.y, d1);
+                                            d0 = fmaf(gq[2 * i].z, f.z, d0); d1 = fmaf(gq[2 * i].w, f.w, d1);
+                                        }
+                                        if (q0 + 1 < NQ) {
+                                            const float4 f = row[8 * i + 1];
+                                            d0 = fmaf(gq[2 * i + 1].x, f.x, d0); d1 = fmaf(gq[2 * i + 1].y, f.y, d1);
+                                            d0 = fmaf(gq[2 * i + 1].z, f.z, d0); d1 = fmaf(gq[2 * i + 1].w, f.w, d1);
+                                        }
                                     }
                                 }
                             }
@@ -458,6 +497,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
                                 st_tagged(ibw + (int)(j * inbox_chunk) + off, d, gstep + 1u);
                             }
                         }
+                        if (PROF && tid == 0) t_store[j] = clock64();
                     }
                 }
                 if (PROF && tid == 0) { long long n = clock64(); t_acc[3] += n - tk0; tk0 = n; }
@@ -468,7 +508,6 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
                 if (PROF && tid == 0) tk0 = clock64();
 #pragma unroll
                 for (int j = 0; j < RES_KCH; ++j) wait_applied(j, gstep - 1u);
-                if (PROF && tid == 0) t_acc[4] += clock64() - tk0;
             }
         }
         __syncthreads();
