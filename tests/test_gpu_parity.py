@@ -468,3 +468,17 @@ def test_torch_custom_ops_registered(cuda_device):
     lg = torch.randn(2, 2, 12, 12, device=cuda_device)
     tg = torch.zeros(2, 89, 89, dtype=torch.uint8, device=cuda_device)
     assert torch.equal(torch.ops.cwt_b200.upsample_argmax_iou(lg, tg), ops.upsample_argmax_iou(lg, tg)[0])
+
+
+def test_sweep_cli_small_with_oracle_check(cuda_device, capsys):
+    """few_shot_seg_cwt_b200.sweep: loader workers -> pinned host -> HostPipeline -> IoU table, oracle spot-check."""
+    import json
+    from few_shot_seg_cwt_b200 import sweep
+    sweep.main(["--small", "--episodes", "24", "--batch", "8", "--workers", "0", "--oracle-sample", "6",
+                "--adapt-iter", "40", "--heads", "2"])
+    out = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert out["episodes"] == 24
+    chk = out["oracle_check"]
+    assert chk["episodes"] == 6
+    assert chk["max_count_diff"] <= chk["tie_set_pixels"]
+    assert chk["mIoU_gap_points"] < 0.05 and chk["FBIoU_gap_points"] < 0.05
