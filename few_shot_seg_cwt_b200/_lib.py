@@ -28,6 +28,7 @@ SIGNATURES = {
     "cwt_last_error": (C.c_char_p, []),
     "cwt_launch_count": (_ll, []),
     "cwt_debug_set_prof_buffer": (None, [_vp]),
+    "cwt_debug_l2_read": (_i, [_vp, _sz, _i, _i, _vp, _vp]),
     "cwt_prep_labels": (_i, [_vp, _i, _i, _ll, _i, _vp, _vp, _vp]),
     "cwt_fit_workspace_bytes": (_sz, [_i] * 7),
     "cwt_fit_classifier_f32": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp] + [_i] * 8 + [_f, _i, _i, _vp, _sz, _vp]),

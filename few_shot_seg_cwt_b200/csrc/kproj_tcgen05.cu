@@ -32,40 +32,48 @@ __host__ __device__ static inline int kp_hwpad(int HW) { return (HW + KP_BM - 1)
 __host__ __device__ static inline int kp_npass(int C) { return (C + 255) / 256; }
 
 // ---- pre-pass: transpose + bf16 hi/lo split + squared norms -------------------------------------------------
-// grid (HWpad/64, E), block 256: 64 pixels x all channels, 64-channel chunks through shared memory
+// grid (HWpad/32, E), block 256: 32 pixels x all channels, 64-channel chunks through shared memory.
+// read: 128-byte pixel rows per channel (coalesced); write: thread = (pixel, 8 channels) -> one 16-byte store of hi
+// and one of lo, 8 adjacent lanes cover 128 contiguous bytes of the K-major row.
 __global__ void __launch_bounds__(256)
 k_split_transpose(const float* __restrict__ k, __nv_bfloat16* __restrict__ Xh, __nv_bfloat16* __restrict__ Xl,
                   float* __restrict__ n2, int C, int HW, int HWpad) {
-    __shared__ float tile[64][65];
-    const int e = blockIdx.y, p0 = blockIdx.x * 64, tid = threadIdx.x;
-    const int wp = tid >> 2, wq = tid & 3;                 // write phase: pixel, 16-channel quarter
+    __shared__ float tile[64][33];
+    const int e = blockIdx.y, p0 = blockIdx.x * 32, tid = threadIdx.x;
+    const int rc = tid >> 5, rp = tid & 31;                // read phase: 8 channel rows x 32 pixels per pass
+    const int wp = tid >> 3, wg = tid & 7;                 // write phase: pixel, group of 8 channels
     float nsum = 0.f;
     for (int c0 = 0; c0 < C; c0 += 64) {
-        for (int i = tid; i < 64 * 64; i += 256) {
-            const int c = i >> 6, pp = i & 63;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = rc + 8 * i;
             float v = 0.f;
-            if (c0 + c < C && p0 + pp < HW) v = k[((size_t)e * C + c0 + c) * HW + p0 + pp];
-            tile[c][pp] = v;
+            if (c0 + c < C && p0 + rp < HW) v = k[((size_t)e * C + c0 + c) * HW + p0 + rp];
+            tile[c][rp] = v;
         }
         __syncthreads();
-        const size_t row = ((size_t)e * HWpad + p0 + wp) * C + c0 + wq * 16;
+        uint32_t hi[4], lo[4];
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-            const float a = tile[wq * 16 + j][wp], b = tile[wq * 16 + j + 1][wp];
+        for (int j = 0; j < 4; ++j) {
+            const float a = tile[wg * 8 + 2 * j][wp], b = tile[wg * 8 + 2 * j + 1][wp];
             const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
             const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
             const __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bh));
-            if (c0 + wq * 16 + j < C) {
-                *reinterpret_cast<__nv_bfloat162*>(Xh + row + j) = __nv_bfloat162(ah, bh);
-                *reinterpret_cast<__nv_bfloat162*>(Xl + row + j) = __nv_bfloat162(al, bl);
-            }
+            hi[j] = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
+            lo[j] = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
             nsum = fmaf(a, a, fmaf(b, b, nsum));
+        }
+        if (c0 + wg * 8 < C) {
+            const size_t row = ((size_t)e * HWpad + p0 + wp) * C + c0 + wg * 8;
+            *reinterpret_cast<uint4*>(Xh + row) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(Xl + row) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
         __syncthreads();
     }
     nsum += __shfl_xor_sync(0xffffffffu, nsum, 1);
     nsum += __shfl_xor_sync(0xffffffffu, nsum, 2);
-    if (n2 && wq == 0 && p0 + wp < HW) n2[(size_t)e * HW + p0 + wp] = nsum;
+    nsum += __shfl_xor_sync(0xffffffffu, nsum, 4);
+    if (n2 && wg == 0 && p0 + wp < HW) n2[(size_t)e * HW + p0 + wp] = nsum;
 }
 
 __global__ void __launch_bounds__(256)
@@ -306,7 +314,7 @@ int kproj_scores_tcgen05(const float* k, const float* w_qkvs, const float* Qp, f
     __nv_bfloat16* Al = cv.take<__nv_bfloat16>((size_t)nH * C * C);
     CWT_REQUIRE(ws && cv.ok(), CWT_ERR_WORKSPACE, "kproj_tcgen05: workspace too small");
 
-    k_split_transpose<<<dim3(HWpad / 64, E), 256, 0, st>>>(k, Xh, Xl, n2, C, HW, HWpad);
+    k_split_transpose<<<dim3(HWpad / 32, E), 256, 0, st>>>(k, Xh, Xl, n2, C, HW, HWpad);
     CWT_LAUNCHED("split_transpose");
     const size_t na = (size_t)nH * C * C;
     k_split_weights<<<(unsigned)((na + 255) / 256), 256, 0, st>>>(w_qkvs, Ah, Al, na);

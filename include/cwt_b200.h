@@ -57,6 +57,9 @@ long long   cwt_launch_count(void);
 /* debug: device buffer [grid][8] int64 that receives the resident fit kernel's per-phase cycle
  * counters (P1, X1, HR, P3, X2) on its next launches; NULL switches the instrumented build off */
 void        cwt_debug_set_prof_buffer(void* dev_buffer);
+/* debug: L2 read-bandwidth microbenchmark — `ctas` x 512 threads sweep `bytes` of `buf` `iters` times with
+ * L1-bypassing 128-bit loads (time it with events; bytes * iters / time = bandwidth) */
+int         cwt_debug_l2_read(const void* buf, size_t bytes, int iters, int ctas, void* sink, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * (a-2) label statistics.  Replaces the per-episode D2H copy + numpy `where` of
