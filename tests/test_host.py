@@ -165,3 +165,38 @@ def test_sharded_sweep_all_reduce_world2_gloo():
     for rank, cls, fb, ne, m0, m1 in res:
         assert cls == single.cls.tolist() and fb == single.fb.tolist() and ne == n
         assert m0 == single.miou(0) and m1 == single.miou(1)
+
+
+def test_header_is_plain_c():
+    """include/cwt_b200.h is a C ABI: it must compile as C (no C++/torch types in the signatures)."""
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c",
+                        os.path.join(ROOT, "include", "cwt_b200.h")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: no module of the product package may import it at import time,
+    and the only mention allowed is the sweep tool's opt-in --oracle-sample checker."""
+    import ast
+    pkg = os.path.join(ROOT, "few_shot_seg_cwt_b200")
+    for fn in sorted(os.listdir(pkg)):
+        if not fn.endswith(".py"):
+            continue
+        tree = ast.parse(open(os.path.join(pkg, fn)).read())
+        for node in tree.body:                      # module level only
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""]
+            assert not any(n.split(".")[0] == "oracle" for n in names), f"{fn} imports the oracle at module level"
+    code = "import sys, few_shot_seg_cwt_b200; assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules)"
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.load()
