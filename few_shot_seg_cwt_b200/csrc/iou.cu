@@ -56,26 +56,37 @@ __device__ __forceinline__ void iou_band(const float* __restrict__ lsm, int lrow
                     t1[v][ch] = (a + 1 < h) ? __fmaf_rn(row[b0], w0, __fmul_rn(row[b1], w1)) : t0[v][ch];
                 }
             const int nr = min(8, H - 8 * a);
-#pragma unroll 2
-            for (int r = 0; r < nr; ++r) {
-                const int Y = 8 * a + r;
+            // the 8 label bytes of this column's cell row are requested together (one dependent-load latency, not eight)
+            int codes[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                codes[r] = (r < nr) ? load_label_code<I64>(lab, lbase + (size_t)(8 * a + r) * W + X, ignore_index) : 2;
+            unsigned packed[V];                            // four 8-bit counters [pred*2+code] per variant (<= 8 per cell row)
+#pragma unroll
+            for (int v = 0; v < V; ++v) packed[v] = 0u;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
                 const float h1 = r * 0.125f, h0 = 1.f - h1;
-                const int code = load_label_code<I64>(lab, lbase + (size_t)Y * W + X, ignore_index);
+                const int code = codes[r];
                 const bool valid = code < 2;
                 nvalid += valid;
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
                     const float u0 = __fmaf_rn(t0[v][0], h0, __fmul_rn(t1[v][0], h1));
                     const float u1 = __fmaf_rn(t0[v][1], h0, __fmul_rn(t1[v][1], h1));
-                    const int pred = (u1 > u0) ? 1 : 0;    // torch.argmax: first index wins ties
-                    if (valid) {
-                        cnt[v][pred * 2 + code] += 1;
-                        if ((ce_mask >> v) & 1u) {
-                            const float t = (code == 1) ? (u0 - u1) : (u1 - u0);   // -log softmax(u)[y] = softplus(t)
-                            loss[v] += fmaxf(t, 0.f) + __logf(1.f + __expf(-fabsf(t)));
-                        }
+                    const unsigned sh = (u1 > u0 ? 16u : 0u) + (unsigned)code * 8u;      // torch.argmax: first index wins ties
+                    packed[v] += valid ? (1u << sh) : 0u;
+                    if ((ce_mask >> v) & 1u) {
+                        const float t = (code == 1) ? (u0 - u1) : (u1 - u0);             // -log softmax(u)[y] = softplus(t)
+                        const float sp = fmaxf(t, 0.f) + __logf(1.f + __expf(-fabsf(t)));
+                        loss[v] += valid ? sp : 0.f;
                     }
                 }
+            }
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                cnt[v][0] += packed[v] & 0xffu; cnt[v][1] += (packed[v] >> 8) & 0xffu;
+                cnt[v][2] += (packed[v] >> 16) & 0xffu; cnt[v][3] += packed[v] >> 24;
             }
         }
     }
@@ -172,13 +183,24 @@ static int launch_upsample_iou(const float* l60, const void* lab, int label_kind
 // the 2V logit rows (+ |f_p|^2 for F.normalize) in shared memory; phase 2 is iou_band.
 // ------------------------------------------------------------------------------------------------
 template <bool I64, int V>
-__global__ void __launch_bounds__(IOU_THREADS, 3)
+__global__ void __launch_bounds__(IOU_THREADS, 4)
 k_logits_iou_fused(const float* __restrict__ wts, const float* __restrict__ f_q, const void* __restrict__ lab,
                    int normalize_mask, unsigned ce_mask, unsigned long long* __restrict__ counts, float* __restrict__ logits_out,
-                   double* __restrict__ ce, int C, int h, int w, int H, int W, int ignore_index) {
+                   double* __restrict__ ce, int C, int h, int w, int H, int W, int ignore_index,
+                   int nbands, int n_items, unsigned* __restrict__ work_counter) {
     extern __shared__ __align__(16) float fsm[];
     constexpr int R2 = 2 * V;                          // logit rows
-    const int e = blockIdx.y, a0 = blockIdx.x * IOU_R, tid = threadIdx.x;
+    __shared__ int s_item;
+    const int tid = threadIdx.x;
+  // persistent CTAs pull (band, episode) items from a queue: after the first item the CTAs of an SM are in
+  // different phases, so one CTA's up-sample/count phase overlaps the others' streaming phase
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_item = (int)atomicAdd(work_counter, 1u);
+    __syncthreads();
+    const int item = s_item;
+    if (item >= n_items) break;
+    const int e = item / nbands, a0 = (item - e * nbands) * IOU_R;
     const int nlo = min(IOU_R, h - a0), lrows = min(IOU_R + 1, h - a0);
     const int HW = h * w, npx = lrows * w, nq = (npx + 3) >> 2;          // band pixels, float4 quads (HW % 4 == 0)
     const int ng = IOU_THREADS / nq;                   // channel groups
@@ -259,19 +281,26 @@ k_logits_iou_fused(const float* __restrict__ wts, const float* __restrict__ f_q,
     int nvalid = 0;
     iou_band<I64, V>(lsm, lrows, lab, (size_t)e * H * W, a0, nlo, h, w, H, W, ignore_index, ce ? ce_mask : 0u, cnt, loss, nvalid);
     iou_flush<V>(cnt, loss, nvalid, (size_t)e * V, counts, ce, sred, fred);
+  }
 }
 
 template <bool I64, int V>
 static int launch_fused_t(const float* wts, const float* f_q, const void* lab, int normalize_mask, unsigned ce_mask,
                           unsigned long long* counts, float* logits_out, double* ce, int E, int C, int h, int w, int H, int W,
-                          int ignore_index, cudaStream_t st) {
+                          int ignore_index, unsigned* work_counter, cudaStream_t st) {
     const int npx = (IOU_R + 1) * w;
     const size_t sm = sizeof(float) * ((size_t)C * 2 * V + (size_t)IOU_THREADS * (2 * V + 1) * 4 + (size_t)2 * V * npx);
     CWT_REQUIRE(sm <= 200 * 1024, CWT_ERR_UNSUPPORTED, "logits_iou: C=%d too large for the fused kernel", C);
     auto kern = k_logits_iou_fused<I64, V>;
     if (sm > 48 * 1024) CWT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    dim3 grid((h + IOU_R - 1) / IOU_R, E);
-    kern<<<grid, IOU_THREADS, sm, st>>>(wts, f_q, lab, normalize_mask, ce_mask, counts, logits_out, ce, C, h, w, H, W, ignore_index);
+    const int nbands = (h + IOU_R - 1) / IOU_R, n_items = nbands * E;
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = n_items < n_sm * 4 ? n_items : n_sm * 4;
+    CWT_CUDA(cudaMemsetAsync(work_counter, 0, sizeof(unsigned), st));
+    kern<<<grid, IOU_THREADS, sm, st>>>(wts, f_q, lab, normalize_mask, ce_mask, counts, logits_out, ce, C, h, w, H, W, ignore_index,
+                                        nbands, n_items, work_counter);
     CWT_LAUNCHED("logits_iou_fused");
     return CWT_OK;
 }
@@ -336,10 +365,11 @@ __global__ void k_spread_grad(const float* __restrict__ g60, float* __restrict__
     dl[(e * 2 + 1) * HW + p] = g;
 }
 
-struct LogitsIouWs { float* l60; float* n2; };
+struct LogitsIouWs { float* l60; float* n2; unsigned* work; };
 static size_t carve_logits_iou(Carver& cv, LogitsIouWs& ws, int E, int V, int HW) {
     ws.l60 = cv.take<float>((size_t)E * V * 2 * HW);
     ws.n2 = cv.take<float>((size_t)E * HW);
+    ws.work = cv.take<unsigned>(64);
     return align_up(cv.off);
 }
 
@@ -399,9 +429,9 @@ extern "C" int cwt_logits_iou(const float* wts, const float* f_q, const void* q_
         const bool i64 = label_kind == CWT_LABEL_I64;
 #define CWT_FUSED(VV)                                                                                                       \
         return i64 ? launch_fused_t<true, VV>(wts, f_q, q_label, normalize_mask, ce_mask, cnt, logits60_or_null, ce_or_null, \
-                                              E, C, h, w, H, W, ignore_index, st)                                          \
+                                              E, C, h, w, H, W, ignore_index, ws.work, st)                                 \
                    : launch_fused_t<false, VV>(wts, f_q, q_label, normalize_mask, ce_mask, cnt, logits60_or_null, ce_or_null, \
-                                               E, C, h, w, H, W, ignore_index, st)
+                                               E, C, h, w, H, W, ignore_index, ws.work, st)
         switch (V) {
             case 1: CWT_FUSED(1);
             case 2: CWT_FUSED(2);
