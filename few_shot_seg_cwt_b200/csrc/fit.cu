@@ -20,7 +20,7 @@ namespace cwt {
 
 int pack_label_cells(const void* labels, int label_kind, int n_img, int h, int w, int H, int W, int ignore_index,
                      uint4* cells, int32_t* counts, cudaStream_t st);
-size_t fit_resident_workspace_bytes(int C, int h, int w);
+size_t fit_resident_workspace_bytes(int E, int C, int h, int w);
 int fit_resident(const float* f_s, const uint4* cells, const float2* cw, float* w_io, int E, int C, int h, int w,
                  int n_iter, float lr, void* ws, size_t ws_bytes, long long* prof_out, cudaStream_t st);
 static long long* g_prof_buffer = nullptr;   // debug: per-CTA phase cycle counters of the resident kernel
@@ -66,7 +66,7 @@ static size_t carve_fit(Carver& cv, FitWs& ws, int E, int S, int C, int h, int w
     ws.zd = cv.take<float>((size_t)E * S * h * w);
     ws.g60 = cv.take<float>((size_t)E * S * h * w);
     ws.loss_part = cv.take<float>((size_t)E * S * ws.nblk);
-    ws.resident_bytes = (S == 1) ? fit_resident_workspace_bytes(C, h, w) : 0;
+    ws.resident_bytes = (S == 1) ? fit_resident_workspace_bytes(E, C, h, w) : 0;
     ws.resident = cv.take<char>(ws.resident_bytes);
     return align_up(cv.off);
 }

@@ -12,14 +12,22 @@
 //   P3  dW[c]  = sum_p g[p] F[c][p]           second sweep of the strip, 4 threads per channel
 //   AR  group all-reduce of dW, SGD update of W0 / W1 / Wd
 //
-// All cross-CTA traffic uses SEQUENCE-TAGGED 8-byte words {fp32 value, step number}: 64-bit stores are
+// The halo exchange uses SEQUENCE-TAGGED 8-byte words {fp32 value, step number}: 64-bit stores are
 // single-copy atomic, so a reader simply polls the data word until its tag matches — no fences, no
-// atomics, no barriers, and a stale value can never be consumed. The all-reduce is two such hops,
-// pipelined in RES_KCH channel chunks underneath P3 / P1: every CTA owns a slice of the channels; its
-// REDUCER WARP (warp 16, never computes) collects the CPG partials of the slice, adds them in a fixed
-// order (deterministic), and republishes the sums; the APPLIER WARP (warp 17) picks the sums up, applies
-// the SGD update to W0 / W1 / Wd in shared memory and releases the compute warps chunk by chunk through a
+// barriers, and a stale value can never be consumed.
+//
+// The all-reduce is ONE hop through the L2 atomic units, pipelined in RES_KCH channel chunks underneath
+// P3 / P1: every channel of every episode has one 64-bit accumulator word {fixed-point sum of dW : V bits,
+// arrival count : K bits}. A CTA adds its partial with a single fire-and-forget `red.add.u64` of
+// (fix(d) << K) + 1 — value and arrival land in the same atomic, so no fence is needed, and integer
+// addition makes the sum exact, order-independent and therefore deterministic. The word is cumulative over
+// the steps of the episode (never reset): the APPLIER WARP (warp 16) polls the chunk's words until the count
+// field reads CPG*(t+1), takes the difference to the previous cumulative value (exact), applies the SGD
+// update to W0 / W1 / Wd in shared memory and releases the compute warps chunk by chunk through a
 // shared-memory mbarrier. The compute warps never wait on global memory for the all-reduce.
+// The fixed-point unit is a power of two chosen per episode from max|F| (|dW_c| <= max|F| because the
+// gradient w.r.t. the logits has l1 norm <= 1 under the weighted-mean CE), exchanged once per episode with
+// tagged words; a partial loses nothing unless it is < 2^-26 of that bound.
 //
 // HBM traffic per episode drops from (2T+1) F to F (+ labels); the per-step bound becomes the shared
 // memory sweep (2 x C*NP*4 B at 128 B/clk/SM). floor(#SM / CPG) groups run concurrently
@@ -38,12 +46,13 @@
 namespace cwt {
 
 constexpr int RES_CTHREADS = 512;               // 16 compute warps
-constexpr int RES_THREADS = RES_CTHREADS + 64;  // + the reducer warp (16) and the applier warp (17)
+constexpr int RES_THREADS = RES_CTHREADS + 32;  // + the applier warp (16)
 constexpr unsigned RES_SPIN_LIMIT = 1u << 24;
 constexpr int RES_KCH = 4;        // channel chunks of the pipelined all-reduce
 constexpr int RES_MAXQ = 8;       // float4 pixel-quads per P3 thread (NP <= 128)
-constexpr int RES_RW = 5;         // tagged words a reducer lane keeps in flight per chunk
-constexpr int RES_AW = 4;         // tagged words an applier lane keeps in flight
+constexpr int RES_AW = 4;         // accumulator words an applier lane keeps in flight
+constexpr int RES_ACC_STRIDE = 1; // words between the accumulators of adjacent channels (episodes of a group fill the gaps)
+constexpr int RES_NPROF = 12;     // profile counters per CTA
 constexpr int RES_MAXTASK = 4;    // HR row-tasks per compute thread (8*(NP+w+1) <= 4*512)
 
 struct ResidentParams {
@@ -52,11 +61,12 @@ struct ResidentParams {
     const float2* cw;          // [E]
     float* w;                  // [E][2][C]  in: W0, out: fitted
     unsigned long long* zll;   // [G][2][HW]                            {z, step} words of the halo exchange
-    unsigned long long* inbox; // [G][2][KCH][CPG owner][CPG src][SLS]  {partial dW, step} words (hop 1)
-    unsigned long long* sums;  // [G][2][C]                             {all-reduced dW, step} words (hop 2)
+    unsigned long long* sums;  // [G][SPL][C][RES_ACC_STRIDE]           {fixed-point cumulative dW : 64-K bits, arrivals : K bits};
+                               //   the gaps between channels are filled by consecutive episodes of the same group (never concurrent)
+    unsigned long long* fmaxw; // [G][CPG]                              {max|F| of the strip (bits), episode+1} words
     unsigned* abort_flag;      // [1]
-    long long* prof;           // [grid][8] or null
-    int E, C, HW, h, w_lo, NP, CPG, G, T, SLS;
+    long long* prof;           // [grid][RES_NPROF] or null
+    int E, C, HW, h, w_lo, NP, CPG, G, T, KBITS, SPL;
     float lr;
 };
 
@@ -94,6 +104,17 @@ __device__ __forceinline__ void ld_tagged(const unsigned long long* p, unsigned&
     asm volatile("{\n .reg .b64 t;\n ld.relaxed.gpu.global.u64 t, [%2];\n mov.b64 {%0, %1}, t;\n}"
                  : "=r"(bits), "=r"(seq) : "l"(p) : "memory");
 }
+// fire-and-forget 64-bit add at the L2 atomic unit (SASS: RED.E.ADD.64) / relaxed 64-bit poll load
+__device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v) {
+    // no "memory" clobber: the add depends on registers only, so the compiler may hoist the next chunk's
+    // shared-memory loads above it
+    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v));
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 // poll a tagged word until it carries step number `seq`; returns the payload (0 on abort)
 __device__ __noinline__ float poll_word(const unsigned long long* src, unsigned seq, unsigned* abort_flag) {
     unsigned bits, tag, it = 0;
@@ -125,21 +146,22 @@ __device__ __forceinline__ void hires_row(float left, float right, uint32_t rb, 
 }
 
 struct ResSmem {
-    size_t F, W0, W1, Wd, zfull, g, scratch, mbar, total;
+    size_t F, W0, W1, Wd, zfull, g, scratch, mbar, cum, total;
 };
 static __host__ __device__ inline ResSmem res_smem_layout(int C, int NP, int w_lo) {
     ResSmem s;
     const int NQ = NP / 4, NG = RES_CTHREADS / NQ, NCELL = NP + w_lo + 1;
     size_t o = 0;
-    size_t sz[8];
+    size_t sz[9];
     sz[0] = (size_t)C * NP * 4; sz[1] = sz[2] = sz[3] = (size_t)C * 4;
     sz[4] = (size_t)(NP + 2 * (w_lo + 1)) * 4; sz[5] = (size_t)NP * 4;
     const size_t sc1 = (size_t)NG * NP * 4, sc2 = (size_t)16 * NCELL * 4;
-    sz[6] = sc1 > sc2 ? sc1 : sc2; sz[7] = 8 * (1 + RES_KCH);
-    size_t off[8];
-    for (int i = 0; i < 8; ++i) { off[i] = o; o = (o + sz[i] + 127) / 128 * 128; }
+    sz[6] = sc1 > sc2 ? sc1 : sc2; sz[7] = 8 * (1 + RES_KCH) + 16;   // mbarriers + two words of the max|F| exchange
+    sz[8] = (size_t)C * 8;                                           // previous cumulative dW per channel (applier warp)
+    size_t off[9];
+    for (int i = 0; i < 9; ++i) { off[i] = o; o = (o + sz[i] + 127) / 128 * 128; }
     s.F = off[0]; s.W0 = off[1]; s.W1 = off[2]; s.Wd = off[3]; s.zfull = off[4]; s.g = off[5];
-    s.scratch = off[6]; s.mbar = off[7]; s.total = o;
+    s.scratch = off[6]; s.mbar = off[7]; s.cum = off[8]; s.total = o;
     return s;
 }
 
@@ -151,7 +173,6 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
     const int HW = (TWL && THL) ? TWL * THL : p.HW;
     const int CPG = (TNP && TWL && THL) ? (TWL * THL) / (TNP ? TNP : 1) : p.CPG;
     const int CCH = C / RES_KCH;                     // channels per chunk (C % RES_KCH == 0)
-    const int SLS = (CCH + CPG - 1) / CPG;           // channels of a chunk owned by one CTA
     constexpr bool kStatic = (TC == 512 && TNP == 100);          // PSPNet head geometry: fully unrolled sweeps
     const int NQ = NP / 4, NG = kStatic ? 16 : RES_CTHREADS / NQ, NCELL = NP + wl + 1, HALO = wl + 1;
     const ResSmem L = res_smem_layout(C, NP, wl);
@@ -163,9 +184,11 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
     float* gsm = reinterpret_cast<float*>(smem_raw + L.g);
     float* scratch = reinterpret_cast<float*>(smem_raw + L.scratch);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + L.mbar);
+    unsigned* smax = reinterpret_cast<unsigned*>(mbar + 1 + RES_KCH);   // [0] strip max|F| bits, [1] episode max|F| bits
+    long long* cum = reinterpret_cast<long long*>(smem_raw + L.cum);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool is_reducer = warp == RES_CTHREADS / 32, is_applier = warp == RES_CTHREADS / 32 + 1;
+    const bool is_applier = warp == RES_CTHREADS / 32;
     const int group = blockIdx.x / CPG, k = blockIdx.x - group * CPG;
     const bool p1_active = tid < NQ * NG;
     const int v = tid % NQ, grp = tid / NQ;
@@ -174,9 +197,9 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
 
     // group-private exchange areas (all words are {value, step}; step numbers start at 1)
     unsigned long long* zll = p.zll + (size_t)group * 2 * HW;
-    unsigned long long* inbox = p.inbox + (size_t)group * 2 * RES_KCH * CPG * CPG * SLS;
-    unsigned long long* sums = p.sums + (size_t)group * 2 * C;
-    const unsigned inbox_chunk = (unsigned)(CPG * CPG * SLS);          // words per (parity, chunk)
+    unsigned long long* fmaxw = p.fmaxw + (size_t)group * CPG;
+    const int KB = p.KBITS;                                            // arrival-count bits of an accumulator word
+    const unsigned long long cnt_mask = (1ull << KB) - 1ull;
 
     uint64_t* applied = mbar + 1;                     // [RES_KCH] chunk j of the previous step has been applied to Wd
     if (tid == 0) { mbar_init(mbar, 1); for (int j = 0; j < RES_KCH; ++j) mbar_init(&applied[j], 1); }
@@ -186,11 +209,11 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
     unsigned gstep = 0, tma_parity = 0;
     bool ok = true;
     long long t_acc[6] = {0, 0, 0, 0, 0, 0};
+    long long a_acc[4] = {0, 0, 0, 0};               // PROF, applier lane: poll rounds, cycles polling, sum(done - own store), chunks
+    __shared__ long long tstore_sm[RES_KCH];
 
     // P3 thread mapping: 4 threads per channel (adjacent lanes), interleaved pixel-quads -> conflict-free LDS.128
     const int p3_cl = tid >> 2, p3_part = tid & 3;
-    // where this thread's partial of a chunk goes: owner CTA's inbox row of this CTA, slot of the channel
-    const unsigned p3_inbox_off = (unsigned)(((p3_cl / SLS) * CPG + k) * SLS + (p3_cl % SLS));
 
     // compute warps: chunk j of global step gs has been folded into W0 / W1 / Wd by the applier warp
     long long t_store[RES_KCH] = {0, 0, 0, 0};        // PROF: when chunk j's partials left this CTA
@@ -248,79 +271,90 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
             while (!mbar_try_wait(mbar, tma_parity)) { if (++it > RES_SPIN_LIMIT) { ok = false; break; } }
             tma_parity ^= 1u;
         }
+        if (tid < 2) smax[tid] = 0u;
+        for (int c = tid; c < C; c += RES_THREADS) cum[c] = 0ll;
         __syncthreads();
-
-        if (is_reducer) {
-            // ================= reducer warp: hop 1 (collect + add the CPG partials of the own slice), hop 2 (republish) =================
-            const int n_own = max(0, min(SLS, CCH - k * SLS));       // channels of every chunk owned by this CTA
-            int slp = 1;
-            while (slp < n_own) slp <<= 1;                            // lanes per source-CTA row (power of two)
-            const int sl = lane % slp, kg = lane / slp, nkg = 32 / slp;
-            for (int t = 0; t < p.T; ++t) {
-                const unsigned gs = gstep + (unsigned)t;
-                if (n_own > 0) {
-                    for (int j = 0; j < RES_KCH; ++j) {
-                        const unsigned long long* ib = inbox + ((gs & 1u) * RES_KCH + j) * inbox_chunk + (unsigned)(k * CPG * SLS);
-                        float acc = 0.f;
-                        if (sl < n_own) {
-                            // every load of this lane is issued before any tag is looked at (independent L2 round
-                            // trips); words that are not there yet are re-requested together, again as one batch
-                            unsigned wb[RES_RW], wt[RES_RW];
-                            unsigned pending = 0u, it = 0u;
-#pragma unroll
-                            for (int m = 0; m < RES_RW; ++m) { wb[m] = 0u; if (kg + m * nkg < CPG) pending |= 1u << m; }
-                            while (pending) {
-#pragma unroll
-                                for (int m = 0; m < RES_RW; ++m)
-                                    if (pending & (1u << m)) ld_tagged(&ib[(kg + m * nkg) * SLS + sl], wb[m], wt[m]);
-#pragma unroll
-                                for (int m = 0; m < RES_RW; ++m)
-                                    if ((pending & (1u << m)) && wt[m] == gs + 1u) pending &= ~(1u << m);
-                                if (pending && (++it & 0xffu) == 0u) {
-                                    if (*reinterpret_cast<volatile unsigned*>(p.abort_flag) != 0u) break;
-                                    if (it > (RES_SPIN_LIMIT >> 2)) { atomicExch(p.abort_flag, 1u); break; }
-                                }
-                            }
-#pragma unroll
-                            for (int m = 0; m < RES_RW; ++m) acc += __uint_as_float(wb[m]);       // fixed order: deterministic
-                            for (int kk = kg + RES_RW * nkg; kk < CPG; kk += nkg)                  // (unusual shapes only)
-                                acc += poll_word(&ib[kk * SLS + sl], gs + 1u, p.abort_flag);
-                        }
-                        for (int o = slp; o < 32; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                        if (lane < n_own) st_tagged(&sums[(gs & 1u) * (unsigned)C + j * CCH + k * SLS + lane], acc, gs + 1u);
-                    }
-                }
+        // ---------------- fixed-point unit of the episode: power of two from the group-wide max|F| ----------------
+        {
+            unsigned mb = 0u;
+            const uint4* F4u = reinterpret_cast<const uint4*>(F);
+            for (int i = tid; i < C * NQ; i += RES_THREADS) {
+                const uint4 f = F4u[i];
+                mb = max(max(mb, f.x & 0x7fffffffu), max(max(f.y & 0x7fffffffu, f.z & 0x7fffffffu), f.w & 0x7fffffffu));
             }
-            gstep += (unsigned)p.T;
-        } else if (is_applier) {
-            // ================= applier warp: sums -> SGD update in shared memory -> release the compute warps =================
+            mb = __reduce_max_sync(0xffffffffu, mb);          // |x| as bits: ordered like the values; NaN / Inf sort above every finite
+            if (lane == 0) atomicMax(&smax[0], mb);
+            __syncthreads();
+            if (tid == 0) st_tagged(&fmaxw[k], __uint_as_float(smax[0]), (unsigned)e + 1u);
+            for (int kk = tid; kk < CPG; kk += RES_THREADS)
+                atomicMax(&smax[1], __float_as_uint(poll_word(&fmaxw[kk], (unsigned)e + 1u, p.abort_flag)));
+            __syncthreads();
+        }
+        const unsigned fmax_bits = smax[1];
+        const bool ep_finite = fmax_bits < 0x7f800000u;
+        float fx_unit, fx_inv;
+        {
+            // |dW_c| <= max|F| per step (l1 norm of the logit gradient <= 1), cumulative over T steps, x4 head-room
+            int ex = 0;
+            (void)frexpf(4.f * (float)p.T * (ep_finite ? __uint_as_float(fmax_bits) : 1.f), &ex);
+            ex = min(max(ex, -40), 100);
+            const int vb = 63 - KB;                            // magnitude bits of the value field
+            fx_unit = ldexpf(1.f, ex - vb);
+            fx_inv = ldexpf(1.f, vb - ex);
+        }
+
+        // accumulator words of this episode: channel c at acc_ep[32 c]
+        unsigned long long* acc_ep;
+        {
+            const int slot = e / p.G;                              // e = group + slot * G
+            acc_ep = p.sums + (((size_t)group * p.SPL + slot / RES_ACC_STRIDE) * C) * RES_ACC_STRIDE + slot % RES_ACC_STRIDE;
+        }
+
+        if (is_applier) {
+            // ================= applier warp: accumulator words -> SGD update in shared memory -> release the compute warps =================
+            const unsigned long long* sw_ep = acc_ep;
             for (int t = 0; t < p.T; ++t) {
                 const unsigned gs = gstep + (unsigned)t;
+                const unsigned long long expect = (unsigned long long)CPG * (unsigned)(t + 1);     // arrivals so far on every word
                 for (int j = 0; j < RES_KCH; ++j) {
-                    const unsigned long long* sw = sums + (gs & 1u) * (unsigned)C + j * CCH;
+                    const unsigned long long* sw = sw_ep + (size_t)j * CCH * RES_ACC_STRIDE;
                     for (int c0 = 0; c0 < CCH; c0 += 32 * RES_AW) {
-                        unsigned wb[RES_AW], wt[RES_AW];
+                        // every load of this lane is issued before any count is looked at (independent L2 round
+                        // trips); words that are not complete yet are re-requested together, again as one batch
+                        unsigned long long wv[RES_AW];
                         unsigned pending = 0u, it = 0u;
+                        long long tp0 = 0;
+                        if (PROF) tp0 = clock64();
 #pragma unroll
-                        for (int m = 0; m < RES_AW; ++m) { wb[m] = 0u; if (c0 + m * 32 + lane < CCH) pending |= 1u << m; }
+                        for (int m = 0; m < RES_AW; ++m) { wv[m] = 0ull; if (c0 + m * 32 + lane < CCH) pending |= 1u << m; }
                         while (pending) {
 #pragma unroll
                             for (int m = 0; m < RES_AW; ++m)
-                                if (pending & (1u << m)) ld_tagged(&sw[c0 + m * 32 + lane], wb[m], wt[m]);
+                                if (pending & (1u << m)) wv[m] = ld_relaxed_u64(&sw[(c0 + m * 32 + lane) * RES_ACC_STRIDE]);
 #pragma unroll
                             for (int m = 0; m < RES_AW; ++m)
-                                if ((pending & (1u << m)) && wt[m] == gs + 1u) pending &= ~(1u << m);
+                                if ((pending & (1u << m)) && (wv[m] & cnt_mask) == expect) pending &= ~(1u << m);
                             if (pending && (++it & 0xffu) == 0u) {
                                 if (*reinterpret_cast<volatile unsigned*>(p.abort_flag) != 0u) break;
                                 if (it > (RES_SPIN_LIMIT >> 2)) { atomicExch(p.abort_flag, 1u); break; }
                             }
+                            if (PROF) ++a_acc[0];
+                        }
+                        if (PROF) {
+                            __syncwarp();
+                            const long long n = clock64();
+                            a_acc[1] += n - tp0;
+                            a_acc[2] += n - *reinterpret_cast<volatile long long*>(&tstore_sm[j]);
+                            a_acc[3] += 1;
                         }
 #pragma unroll
                         for (int m = 0; m < RES_AW; ++m) {
                             const int cl = c0 + m * 32 + lane;
                             if (cl < CCH) {
                                 const int c = j * CCH + cl;
-                                const float dw = __uint_as_float(wb[m]);
+                                const long long cur = (long long)wv[m] >> KB;                  // cumulative sum over steps 0..t (exact)
+                                const float dw = __ll2float_rn(cur - cum[c]) * fx_unit;          // this step's all-reduced dW
+                                cum[c] = cur;
                                 const float n0 = fmaf(p.lr, dw, W0[c]), n1 = fmaf(-p.lr, dw, W1[c]);
                                 W0[c] = n0; W1[c] = n1; Wd[c] = n1 - n0;
                             }
@@ -328,6 +362,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&applied[j]);          // release.cta: the Wd stores above are visible to the waiters
+                    (void)gs;
                 }
             }
             gstep += (unsigned)p.T;
@@ -440,7 +475,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
                 }
                 compute_sync();
                 if (PROF && tid == 0) { long long n = clock64(); t_acc[2] += n - tk0; tk0 = n; }
-                // ------------ P3: dW = g . F^T chunk by chunk; every partial goes straight to its owner's inbox ------------
+                // ------------ P3: dW = g . F^T chunk by chunk; every partial goes straight to the channel's accumulator word ------------
                 {
                     // this thread's pixel-quads of g are the same for every channel: keep them in registers
                     float4 gq[RES_MAXQ];
@@ -450,7 +485,6 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
                         gq[2 * i] = (q0 < NQ) ? reinterpret_cast<const float4*>(gsm)[q0] : make_float4(0.f, 0.f, 0.f, 0.f);
                         gq[2 * i + 1] = (q0 + 1 < NQ) ? reinterpret_cast<const float4*>(gsm)[q0 + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
-                    unsigned long long* ibw = inbox + (gstep & 1u) * RES_KCH * inbox_chunk + p3_inbox_off;
 #pragma unroll
                     for (int j = 0; j < RES_KCH; ++j) {
                         for (int cb = 0; cb < CCH; cb += RES_CTHREADS / 4) {
@@ -492,12 +526,10 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
                             float d = d0 + d1;
                             d += __shfl_xor_sync(0xffffffffu, d, 1);
                             d += __shfl_xor_sync(0xffffffffu, d, 2);
-                            if (cl < CCH && p3_part == 0) {
-                                const int off = (cb == 0) ? 0 : (((cl / SLS) * CPG + k) * SLS + (cl % SLS)) - (int)p3_inbox_off;
-                                st_tagged(ibw + (int)(j * inbox_chunk) + off, d, gstep + 1u);
-                            }
+                            if (cl < CCH && p3_part == 0)        // value and arrival in ONE atomic: (fix(d) << K) + 1
+                                red_add_u64(acc_ep + (j * CCH + cl) * RES_ACC_STRIDE, ((unsigned long long)__float2ll_rn(d * fx_inv) << KB) + 1ull);
                         }
-                        if (PROF && tid == 0) t_store[j] = clock64();
+                        if (PROF && tid == 0) { t_store[j] = clock64(); *reinterpret_cast<volatile long long*>(&tstore_sm[j]) = t_store[j]; }
                     }
                 }
                 if (PROF && tid == 0) { long long n = clock64(); t_acc[3] += n - tk0; tk0 = n; }
@@ -512,24 +544,27 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
         }
         __syncthreads();
         if (k == 0) {
-            const bool bad = *reinterpret_cast<volatile unsigned*>(p.abort_flag) != 0u;
+            const bool bad = *reinterpret_cast<volatile unsigned*>(p.abort_flag) != 0u || !ep_finite;   // NaN / Inf features give NaN weights
             for (int c = tid; c < C; c += RES_THREADS) {
                 p.w[((size_t)e * 2) * C + c] = bad ? __int_as_float(0x7fc00000) : W0[c];
                 p.w[((size_t)e * 2 + 1) * C + c] = bad ? __int_as_float(0x7fc00000) : W1[c];
             }
         }
     }
+    if (PROF && tid == RES_CTHREADS && p.prof) {
+        for (int i = 0; i < 4; ++i) p.prof[(size_t)blockIdx.x * RES_NPROF + 6 + i] = a_acc[i];
+    }
     if (PROF && tid == 0 && p.prof) {
-        for (int i = 0; i < 6; ++i) p.prof[(size_t)blockIdx.x * 8 + i] = t_acc[i];
+        for (int i = 0; i < 6; ++i) p.prof[(size_t)blockIdx.x * RES_NPROF + i] = t_acc[i];
     }
     if (tid == 0 && !ok) atomicExch(p.abort_flag, 1u);
 }
 
 // ---- host side ---------------------------------------------------------------------------------
-struct ResidentPlan { int NP, CPG, G; size_t smem; bool ok; int SLS; size_t inbox_words; };
+struct ResidentPlan { int NP, CPG, G; size_t smem; bool ok; };
 
 static ResidentPlan plan_resident(int E, int C, int h, int w, int n_sm, size_t smem_cap) {
-    ResidentPlan best{0, 0, 0, 0, false, 0, 0};
+    ResidentPlan best{0, 0, 0, 0, false};
     const int HW = h * w;
     int forced = 0;
     if (const char* s = getenv("CWT_RESIDENT_NP")) forced = atoi(s);
@@ -548,20 +583,37 @@ static ResidentPlan plan_resident(int E, int C, int h, int w, int n_sm, size_t s
         int G = n_sm / CPG;
         if (G > E) G = E;
         const double score = (double)G / NP + 1e-9 * NP;
-        const int CCH = C / RES_KCH, SLS = (CCH + CPG - 1) / CPG;
-        if (score > best_score) { best_score = score; best = ResidentPlan{NP, CPG, G, sm, true, SLS, (size_t)2 * RES_KCH * CPG * CPG * SLS}; }
+        if (score > best_score) { best_score = score; best = ResidentPlan{NP, CPG, G, sm, true}; }
     }
     return best;
 }
 
-size_t fit_resident_workspace_bytes(int C, int h, int w) {
+static void resident_device_limits(int& n_sm, int& smem_cap) {
+    int dev = 0, a = 0, b = 0;
+    n_sm = 148; smem_cap = 232448;                     // B200 (used when no device is visible: sizing only)
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&a, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&b, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess && a > 0 && b > 0) {
+        n_sm = a > 148 ? 148 : a; smem_cap = b;
+    } else {
+        (void)cudaGetLastError();
+    }
+}
+
+static size_t resident_sum_words(const ResidentPlan& pl, int E, int C) {
+    const int nslots = (E + pl.G - 1) / pl.G, spl = (nslots + RES_ACC_STRIDE - 1) / RES_ACC_STRIDE;
+    return (size_t)pl.G * spl * C * RES_ACC_STRIDE;
+}
+
+size_t fit_resident_workspace_bytes(int E, int C, int h, int w) {
     const int HW = h * w;
-    const int maxG = 148;
-    // zll: 2*HW words per group; inbox: 2*KCH*CPG*CPG*SLS words per group (CPG*SLS < C/KCH + CPG, G*CPG <= 148);
-    // sums: 2*C words per group; abort flag; profile counters
-    const size_t inbox_words_all = (size_t)2 * RES_KCH * 148 * ((size_t)C / RES_KCH + 148);
-    return align_up(sizeof(unsigned long long) * 2 * HW * maxG) + align_up(sizeof(unsigned long long) * inbox_words_all) +
-           align_up(sizeof(unsigned long long) * 2 * (size_t)C * maxG) + 512 + align_up(sizeof(long long) * 8 * 160);
+    int n_sm, smem_cap;
+    resident_device_limits(n_sm, smem_cap);
+    const ResidentPlan pl = plan_resident(E, C, h, w, n_sm, (size_t)smem_cap);
+    if (!pl.ok) return 0;
+    // zll: 2*HW words per group; sums: C * RES_ACC_STRIDE words per RES_ACC_STRIDE episodes of a group; fmaxw: one word per CTA;
+    // abort flag; profile counters
+    return align_up(sizeof(unsigned long long) * 2 * HW * pl.G) + align_up(sizeof(unsigned long long) * resident_sum_words(pl, E, C)) +
+           align_up(sizeof(unsigned long long) * 160) + 512 + align_up(sizeof(long long) * RES_NPROF * 160);
 }
 
 template <int TC, int TNP, int TWL, int THL>
@@ -580,33 +632,36 @@ int fit_resident(const float* f_s, const uint4* cells, const float2* cw, float* 
                  int n_iter, float lr, void* ws, size_t ws_bytes, long long* prof_out, cudaStream_t st) {
     int dev = 0, n_sm = 0, smem_cap = 0, coop = 0;
     CWT_CUDA(cudaGetDevice(&dev));
-    CWT_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    CWT_CUDA(cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    resident_device_limits(n_sm, smem_cap);
     CWT_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
     CWT_REQUIRE(coop, CWT_ERR_UNSUPPORTED, "fit_resident: device lacks cooperative launch");
     CWT_REQUIRE(C <= RES_CTHREADS * RES_KCH, CWT_ERR_UNSUPPORTED, "fit_resident: C=%d too large", C);
-    if (n_sm > 148) n_sm = 148;
     const ResidentPlan pl = plan_resident(E, C, h, w, n_sm, (size_t)smem_cap);
     CWT_REQUIRE(pl.ok, CWT_ERR_UNSUPPORTED, "fit_resident: no strip size fits C=%d, %dx%d in %d B of shared memory", C, h, w, smem_cap);
     const int HW = h * w;
     Carver cv(ws, ws_bytes);
     ResidentParams p{};
     p.zll = cv.take<unsigned long long>((size_t)2 * HW * pl.G);
-    p.inbox = cv.take<unsigned long long>(pl.inbox_words * pl.G);
-    p.sums = cv.take<unsigned long long>((size_t)2 * C * pl.G);
+    p.sums = cv.take<unsigned long long>(resident_sum_words(pl, E, C));
+    p.SPL = ((E + pl.G - 1) / pl.G + RES_ACC_STRIDE - 1) / RES_ACC_STRIDE;
+    p.fmaxw = cv.take<unsigned long long>(160);
     p.abort_flag = cv.take<unsigned>(64);
-    p.prof = prof_out ? cv.take<long long>((size_t)8 * pl.G * pl.CPG) : nullptr;
+    p.prof = prof_out ? cv.take<long long>((size_t)RES_NPROF * pl.G * pl.CPG) : nullptr;
     CWT_REQUIRE(ws && cv.ok(), CWT_ERR_WORKSPACE, "fit_resident: workspace too small");
-    // every tagged word and the abort flag start at zero (step numbers start at 1)
+    // every tagged word, every accumulator and the abort flag start at zero (step / episode tags start at 1)
     const size_t sync_bytes = (size_t)(reinterpret_cast<char*>(p.abort_flag + 64) - reinterpret_cast<char*>(p.zll));
     CWT_CUDA(cudaMemsetAsync(p.zll, 0, sync_bytes, st));
     p.f_s = f_s; p.cells = cells; p.cw = cw; p.w = w_io;
-    p.E = E; p.C = C; p.HW = HW; p.h = h; p.w_lo = w; p.NP = pl.NP; p.CPG = pl.CPG; p.G = pl.G; p.T = n_iter; p.lr = lr; p.SLS = pl.SLS;
+    p.E = E; p.C = C; p.HW = HW; p.h = h; p.w_lo = w; p.NP = pl.NP; p.CPG = pl.CPG; p.G = pl.G; p.T = n_iter; p.lr = lr;
+    // arrival-count field: CPG * n_iter arrivals per accumulator word over an episode
+    p.KBITS = 1;
+    while ((1ll << p.KBITS) <= (long long)pl.CPG * n_iter) ++p.KBITS;
+    CWT_REQUIRE(p.KBITS <= 24, CWT_ERR_UNSUPPORTED, "fit_resident: n_iter=%d too large for the on-chip all-reduce", n_iter);
     int rc;
     if (C == 512 && h == 60 && w == 60 && pl.NP == 100) rc = launch_resident<512, 100, 60, 60>(p, pl, prof_out != nullptr, st);
     else rc = launch_resident<0, 0, 0, 0>(p, pl, prof_out != nullptr, st);
     if (rc != CWT_OK) return rc;
-    if (prof_out) CWT_CUDA(cudaMemcpyAsync(prof_out, p.prof, sizeof(long long) * 8 * pl.G * pl.CPG, cudaMemcpyDeviceToDevice, st));
+    if (prof_out) CWT_CUDA(cudaMemcpyAsync(prof_out, p.prof, sizeof(long long) * RES_NPROF * pl.G * pl.CPG, cudaMemcpyDeviceToDevice, st));
     return CWT_OK;
 }
 

@@ -30,7 +30,7 @@ wr, tr = run(L.FIT_RESIDENT); wr, tr = run(L.FIT_RESIDENT)
 err = float((wr - ws).norm() / ws.norm())
 print(f"E={E} iters={a.iters}: stream {ts:.2f} ms ({E/ts*1e3:.0f} ep/s)  resident {tr:.2f} ms ({E/tr*1e3:.0f} ep/s)  rel diff {err:.2e} finite={bool(torch.isfinite(wr).all())}")
 if a.prof:
-    buf = torch.zeros(160, 8, dtype=torch.int64, device=dev)
+    buf = torch.zeros(160, 12, dtype=torch.int64, device=dev)
     lib.cwt_debug_set_prof_buffer(ctypes.c_void_p(buf.data_ptr()))
     wr, tp = run(L.FIT_RESIDENT)
     lib.cwt_debug_set_prof_buffer(None)
@@ -43,4 +43,6 @@ if a.prof:
         col = c[used, i] / n_steps
         print(f"  {n}: mean {col.mean():8.0f}  min {col.min():8.0f}  max {col.max():8.0f}")
     print(f"  total/step {c[used, :4].sum(1).mean() / n_steps:8.0f} cycles")
+    print(f"  applier lane 0: {c[used,6].sum()/c[used,9].sum():.2f} poll rounds per chunk, {c[used,7].sum()/c[used,9].sum():.0f} cycles polling per chunk "
+          f"({c[used,7].sum()/c[used,6].sum():.0f} per round), own store -> chunk complete {c[used,8].sum()/c[used,9].sum():.0f} cycles")
     print(f"  all-reduce latency seen by waiting compute warps: {(c[used,5].sum()/c[used,4].sum()):.0f} cycles (waited on {c[used,4].mean()/n_steps:.2f} chunks/step)")
