@@ -2,14 +2,17 @@
 //
 // The streaming fit re-reads the [C, h*w] feature map from HBM twice per SGD step ((2T+1) F bytes per
 // episode). Here one episode is spread over a GROUP of CPG = h*w / NP co-resident CTAs (one per SM);
-// CTA k stages its strip of NP consecutive low-res pixels x all C channels (C*NP*4 B, 204.8 KB for
-// 512 x 100) into shared memory ONCE with bulk-TMA copies (cp.async.bulk + mbarrier complete_tx) and
-// then runs every step out of shared memory:
+// CTA k stages a rectangular TILE of TW x TH low-res pixels x all C channels (C*NP*4 B, 204.8 KB for
+// 512 x (20 x 5)) into shared memory ONCE with bulk-TMA copies (cp.async.bulk + mbarrier complete_tx)
+// and then runs every step out of shared memory:
 //
-//   P1  z[p]   = sum_c Wd[c] F[c][p]          linear conflict-free sweep of the strip, own NP pixels
-//   X1  halo exchange of z with strips k-1 / k+1 (w+1 pixels each side)
-//   HR  full-resolution stage on the NP + w + 1 cells that touch the strip (one task = one cell row)
-//   P3  dW[c]  = sum_p g[p] F[c][p]           second sweep of the strip, 4 threads per channel
+//   P1  z[p]   = sum_c Wd[c] F[c][p]          linear conflict-free sweep of the tile, own NP pixels
+//   X1  halo exchange of z: the ring of pixels around the tile (2 TW + 2 TH + 4 values), fetched by the
+//       HALO WARP while the compute warps already work on the interior cells
+//   HR  full-resolution stage on the (TW+1) x (TH+1) cells that touch the tile (one task = one row of a
+//       cell; 126 cells = 1008 tasks = two full rounds of the 512 compute threads for 20 x 5)
+//   P3  dW[c]  = sum_p g[p] F[c][p]           second sweep, 4 threads per channel with their pixel-quads of g
+//       in registers
 //   AR  group all-reduce of dW, SGD update of W0 / W1 / Wd
 //
 // The halo exchange uses SEQUENCE-TAGGED 8-byte words {fp32 value, step number}: 64-bit stores are
@@ -24,7 +27,7 @@
 // the steps of the episode (never reset): the APPLIER WARP (warp 16) polls the chunk's words until the count
 // field reads CPG*(t+1), takes the difference to the previous cumulative value (exact), applies the SGD
 // update to W0 / W1 / Wd in shared memory and releases the compute warps chunk by chunk through a
-// shared-memory mbarrier. The compute warps never wait on global memory for the all-reduce.
+// shared-memory mbarrier. The compute warps never wait on global memory.
 // The fixed-point unit is a power of two chosen per episode from max|F| (|dW_c| <= max|F| because the
 // gradient w.r.t. the logits has l1 norm <= 1 under the weighted-mean CE), exchanged once per episode with
 // tagged words; a partial loses nothing unless it is < 2^-26 of that bound.
@@ -33,7 +36,7 @@
 // memory sweep (2 x C*NP*4 B at 128 B/clk/SM). floor(#SM / CPG) groups run concurrently
 // (4 x 36 = 144 of 148 SMs for 60x60x512), each looping over its share of the batch.
 //
-// The kernel is compiled twice: specialised for the PSPNet head geometry (C=512, 60x60, NP=100: all
+// The kernel is compiled twice: specialised for the PSPNet head geometry (C=512, 60x60, tile 20x5: all
 // loop bounds, divisions and predicates become compile-time) and generic (run-time shapes).
 //
 // Launch: cooperative (all CTAs must be co-resident: they poll each other's words). Every poll loop
@@ -41,19 +44,20 @@
 // rather than hanging the GPU.
 #include "common.cuh"
 #include "hires.cuh"
+#include <cstdio>
 #include <cstdlib>
 
 namespace cwt {
 
 constexpr int RES_CTHREADS = 512;               // 16 compute warps
-constexpr int RES_THREADS = RES_CTHREADS + 32;  // + the applier warp (16)
+constexpr int RES_THREADS = RES_CTHREADS + 64;  // + the applier warp (16) and the halo warp (17)
 constexpr unsigned RES_SPIN_LIMIT = 1u << 24;
 constexpr int RES_KCH = 4;        // channel chunks of the pipelined all-reduce
-constexpr int RES_MAXQ = 8;       // float4 pixel-quads per P3 thread (NP <= 128)
 constexpr int RES_AW = 4;         // accumulator words an applier lane keeps in flight
+constexpr int RES_HWORDS = 4;     // halo words per lane of the halo warp (ring <= 128 pixels)
+constexpr int RES_MAXTASK = 4;    // HR row-tasks per compute thread (8 * cells <= 4 * 512)
 constexpr int RES_ACC_STRIDE = 1; // words between the accumulators of adjacent channels (episodes of a group fill the gaps)
 constexpr int RES_NPROF = 12;     // profile counters per CTA
-constexpr int RES_MAXTASK = 4;    // HR row-tasks per compute thread (8*(NP+w+1) <= 4*512)
 
 struct ResidentParams {
     const float* f_s;          // [E][C][HW]
@@ -63,10 +67,10 @@ struct ResidentParams {
     unsigned long long* zll;   // [G][2][HW]                            {z, step} words of the halo exchange
     unsigned long long* sums;  // [G][SPL][C][RES_ACC_STRIDE]           {fixed-point cumulative dW : 64-K bits, arrivals : K bits};
                                //   the gaps between channels are filled by consecutive episodes of the same group (never concurrent)
-    unsigned long long* fmaxw; // [G][CPG]                              {max|F| of the strip (bits), episode+1} words
+    unsigned long long* fmaxw; // [G][CPG]                              {max|F| of the tile (bits), episode+1} words
     unsigned* abort_flag;      // [1]
     long long* prof;           // [grid][RES_NPROF] or null
-    int E, C, HW, h, w_lo, NP, CPG, G, T, KBITS, SPL;
+    int E, C, HW, h, w_lo, TW, TH, CPG, G, T, KBITS, SPL;
     float lr;
 };
 
@@ -104,15 +108,20 @@ __device__ __forceinline__ void ld_tagged(const unsigned long long* p, unsigned&
     asm volatile("{\n .reg .b64 t;\n ld.relaxed.gpu.global.u64 t, [%2];\n mov.b64 {%0, %1}, t;\n}"
                  : "=r"(bits), "=r"(seq) : "l"(p) : "memory");
 }
-// fire-and-forget 64-bit add at the L2 atomic unit (SASS: RED.E.ADD.64) / relaxed 64-bit poll load
+// fire-and-forget 64-bit add at the L2 atomic unit (SASS: REDG.E.ADD.64) / relaxed 64-bit poll load
 __device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v) {
-    // no "memory" clobber: the add depends on registers only, so the compiler may hoist the next chunk's
-    // shared-memory loads above it
+    // no "memory" clobber: the add depends on registers only
     asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v));
 }
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
     unsigned long long v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// 128-bit shared-memory load that the compiler may neither reorder against other volatile asm nor merge
+__device__ __forceinline__ float4 lds128_v(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
     return v;
 }
 // poll a tagged word until it carries step number `seq`; returns the payload (0 on abort)
@@ -145,179 +154,407 @@ __device__ __forceinline__ void hires_row(float left, float right, uint32_t rb, 
     gr_out = gr;
 }
 
+// fixed-point unit of an episode: |dW_c| <= max|F| per step (l1 norm of the logit gradient <= 1), cumulative over T
+// steps, x4 head-room, rounded up to a power of two; vb = magnitude bits of the value field
+__device__ __forceinline__ void fixed_point_unit(unsigned fmax_bits, int T, int KB, float& unit, float& inv) {
+    int ex = 0;
+    (void)frexpf(4.f * (float)T * (fmax_bits < 0x7f800000u ? __uint_as_float(fmax_bits) : 1.f), &ex);
+    ex = min(max(ex, -40), 100);
+    const int vb = 63 - KB;
+    unit = ldexpf(1.f, ex - vb);
+    inv = ldexpf(1.f, vb - ex);
+}
+// accumulator words of episode e (= group + slot * G): channel c at sums[acc_offset + RES_ACC_STRIDE * c]
+__device__ __forceinline__ size_t acc_offset(int e, int group, int G, int SPL, int C) {
+    const int slot = e / G;
+    return (((size_t)group * SPL + slot / RES_ACC_STRIDE) * C) * RES_ACC_STRIDE + slot % RES_ACC_STRIDE;
+}
+
 struct ResSmem {
-    size_t F, W0, W1, Wd, zfull, g, scratch, mbar, cum, total;
+    size_t F, W0, W1, Wd, zt, g, scratch, mbar, cum, total;
 };
-static __host__ __device__ inline ResSmem res_smem_layout(int C, int NP, int w_lo) {
+static __host__ __device__ inline ResSmem res_smem_layout(int C, int TW, int TH) {
     ResSmem s;
-    const int NQ = NP / 4, NG = RES_CTHREADS / NQ, NCELL = NP + w_lo + 1;
+    const int NP = TW * TH, NQ = NP / 4, NG = RES_CTHREADS / NQ, NCELL = (TW + 1) * (TH + 1);
     size_t o = 0;
     size_t sz[9];
     sz[0] = (size_t)C * NP * 4; sz[1] = sz[2] = sz[3] = (size_t)C * 4;
-    sz[4] = (size_t)(NP + 2 * (w_lo + 1)) * 4; sz[5] = (size_t)NP * 4;
+    sz[4] = (size_t)(TW + 2) * (TH + 2) * 4; sz[5] = (size_t)NP * 4;
     const size_t sc1 = (size_t)NG * NP * 4, sc2 = (size_t)16 * NCELL * 4;
-    sz[6] = sc1 > sc2 ? sc1 : sc2; sz[7] = 8 * (1 + RES_KCH) + 16;   // mbarriers + two words of the max|F| exchange
+    sz[6] = sc1 > sc2 ? sc1 : sc2;
+    sz[7] = 8 * (2 + RES_KCH) + 16;                                  // mbarriers + two words of the max|F| exchange
     sz[8] = (size_t)C * 8;                                           // previous cumulative dW per channel (applier warp)
     size_t off[9];
     for (int i = 0; i < 9; ++i) { off[i] = o; o = (o + sz[i] + 127) / 128 * 128; }
-    s.F = off[0]; s.W0 = off[1]; s.W1 = off[2]; s.Wd = off[3]; s.zfull = off[4]; s.g = off[5];
+    s.F = off[0]; s.W0 = off[1]; s.W1 = off[2]; s.Wd = off[3]; s.zt = off[4]; s.g = off[5];
     s.scratch = off[6]; s.mbar = off[7]; s.cum = off[8]; s.total = o;
     return s;
 }
 
-// TC/TNP/TWL/THL > 0: compile-time shape (C, strip pixels, low-res width / height); 0: run-time shape.
-template <int TC, int TNP, int TWL, int THL, bool PROF>
+// TC / TTW / TTH / TWL / THL > 0: compile-time shape (C, tile width / height, low-res width / height); 0: run-time shape.
+template <int TC, int TTW, int TTH, int TWL, int THL, bool PROF>
 __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int C = TC ? TC : p.C, NP = TNP ? TNP : p.NP, wl = TWL ? TWL : p.w_lo, h = THL ? THL : p.h;
-    const int HW = (TWL && THL) ? TWL * THL : p.HW;
-    const int CPG = (TNP && TWL && THL) ? (TWL * THL) / (TNP ? TNP : 1) : p.CPG;
+    const int C = TC ? TC : p.C, TW = TTW ? TTW : p.TW, TH = TTH ? TTH : p.TH, wl = TWL ? TWL : p.w_lo, h = THL ? THL : p.h;
+    const int NP = TW * TH, HW = wl * h, TPR = wl / TW, CPG = HW / NP;
     const int CCH = C / RES_KCH;                     // channels per chunk (C % RES_KCH == 0)
-    constexpr bool kStatic = (TC == 512 && TNP == 100);          // PSPNet head geometry: fully unrolled sweeps
-    const int NQ = NP / 4, NG = kStatic ? 16 : RES_CTHREADS / NQ, NCELL = NP + wl + 1, HALO = wl + 1;
-    const ResSmem L = res_smem_layout(C, NP, wl);
+    constexpr bool kStatic = (TC == 512 && TTW * TTH == 100);    // PSPNet head geometry: fully unrolled sweeps
+    const int NQ = NP / 4, NG = kStatic ? 16 : RES_CTHREADS / NQ;
+    const int ZW = TW + 2, ZH = TH + 2, CW = TW + 1, NCELL = CW * (TH + 1);
+    const int NINT = (TW - 1) * (TH - 1);            // cells whose four corners are own pixels: need no halo
+    const bool round0_interior = 8 * NINT >= RES_CTHREADS;       // HR round 0 can run before the halo has arrived
+    const int NRING = 2 * ZW + 2 * (ZH - 2);         // halo pixels around the tile
+    const ResSmem L = res_smem_layout(C, TW, TH);
     float* F = reinterpret_cast<float*>(smem_raw + L.F);
     float* W0 = reinterpret_cast<float*>(smem_raw + L.W0);
     float* W1 = reinterpret_cast<float*>(smem_raw + L.W1);
     float* Wd = reinterpret_cast<float*>(smem_raw + L.Wd);
-    float* zfull = reinterpret_cast<float*>(smem_raw + L.zfull);
+    float* zt = reinterpret_cast<float*>(smem_raw + L.zt);       // [ZH][ZW]: the tile's z plus the ring around it
     float* gsm = reinterpret_cast<float*>(smem_raw + L.g);
     float* scratch = reinterpret_cast<float*>(smem_raw + L.scratch);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + L.mbar);
-    unsigned* smax = reinterpret_cast<unsigned*>(mbar + 1 + RES_KCH);   // [0] strip max|F| bits, [1] episode max|F| bits
+    uint64_t* applied = mbar + 1;                     // [RES_KCH] chunk j of the previous step has been applied to Wd
+    uint64_t* halo_ready = mbar + 1 + RES_KCH;        // the ring of this step is in zt
+    unsigned* smax = reinterpret_cast<unsigned*>(mbar + 2 + RES_KCH);   // [0] tile max|F| bits, [1] episode max|F| bits
     long long* cum = reinterpret_cast<long long*>(smem_raw + L.cum);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool is_applier = warp == RES_CTHREADS / 32;
     const int group = blockIdx.x / CPG, k = blockIdx.x - group * CPG;
-    const bool p1_active = tid < NQ * NG;
-    const int v = tid % NQ, grp = tid / NQ;
-    const int strip0 = k * NP;                       // first own pixel
-    const int cell0 = strip0 - HALO;                 // pixel / cell index of zfull[0] / cell 0
+    const int ty = k / TPR, tx = k - ty * TPR, y0 = ty * TH, x0 = tx * TW;     // tile origin in the low-res map
 
-    // group-private exchange areas (all words are {value, step}; step numbers start at 1)
+    // group-private exchange areas (halo words are {value, step}; step numbers start at 1)
     unsigned long long* zll = p.zll + (size_t)group * 2 * HW;
     unsigned long long* fmaxw = p.fmaxw + (size_t)group * CPG;
     const int KB = p.KBITS;                                            // arrival-count bits of an accumulator word
-    const unsigned long long cnt_mask = (1ull << KB) - 1ull;
 
-    uint64_t* applied = mbar + 1;                     // [RES_KCH] chunk j of the previous step has been applied to Wd
-    if (tid == 0) { mbar_init(mbar, 1); for (int j = 0; j < RES_KCH; ++j) mbar_init(&applied[j], 1); }
+    if (tid == 0) {
+        mbar_init(mbar, 1);
+        for (int j = 0; j < RES_KCH; ++j) mbar_init(&applied[j], 1);
+        mbar_init(halo_ready, 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
-    unsigned gstep = 0, tma_parity = 0;
-    bool ok = true;
-    long long t_acc[6] = {0, 0, 0, 0, 0, 0};
-    long long a_acc[4] = {0, 0, 0, 0};               // PROF, applier lane: poll rounds, cycles polling, sum(done - own store), chunks
-    __shared__ long long tstore_sm[RES_KCH];
+    __shared__ long long tstore_sm[RES_KCH];          // PROF: when chunk j's partials left this CTA
 
-    // P3 thread mapping: 4 threads per channel (adjacent lanes), interleaved pixel-quads -> conflict-free LDS.128
-    const int p3_cl = tid >> 2, p3_part = tid & 3;
+    // Every role has its own episode loop (so that the state of one role never occupies registers of another); all of
+    // them execute the same five CTA-wide barriers per episode: S1 previous episode done, S2 tile staged, S3 tile max
+    // known, S4 episode max known, S5 steps done.
+    if (warp < RES_CTHREADS / 32) {
+        // =====================================================================================================
+        // compute warps
+        // =====================================================================================================
+        unsigned gstep = 0, tma_parity = 0;
+        bool ok = true;
+        long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const bool p1_active = tid < NQ * NG;
+        const int v = tid % NQ, grp = tid / NQ;
 
-    // compute warps: chunk j of global step gs has been folded into W0 / W1 / Wd by the applier warp
-    long long t_store[RES_KCH] = {0, 0, 0, 0};        // PROF: when chunk j's partials left this CTA
-    auto wait_applied = [&](int j, unsigned gs) {
-        unsigned it = 0;
-        if (PROF && tid == 0 && !mbar_try_wait(&applied[j], gs & 1u)) {      // had to wait: latency = now - store time
-            while (!mbar_try_wait(&applied[j], gs & 1u)) { if (++it > RES_SPIN_LIMIT) break; }
-            t_acc[5] += clock64() - t_store[j];
-            t_acc[4] += 1;
-            return;
-        }
-        while (!mbar_try_wait(&applied[j], gs & 1u)) {
-            if ((++it & 0xfffu) == 0u) {
-                if (*reinterpret_cast<volatile unsigned*>(p.abort_flag) != 0u) break;
-                if (it > RES_SPIN_LIMIT) { atomicExch(p.abort_flag, 1u); break; }
+        // chunk j of global step gs has been folded into W0 / W1 / Wd by the applier warp
+        auto wait_applied = [&](int j, unsigned gs) {
+            unsigned it = 0;
+            if (PROF && tid == 0 && !mbar_try_wait(&applied[j], gs & 1u)) {      // had to wait: latency = now - store time
+                while (!mbar_try_wait(&applied[j], gs & 1u)) { if (++it > RES_SPIN_LIMIT) break; }
+                t_acc[5] += clock64() - *reinterpret_cast<volatile long long*>(&tstore_sm[j]);
+                t_acc[4] += 1;
+                return;
             }
-        }
-    };
-
-    for (int e = group; e < p.E; e += p.G) {
-        // ---------------- stage the episode: strip of F via bulk-TMA, weights, HR task descriptors ----------------
-        __syncthreads();                                           // previous episode is done with shared memory
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads before async-proxy writes
-        if (tid == 0) mbar_expect_tx(mbar, (unsigned)(C * NP * 4));
-        const float* fsrc = p.f_s + (size_t)e * C * HW + strip0;
-        for (int c = tid; c < C; c += RES_THREADS) bulk_g2s(F + (size_t)c * NP, fsrc + (size_t)c * HW, (unsigned)(NP * 4), mbar);
-        for (int c = tid; c < C; c += RES_THREADS) {
-            const float a = p.w[((size_t)e * 2) * C + c], b = p.w[((size_t)e * 2 + 1) * C + c];
-            W0[c] = a; W1[c] = b; Wd[c] = b - a;
-        }
-        // HR task descriptors (static for the episode): task = (cell ci, row r); 8 adjacent lanes = one cell.
-        // desc = row label bits | dx << 16 | dy_flag << 17 | live << 18
-        unsigned hr_desc[RES_MAXTASK];
-#pragma unroll
-        for (int m = 0; m < RES_MAXTASK; ++m) {
-            const int task = m * RES_CTHREADS + tid;
-            const int ci = task >> 3, r = task & 7;
-            unsigned d = 0u;
-            if (tid < RES_CTHREADS && ci < NCELL) {
-                const int q = cell0 + ci;
-                if (q >= 0) {
-                    const uint4 bits = p.cells[(size_t)e * HW + q];
-                    const uint32_t wsel = (r < 4) ? ((r < 2) ? bits.x : bits.y) : ((r < 6) ? bits.z : bits.w);
-                    const uint32_t rb = (wsel >> ((r & 1) * 16)) & 0xffffu;
-                    const int a = q / wl, b = q - a * wl;
-                    if (rb != 0xAAAAu)                              // rows with only ignored pixels send nothing
-                        d = rb | ((b + 1 < wl) ? (1u << 16) : 0u) | ((a + 1 < h) ? (1u << 17) : 0u) | (1u << 18);
+            while (!mbar_try_wait(&applied[j], gs & 1u)) {
+                if ((++it & 0xfffu) == 0u) {
+                    if (*reinterpret_cast<volatile unsigned*>(p.abort_flag) != 0u) break;
+                    if (it > RES_SPIN_LIMIT) { atomicExch(p.abort_flag, 1u); break; }
                 }
             }
-            hr_desc[m] = d;
-        }
-        const float2 c01 = p.cw[e];
-        {
-            unsigned it = 0;
-            while (!mbar_try_wait(mbar, tma_parity)) { if (++it > RES_SPIN_LIMIT) { ok = false; break; } }
-            tma_parity ^= 1u;
-        }
-        if (tid < 2) smax[tid] = 0u;
-        for (int c = tid; c < C; c += RES_THREADS) cum[c] = 0ll;
-        __syncthreads();
-        // ---------------- fixed-point unit of the episode: power of two from the group-wide max|F| ----------------
-        {
-            unsigned mb = 0u;
-            const uint4* F4u = reinterpret_cast<const uint4*>(F);
-            for (int i = tid; i < C * NQ; i += RES_THREADS) {
-                const uint4 f = F4u[i];
-                mb = max(max(mb, f.x & 0x7fffffffu), max(max(f.y & 0x7fffffffu, f.z & 0x7fffffffu), f.w & 0x7fffffffu));
+        };
+
+        for (int e = group; e < p.E; e += p.G) {
+            // ---------------- stage the episode: tile of F via bulk-TMA, weights, HR task descriptors ----------------
+            __syncthreads();                                           // S1: previous episode is done with shared memory
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads before async-proxy writes
+            if (tid == 0) mbar_expect_tx(mbar, (unsigned)(C * NP * 4));
+            const float* fsrc = p.f_s + (size_t)e * C * HW + (size_t)y0 * wl + x0;
+            for (int i = tid; i < C * TH; i += RES_CTHREADS) {         // one copy per (channel, tile row): TW * 4 bytes
+                const int c = i / TH, py = i - c * TH;
+                bulk_g2s(F + (size_t)c * NP + py * TW, fsrc + (size_t)c * HW + (size_t)py * wl, (unsigned)(TW * 4), mbar);
             }
-            mb = __reduce_max_sync(0xffffffffu, mb);          // |x| as bits: ordered like the values; NaN / Inf sort above every finite
-            if (lane == 0) atomicMax(&smax[0], mb);
-            __syncthreads();
+            for (int c = tid; c < C; c += RES_CTHREADS) {
+                const float a = p.w[((size_t)e * 2) * C + c], b = p.w[((size_t)e * 2 + 1) * C + c];
+                W0[c] = a; W1[c] = b; Wd[c] = b - a;
+            }
+            if (tid < 2) smax[tid] = 0u;
+            // HR task descriptors (static for the episode): task = (cell, row r); 8 adjacent lanes = one cell. Interior cells
+            // come first so that the first round needs no halo.
+            // desc = row label bits | dx << 16 | dy_flag << 17 | live << 18 | cell << 19 | cell_row << 27 | valid << 31
+            unsigned hr_desc[RES_MAXTASK];
+#pragma unroll
+            for (int m = 0; m < RES_MAXTASK; ++m) {
+                const int task = m * RES_CTHREADS + tid;
+                const int o = task >> 3, r = task & 7;
+                unsigned d = 0u;
+                if (o < NCELL) {
+                    int cy, cx;
+                    if (o < NINT) { cy = 1 + o / (TW - 1); cx = 1 + o % (TW - 1); }
+                    else {
+                        const int bo = o - NINT;
+                        if (bo < CW) { cy = 0; cx = bo; }
+                        else if (bo < 2 * CW) { cy = TH; cx = bo - CW; }
+                        else if (bo < 2 * CW + TH - 1) { cy = 1 + (bo - 2 * CW); cx = 0; }
+                        else { cy = 1 + (bo - 2 * CW - (TH - 1)); cx = TW; }
+                    }
+                    d = (1u << 31) | ((unsigned)(cy * CW + cx) << 19) | ((unsigned)cy << 27);
+                    const int a = y0 - 1 + cy, b = x0 - 1 + cx;
+                    if (a >= 0 && b >= 0) {
+                        const uint4 bits = p.cells[(size_t)e * HW + a * wl + b];
+                        const uint32_t wsel = (r < 4) ? ((r < 2) ? bits.x : bits.y) : ((r < 6) ? bits.z : bits.w);
+                        const uint32_t rb = (wsel >> ((r & 1) * 16)) & 0xffffu;
+                        if (rb != 0xAAAAu)                              // rows with only ignored pixels send nothing
+                            d |= rb | ((b + 1 < wl) ? (1u << 16) : 0u) | ((a + 1 < h) ? (1u << 17) : 0u) | (1u << 18);
+                    }
+                }
+                hr_desc[m] = d;
+            }
+            const float2 c01 = p.cw[e];
+            {
+                unsigned it = 0;
+                while (!mbar_try_wait(mbar, tma_parity)) { if (++it > RES_SPIN_LIMIT) { ok = false; break; } }
+                tma_parity ^= 1u;
+            }
+            __syncthreads();                                           // S2
+            // ---------------- fixed-point unit of the episode: power of two from the group-wide max|F| ----------------
+            {
+                unsigned mb = 0u;
+                const uint4* F4u = reinterpret_cast<const uint4*>(F);
+                for (int i = tid; i < C * NQ; i += RES_CTHREADS) {
+                    const uint4 f = F4u[i];
+                    mb = max(max(mb, f.x & 0x7fffffffu), max(max(f.y & 0x7fffffffu, f.z & 0x7fffffffu), f.w & 0x7fffffffu));
+                }
+                mb = __reduce_max_sync(0xffffffffu, mb);      // |x| as bits: ordered like the values; NaN / Inf sort above every finite
+                if (lane == 0) atomicMax(&smax[0], mb);
+            }
+            __syncthreads();                                           // S3
             if (tid == 0) st_tagged(&fmaxw[k], __uint_as_float(smax[0]), (unsigned)e + 1u);
-            for (int kk = tid; kk < CPG; kk += RES_THREADS)
+            for (int kk = tid; kk < CPG; kk += RES_CTHREADS)
                 atomicMax(&smax[1], __float_as_uint(poll_word(&fmaxw[kk], (unsigned)e + 1u, p.abort_flag)));
-            __syncthreads();
-        }
-        const unsigned fmax_bits = smax[1];
-        const bool ep_finite = fmax_bits < 0x7f800000u;
-        float fx_unit, fx_inv;
-        {
-            // |dW_c| <= max|F| per step (l1 norm of the logit gradient <= 1), cumulative over T steps, x4 head-room
-            int ex = 0;
-            (void)frexpf(4.f * (float)p.T * (ep_finite ? __uint_as_float(fmax_bits) : 1.f), &ex);
-            ex = min(max(ex, -40), 100);
-            const int vb = 63 - KB;                            // magnitude bits of the value field
-            fx_unit = ldexpf(1.f, ex - vb);
-            fx_inv = ldexpf(1.f, vb - ex);
-        }
+            __syncthreads();                                           // S4
+            const bool ep_finite = smax[1] < 0x7f800000u;
+            float fx_inv;
+            { float unit; fixed_point_unit(smax[1], p.T, KB, unit, fx_inv); }
+            unsigned long long* acc_ep = p.sums + acc_offset(e, group, p.G, p.SPL, C);
 
-        // accumulator words of this episode: channel c at acc_ep[32 c]
-        unsigned long long* acc_ep;
-        {
-            const int slot = e / p.G;                              // e = group + slot * G
-            acc_ep = p.sums + (((size_t)group * p.SPL + slot / RES_ACC_STRIDE) * C) * RES_ACC_STRIDE + slot % RES_ACC_STRIDE;
+            for (int t = 0; t < p.T; ++t, ++gstep) {
+                long long tk0 = 0, tstep0 = 0;
+                if (PROF && tid == 0) { tk0 = clock64(); tstep0 = tk0; }
+                // ------------ P1 (each chunk first picks up the previous step's all-reduced dW) ------------
+                {
+                    float4 za = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4* F4 = reinterpret_cast<const float4*>(F) + tid;
+                    const int stride = NQ * NG;
+                    int c = grp;
+#pragma unroll
+                    for (int j = 0; j < RES_KCH; ++j) {
+                        if (t > 0) wait_applied(j, gstep - 1u);
+                        if (p1_active) {
+                            if constexpr (kStatic) {
+                                // chunk j = channels grp + 16*(8j .. 8j+7): 8 independent LDS.128 + 8 broadcast LDS.32, immediate offsets
+                                const float4* Fj = reinterpret_cast<const float4*>(F) + tid + j * (8 * 400);
+                                const float* Wj = Wd + grp + j * 128;
+                                float4 f[8];
+                                float wd[8];
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) { f[u] = Fj[u * 400]; wd[u] = Wj[u * 16]; }
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) {
+                                    za.x = fmaf(wd[u], f[u].x, za.x); za.y = fmaf(wd[u], f[u].y, za.y);
+                                    za.z = fmaf(wd[u], f[u].z, za.z); za.w = fmaf(wd[u], f[u].w, za.w);
+                                }
+                            } else {
+                                const int cend = (j + 1) * CCH;
+#pragma unroll 8
+                                for (; c < cend; c += NG) {
+                                    const float4 f = *F4;
+                                    F4 += stride;
+                                    const float wd = Wd[c];
+                                    za.x = fmaf(wd, f.x, za.x); za.y = fmaf(wd, f.y, za.y);
+                                    za.z = fmaf(wd, f.z, za.z); za.w = fmaf(wd, f.w, za.w);
+                                }
+                            }
+                        }
+                    }
+                    if (p1_active) *reinterpret_cast<float4*>(scratch + grp * NP + 4 * v) = za;
+                    compute_sync();
+                    if (tid < NP) {
+                        float z = 0.f;
+#pragma unroll 4
+                        for (int g2 = 0; g2 < NG; ++g2) z += scratch[g2 * NP + tid];
+                        const int py = tid / TW, px = tid - py * TW;
+                        zt[(py + 1) * ZW + px + 1] = z;
+                        st_tagged(&zll[(gstep & 1u) * (unsigned)HW + (y0 + py) * wl + x0 + px], z, gstep + 1u);
+                    }
+                    compute_sync();
+                }
+                if (PROF && tid == 0) { long long n = clock64(); t_acc[0] += n - tk0; tk0 = n; }
+                // ------------ HR: one task = one row of one cell -> (gl, gr) of that row in shared memory ------------
+                // round 0 (interior cells) runs while the halo warp is still fetching the ring
+#pragma unroll
+                for (int m = 0; m < RES_MAXTASK; ++m) {
+                    if (m * RES_CTHREADS < 8 * NCELL) {                     // uniform: does this round have tasks at all
+                        if (m == (round0_interior ? 1 : 0)) {
+                            long long tw0 = 0;
+                            if (PROF && tid == 0) tw0 = clock64();
+                            unsigned it = 0;
+                            while (!mbar_try_wait(halo_ready, gstep & 1u)) {
+                                if ((++it & 0xfffu) == 0u) {
+                                    if (*reinterpret_cast<volatile unsigned*>(p.abort_flag) != 0u) break;
+                                    if (it > RES_SPIN_LIMIT) { atomicExch(p.abort_flag, 1u); break; }
+                                }
+                            }
+                            if (PROF && tid == 0) t_acc[1] += clock64() - tw0;
+                        }
+                        const unsigned d = hr_desc[m];
+                        if (d >> 31) {
+                            const int ci = (d >> 19) & 0xff, r = tid & 7;
+                            float gl = 0.f, gr = 0.f;
+                            if (d & (1u << 18)) {
+                                const int zi = ci + (int)((d >> 27) & 0xfu);     // cy * ZW + cx = ci + cy
+                                const int dx = (d >> 16) & 1, dy = (d & (1u << 17)) ? ZW : 0;
+                                const float z00 = zt[zi], z01 = zt[zi + dx], z10 = zt[zi + dy], z11 = zt[zi + dy + dx];
+                                const float fr = (float)r * 0.125f;
+                                hires_row(fmaf(fr, z10 - z00, z00), fmaf(fr, z11 - z01, z01), d & 0xffffu, c01.x, c01.y, gl, gr);
+                            }
+                            *reinterpret_cast<float2*>(scratch + 2 * (ci * 8 + r)) = make_float2(gl, gr);   // [cell][row][gl,gr]
+                        }
+                    }
+                }
+                compute_sync();
+                // g(q) = sum_r (1-r/8) [gl(q,r) + gr(q-1,r)] + (r/8) [gl(q-w,r) + gr(q-w-1,r)]; 4 threads per own pixel, 2 rows each
+                {
+                    const int pl = tid >> 2, rq = tid & 3;
+                    float s2 = 0.f;
+                    if (pl < NP) {
+                        const int py = pl / TW, px = pl - py * TW;
+                        const int ci = (py + 1) * CW + px + 1;             // the cell whose top-left corner is this pixel
+                        const int a = y0 + py, b = x0 + px;
+#pragma unroll
+                        for (int rr = 0; rr < 2; ++rr) {
+                            const int r = 2 * rq + rr;
+                            const float h1 = (float)r * 0.125f, h0 = 1.f - h1;
+                            float top = scratch[(ci * 8 + r) * 2];                               // gl(q, r)
+                            if (b > 0) top += scratch[((ci - 1) * 8 + r) * 2 + 1];               // gr(q-1, r)
+                            float bot = 0.f;
+                            if (a > 0) {
+                                bot = scratch[((ci - CW) * 8 + r) * 2];                          // gl(q-w, r)
+                                if (b > 0) bot += scratch[((ci - CW - 1) * 8 + r) * 2 + 1];      // gr(q-w-1, r)
+                            }
+                            s2 = fmaf(h0, top, fmaf(h1, bot, s2));
+                        }
+                    }
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+                    if (pl < NP && rq == 0) gsm[pl] = s2;
+                }
+                compute_sync();
+                if (PROF && tid == 0) { long long n = clock64(); t_acc[2] += n - tk0; tk0 = n; }
+                // ------------ P3: dW = g . F^T chunk by chunk; every partial goes straight to the channel's accumulator word,
+                // so chunk j's all-reduce runs under the rest of P3 and the next P1 ------------
+                if constexpr (kStatic) {
+                    // 4 threads per channel (adjacent lanes), interleaved pixel-quads -> conflict-free LDS.128; parts own quads
+                    // {2p, 2p+1} + 8i for i = 0..2, quad 24 belongs to part 0. The thread's quads of g live in registers.
+                    const int p3_cl = tid >> 2, p3_part = tid & 3;
+                    float4 gq[7];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        gq[2 * i] = reinterpret_cast<const float4*>(gsm)[2 * p3_part + 8 * i];
+                        gq[2 * i + 1] = reinterpret_cast<const float4*>(gsm)[2 * p3_part + 8 * i + 1];
+                    }
+                    gq[6] = (p3_part == 0) ? reinterpret_cast<const float4*>(gsm)[24] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    // volatile loads: all 7 quads of a chunk are in flight together, and the next chunk's loads are issued
+                    // before the current chunk's cross-lane reduction (the compiler would otherwise serialise them through
+                    // one register quad to save registers)
+                    const uint32_t row0 = smem_u32(F) + (uint32_t)(p3_cl * 400 + p3_part * 32);
+                    float4 f[7];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) { f[2 * i] = lds128_v(row0 + 128 * i); f[2 * i + 1] = lds128_v(row0 + 128 * i + 16); }
+                    f[6] = lds128_v(row0 - p3_part * 32 + 384);                // quad 24 (gq[6] is zero for parts 1..3)
+#pragma unroll
+                    for (int j = 0; j < RES_KCH; ++j) {
+                        float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 7; ++i) {
+                            d0 = fmaf(gq[i].x, f[i].x, d0); d1 = fmaf(gq[i].y, f[i].y, d1);
+                            d0 = fmaf(gq[i].z, f[i].z, d0); d1 = fmaf(gq[i].w, f[i].w, d1);
+                        }
+                        if (j + 1 < RES_KCH) {
+                            const uint32_t rown = row0 + (uint32_t)((j + 1) * 128 * 400);
+#pragma unroll
+                            for (int i = 0; i < 3; ++i) { f[2 * i] = lds128_v(rown + 128 * i); f[2 * i + 1] = lds128_v(rown + 128 * i + 16); }
+                            f[6] = lds128_v(rown - p3_part * 32 + 384);
+                        }
+                        float d = d0 + d1;
+                        d += __shfl_xor_sync(0xffffffffu, d, 1);
+                        d += __shfl_xor_sync(0xffffffffu, d, 2);
+                        if (p3_part == 0)                          // value and arrival in ONE atomic: (fix(d) << K) + 1
+                            red_add_u64(acc_ep + (j * 128 + p3_cl) * RES_ACC_STRIDE,
+                                        ((unsigned long long)__float2ll_rn(d * fx_inv) << KB) + 1ull);
+                        if (PROF && tid == 0) *reinterpret_cast<volatile long long*>(&tstore_sm[j]) = clock64();
+                    }
+                } else {
+                    const float4* g4 = reinterpret_cast<const float4*>(gsm);
+                    for (int c = tid; c < C; c += RES_CTHREADS) {
+                        const float4* row = reinterpret_cast<const float4*>(F + (size_t)c * NP);
+                        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll 4
+                        for (int i = 0; i < NQ; ++i) {
+                            const float4 f = row[i], g = g4[i];
+                            d0 = fmaf(g.x, f.x, d0); d1 = fmaf(g.y, f.y, d1); d2 = fmaf(g.z, f.z, d2); d3 = fmaf(g.w, f.w, d3);
+                        }
+                        const float d = (d0 + d1) + (d2 + d3);
+                        red_add_u64(acc_ep + c * RES_ACC_STRIDE, ((unsigned long long)__float2ll_rn(d * fx_inv) << KB) + 1ull);
+                    }
+                    if (PROF && tid == 0) {
+                        const long long n = clock64();
+                        for (int j = 0; j < RES_KCH; ++j) *reinterpret_cast<volatile long long*>(&tstore_sm[j]) = n;
+                    }
+                }
+                if (PROF && tid == 0) { long long n = clock64(); t_acc[3] += n - tk0; t_acc[6] += n - tstep0; }
+            }
+            // ------------ drain the last step's all-reduce ------------
+            if (p.T > 0) {
+#pragma unroll
+                for (int j = 0; j < RES_KCH; ++j) wait_applied(j, gstep - 1u);
+            }
+            __syncthreads();                                           // S5
+            if (k == 0) {
+                const bool bad = *reinterpret_cast<volatile unsigned*>(p.abort_flag) != 0u || !ep_finite;   // NaN / Inf features give NaN weights
+                for (int c = tid; c < C; c += RES_CTHREADS) {
+                    p.w[((size_t)e * 2) * C + c] = bad ? __int_as_float(0x7fc00000) : W0[c];
+                    p.w[((size_t)e * 2 + 1) * C + c] = bad ? __int_as_float(0x7fc00000) : W1[c];
+                }
+            }
         }
-
-        if (is_applier) {
-            // ================= applier warp: accumulator words -> SGD update in shared memory -> release the compute warps =================
-            const unsigned long long* sw_ep = acc_ep;
+        if (PROF && tid == 0 && p.prof) {
+            for (int i = 0; i < 6; ++i) p.prof[(size_t)blockIdx.x * RES_NPROF + i] = t_acc[i];
+            p.prof[(size_t)blockIdx.x * RES_NPROF + 10] = t_acc[6];
+        }
+        if (tid == 0 && !ok) atomicExch(p.abort_flag, 1u);
+    } else if (warp == RES_CTHREADS / 32) {
+        // =====================================================================================================
+        // applier warp: accumulator words -> SGD update in shared memory -> release the compute warps
+        // =====================================================================================================
+        long long a_acc[4] = {0, 0, 0, 0};               // PROF: poll rounds, cycles polling, sum(done - own store), chunks
+        const unsigned long long cnt_mask = (1ull << KB) - 1ull;
+        for (int e = group; e < p.E; e += p.G) {
+            __syncthreads();                                           // S1
+            for (int c = lane; c < C; c += 32) cum[c] = 0ll;
+            __syncthreads();                                           // S2
+            __syncthreads();                                           // S3
+            __syncthreads();                                           // S4
+            float fx_unit;
+            { float inv; fixed_point_unit(smax[1], p.T, KB, fx_unit, inv); }
+            const unsigned long long* acc_ep = p.sums + acc_offset(e, group, p.G, p.SPL, C);
             for (int t = 0; t < p.T; ++t) {
-                const unsigned gs = gstep + (unsigned)t;
                 const unsigned long long expect = (unsigned long long)CPG * (unsigned)(t + 1);     // arrivals so far on every word
                 for (int j = 0; j < RES_KCH; ++j) {
-                    const unsigned long long* sw = sw_ep + (size_t)j * CCH * RES_ACC_STRIDE;
+                    const unsigned long long* sw = acc_ep + (size_t)j * CCH * RES_ACC_STRIDE;
                     for (int c0 = 0; c0 < CCH; c0 += 32 * RES_AW) {
                         // every load of this lane is issued before any count is looked at (independent L2 round
                         // trips); words that are not complete yet are re-requested together, again as one batch
@@ -362,228 +599,101 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&applied[j]);          // release.cta: the Wd stores above are visible to the waiters
-                    (void)gs;
                 }
             }
-            gstep += (unsigned)p.T;
-        } else {
-            // ================= compute warps =================
+            __syncthreads();                                           // S5
+        }
+        if (PROF && lane == 0 && p.prof) {
+            for (int i = 0; i < 4; ++i) p.prof[(size_t)blockIdx.x * RES_NPROF + 6 + i] = a_acc[i];
+        }
+    } else {
+        // =====================================================================================================
+        // halo warp: fetch the ring of z around the tile, step after step
+        // =====================================================================================================
+        // the ring positions of this lane (static for the whole kernel): index into zt, global pixel or -1
+        int ring_zi[RES_HWORDS], ring_q[RES_HWORDS];
+#pragma unroll
+        for (int m = 0; m < RES_HWORDS; ++m) {
+            const int i = lane + 32 * m;
+            int zy = 0, zx = 0;
+            ring_zi[m] = -1; ring_q[m] = -1;
+            if (i < NRING) {
+                if (i < ZW) { zy = 0; zx = i; }
+                else if (i < 2 * ZW) { zy = ZH - 1; zx = i - ZW; }
+                else if (i < 2 * ZW + (ZH - 2)) { zy = 1 + (i - 2 * ZW); zx = 0; }
+                else { zy = 1 + (i - 2 * ZW - (ZH - 2)); zx = ZW - 1; }
+                const int a = y0 - 1 + zy, b = x0 - 1 + zx;
+                ring_zi[m] = zy * ZW + zx;
+                if (a >= 0 && a < h && b >= 0 && b < wl) ring_q[m] = a * wl + b;
+            }
+        }
+        unsigned gstep = 0;
+        for (int e = group; e < p.E; e += p.G) {
+            __syncthreads();                                           // S1
+            __syncthreads();                                           // S2
+            __syncthreads();                                           // S3
+            __syncthreads();                                           // S4
             for (int t = 0; t < p.T; ++t, ++gstep) {
-                long long tk0 = 0;
-                if (PROF && tid == 0) tk0 = clock64();
-                // ------------ P1 (each chunk first picks up the previous step's all-reduced dW) ------------
-                {
-                    float4 za = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float4* F4 = reinterpret_cast<const float4*>(F) + tid;
-                    const int stride = NQ * NG;
-                    int c = grp;
+                const unsigned long long* zsrc = zll + (gstep & 1u) * (unsigned)HW;
+                unsigned bits[RES_HWORDS], tag[RES_HWORDS];
+                unsigned pending = 0u, it = 0u;
 #pragma unroll
-                    for (int j = 0; j < RES_KCH; ++j) {
-                        if (t > 0) wait_applied(j, gstep - 1u);
-                        if (p1_active) {
-                            if constexpr (kStatic) {
-                                // chunk j = channels grp + 16*(8j .. 8j+7): 8 independent LDS.128 + 8 broadcast LDS.32, immediate offsets
-                                const float4* Fj = reinterpret_cast<const float4*>(F) + tid + j * (8 * 400);
-                                const float* Wj = Wd + grp + j * 128;
-                                float4 f[8];
-                                float wd[8];
+                for (int m = 0; m < RES_HWORDS; ++m) { bits[m] = 0u; tag[m] = 0u; if (ring_q[m] >= 0) pending |= 1u << m; }
+                while (pending) {
 #pragma unroll
-                                for (int u = 0; u < 8; ++u) { f[u] = Fj[u * 400]; wd[u] = Wj[u * 16]; }
+                    for (int m = 0; m < RES_HWORDS; ++m)
+                        if (pending & (1u << m)) ld_tagged(&zsrc[ring_q[m]], bits[m], tag[m]);
 #pragma unroll
-                                for (int u = 0; u < 8; ++u) {
-                                    za.x = fmaf(wd[u], f[u].x, za.x); za.y = fmaf(wd[u], f[u].y, za.y);
-                                    za.z = fmaf(wd[u], f[u].z, za.z); za.w = fmaf(wd[u], f[u].w, za.w);
-                                }
-                            } else {
-                                const int cend = (j + 1) * CCH;
-#pragma unroll 8
-                                for (; c < cend; c += NG) {
-                                    const float4 f = *F4;
-                                    F4 += stride;
-                                    const float wd = Wd[c];
-                                    za.x = fmaf(wd, f.x, za.x); za.y = fmaf(wd, f.y, za.y);
-                                    za.z = fmaf(wd, f.z, za.z); za.w = fmaf(wd, f.w, za.w);
-                                }
-                            }
-                        }
-                    }
-                    if (p1_active) *reinterpret_cast<float4*>(scratch + grp * NP + 4 * v) = za;
-                    compute_sync();
-                    if (tid < NP) {
-                        float z = 0.f;
-#pragma unroll 4
-                        for (int g2 = 0; g2 < NG; ++g2) z += scratch[g2 * NP + tid];
-                        zfull[HALO + tid] = z;
-                        st_tagged(&zll[(gstep & 1u) * (unsigned)HW + strip0 + tid], z, gstep + 1u);
+                    for (int m = 0; m < RES_HWORDS; ++m)
+                        if ((pending & (1u << m)) && tag[m] == gstep + 1u) pending &= ~(1u << m);
+                    if (pending && (++it & 0xffu) == 0u) {
+                        if (*reinterpret_cast<volatile unsigned*>(p.abort_flag) != 0u) break;
+                        if (it > (RES_SPIN_LIMIT >> 2)) { atomicExch(p.abort_flag, 1u); break; }
                     }
                 }
-                if (PROF && tid == 0) { long long n = clock64(); t_acc[0] += n - tk0; tk0 = n; }
-                // ------------ X1: fetch both halos from the neighbouring strips ------------
-                if (tid < 2 * HALO) {
-                    const bool before = tid < HALO;
-                    const int j = before ? tid : tid - HALO;
-                    const int q = before ? cell0 + j : strip0 + NP + j;
-                    float z = 0.f;
-                    if (q >= 0 && q < HW) z = poll_word(&zll[(gstep & 1u) * (unsigned)HW + q], gstep + 1u, p.abort_flag);
-                    zfull[before ? j : HALO + NP + j] = z;
-                }
-                compute_sync();
-                if (PROF && tid == 0) { long long n = clock64(); t_acc[1] += n - tk0; tk0 = n; }
-                // ------------ HR: one task = one row of one cell -> (gl, gr) of that row in shared memory ------------
 #pragma unroll
-                for (int m = 0; m < RES_MAXTASK; ++m) {
-                    if (m * RES_CTHREADS < 8 * NCELL) {                     // uniform: does this round have tasks at all
-                        const int task = m * RES_CTHREADS + tid;
-                        const int ci = task >> 3, r = tid & 7;
-                        const unsigned d = hr_desc[m];
-                        float gl = 0.f, gr = 0.f;
-                        if (d & (1u << 18)) {
-                            const int dx = (d >> 16) & 1, dy = (d & (1u << 17)) ? wl : 0;
-                            const float z00 = zfull[ci], z01 = zfull[ci + dx], z10 = zfull[ci + dy], z11 = zfull[ci + dy + dx];
-                            const float fr = (float)r * 0.125f;
-                            hires_row(fmaf(fr, z10 - z00, z00), fmaf(fr, z11 - z01, z01), d & 0xffffu, c01.x, c01.y, gl, gr);
-                        }
-                        if (ci < NCELL) *reinterpret_cast<float2*>(scratch + 2 * task) = make_float2(gl, gr);   // [cell][row][gl,gr]
-                    }
-                }
-                compute_sync();
-                // g(q) = sum_r (1-r/8) [gl(q,r) + gr(q-1,r)] + (r/8) [gl(q-w,r) + gr(q-w-1,r)]; 4 threads per own pixel, 2 rows each
-                {
-                    const int pl = tid >> 2, rq = tid & 3;
-                    float s2 = 0.f;
-                    if (pl < NP) {
-                        const int ci = HALO + pl;
-                        const int q = strip0 + pl;
-                        const int a = q / wl, b = q - a * wl;
-#pragma unroll
-                        for (int rr = 0; rr < 2; ++rr) {
-                            const int r = 2 * rq + rr;
-                            const float h1 = (float)r * 0.125f, h0 = 1.f - h1;
-                            float top = scratch[(ci * 8 + r) * 2];                               // gl(q, r)
-                            if (b > 0) top += scratch[((ci - 1) * 8 + r) * 2 + 1];               // gr(q-1, r)
-                            float bot = 0.f;
-                            if (a > 0) {
-                                bot = scratch[((ci - wl) * 8 + r) * 2];                          // gl(q-w, r)
-                                if (b > 0) bot += scratch[((ci - wl - 1) * 8 + r) * 2 + 1];      // gr(q-w-1, r)
-                            }
-                            s2 = fmaf(h0, top, fmaf(h1, bot, s2));
-                        }
-                    }
-                    s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
-                    s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
-                    if (pl < NP && rq == 0) gsm[pl] = s2;
-                }
-                compute_sync();
-                if (PROF && tid == 0) { long long n = clock64(); t_acc[2] += n - tk0; tk0 = n; }
-                // ------------ P3: dW = g . F^T chunk by chunk; every partial goes straight to the channel's accumulator word ------------
-                {
-                    // this thread's pixel-quads of g are the same for every channel: keep them in registers
-                    float4 gq[RES_MAXQ];
-#pragma unroll
-                    for (int i = 0; i < RES_MAXQ / 2; ++i) {
-                        const int q0 = 2 * p3_part + 8 * i;
-                        gq[2 * i] = (q0 < NQ) ? reinterpret_cast<const float4*>(gsm)[q0] : make_float4(0.f, 0.f, 0.f, 0.f);
-                        gq[2 * i + 1] = (q0 + 1 < NQ) ? reinterpret_cast<const float4*>(gsm)[q0 + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-#pragma unroll
-                    for (int j = 0; j < RES_KCH; ++j) {
-                        for (int cb = 0; cb < CCH; cb += RES_CTHREADS / 4) {
-                            const int cl = cb + p3_cl;
-                            float d0 = 0.f, d1 = 0.f;
-                            if (cl < CCH) {
-                                const float4* row = reinterpret_cast<const float4*>(F + (size_t)(j * CCH + cl) * NP) + 2 * p3_part;
-                                if constexpr (kStatic) {
-                                    // 25 quads per channel row: parts own quads {2p, 2p+1} + 8i for i = 0..2; quad 24 belongs to part 0
-                                    float4 f[6];
-#pragma unroll
-                                    for (int i = 0; i < 3; ++i) { f[2 * i] = row[8 * i]; f[2 * i + 1] = row[8 * i + 1]; }
-                                    float4 f6 = make_float4(0.f, 0.f, 0.f, 0.f);
-                                    if (p3_part == 0) f6 = row[24];
-#pragma unroll
-                                    for (int i = 0; i < 6; ++i) {
-                                        d0 = fmaf(gq[i].x, f[i].x, d0); d1 = fmaf(gq[i].y, f[i].y, d1);
-                                        d0 = fmaf(gq[i].z, f[i].z, d0); d1 = fmaf(gq[i].w, f[i].w, d1);
-                                    }
-                                    d0 = fmaf(gq[6].x, f6.x, d0); d1 = fmaf(gq[6].y, f6.y, d1);
-                                    d0 = fmaf(gq[6].z, f6.z, d0); d1 = fmaf(gq[6].w, f6.w, d1);
-                                } else {
-#pragma unroll
-                                    for (int i = 0; i < RES_MAXQ / 2; ++i) {
-                                        const int q0 = 2 * p3_part + 8 * i;
-                                        if (q0 < NQ) {
-                                            const float4 f = row[8 * i];
-                                            d0 = fmaf(gq[2 * i].x, f.x, d0); d1 = fmaf(gq[2 * i].y, f.y, d1);
-                                            d0 = fmaf(gq[2 * i].z, f.z, d0); d1 = fmaf(gq[2 * i].w, f.w, d1);
-                                        }
-                                        if (q0 + 1 < NQ) {
-                                            const float4 f = row[8 * i + 1];
-                                            d0 = fmaf(gq[2 * i + 1].x, f.x, d0); d1 = fmaf(gq[2 * i + 1].y, f.y, d1);
-                                            d0 = fmaf(gq[2 * i + 1].z, f.z, d0); d1 = fmaf(gq[2 * i + 1].w, f.w, d1);
-                                        }
-                                    }
-                                }
-                            }
-                            float d = d0 + d1;
-                            d += __shfl_xor_sync(0xffffffffu, d, 1);
-                            d += __shfl_xor_sync(0xffffffffu, d, 2);
-                            if (cl < CCH && p3_part == 0)        // value and arrival in ONE atomic: (fix(d) << K) + 1
-                                red_add_u64(acc_ep + (j * CCH + cl) * RES_ACC_STRIDE, ((unsigned long long)__float2ll_rn(d * fx_inv) << KB) + 1ull);
-                        }
-                        if (PROF && tid == 0) { t_store[j] = clock64(); *reinterpret_cast<volatile long long*>(&tstore_sm[j]) = t_store[j]; }
-                    }
-                }
-                if (PROF && tid == 0) { long long n = clock64(); t_acc[3] += n - tk0; tk0 = n; }
+                for (int m = 0; m < RES_HWORDS; ++m)
+                    if (ring_zi[m] >= 0) zt[ring_zi[m]] = (ring_q[m] >= 0) ? __uint_as_float(bits[m]) : 0.f;   // outside the image: 0
+                // a tile without neighbours has nothing to poll: pace this warp on the tile's own z instead, so that it can
+                // never run a whole mbarrier phase ahead of the compute warps
+                if (CPG == 1 && lane == 0) (void)poll_word(&zsrc[y0 * wl + x0], gstep + 1u, p.abort_flag);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(halo_ready);
             }
-            // ------------ drain the last step's all-reduce ------------
-            if (p.T > 0) {
-                long long tk0 = 0;
-                if (PROF && tid == 0) tk0 = clock64();
-#pragma unroll
-                for (int j = 0; j < RES_KCH; ++j) wait_applied(j, gstep - 1u);
-            }
-        }
-        __syncthreads();
-        if (k == 0) {
-            const bool bad = *reinterpret_cast<volatile unsigned*>(p.abort_flag) != 0u || !ep_finite;   // NaN / Inf features give NaN weights
-            for (int c = tid; c < C; c += RES_THREADS) {
-                p.w[((size_t)e * 2) * C + c] = bad ? __int_as_float(0x7fc00000) : W0[c];
-                p.w[((size_t)e * 2 + 1) * C + c] = bad ? __int_as_float(0x7fc00000) : W1[c];
-            }
+            __syncthreads();                                           // S5
         }
     }
-    if (PROF && tid == RES_CTHREADS && p.prof) {
-        for (int i = 0; i < 4; ++i) p.prof[(size_t)blockIdx.x * RES_NPROF + 6 + i] = a_acc[i];
-    }
-    if (PROF && tid == 0 && p.prof) {
-        for (int i = 0; i < 6; ++i) p.prof[(size_t)blockIdx.x * RES_NPROF + i] = t_acc[i];
-    }
-    if (tid == 0 && !ok) atomicExch(p.abort_flag, 1u);
 }
 
 // ---- host side ---------------------------------------------------------------------------------
-struct ResidentPlan { int NP, CPG, G; size_t smem; bool ok; };
+struct ResidentPlan { int TW, TH, NP, CPG, G; size_t smem; bool ok; };
 
 static ResidentPlan plan_resident(int E, int C, int h, int w, int n_sm, size_t smem_cap) {
-    ResidentPlan best{0, 0, 0, 0, false};
+    ResidentPlan best{0, 0, 0, 0, 0, 0, false};
     const int HW = h * w;
-    int forced = 0;
-    if (const char* s = getenv("CWT_RESIDENT_NP")) forced = atoi(s);
+    int ftw = 0, fth = 0;
+    if (const char* s = getenv("CWT_RESIDENT_TILE")) sscanf(s, "%dx%d", &ftw, &fth);
     double best_score = -1.0;
-    for (int NP = 4; NP <= HW; NP += 4) {
-        if (HW % NP) continue;
-        if (forced && NP != forced) continue;
-        if (NP < w + 1 && HW != NP) continue;          // halos must come from the adjacent strips only
-        if (NP > 16 * RES_MAXQ) continue;              // P3 register tiling
-        if (8 * (NP + w + 1) > RES_MAXTASK * RES_CTHREADS) continue;   // HR task descriptors
-        if (C % RES_KCH) continue;
-        const size_t sm = res_smem_layout(C, NP, w).total;
-        if (sm > smem_cap) continue;
-        const int CPG = HW / NP;
-        if (CPG > n_sm) continue;
-        int G = n_sm / CPG;
-        if (G > E) G = E;
-        const double score = (double)G / NP + 1e-9 * NP;
-        if (score > best_score) { best_score = score; best = ResidentPlan{NP, CPG, G, sm, true}; }
+    if (C % RES_KCH) return best;
+    for (int TW = 4; TW <= w; TW += 4) {
+        if (w % TW) continue;
+        for (int TH = 1; TH <= h && TH <= 14; ++TH) {
+            if (h % TH) continue;
+            if (ftw && (TW != ftw || TH != fth)) continue;
+            const int NP = TW * TH;
+            if (NP > 128) continue;                                       // P1 pixel-quad mapping
+            if (8 * (TW + 1) * (TH + 1) > RES_MAXTASK * RES_CTHREADS) continue;   // HR task descriptors
+            if (2 * (TW + 2) + 2 * TH > 32 * RES_HWORDS) continue;        // halo ring words
+            const size_t sm = res_smem_layout(C, TW, TH).total;
+            if (sm > smem_cap) continue;
+            const int CPG = HW / NP;
+            if (CPG > n_sm) continue;
+            int G = n_sm / CPG;
+            if (G > E) G = E;
+            // most concurrent episodes per on-chip byte first, then the largest tile, then the fewest cells
+            const double score = (double)G / NP + 1e-9 * NP - 1e-12 * (TW + 1) * (TH + 1);
+            if (score > best_score) { best_score = score; best = ResidentPlan{TW, TH, NP, CPG, G, sm, true}; }
+        }
     }
     return best;
 }
@@ -616,11 +726,12 @@ size_t fit_resident_workspace_bytes(int E, int C, int h, int w) {
            align_up(sizeof(unsigned long long) * 160) + 512 + align_up(sizeof(long long) * RES_NPROF * 160);
 }
 
-template <int TC, int TNP, int TWL, int THL>
+template <int TC, int TTW, int TTH, int TWL, int THL>
 static int launch_resident(const ResidentParams& p, const ResidentPlan& pl, bool prof, cudaStream_t st) {
     void* args[] = {const_cast<ResidentParams*>(&p)};
     dim3 grid(pl.G * pl.CPG), block(RES_THREADS);
-    const void* fn = prof ? (const void*)k_fit_resident<TC, TNP, TWL, THL, true> : (const void*)k_fit_resident<TC, TNP, TWL, THL, false>;
+    const void* fn = prof ? (const void*)k_fit_resident<TC, TTW, TTH, TWL, THL, true>
+                          : (const void*)k_fit_resident<TC, TTW, TTH, TWL, THL, false>;
     CWT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     CWT_CUDA(cudaLaunchCooperativeKernel(fn, grid, block, args, pl.smem, st));
     count_launch();
@@ -635,9 +746,8 @@ int fit_resident(const float* f_s, const uint4* cells, const float2* cw, float* 
     resident_device_limits(n_sm, smem_cap);
     CWT_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
     CWT_REQUIRE(coop, CWT_ERR_UNSUPPORTED, "fit_resident: device lacks cooperative launch");
-    CWT_REQUIRE(C <= RES_CTHREADS * RES_KCH, CWT_ERR_UNSUPPORTED, "fit_resident: C=%d too large", C);
     const ResidentPlan pl = plan_resident(E, C, h, w, n_sm, (size_t)smem_cap);
-    CWT_REQUIRE(pl.ok, CWT_ERR_UNSUPPORTED, "fit_resident: no strip size fits C=%d, %dx%d in %d B of shared memory", C, h, w, smem_cap);
+    CWT_REQUIRE(pl.ok, CWT_ERR_UNSUPPORTED, "fit_resident: no tile fits C=%d, %dx%d in %d B of shared memory", C, h, w, smem_cap);
     const int HW = h * w;
     Carver cv(ws, ws_bytes);
     ResidentParams p{};
@@ -652,14 +762,14 @@ int fit_resident(const float* f_s, const uint4* cells, const float2* cw, float* 
     const size_t sync_bytes = (size_t)(reinterpret_cast<char*>(p.abort_flag + 64) - reinterpret_cast<char*>(p.zll));
     CWT_CUDA(cudaMemsetAsync(p.zll, 0, sync_bytes, st));
     p.f_s = f_s; p.cells = cells; p.cw = cw; p.w = w_io;
-    p.E = E; p.C = C; p.HW = HW; p.h = h; p.w_lo = w; p.NP = pl.NP; p.CPG = pl.CPG; p.G = pl.G; p.T = n_iter; p.lr = lr;
+    p.E = E; p.C = C; p.HW = HW; p.h = h; p.w_lo = w; p.TW = pl.TW; p.TH = pl.TH; p.CPG = pl.CPG; p.G = pl.G; p.T = n_iter; p.lr = lr;
     // arrival-count field: CPG * n_iter arrivals per accumulator word over an episode
     p.KBITS = 1;
     while ((1ll << p.KBITS) <= (long long)pl.CPG * n_iter) ++p.KBITS;
     CWT_REQUIRE(p.KBITS <= 24, CWT_ERR_UNSUPPORTED, "fit_resident: n_iter=%d too large for the on-chip all-reduce", n_iter);
     int rc;
-    if (C == 512 && h == 60 && w == 60 && pl.NP == 100) rc = launch_resident<512, 100, 60, 60>(p, pl, prof_out != nullptr, st);
-    else rc = launch_resident<0, 0, 0, 0>(p, pl, prof_out != nullptr, st);
+    if (C == 512 && h == 60 && w == 60 && pl.TW == 20 && pl.TH == 5) rc = launch_resident<512, 20, 5, 60, 60>(p, pl, prof_out != nullptr, st);
+    else rc = launch_resident<0, 0, 0, 0, 0>(p, pl, prof_out != nullptr, st);
     if (rc != CWT_OK) return rc;
     if (prof_out) CWT_CUDA(cudaMemcpyAsync(prof_out, p.prof, sizeof(long long) * RES_NPROF * pl.G * pl.CPG, cudaMemcpyDeviceToDevice, st));
     return CWT_OK;

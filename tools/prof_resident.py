@@ -37,12 +37,12 @@ if a.prof:
     c = buf.cpu().double()
     used = c[:, 0] > 0
     n_steps = a.iters * ((E + 3) // 4)
-    names = ["P1", "X1", "HR", "P3", "n_waited_chunks", "sum(store->applied latency when waited)"]
+    names = ["P1 (incl. all-reduce waits)", "halo wait (inside HR)", "HR (incl. halo wait)", "P3 (quad 0 only)", "n_waited_chunks", "sum(store->applied latency when waited)"]
     print(f"instrumented run {tp:.2f} ms; per-step cycles (mean over {int(used.sum())} CTAs, ~{n_steps} steps each; min/max over CTAs):")
     for i, n in enumerate(names):
         col = c[used, i] / n_steps
         print(f"  {n}: mean {col.mean():8.0f}  min {col.min():8.0f}  max {col.max():8.0f}")
-    print(f"  total/step {c[used, :4].sum(1).mean() / n_steps:8.0f} cycles")
+    print(f"  total/step {c[used, 10].mean() / n_steps:8.0f} cycles (thread 0: P1 start -> its P3 store)")
     print(f"  applier lane 0: {c[used,6].sum()/c[used,9].sum():.2f} poll rounds per chunk, {c[used,7].sum()/c[used,9].sum():.0f} cycles polling per chunk "
           f"({c[used,7].sum()/c[used,6].sum():.0f} per round), own store -> chunk complete {c[used,8].sum()/c[used,9].sum():.0f} cycles")
     print(f"  all-reduce latency seen by waiting compute warps: {(c[used,5].sum()/c[used,4].sum()):.0f} cycles (waited on {c[used,4].mean()/n_steps:.2f} chunks/step)")
