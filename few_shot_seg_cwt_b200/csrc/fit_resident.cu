@@ -23,11 +23,14 @@
 // P3 / P1: every channel of every episode has one 64-bit accumulator word {fixed-point sum of dW : V bits,
 // arrival count : K bits}. A CTA adds its partial with a single fire-and-forget `red.add.u64` of
 // (fix(d) << K) + 1 — value and arrival land in the same atomic, so no fence is needed, and integer
-// addition makes the sum exact, order-independent and therefore deterministic. The word is cumulative over
-// the steps of the episode (never reset): the APPLIER WARP (warp 16) polls the chunk's words until the count
-// field reads CPG*(t+1), takes the difference to the previous cumulative value (exact), applies the SGD
-// update to W0 / W1 / Wd in shared memory and releases the compute warps chunk by chunk through a
-// shared-memory mbarrier. The compute warps never wait on global memory.
+// addition makes the sum exact, order-independent and therefore deterministic. Words are cumulative (never
+// reset) and there are two sets, for the even and the odd steps: a CTA that is not a neighbour of this one
+// may run a whole step ahead, but it cannot add to step t+2 before every CTA has contributed to step t+1,
+// i.e. has consumed step t — so the count of a set can never run past the value a reader is waiting for.
+// The APPLIER WARP polls the chunk's words until the count field reads CPG*(t/2+1), takes the difference to
+// the previous cumulative value of that set (exact), applies the SGD update to W0 / W1 / Wd in shared
+// memory and releases the compute warps chunk by chunk through a shared-memory mbarrier. The compute warps
+// never wait on global memory.
 // The fixed-point unit is a power of two chosen per episode from max|F| (|dW_c| <= max|F| because the
 // gradient w.r.t. the logits has l1 norm <= 1 under the weighted-mean CE), exchanged once per episode with
 // tagged words; a partial loses nothing unless it is < 2^-26 of that bound.
@@ -49,15 +52,18 @@
 
 namespace cwt {
 
-constexpr int RES_CTHREADS = 512;               // 16 compute warps
-constexpr int RES_THREADS = RES_CTHREADS + 64;  // + the applier warp (16) and the halo warp (17)
+// A CTA has CT compute threads + the applier warp + the halo warp. Two configurations are built:
+//   CT = 512, one CTA per SM   (tile 20 x 5 for the PSPNet head: the whole shared memory holds one tile)
+//   CT = 256, two CTAs per SM  (tile 4 x 10: while one CTA waits for the halo / the all-reduce or runs the ALU-bound
+//                               full-resolution stage, the other one keeps the shared-memory pipe busy)
+constexpr int RES_HELPER_THREADS = 64;
 constexpr unsigned RES_SPIN_LIMIT = 1u << 24;
 constexpr int RES_KCH = 4;        // channel chunks of the pipelined all-reduce
 constexpr int RES_AW = 4;         // accumulator words an applier lane keeps in flight
 constexpr int RES_HWORDS = 4;     // halo words per lane of the halo warp (ring <= 128 pixels)
 constexpr int RES_MAXTASK = 4;    // HR row-tasks per compute thread (8 * cells <= 4 * 512)
-constexpr int RES_ACC_STRIDE = 1; // words between the accumulators of adjacent channels (episodes of a group fill the gaps)
 constexpr int RES_NPROF = 12;     // profile counters per CTA
+constexpr int RES_P3_DEPTH = 8;   // pixel-quads a P3 thread keeps in flight per operand
 
 struct ResidentParams {
     const float* f_s;          // [E][C][HW]
@@ -65,8 +71,8 @@ struct ResidentParams {
     const float2* cw;          // [E]
     float* w;                  // [E][2][C]  in: W0, out: fitted
     unsigned long long* zll;   // [G][2][HW]                            {z, step} words of the halo exchange
-    unsigned long long* sums;  // [G][SPL][C][RES_ACC_STRIDE]           {fixed-point cumulative dW : 64-K bits, arrivals : K bits};
-                               //   the gaps between channels are filled by consecutive episodes of the same group (never concurrent)
+    unsigned long long* sums;  // [G][SPL][2][C]                        {fixed-point cumulative dW : 64-K bits, arrivals : K bits},
+                               //   one set for the even and one for the odd steps of every episode
     unsigned long long* fmaxw; // [G][CPG]                              {max|F| of the tile (bits), episode+1} words
     unsigned* abort_flag;      // [1]
     long long* prof;           // [grid][RES_NPROF] or null
@@ -97,7 +103,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // compute warps only (the helper warps never join): named barrier 1
-__device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(RES_CTHREADS) : "memory"); }
+template <int CT>
+__device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory"); }
 
 // tagged words: {payload bits, step number} in one 64-bit access (single-copy atomic)
 __device__ __forceinline__ void st_tagged(unsigned long long* p, float v, unsigned seq) {
@@ -138,18 +145,64 @@ __device__ __noinline__ float poll_word(const unsigned long long* src, unsigned 
     return __uint_as_float(bits);
 }
 
-// one row (8 pixels) of a cell: gradient mass sent to the left / right low-res column of that row
+// p_s = sigmoid(d_s) for the 8 pixels of a cell row; d_s is linear in s (from `left` at s = 0 towards `right` at s = 8).
+// While |d| log2(e) <= 60 over the row, e_s = exp(-d_s) comes from the recurrence e_s = e_{s-1} * r (2 MUFU.EX2 per row
+// instead of 8); rows with larger logits evaluate every exponent separately, clamped to +-60 (the sigmoid is within 1e-18
+// of 0 / 1 beyond that). 1/(1+e) for two pixels from one MUFU.RCP: iq = 1/((1+e_a)(1+e_b)), p_a = iq (1+e_b),
+// p_b = iq (1+e_a); the product stays below 2^122.
+__device__ __forceinline__ void sigmoid_row(float left, float right, float (&p)[8]) {
+    const float nleft = NEG_LOG2E * left, nslope = NEG_LOG2E * (right - left) * 0.125f;
+    float e[8];
+    if (fmaxf(fabsf(nleft), fabsf(fmaf(7.f, nslope, nleft))) <= 60.f) {
+        const float r = fast_ex2(nslope);
+        e[0] = fast_ex2(nleft);
+#pragma unroll
+        for (int s = 1; s < 8; ++s) e[s] = e[s - 1] * r;
+    } else {
+#pragma unroll
+        for (int s = 0; s < 8; ++s) e[s] = fast_ex2(fminf(fmaxf(fmaf((float)s, nslope, nleft), -60.f), 60.f));
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float a = 1.f + e[2 * k], b = 1.f + e[2 * k + 1];
+        const float iq = fast_rcp(a * b);
+        p[2 * k] = iq * b;
+        p[2 * k + 1] = iq * a;
+    }
+}
+// one row (8 pixels) of a cell: gradient mass sent to the left / right low-res column of that row.
+// General form: any mix of labels (code 0: g = c0 p; code 1: g = c1 (p - 1); ignored: 0).
 __device__ __forceinline__ void hires_row(float left, float right, uint32_t rb, float c0, float c1,
                                           float& gl_out, float& gr_out) {
-    const float nleft = NEG_LOG2E * left, nslope = NEG_LOG2E * (right - left) * 0.125f;
+    float p[8];
+    sigmoid_row(left, right, p);
     float gs = 0.f, gr = 0.f;
 #pragma unroll
     for (int s = 0; s < 8; ++s) {
-        const float g = ce_grad_pixel(fmaf((float)s, nslope, nleft), rb & (3u << (2 * s)), 1u << (2 * s), c0, c1);
+        const uint32_t sel = rb & (3u << (2 * s)), one = 1u << (2 * s);
+        const uint32_t bB = (sel == one) ? __float_as_uint(c1) : 0u;
+        const uint32_t bA = (sel == 0u) ? __float_as_uint(c0) : bB;
+        const float g = fmaf(__uint_as_float(bA), p[s], -__uint_as_float(bB));
         gs += g;
         gr = fmaf((float)s, g, gr);
     }
     gr *= 0.125f;
+    gl_out = gs - gr;
+    gr_out = gr;
+}
+// the same for a row whose 8 pixels carry one label y (the common case away from object boundaries):
+// sum_s g = c_y (sum p - 8 y), sum_s s g = c_y (sum s p - 28 y)
+__device__ __forceinline__ void hires_row_uniform(float left, float right, bool y, float c0, float c1,
+                                                  float& gl_out, float& gr_out) {
+    float p[8];
+    sigmoid_row(left, right, p);
+    const float sp = ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
+    float ssp = p[1];
+#pragma unroll
+    for (int s = 2; s < 8; ++s) ssp = fmaf((float)s, p[s], ssp);
+    const float c = y ? c1 : c0;
+    const float gs = c * (sp - (y ? 8.f : 0.f));
+    const float gr = c * (ssp - (y ? 28.f : 0.f)) * 0.125f;
     gl_out = gs - gr;
     gr_out = gr;
 }
@@ -164,18 +217,18 @@ __device__ __forceinline__ void fixed_point_unit(unsigned fmax_bits, int T, int 
     unit = ldexpf(1.f, ex - vb);
     inv = ldexpf(1.f, vb - ex);
 }
-// accumulator words of episode e (= group + slot * G): channel c at sums[acc_offset + RES_ACC_STRIDE * c]
+// accumulator words of episode e (= group + slot * G): channel c of a step with parity q at sums[acc_offset + q * C + c]
 __device__ __forceinline__ size_t acc_offset(int e, int group, int G, int SPL, int C) {
     const int slot = e / G;
-    return (((size_t)group * SPL + slot / RES_ACC_STRIDE) * C) * RES_ACC_STRIDE + slot % RES_ACC_STRIDE;
+    return ((size_t)group * SPL + slot) * 2 * C;
 }
 
 struct ResSmem {
     size_t F, W0, W1, Wd, zt, g, scratch, mbar, cum, total;
 };
-static __host__ __device__ inline ResSmem res_smem_layout(int C, int TW, int TH) {
+static __host__ __device__ inline ResSmem res_smem_layout(int C, int TW, int TH, int CT) {
     ResSmem s;
-    const int NP = TW * TH, NQ = NP / 4, NG = RES_CTHREADS / NQ, NCELL = (TW + 1) * (TH + 1);
+    const int NP = TW * TH, NQ = NP / 4, NG = CT / NQ, NCELL = (TW + 1) * (TH + 1);
     size_t o = 0;
     size_t sz[9];
     sz[0] = (size_t)C * NP * 4; sz[1] = sz[2] = sz[3] = (size_t)C * 4;
@@ -183,7 +236,7 @@ static __host__ __device__ inline ResSmem res_smem_layout(int C, int TW, int TH)
     const size_t sc1 = (size_t)NG * NP * 4, sc2 = (size_t)16 * NCELL * 4;
     sz[6] = sc1 > sc2 ? sc1 : sc2;
     sz[7] = 8 * (2 + RES_KCH) + 16;                                  // mbarriers + two words of the max|F| exchange
-    sz[8] = (size_t)C * 8;                                           // previous cumulative dW per channel (applier warp)
+    sz[8] = (size_t)C * 16;                                          // previous cumulative dW per channel and step parity (applier warp)
     size_t off[9];
     for (int i = 0; i < 9; ++i) { off[i] = o; o = (o + sz[i] + 127) / 128 * 128; }
     s.F = off[0]; s.W0 = off[1]; s.W1 = off[2]; s.Wd = off[3]; s.zt = off[4]; s.g = off[5];
@@ -191,20 +244,22 @@ static __host__ __device__ inline ResSmem res_smem_layout(int C, int TW, int TH)
     return s;
 }
 
-// TC / TTW / TTH / TWL / THL > 0: compile-time shape (C, tile width / height, low-res width / height); 0: run-time shape.
-template <int TC, int TTW, int TTH, int TWL, int THL, bool PROF>
-__global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams p) {
+// CT: compute threads, MINB: CTAs per SM. TC / TTW / TTH / TWL / THL > 0: compile-time shape (C, tile width / height,
+// low-res width / height); 0: run-time shape.
+template <int CT, int MINB, int TC, int TTW, int TTH, int TWL, int THL, bool PROF>
+__global__ void __launch_bounds__(CT + RES_HELPER_THREADS, MINB) k_fit_resident(ResidentParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int C = TC ? TC : p.C, TW = TTW ? TTW : p.TW, TH = TTH ? TTH : p.TH, wl = TWL ? TWL : p.w_lo, h = THL ? THL : p.h;
     const int NP = TW * TH, HW = wl * h, TPR = wl / TW, CPG = HW / NP;
     const int CCH = C / RES_KCH;                     // channels per chunk (C % RES_KCH == 0)
-    constexpr bool kStatic = (TC == 512 && TTW * TTH == 100);    // PSPNet head geometry: fully unrolled sweeps
-    const int NQ = NP / 4, NG = kStatic ? 16 : RES_CTHREADS / NQ;
+    constexpr bool kStatic = (CT == 512 && TC == 512 && TTW * TTH == 100);   // PSPNet head geometry, one CTA per SM: fully unrolled sweeps
+    constexpr bool kStatic40 = (CT == 256 && TC == 512 && TTW * TTH == 40);  // ... two CTAs per SM
+    const int NQ = NP / 4, NG = kStatic ? 16 : CT / NQ;
     const int ZW = TW + 2, ZH = TH + 2, CW = TW + 1, NCELL = CW * (TH + 1);
     const int NINT = (TW - 1) * (TH - 1);            // cells whose four corners are own pixels: need no halo
-    const bool round0_interior = 8 * NINT >= RES_CTHREADS;       // HR round 0 can run before the halo has arrived
+    const bool round0_interior = 8 * NINT >= CT;       // HR round 0 can run before the halo has arrived
     const int NRING = 2 * ZW + 2 * (ZH - 2);         // halo pixels around the tile
-    const ResSmem L = res_smem_layout(C, TW, TH);
+    const ResSmem L = res_smem_layout(C, TW, TH, CT);
     float* F = reinterpret_cast<float*>(smem_raw + L.F);
     float* W0 = reinterpret_cast<float*>(smem_raw + L.W0);
     float* W1 = reinterpret_cast<float*>(smem_raw + L.W1);
@@ -240,7 +295,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
     // Every role has its own episode loop (so that the state of one role never occupies registers of another); all of
     // them execute the same five CTA-wide barriers per episode: S1 previous episode done, S2 tile staged, S3 tile max
     // known, S4 episode max known, S5 steps done.
-    if (warp < RES_CTHREADS / 32) {
+    if (warp < CT / 32) {
         // =====================================================================================================
         // compute warps
         // =====================================================================================================
@@ -273,11 +328,11 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads before async-proxy writes
             if (tid == 0) mbar_expect_tx(mbar, (unsigned)(C * NP * 4));
             const float* fsrc = p.f_s + (size_t)e * C * HW + (size_t)y0 * wl + x0;
-            for (int i = tid; i < C * TH; i += RES_CTHREADS) {         // one copy per (channel, tile row): TW * 4 bytes
+            for (int i = tid; i < C * TH; i += CT) {         // one copy per (channel, tile row): TW * 4 bytes
                 const int c = i / TH, py = i - c * TH;
                 bulk_g2s(F + (size_t)c * NP + py * TW, fsrc + (size_t)c * HW + (size_t)py * wl, (unsigned)(TW * 4), mbar);
             }
-            for (int c = tid; c < C; c += RES_CTHREADS) {
+            for (int c = tid; c < C; c += CT) {
                 const float a = p.w[((size_t)e * 2) * C + c], b = p.w[((size_t)e * 2 + 1) * C + c];
                 W0[c] = a; W1[c] = b; Wd[c] = b - a;
             }
@@ -286,9 +341,10 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
             // come first so that the first round needs no halo.
             // desc = row label bits | dx << 16 | dy_flag << 17 | live << 18 | cell << 19 | cell_row << 27 | valid << 31
             unsigned hr_desc[RES_MAXTASK];
+            unsigned hr_uniform = 0u;
 #pragma unroll
             for (int m = 0; m < RES_MAXTASK; ++m) {
-                const int task = m * RES_CTHREADS + tid;
+                const int task = m * CT + tid;
                 const int o = task >> 3, r = task & 7;
                 unsigned d = 0u;
                 if (o < NCELL) {
@@ -312,6 +368,9 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
                     }
                 }
                 hr_desc[m] = d;
+                // rows without a label boundary take the cheaper uniform form; decided per warp and round (no divergence)
+                const uint32_t rbits = d & 0xffffu;
+                if (__all_sync(0xffffffffu, !(d & (1u << 18)) || rbits == 0u || rbits == 0x5555u)) hr_uniform |= 1u << m;
             }
             const float2 c01 = p.cw[e];
             {
@@ -324,7 +383,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
             {
                 unsigned mb = 0u;
                 const uint4* F4u = reinterpret_cast<const uint4*>(F);
-                for (int i = tid; i < C * NQ; i += RES_CTHREADS) {
+                for (int i = tid; i < C * NQ; i += CT) {
                     const uint4 f = F4u[i];
                     mb = max(max(mb, f.x & 0x7fffffffu), max(max(f.y & 0x7fffffffu, f.z & 0x7fffffffu), f.w & 0x7fffffffu));
                 }
@@ -333,7 +392,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
             }
             __syncthreads();                                           // S3
             if (tid == 0) st_tagged(&fmaxw[k], __uint_as_float(smax[0]), (unsigned)e + 1u);
-            for (int kk = tid; kk < CPG; kk += RES_CTHREADS)
+            for (int kk = tid; kk < CPG; kk += CT)
                 atomicMax(&smax[1], __float_as_uint(poll_word(&fmaxw[kk], (unsigned)e + 1u, p.abort_flag)));
             __syncthreads();                                           // S4
             const bool ep_finite = smax[1] < 0x7f800000u;
@@ -381,7 +440,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
                         }
                     }
                     if (p1_active) *reinterpret_cast<float4*>(scratch + grp * NP + 4 * v) = za;
-                    compute_sync();
+                    compute_sync<CT>();
                     if (tid < NP) {
                         float z = 0.f;
 #pragma unroll 4
@@ -390,14 +449,14 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
                         zt[(py + 1) * ZW + px + 1] = z;
                         st_tagged(&zll[(gstep & 1u) * (unsigned)HW + (y0 + py) * wl + x0 + px], z, gstep + 1u);
                     }
-                    compute_sync();
+                    compute_sync<CT>();
                 }
                 if (PROF && tid == 0) { long long n = clock64(); t_acc[0] += n - tk0; tk0 = n; }
                 // ------------ HR: one task = one row of one cell -> (gl, gr) of that row in shared memory ------------
                 // round 0 (interior cells) runs while the halo warp is still fetching the ring
 #pragma unroll
                 for (int m = 0; m < RES_MAXTASK; ++m) {
-                    if (m * RES_CTHREADS < 8 * NCELL) {                     // uniform: does this round have tasks at all
+                    if (m * CT < 8 * NCELL) {                     // uniform: does this round have tasks at all
                         if (m == (round0_interior ? 1 : 0)) {
                             long long tw0 = 0;
                             if (PROF && tid == 0) tw0 = clock64();
@@ -419,14 +478,17 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
                                 const int dx = (d >> 16) & 1, dy = (d & (1u << 17)) ? ZW : 0;
                                 const float z00 = zt[zi], z01 = zt[zi + dx], z10 = zt[zi + dy], z11 = zt[zi + dy + dx];
                                 const float fr = (float)r * 0.125f;
-                                hires_row(fmaf(fr, z10 - z00, z00), fmaf(fr, z11 - z01, z01), d & 0xffffu, c01.x, c01.y, gl, gr);
+                                const float left = fmaf(fr, z10 - z00, z00), right = fmaf(fr, z11 - z01, z01);
+                                if (hr_uniform & (1u << m)) hires_row_uniform(left, right, (d & 1u) != 0u, c01.x, c01.y, gl, gr);
+                                else hires_row(left, right, d & 0xffffu, c01.x, c01.y, gl, gr);
                             }
                             *reinterpret_cast<float2*>(scratch + 2 * (ci * 8 + r)) = make_float2(gl, gr);   // [cell][row][gl,gr]
                         }
                     }
                 }
-                compute_sync();
-                // g(q) = sum_r (1-r/8) [gl(q,r) + gr(q-1,r)] + (r/8) [gl(q-w,r) + gr(q-w-1,r)]; 4 threads per own pixel, 2 rows each
+                compute_sync<CT>();
+                // g(q) = sum_r (1-r/8) [gl(q,r) + gr(q-1,r)] + (r/8) [gl(q-w,r) + gr(q-w-1,r)]; 4 threads per own pixel, 2 rows each:
+                // the (gl, gr) pairs of rows 2k, 2k+1 of a cell are one aligned 16-byte word -> conflict-free LDS.128
                 {
                     const int pl = tid >> 2, rq = tid & 3;
                     float s2 = 0.f;
@@ -434,72 +496,84 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
                         const int py = pl / TW, px = pl - py * TW;
                         const int ci = (py + 1) * CW + px + 1;             // the cell whose top-left corner is this pixel
                         const int a = y0 + py, b = x0 + px;
-#pragma unroll
-                        for (int rr = 0; rr < 2; ++rr) {
-                            const int r = 2 * rq + rr;
-                            const float h1 = (float)r * 0.125f, h0 = 1.f - h1;
-                            float top = scratch[(ci * 8 + r) * 2];                               // gl(q, r)
-                            if (b > 0) top += scratch[((ci - 1) * 8 + r) * 2 + 1];               // gr(q-1, r)
-                            float bot = 0.f;
-                            if (a > 0) {
-                                bot = scratch[((ci - CW) * 8 + r) * 2];                          // gl(q-w, r)
-                                if (b > 0) bot += scratch[((ci - CW - 1) * 8 + r) * 2 + 1];      // gr(q-w-1, r)
-                            }
-                            s2 = fmaf(h0, top, fmaf(h1, bot, s2));
-                        }
+                        const float4* sc4 = reinterpret_cast<const float4*>(scratch) + rq;     // [cell][4 row pairs]
+                        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 own = sc4[ci * 4];
+                        const float4 lft = (b > 0) ? sc4[(ci - 1) * 4] : zero4;
+                        const float4 up = (a > 0) ? sc4[(ci - CW) * 4] : zero4;
+                        const float4 ul = (a > 0 && b > 0) ? sc4[(ci - CW - 1) * 4] : zero4;
+                        const float ha = (float)(2 * rq) * 0.125f, hb = (float)(2 * rq + 1) * 0.125f;
+                        s2 = fmaf(1.f - ha, own.x + lft.y, ha * (up.x + ul.y)) + fmaf(1.f - hb, own.z + lft.w, hb * (up.z + ul.w));
                     }
                     s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
                     s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
                     if (pl < NP && rq == 0) gsm[pl] = s2;
                 }
-                compute_sync();
+                compute_sync<CT>();
                 if (PROF && tid == 0) { long long n = clock64(); t_acc[2] += n - tk0; tk0 = n; }
                 // ------------ P3: dW = g . F^T chunk by chunk; every partial goes straight to the channel's accumulator word,
                 // so chunk j's all-reduce runs under the rest of P3 and the next P1 ------------
+                unsigned long long* acc_t = acc_ep + (t & 1) * C;          // even / odd steps use different words (see header)
                 if constexpr (kStatic) {
-                    // 4 threads per channel (adjacent lanes), interleaved pixel-quads -> conflict-free LDS.128; parts own quads
-                    // {2p, 2p+1} + 8i for i = 0..2, quad 24 belongs to part 0. The thread's quads of g live in registers.
-                    const int p3_cl = tid >> 2, p3_part = tid & 3;
-                    float4 gq[7];
+                    // One thread per channel, no cross-thread reduction; g is broadcast from shared memory. The four warp
+                    // quads take turns (quad j = channel chunk j, handed over through named barriers 2..4): the sweep of a
+                    // quad is latency-bound anyway, a finished quad moves on to the next step's P1 at once, and chunk j's
+                    // partials leave at (j+1)/4 of P3 so that its all-reduce runs under the rest of P3 and the next P1.
+                    // (Measured alternatives at E = 64: all quads at once 20.3 ms, 4 threads per channel + shuffles 18.8 ms,
+                    // two channels per thread 18.0 ms, this 17.5 ms.)
+                    const int j = warp >> 2;
+                    if (j > 0) asm volatile("bar.sync %0, 256;" ::"r"(1 + j) : "memory");
+                    const uint32_t row = smem_u32(F) + (uint32_t)tid * 400u, gad = smem_u32(gsm);
+                    constexpr int D = RES_P3_DEPTH;                 // quads in flight per operand
+                    float4 fb[D], gb[D];
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        gq[2 * i] = reinterpret_cast<const float4*>(gsm)[2 * p3_part + 8 * i];
-                        gq[2 * i + 1] = reinterpret_cast<const float4*>(gsm)[2 * p3_part + 8 * i + 1];
+                    for (int i = 0; i < D; ++i) { fb[i] = lds128_v(row + 16 * i); gb[i] = lds128_v(gad + 16 * i); }
+                    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 25; ++i) {
+                        const float4 f = fb[i % D], g = gb[i % D];
+                        if (i + D < 25) { fb[i % D] = lds128_v(row + 16 * (i + D)); gb[i % D] = lds128_v(gad + 16 * (i + D)); }
+                        d0 = fmaf(g.x, f.x, d0); d1 = fmaf(g.y, f.y, d1); d2 = fmaf(g.z, f.z, d2); d3 = fmaf(g.w, f.w, d3);
                     }
-                    gq[6] = (p3_part == 0) ? reinterpret_cast<const float4*>(gsm)[24] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    // volatile loads: all 7 quads of a chunk are in flight together, and the next chunk's loads are issued
-                    // before the current chunk's cross-lane reduction (the compiler would otherwise serialise them through
-                    // one register quad to save registers)
-                    const uint32_t row0 = smem_u32(F) + (uint32_t)(p3_cl * 400 + p3_part * 32);
-                    float4 f[7];
+                    if (j < RES_KCH - 1) asm volatile("bar.arrive %0, 256;" ::"r"(2 + j) : "memory");
+                    const float d = (d0 + d1) + (d2 + d3);
+                    // value and arrival in ONE atomic: (fix(d) << K) + 1
+                    red_add_u64(acc_t + tid, ((unsigned long long)__float2ll_rn(d * fx_inv) << KB) + 1ull);
+                    if (PROF && lane == 0 && (warp & 3) == 3) *reinterpret_cast<volatile long long*>(&tstore_sm[j]) = clock64();
+                } else if constexpr (kStatic40) {
+                    // 2 threads per channel (adjacent lanes), part p owns quads p + 2i (i = 0..4): a quarter-warp reads 4 rows
+                    // of 160 B at 32-byte granularity -> conflict-free LDS.128; 128 channels per pass = one chunk
+                    const int p3_cl = tid >> 1, p3_part = tid & 1;
+                    float4 gq[5];
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) { f[2 * i] = lds128_v(row0 + 128 * i); f[2 * i + 1] = lds128_v(row0 + 128 * i + 16); }
-                    f[6] = lds128_v(row0 - p3_part * 32 + 384);                // quad 24 (gq[6] is zero for parts 1..3)
+                    for (int i = 0; i < 5; ++i) gq[i] = reinterpret_cast<const float4*>(gsm)[p3_part + 2 * i];
+                    const uint32_t row0 = smem_u32(F) + (uint32_t)(p3_cl * 160 + p3_part * 16);
+                    float4 f[5];
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) f[i] = lds128_v(row0 + 32 * i);
 #pragma unroll
                     for (int j = 0; j < RES_KCH; ++j) {
                         float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-                        for (int i = 0; i < 7; ++i) {
+                        for (int i = 0; i < 5; ++i) {
                             d0 = fmaf(gq[i].x, f[i].x, d0); d1 = fmaf(gq[i].y, f[i].y, d1);
                             d0 = fmaf(gq[i].z, f[i].z, d0); d1 = fmaf(gq[i].w, f[i].w, d1);
                         }
                         if (j + 1 < RES_KCH) {
-                            const uint32_t rown = row0 + (uint32_t)((j + 1) * 128 * 400);
+                            const uint32_t rown = row0 + (uint32_t)((j + 1) * 128 * 160);
 #pragma unroll
-                            for (int i = 0; i < 3; ++i) { f[2 * i] = lds128_v(rown + 128 * i); f[2 * i + 1] = lds128_v(rown + 128 * i + 16); }
-                            f[6] = lds128_v(rown - p3_part * 32 + 384);
+                            for (int i = 0; i < 5; ++i) f[i] = lds128_v(rown + 32 * i);
                         }
                         float d = d0 + d1;
                         d += __shfl_xor_sync(0xffffffffu, d, 1);
-                        d += __shfl_xor_sync(0xffffffffu, d, 2);
                         if (p3_part == 0)                          // value and arrival in ONE atomic: (fix(d) << K) + 1
-                            red_add_u64(acc_ep + (j * 128 + p3_cl) * RES_ACC_STRIDE,
+                            red_add_u64(acc_t + j * 128 + p3_cl,
                                         ((unsigned long long)__float2ll_rn(d * fx_inv) << KB) + 1ull);
                         if (PROF && tid == 0) *reinterpret_cast<volatile long long*>(&tstore_sm[j]) = clock64();
                     }
                 } else {
                     const float4* g4 = reinterpret_cast<const float4*>(gsm);
-                    for (int c = tid; c < C; c += RES_CTHREADS) {
+                    for (int c = tid; c < C; c += CT) {
                         const float4* row = reinterpret_cast<const float4*>(F + (size_t)c * NP);
                         float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll 4
@@ -508,7 +582,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
                             d0 = fmaf(g.x, f.x, d0); d1 = fmaf(g.y, f.y, d1); d2 = fmaf(g.z, f.z, d2); d3 = fmaf(g.w, f.w, d3);
                         }
                         const float d = (d0 + d1) + (d2 + d3);
-                        red_add_u64(acc_ep + c * RES_ACC_STRIDE, ((unsigned long long)__float2ll_rn(d * fx_inv) << KB) + 1ull);
+                        red_add_u64(acc_t + c, ((unsigned long long)__float2ll_rn(d * fx_inv) << KB) + 1ull);
                     }
                     if (PROF && tid == 0) {
                         const long long n = clock64();
@@ -525,7 +599,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
             __syncthreads();                                           // S5
             if (k == 0) {
                 const bool bad = *reinterpret_cast<volatile unsigned*>(p.abort_flag) != 0u || !ep_finite;   // NaN / Inf features give NaN weights
-                for (int c = tid; c < C; c += RES_CTHREADS) {
+                for (int c = tid; c < C; c += CT) {
                     p.w[((size_t)e * 2) * C + c] = bad ? __int_as_float(0x7fc00000) : W0[c];
                     p.w[((size_t)e * 2 + 1) * C + c] = bad ? __int_as_float(0x7fc00000) : W1[c];
                 }
@@ -536,7 +610,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
             p.prof[(size_t)blockIdx.x * RES_NPROF + 10] = t_acc[6];
         }
         if (tid == 0 && !ok) atomicExch(p.abort_flag, 1u);
-    } else if (warp == RES_CTHREADS / 32) {
+    } else if (warp == CT / 32) {
         // =====================================================================================================
         // applier warp: accumulator words -> SGD update in shared memory -> release the compute warps
         // =====================================================================================================
@@ -544,7 +618,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
         const unsigned long long cnt_mask = (1ull << KB) - 1ull;
         for (int e = group; e < p.E; e += p.G) {
             __syncthreads();                                           // S1
-            for (int c = lane; c < C; c += 32) cum[c] = 0ll;
+            for (int c = lane; c < 2 * C; c += 32) cum[c] = 0ll;
             __syncthreads();                                           // S2
             __syncthreads();                                           // S3
             __syncthreads();                                           // S4
@@ -552,9 +626,10 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
             { float inv; fixed_point_unit(smax[1], p.T, KB, fx_unit, inv); }
             const unsigned long long* acc_ep = p.sums + acc_offset(e, group, p.G, p.SPL, C);
             for (int t = 0; t < p.T; ++t) {
-                const unsigned long long expect = (unsigned long long)CPG * (unsigned)(t + 1);     // arrivals so far on every word
+                const unsigned long long expect = (unsigned long long)CPG * (unsigned)(t / 2 + 1);   // arrivals so far on every word of this parity
+                long long* cum_t = cum + (t & 1) * C;
                 for (int j = 0; j < RES_KCH; ++j) {
-                    const unsigned long long* sw = acc_ep + (size_t)j * CCH * RES_ACC_STRIDE;
+                    const unsigned long long* sw = acc_ep + (t & 1) * C + j * CCH;
                     for (int c0 = 0; c0 < CCH; c0 += 32 * RES_AW) {
                         // every load of this lane is issued before any count is looked at (independent L2 round
                         // trips); words that are not complete yet are re-requested together, again as one batch
@@ -567,7 +642,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
                         while (pending) {
 #pragma unroll
                             for (int m = 0; m < RES_AW; ++m)
-                                if (pending & (1u << m)) wv[m] = ld_relaxed_u64(&sw[(c0 + m * 32 + lane) * RES_ACC_STRIDE]);
+                                if (pending & (1u << m)) wv[m] = ld_relaxed_u64(&sw[c0 + m * 32 + lane]);
 #pragma unroll
                             for (int m = 0; m < RES_AW; ++m)
                                 if ((pending & (1u << m)) && (wv[m] & cnt_mask) == expect) pending &= ~(1u << m);
@@ -590,8 +665,8 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
                             if (cl < CCH) {
                                 const int c = j * CCH + cl;
                                 const long long cur = (long long)wv[m] >> KB;                  // cumulative sum over steps 0..t (exact)
-                                const float dw = __ll2float_rn(cur - cum[c]) * fx_unit;          // this step's all-reduced dW
-                                cum[c] = cur;
+                                const float dw = __ll2float_rn(cur - cum_t[c]) * fx_unit;        // this step's all-reduced dW
+                                cum_t[c] = cur;
                                 const float n0 = fmaf(p.lr, dw, W0[c]), n1 = fmaf(-p.lr, dw, W1[c]);
                                 W0[c] = n0; W1[c] = n1; Wd[c] = n1 - n0;
                             }
@@ -666,13 +741,13 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_fit_resident(ResidentParams 
 }
 
 // ---- host side ---------------------------------------------------------------------------------
-struct ResidentPlan { int TW, TH, NP, CPG, G; size_t smem; bool ok; };
+struct ResidentPlan { int TW, TH, NP, CPG, G, CT, BPS; size_t smem; bool ok; };     // CT compute threads, BPS CTAs per SM
 
-static ResidentPlan plan_resident(int E, int C, int h, int w, int n_sm, size_t smem_cap) {
-    ResidentPlan best{0, 0, 0, 0, 0, 0, false};
+// best tile for CT compute threads and `bps` CTAs per SM
+static ResidentPlan plan_resident_cfg(int E, int C, int h, int w, int n_sm, size_t smem_cap, size_t smem_sm, int CT, int bps,
+                                      int ftw, int fth) {
+    ResidentPlan best{0, 0, 0, 0, 0, CT, bps, 0, false};
     const int HW = h * w;
-    int ftw = 0, fth = 0;
-    if (const char* s = getenv("CWT_RESIDENT_TILE")) sscanf(s, "%dx%d", &ftw, &fth);
     double best_score = -1.0;
     if (C % RES_KCH) return best;
     for (int TW = 4; TW <= w; TW += 4) {
@@ -681,58 +756,78 @@ static ResidentPlan plan_resident(int E, int C, int h, int w, int n_sm, size_t s
             if (h % TH) continue;
             if (ftw && (TW != ftw || TH != fth)) continue;
             const int NP = TW * TH;
-            if (NP > 128) continue;                                       // P1 pixel-quad mapping
-            if (8 * (TW + 1) * (TH + 1) > RES_MAXTASK * RES_CTHREADS) continue;   // HR task descriptors
+            if (NP > CT / 4) continue;                                    // P1 pixel-quad mapping (at least 16 channel groups)
+            if (8 * (TW + 1) * (TH + 1) > RES_MAXTASK * CT) continue;     // HR task descriptors
             if (2 * (TW + 2) + 2 * TH > 32 * RES_HWORDS) continue;        // halo ring words
-            const size_t sm = res_smem_layout(C, TW, TH).total;
-            if (sm > smem_cap) continue;
+            const size_t sm = res_smem_layout(C, TW, TH, CT).total;
+            if (sm > smem_cap || (sm + 1024) * bps > smem_sm) continue;
             const int CPG = HW / NP;
-            if (CPG > n_sm) continue;
-            int G = n_sm / CPG;
+            if (CPG > n_sm * bps) continue;
+            int G = n_sm * bps / CPG;
             if (G > E) G = E;
             // most concurrent episodes per on-chip byte first, then the largest tile, then the fewest cells
             const double score = (double)G / NP + 1e-9 * NP - 1e-12 * (TW + 1) * (TH + 1);
-            if (score > best_score) { best_score = score; best = ResidentPlan{TW, TH, NP, CPG, G, sm, true}; }
+            if (score > best_score) { best_score = score; best = ResidentPlan{TW, TH, NP, CPG, G, CT, bps, sm, true}; }
         }
     }
     return best;
 }
 
-static void resident_device_limits(int& n_sm, int& smem_cap) {
-    int dev = 0, a = 0, b = 0;
-    n_sm = 148; smem_cap = 232448;                     // B200 (used when no device is visible: sizing only)
+// CWT_RESIDENT_TILE=TWxTH forces a tile, CWT_RESIDENT_BPS=1|2 the number of CTAs per SM
+static ResidentPlan plan_resident(int E, int C, int h, int w, int n_sm, size_t smem_cap, size_t smem_sm) {
+    int ftw = 0, fth = 0, fbps = 0;
+    if (const char* s = getenv("CWT_RESIDENT_TILE")) sscanf(s, "%dx%d", &ftw, &fth);
+    if (const char* s = getenv("CWT_RESIDENT_BPS")) fbps = atoi(s);
+    const ResidentPlan one = plan_resident_cfg(E, C, h, w, n_sm, smem_cap, smem_sm, 512, 1, ftw, fth);
+    const ResidentPlan two = plan_resident_cfg(E, C, h, w, n_sm, smem_cap, smem_sm, 256, 2, ftw, fth);
+    if (fbps == 1) return one;
+    if (fbps == 2) return two;
+    // measured on B200 (60x60x512, E = 64): one CTA per SM 18.8 ms, two CTAs per SM 25.4 ms — the step is bound by the
+    // exchange latencies, which grow with the number of CTAs per group, not by the per-SM pipes
+    return one.ok ? one : two;
+}
+
+static void resident_device_limits(int& n_sm, int& smem_cap, int& smem_sm) {
+    int dev = 0, a = 0, b = 0, c = 0;
+    n_sm = 148; smem_cap = 232448; smem_sm = 233472;   // B200 (used when no device is visible: sizing only)
     if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&a, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&b, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess && a > 0 && b > 0) {
-        n_sm = a > 148 ? 148 : a; smem_cap = b;
+        cudaDeviceGetAttribute(&b, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&c, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev) == cudaSuccess && a > 0 && b > 0 && c > 0) {
+        n_sm = a > 148 ? 148 : a; smem_cap = b; smem_sm = c;
     } else {
         (void)cudaGetLastError();
     }
 }
 
 static size_t resident_sum_words(const ResidentPlan& pl, int E, int C) {
-    const int nslots = (E + pl.G - 1) / pl.G, spl = (nslots + RES_ACC_STRIDE - 1) / RES_ACC_STRIDE;
-    return (size_t)pl.G * spl * C * RES_ACC_STRIDE;
+    const int nslots = (E + pl.G - 1) / pl.G;
+    return (size_t)pl.G * nslots * 2 * C;
 }
+
+constexpr int RES_MAXGRID = 320;       // >= 2 * 148
 
 size_t fit_resident_workspace_bytes(int E, int C, int h, int w) {
     const int HW = h * w;
-    int n_sm, smem_cap;
-    resident_device_limits(n_sm, smem_cap);
-    const ResidentPlan pl = plan_resident(E, C, h, w, n_sm, (size_t)smem_cap);
+    int n_sm, smem_cap, smem_sm;
+    resident_device_limits(n_sm, smem_cap, smem_sm);
+    const ResidentPlan pl = plan_resident(E, C, h, w, n_sm, (size_t)smem_cap, (size_t)smem_sm);
     if (!pl.ok) return 0;
-    // zll: 2*HW words per group; sums: C * RES_ACC_STRIDE words per RES_ACC_STRIDE episodes of a group; fmaxw: one word per CTA;
+    // zll: 2*HW words per group; sums: 2 * C words per episode; fmaxw: one word per CTA;
     // abort flag; profile counters
     return align_up(sizeof(unsigned long long) * 2 * HW * pl.G) + align_up(sizeof(unsigned long long) * resident_sum_words(pl, E, C)) +
-           align_up(sizeof(unsigned long long) * 160) + 512 + align_up(sizeof(long long) * RES_NPROF * 160);
+           align_up(sizeof(unsigned long long) * RES_MAXGRID) + 512 + align_up(sizeof(long long) * RES_NPROF * RES_MAXGRID);
 }
 
-template <int TC, int TTW, int TTH, int TWL, int THL>
+template <int CT, int MINB, int TC, int TTW, int TTH, int TWL, int THL>
 static int launch_resident(const ResidentParams& p, const ResidentPlan& pl, bool prof, cudaStream_t st) {
     void* args[] = {const_cast<ResidentParams*>(&p)};
-    dim3 grid(pl.G * pl.CPG), block(RES_THREADS);
-    const void* fn = prof ? (const void*)k_fit_resident<TC, TTW, TTH, TWL, THL, true>
-                          : (const void*)k_fit_resident<TC, TTW, TTH, TWL, THL, false>;
+    dim3 grid(pl.G * pl.CPG), block(CT + RES_HELPER_THREADS);
+    const void* fn = prof ? (const void*)k_fit_resident<CT, MINB, TC, TTW, TTH, TWL, THL, true>
+                          : (const void*)k_fit_resident<CT, MINB, TC, TTW, TTH, TWL, THL, false>;
     CWT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    int resident_ctas = 0;
+    CWT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident_ctas, fn, CT + RES_HELPER_THREADS, pl.smem));
+    CWT_REQUIRE(resident_ctas >= MINB, CWT_ERR_UNSUPPORTED, "fit_resident: only %d of %d CTAs per SM fit", resident_ctas, MINB);
     CWT_CUDA(cudaLaunchCooperativeKernel(fn, grid, block, args, pl.smem, st));
     count_launch();
     return CWT_OK;
@@ -741,20 +836,21 @@ static int launch_resident(const ResidentParams& p, const ResidentPlan& pl, bool
 // returns CWT_ERR_UNSUPPORTED when the shape does not fit on chip
 int fit_resident(const float* f_s, const uint4* cells, const float2* cw, float* w_io, int E, int C, int h, int w,
                  int n_iter, float lr, void* ws, size_t ws_bytes, long long* prof_out, cudaStream_t st) {
-    int dev = 0, n_sm = 0, smem_cap = 0, coop = 0;
+    int dev = 0, n_sm = 0, smem_cap = 0, smem_sm = 0, coop = 0;
     CWT_CUDA(cudaGetDevice(&dev));
-    resident_device_limits(n_sm, smem_cap);
+    resident_device_limits(n_sm, smem_cap, smem_sm);
     CWT_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
     CWT_REQUIRE(coop, CWT_ERR_UNSUPPORTED, "fit_resident: device lacks cooperative launch");
-    const ResidentPlan pl = plan_resident(E, C, h, w, n_sm, (size_t)smem_cap);
+    const ResidentPlan pl = plan_resident(E, C, h, w, n_sm, (size_t)smem_cap, (size_t)smem_sm);
     CWT_REQUIRE(pl.ok, CWT_ERR_UNSUPPORTED, "fit_resident: no tile fits C=%d, %dx%d in %d B of shared memory", C, h, w, smem_cap);
+    CWT_REQUIRE(pl.G * pl.CPG <= RES_MAXGRID, CWT_ERR_UNSUPPORTED, "fit_resident: grid of %d CTAs", pl.G * pl.CPG);
     const int HW = h * w;
     Carver cv(ws, ws_bytes);
     ResidentParams p{};
     p.zll = cv.take<unsigned long long>((size_t)2 * HW * pl.G);
     p.sums = cv.take<unsigned long long>(resident_sum_words(pl, E, C));
-    p.SPL = ((E + pl.G - 1) / pl.G + RES_ACC_STRIDE - 1) / RES_ACC_STRIDE;
-    p.fmaxw = cv.take<unsigned long long>(160);
+    p.SPL = (E + pl.G - 1) / pl.G;
+    p.fmaxw = cv.take<unsigned long long>(RES_MAXGRID);
     p.abort_flag = cv.take<unsigned>(64);
     p.prof = prof_out ? cv.take<long long>((size_t)RES_NPROF * pl.G * pl.CPG) : nullptr;
     CWT_REQUIRE(ws && cv.ok(), CWT_ERR_WORKSPACE, "fit_resident: workspace too small");
@@ -767,9 +863,16 @@ int fit_resident(const float* f_s, const uint4* cells, const float2* cw, float* 
     p.KBITS = 1;
     while ((1ll << p.KBITS) <= (long long)pl.CPG * n_iter) ++p.KBITS;
     CWT_REQUIRE(p.KBITS <= 24, CWT_ERR_UNSUPPORTED, "fit_resident: n_iter=%d too large for the on-chip all-reduce", n_iter);
+    const bool prof = prof_out != nullptr;
+    const bool head = (C == 512 && h == 60 && w == 60);
     int rc;
-    if (C == 512 && h == 60 && w == 60 && pl.TW == 20 && pl.TH == 5) rc = launch_resident<512, 20, 5, 60, 60>(p, pl, prof_out != nullptr, st);
-    else rc = launch_resident<0, 0, 0, 0, 0>(p, pl, prof_out != nullptr, st);
+    if (pl.CT == 512) {
+        if (head && pl.TW == 20 && pl.TH == 5) rc = launch_resident<512, 1, 512, 20, 5, 60, 60>(p, pl, prof, st);
+        else rc = launch_resident<512, 1, 0, 0, 0, 0, 0>(p, pl, prof, st);
+    } else {
+        if (head && pl.TW == 4 && pl.TH == 10) rc = launch_resident<256, 2, 512, 4, 10, 60, 60>(p, pl, prof, st);
+        else rc = launch_resident<256, 2, 0, 0, 0, 0, 0>(p, pl, prof, st);
+    }
     if (rc != CWT_OK) return rc;
     if (prof_out) CWT_CUDA(cudaMemcpyAsync(prof_out, p.prof, sizeof(long long) * RES_NPROF * pl.G * pl.CPG, cudaMemcpyDeviceToDevice, st));
     return CWT_OK;
