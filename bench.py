@@ -273,14 +273,15 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     fit_gbs = bytes_fit / (fit_ms / 1e3) / 1e9
     resident = (a.fit_algo != 1 and a.shot == 1)
-    # measured DRAM traffic of the dominant kernel per launch at E=64 (ncu --set full, profiles/r1_resident_E64_ncu.txt)
-    traffic = {True: 483.9e6, False: None}[resident and E == 64]
+    # measured DRAM traffic of the dominant kernel per launch at E=64 (ncu --set full, profiles/r1_resident_E64_ncu.txt: dram__bytes_read + dram__bytes_write)
+    traffic = {True: 483.4e6, False: None}[resident and E == 64]
     sm_clk = (clocks or {}).get("sm_mhz") or 1965.0
     steps_per_group = a.adapt_iter * ((E + 3) // 4)
     smem_B_per_clk = (2 * 512 * 100 * 4) / (fit_ms * 1e-3 * sm_clk * 1e6 / max(steps_per_group, 1)) if resident else None
     roofline = {
-        "kernel": ("k_fit_resident<512,100,60,60> (one cooperative launch: features staged once into shared memory, "
-                   "200 SGD steps on chip)") if resident else
+        "kernel": ("k_fit_resident<512 compute threads, 1 CTA/SM, C=512, tile 20x5 of 60x60> (one cooperative launch: features "
+                   "staged once into shared memory by bulk-TMA, 200 SGD steps on chip, all-reduce through 64-bit L2 atomics)")
+                  if resident else
                   "fit_classifier streaming: 200 x {rows_times_feat<1>, fit_hires, feat_times_cols<1>+SGD}",
         "bound": "hbm", "achieved": fit_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": fit_gbs / hbm_peak,
         "traffic": traffic, "peak_source": peak_src,

@@ -134,6 +134,44 @@ def test_fit_resident_many_episodes_per_group(cuda_device):
         assert rel_err(wr[i], ws[i]) < 1e-5, i
 
 
+@pytest.mark.parametrize("env", [
+    {"CWT_RESIDENT_BPS": "2"},                                   # two CTAs per SM, tile 4 x 10, 90 CTAs per episode
+    {"CWT_RESIDENT_BPS": "2", "CWT_RESIDENT_TILE": "20x2"},      # ... the plan whose long runs exposed the count-overrun race
+    {"CWT_RESIDENT_BPS": "1", "CWT_RESIDENT_TILE": "12x5"},      # run-time-shape kernel at the full geometry (60 CTAs per episode)
+])
+def test_fit_resident_alternative_plans_long_run(cuda_device, monkeypatch, env):
+    """Every tiling of the on-chip fit gives the streaming result; long enough (many episodes x 200 steps per group) for
+    CTAs of a group to drift a whole step apart, which is what the parity-buffered accumulator words are for."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    big = syn.make_batch(list(range(300, 324)), shot=1, C=512, h=60, w=60, H=473, W=473).to(cuda_device)
+    E = 48
+    f_s = big.f_s.repeat(2, 1, 1, 1, 1)
+    s_label = big.s_label.repeat(2, 1, 1, 1)
+    w0 = big.w0.repeat(2, 1, 1)
+    wr = cwt.fit_classifier(f_s, s_label, w0, 0.1, 200, algo=L.FIT_RESIDENT)
+    monkeypatch.delenv("CWT_RESIDENT_BPS", raising=False)
+    monkeypatch.delenv("CWT_RESIDENT_TILE", raising=False)
+    ws = cwt.fit_classifier(big.f_s, big.s_label, big.w0, 0.1, 200, algo=L.FIT_STREAM)
+    assert torch.isfinite(wr).all()
+    for i in range(E):
+        assert rel_err(wr[i], ws[i % 24]) < TIGHT, i
+    assert torch.equal(wr[:24], wr[24:])                          # integer all-reduce: bit-reproducible whatever the timing
+
+
+def test_fit_resident_non_finite_features_give_nan_weights(cuda_device):
+    """A NaN / Inf in the support features poisons that episode only (the reference's SGD would produce NaN weights too)."""
+    b = syn.make_batch([30, 31, 32, 33, 34], **SMALL).to(cuda_device)
+    f_s = b.f_s.clone()
+    f_s[1, 0, 3, 5, 7] = float("nan")
+    f_s[3, 0, 10, 0, 0] = float("inf")
+    wr = cwt.fit_classifier(f_s, b.s_label, b.w0, 0.1, 20, algo=L.FIT_RESIDENT)
+    ws = cwt.fit_classifier(b.f_s, b.s_label, b.w0, 0.1, 20, algo=L.FIT_STREAM)
+    assert torch.isnan(wr[1]).all() and torch.isnan(wr[3]).all()
+    for i in (0, 2, 4):
+        assert rel_err(wr[i], ws[i]) < 1e-5, i
+
+
 def test_fit_batch_equals_single_and_label_dtypes(cuda_device):
     b = syn.make_batch([20, 21, 22], **SMALL)
     d = b.to(cuda_device)

@@ -47,7 +47,10 @@ def test_library_is_blackwell_native():
 
 def test_workspace_size_queries_need_no_gpu():
     lib = _lib.load()
-    assert lib.cwt_fit_workspace_bytes(4, 1, 512, 60, 60, 473, 473) > 4 * 473 * 473
+    # at least the packed label cells (16 B per low-res cell) and the per-step buffers of the streaming algorithm
+    assert lib.cwt_fit_workspace_bytes(4, 1, 512, 60, 60, 473, 473) > 4 * 60 * 60 * (16 + 8)
+    # ... and it grows with the batch (per-episode accumulator words of the on-chip all-reduce)
+    assert lib.cwt_fit_workspace_bytes(64, 1, 512, 60, 60, 473, 473) > lib.cwt_fit_workspace_bytes(4, 1, 512, 60, 60, 473, 473)
     assert lib.cwt_transformer_workspace_bytes(4, 2, 4, 512, 3600, 0) > 0
     assert lib.cwt_logits_iou_workspace_bytes(4, 2, 512, 60, 60, 473, 473) > 0
 

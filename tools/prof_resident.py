@@ -36,7 +36,8 @@ if a.prof:
     lib.cwt_debug_set_prof_buffer(None)
     c = buf.cpu().double()
     used = c[:, 0] > 0
-    n_steps = a.iters * ((E + 3) // 4)
+    G = 3 if os.environ.get("CWT_RESIDENT_BPS") == "2" else 4          # episode groups of the plan (60x60x512)
+    n_steps = a.iters * ((E + G - 1) // G)
     names = ["P1 (incl. all-reduce waits)", "halo wait (inside HR)", "HR (incl. halo wait)", "P3 (quad 0 only)", "n_waited_chunks", "sum(store->applied latency when waited)"]
     print(f"instrumented run {tp:.2f} ms; per-step cycles (mean over {int(used.sum())} CTAs, ~{n_steps} steps each; min/max over CTAs):")
     for i, n in enumerate(names):
