@@ -11,8 +11,8 @@
 //       HALO WARP while the compute warps already work on the interior cells
 //   HR  full-resolution stage on the (TW+1) x (TH+1) cells that touch the tile (one task = one row of a
 //       cell; 126 cells = 1008 tasks = two full rounds of the 512 compute threads for 20 x 5)
-//   P3  dW[c]  = sum_p g[p] F[c][p]           second sweep, 4 threads per channel with their pixel-quads of g
-//       in registers
+//   P3  dW[c]  = sum_p g[p] F[c][p]           second sweep, one thread per channel (no cross-thread reduction);
+//       the four warp quads take turns, so channel chunk j leaves at (j+1)/4 of the sweep
 //   AR  group all-reduce of dW, SGD update of W0 / W1 / Wd
 //
 // The halo exchange uses SEQUENCE-TAGGED 8-byte words {fp32 value, step number}: 64-bit stores are
@@ -39,8 +39,10 @@
 // memory sweep (2 x C*NP*4 B at 128 B/clk/SM). floor(#SM / CPG) groups run concurrently
 // (4 x 36 = 144 of 148 SMs for 60x60x512), each looping over its share of the batch.
 //
-// The kernel is compiled twice: specialised for the PSPNet head geometry (C=512, 60x60, tile 20x5: all
-// loop bounds, divisions and predicates become compile-time) and generic (run-time shapes).
+// The kernel is compiled for 512 compute threads / one CTA per SM (default) and for 256 / two CTAs per SM
+// (CWT_RESIDENT_BPS=2: measured slower, kept for comparison), each specialised for the PSPNet head geometry
+// (C=512, 60x60, tile 20x5 resp. 4x10: all loop bounds, divisions and predicates become compile-time) and
+// generic (run-time shapes).
 //
 // Launch: cooperative (all CTAs must be co-resident: they poll each other's words). Every poll loop
 // has a watchdog: on timeout the kernel raises an abort flag, stops waiting and writes NaN results
@@ -55,7 +57,8 @@ namespace cwt {
 // A CTA has CT compute threads + the applier warp + the halo warp. Two configurations are built:
 //   CT = 512, one CTA per SM   (tile 20 x 5 for the PSPNet head: the whole shared memory holds one tile)
 //   CT = 256, two CTAs per SM  (tile 4 x 10: while one CTA waits for the halo / the all-reduce or runs the ALU-bound
-//                               full-resolution stage, the other one keeps the shared-memory pipe busy)
+//                               full-resolution stage, the other one could keep the shared-memory pipe busy — measured
+//                               25.4 ms vs 17 ms at E = 64: the exchange latencies grow with the 90 CTAs per episode)
 constexpr int RES_HELPER_THREADS = 64;
 constexpr unsigned RES_SPIN_LIMIT = 1u << 24;
 constexpr int RES_KCH = 4;        // channel chunks of the pipelined all-reduce
@@ -63,7 +66,7 @@ constexpr int RES_AW = 4;         // accumulator words an applier lane keeps in 
 constexpr int RES_HWORDS = 4;     // halo words per lane of the halo warp (ring <= 128 pixels)
 constexpr int RES_MAXTASK = 4;    // HR row-tasks per compute thread (8 * cells <= 4 * 512)
 constexpr int RES_NPROF = 12;     // profile counters per CTA
-constexpr int RES_P3_DEPTH = 8;   // pixel-quads a P3 thread keeps in flight per operand
+constexpr int RES_P3_DEPTH = 4;   // pixel-quads a P3 thread keeps in flight per operand
 
 struct ResidentParams {
     const float* f_s;          // [E][C][HW]
