@@ -9,13 +9,14 @@ wrapped with the reference's own Python call surface:
     intersectionAndUnionGPU        src/util.py:280-308
     validate_transformer           src/test.py:103-254
     meta_train_step                src/train.py:233-267
+    do_epoch                       src/train.py:166-290
 
 Importing the package never needs a GPU; calling an op without the built library or without a CUDA
 tensor raises (there is no CPU fallback).
 """
 from . import _lib, synthetic  # noqa: F401
 from .classifier import draw_initial_weights, get_classifier, inner_loop  # noqa: F401
-from .episodic import (HeadOutput, HostPipeline, IoUTable, episode_head, meta_train_step, query_loss, run_sweep,  # noqa: F401
+from .episodic import (HeadOutput, HostPipeline, IoUTable, do_epoch, episode_head, meta_train_step, query_loss, run_sweep,  # noqa: F401
                        transformer_params, validate_transformer)
 from .metrics import (batch_intersection_union_int, batch_intersectionAndUnionGPU,  # noqa: F401
                       intersection_union_int, intersectionAndUnionGPU)
@@ -28,7 +29,7 @@ __all__ = [
     "MultiHeadAttentionOne", "fit_classifier", "inner_loop", "get_classifier", "draw_initial_weights",
     "batch_intersectionAndUnionGPU", "intersectionAndUnionGPU", "batch_intersection_union_int",
     "intersection_union_int", "validate_transformer", "episode_head", "run_sweep", "IoUTable", "HostPipeline",
-    "meta_train_step", "query_loss", "transformer_forward", "transformer_backward", "logits_iou",
+    "meta_train_step", "do_epoch", "query_loss", "transformer_forward", "transformer_backward", "logits_iou",
     "upsample_argmax_iou", "intersection_union", "label_counts", "query_loss_grad",
     "rows_times_feat", "feat_times_rows", "synthetic",
 ]

@@ -279,6 +279,76 @@ def meta_train_step(transformer, optimizer, f_s, s_label, f_q, q_label, w0, cls_
     return {"loss": loss.detach(), "w_fit": w_fit, "w_adapted": updated.detach(), "logits60": logits}
 
 
+def do_epoch(args, train_loader, model, transformer, optimizer_trans, epoch: int, iter_per_epoch: int, log_iter: int,
+             verbose: bool = True):
+    """Drop-in for the reference's training epoch (src/train.py:166-290), same arguments and return value
+    ``(train_Ious, train_losses)`` (two ``[log_iter]`` tensors). ``args`` needs image_size, bottleneck_dim,
+    num_classes_tr, cls_lr, adapt_iter, batch_size (1 in the reference, config_files/pascal.yaml:25).
+
+    Per iteration: the backbone (the caller's PyTorch module, ``model.extract_features``) produces f_s in train mode
+    and f_q in eval mode exactly as the reference does; the classifier fit, the transformer forward / backward, the
+    weighted query CE and both IoU read-outs run in the fused kernels. In the 1-shot case the reference feeds the
+    support image twice (``expand(2, ...)``, so that train-mode BatchNorm sees a batch) and fits on the two identical
+    shots; the pooled-mean loss of two identical shots equals the 1-shot loss, so the fit runs on the first copy."""
+    device = next(transformer.parameters()).device
+    if device.type != "cuda":
+        raise RuntimeError("do_epoch (cwt_b200): the transformer must live on a CUDA device")
+    C = args.bottleneck_dim
+    bs = int(getattr(args, "batch_size", 1))
+    if bs != 1:
+        raise NotImplementedError("do_epoch keeps the reference's batch size / episode of 1 (src/train.py:194)")
+    train_losses = torch.zeros(log_iter)
+    train_Ious = torch.zeros(log_iter)
+    train_Ious0 = torch.zeros(log_iter)
+    loss_sum, loss_n = 0.0, 0
+    it = iter(train_loader)
+    model.train()
+    transformer.train()
+    for i in range(iter_per_epoch):
+        try:
+            item = next(it)
+        except StopIteration:
+            it = iter(train_loader)
+            item = next(it)
+        qry_img, q_label, spprt_imgs, s_label, subcls = item[:5]
+        spprt_imgs, s_label = spprt_imgs.to(device), s_label.to(device)
+        q_label, qry_img = q_label.to(device), qry_img.to(device)
+        one_shot = spprt_imgs.shape[1] == 1
+        if one_shot:
+            spprt = spprt_imgs.squeeze(0).expand(2, 3, args.image_size, args.image_size)
+        else:
+            spprt = spprt_imgs.squeeze(0)
+        w0 = nn.Conv2d(C, args.num_classes_tr, kernel_size=1, bias=False).weight.detach().view(1, 2, C).to(device)
+        with torch.no_grad():
+            f_s, _ = model.extract_features(spprt)                     # [n_support, c, h, w], backbone in train mode
+        if one_shot:
+            f_s = f_s[:1]
+        model.eval()
+        with torch.no_grad():
+            f_q, _ = model.extract_features(qry_img)                   # [1, c, h, w]
+        f_s, f_q = f_s.float().unsqueeze(0).contiguous(), f_q.float().contiguous()
+        out = meta_train_step(transformer, optimizer_trans, f_s, s_label, f_q, q_label, w0, args.cls_lr, args.adapt_iter)
+        # read-outs (src/train.py:269-279): adapted logits on normalised features, baseline logits on raw features
+        l0 = ops.rows_times_feat(out["w_fit"], f_q, normalize=False).view(1, 2, f_q.shape[-2], f_q.shape[-1])
+        counts, _ = ops.upsample_argmax_iou(torch.cat([out["logits60"], l0]), torch.cat([q_label, q_label]))
+        counts = counts.cpu().double()
+        iou = counts[:, :, 0] / (counts[:, :, 1] + 1e-10)               # [2 read-outs, 2 classes]
+        loss_sum += float(out["loss"]) / bs
+        loss_n += 1
+        if i < log_iter:
+            train_losses[i] = loss_sum / loss_n
+            train_Ious[i] = float(iou[0].mean())
+            train_Ious0[i] = float(iou[1].mean())
+        if verbose and ((epoch == 0 and i % 100 == 0) or i % 500 == 0):
+            print('iter {} IoUf {:.2f}, IoUb {:.2f}, IoUf0 {:.2f}, IoUb0 {:.2f}'.format(
+                i, float(iou[0, 1]), float(iou[0, 0]), float(iou[1, 1]), float(iou[1, 0])))
+        model.train()
+    if verbose:
+        print('Epoch {}: The mIoU {:.2f}, loss {:.2f}, mIoU0 {:.2f}'.format(
+            epoch + 1, train_Ious.mean(), train_losses.mean(), train_Ious0.mean()))
+    return train_Ious, train_losses
+
+
 # ----------------------------------------------------------------------------------------
 # host-resident episodes: double-buffered H2D staging in front of the head
 # ----------------------------------------------------------------------------------------

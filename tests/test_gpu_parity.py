@@ -460,6 +460,50 @@ def test_validate_transformer_dropin(cuda_device):
     assert abs(loss - float(np.mean(losses))) < 1e-4
 
 
+def test_do_epoch_dropin(cuda_device):
+    """The reference's training-epoch signature (src/train.py:166-175) on a fake loader / backbone: the per-iteration losses,
+    both IoU read-outs and the updated transformer equal a replay of the same iterations through meta_train_step, with the
+    IoUs recomputed by the oracle from the returned logits."""
+    kw = dict(shot=1, C=64, h=12, w=12, H=89, W=89, style="unit")
+    n = 4
+    eps = [syn.make_episode(700 + i, label_dtype=torch.int64, **kw) for i in range(n)]
+    feats, items = {}, []
+    for i, ep in enumerate(eps):
+        feats[2 * i], feats[2 * i + 1] = ep.f_s[0], ep.f_q
+        simg = torch.full((1, 1, 3, 89, 89), float(2 * i))
+        qimg = torch.full((1, 3, 89, 89), float(2 * i + 1))
+        items.append((qimg, ep.q_label.unsqueeze(0), simg, ep.s_label.unsqueeze(0), [torch.tensor([ep.subcls])], None, None))
+    args = _Args()
+    args.image_size, args.bottleneck_dim, args.num_classes_tr, args.cls_lr, args.adapt_iter, args.batch_size = 89, 64, 2, 0.1, 30, 1
+    n_head = 2
+    params = syn.make_transformer_params(n_head, 64)
+
+    def fresh():
+        tr = cwt.MultiHeadAttentionOne(n_head, 64, 64, 64, dropout=0.5).to(cuda_device)
+        tr.load_state_dict(params)
+        return tr, torch.optim.SGD(tr.parameters(), lr=0.0025, momentum=0.9, weight_decay=1e-4, nesterov=True)
+
+    tr, opt = fresh()
+    torch.manual_seed(11)
+    ious, losses = cwt.do_epoch(args, items, _FakeBackbone(feats), tr, opt, 0, n, n, verbose=False)
+    assert ious.shape == (n,) and losses.shape == (n,)
+
+    tr2, opt2 = fresh()
+    torch.manual_seed(11)
+    run, ref_ious = 0.0, []
+    for i, ep in enumerate(eps):
+        w0 = torch.nn.Conv2d(64, 2, 1, bias=False).weight.detach().view(1, 2, 64).to(cuda_device)
+        out = cwt.meta_train_step(tr2, opt2, ep.f_s.unsqueeze(0).to(cuda_device), ep.s_label.unsqueeze(0).to(cuda_device),
+                                  ep.f_q.unsqueeze(0).to(cuda_device), ep.q_label.unsqueeze(0).to(cuda_device), w0, 0.1, 30)
+        run += float(out["loss"])
+        assert abs(float(losses[i]) - run / (i + 1)) < 1e-6
+        I, U, _ = O.batch_intersection_and_union_ref(out["logits60"].cpu().unsqueeze(1), ep.q_label.view(1, 1, 89, 89), 2)
+        ref_ious.append(float((I[0, 0] / (U[0, 0] + 1e-10)).mean()))
+    assert torch.allclose(ious, torch.tensor(ref_ious), atol=2e-4)          # (a near-tie pixel moves an 89x89 IoU by ~1e-4)
+    for (k, a), (_, b) in zip(tr.named_parameters(), tr2.named_parameters()):
+        assert torch.equal(a, b), k
+
+
 # ---------------------------------------------------------------------------- (a-13) training step
 @pytest.mark.parametrize("name", ["train_small_h2", "train_full_h1"])
 def test_meta_train_step_vs_golden(cuda_device, name):
