@@ -1,3 +1,4 @@
+// Build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o tools/micro/lds_bench tools/micro/lds_bench.cu ; run on the GPU box.
 // Shared-memory LDS.128 access-pattern microbenchmark (one CTA per SM, 512 threads, 204.8 KB of smem).
 // Patterns are the candidates for the resident fit's second sweep (rows of 100 floats = 400 B per channel).
 #include <cstdio>
