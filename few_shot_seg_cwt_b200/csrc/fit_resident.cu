@@ -157,10 +157,11 @@ __device__ __forceinline__ void sigmoid_row(float left, float right, float (&p)[
     const float nleft = NEG_LOG2E * left, nslope = NEG_LOG2E * (right - left) * 0.125f;
     float e[8];
     if (fmaxf(fabsf(nleft), fabsf(fmaf(7.f, nslope, nleft))) <= 60.f) {
-        const float r = fast_ex2(nslope);
+        const float r = fast_ex2(nslope), r2 = r * r;
         e[0] = fast_ex2(nleft);
+        e[1] = e[0] * r;
 #pragma unroll
-        for (int s = 1; s < 8; ++s) e[s] = e[s - 1] * r;
+        for (int s = 2; s < 8; ++s) e[s] = e[s - 2] * r2;          // two independent chains
     } else {
 #pragma unroll
         for (int s = 0; s < 8; ++s) e[s] = fast_ex2(fminf(fmaxf(fmaf((float)s, nslope, nleft), -60.f), 60.f));
@@ -200,9 +201,7 @@ __device__ __forceinline__ void hires_row_uniform(float left, float right, bool 
     float p[8];
     sigmoid_row(left, right, p);
     const float sp = ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
-    float ssp = p[1];
-#pragma unroll
-    for (int s = 2; s < 8; ++s) ssp = fmaf((float)s, p[s], ssp);
+    const float ssp = (fmaf(2.f, p[2], p[1]) + fmaf(4.f, p[4], 3.f * p[3])) + (fmaf(6.f, p[6], 5.f * p[5]) + 7.f * p[7]);
     const float c = y ? c1 : c0;
     const float gs = c * (sp - (y ? 8.f : 0.f));
     const float gr = c * (ssp - (y ? 28.f : 0.f)) * 0.125f;
