@@ -9,6 +9,9 @@
 #include "common.cuh"
 #include "skinny.cuh"
 #include "hires.cuh"
+#include "iou_stream.cuh"
+#include <cstdlib>
+#include <cstring>
 
 namespace cwt {
 
@@ -305,6 +308,13 @@ static int launch_fused_t(const float* wts, const float* f_q, const void* lab, i
     return CWT_OK;
 }
 
+__global__ void __launch_bounds__(256) k_zero_outputs(unsigned long long* a, size_t na, unsigned long long* b, size_t nb) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // the dependent kernel waits before its first atomic
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < na) a[i] = 0ull;
+    else if (b && i - na < nb) b[i - na] = 0ull;         // 0.0 as a double
+}
+
 // rows of variants flagged in normalize_mask are divided by max(|f_q[:,p]|, 1e-12)  (F.normalize)
 __global__ void __launch_bounds__(256)
 k_scale_by_inv_norm(float* __restrict__ l, const float* __restrict__ n2, int V, int HW, int normalize_mask,
@@ -419,7 +429,28 @@ extern "C" int cwt_logits_iou(const float* wts, const float* f_q, const void* q_
     LogitsIouWs ws;
     size_t need = carve_logits_iou(cv, ws, E, V, HWl);
     CWT_REQUIRE(workspace && ws_bytes >= need, CWT_ERR_WORKSPACE, "logits_iou: workspace %zu < %zu", ws_bytes, need);
-    // fused single pass (north-star (c)) whenever the band loads can be vectorised; otherwise logits pass + histogram pass
+    // streaming single pass (north-star (c)): persistent warp-specialised CTAs fed by a bulk-TMA ring (iou_stream.cuh).
+    // CWT_LOGITS_IOU=band selects the older band-per-CTA fused kernel (kept for V > 2 and odd shapes).
+    const char* algo_env = getenv("CWT_LOGITS_IOU");
+    const bool want_band = algo_env && strcmp(algo_env, "band") == 0;
+    if (!want_band && logits_iou_stream_ok(f_q, V, C, h, w, H, W)) {
+        {   // counters and CE sums start at zero: one launch for both output buffers
+            const size_t n64 = (size_t)6 * E * V + (ce_or_null ? (size_t)2 * E * V : 0);
+            k_zero_outputs<<<(unsigned)((n64 + 255) / 256), 256, 0, st>>>(reinterpret_cast<unsigned long long*>(iu_counts), (size_t)6 * E * V,
+                                                                      reinterpret_cast<unsigned long long*>(ce_or_null), (size_t)2 * E * V);
+            CWT_LAUNCHED("zero_outputs");
+        }
+        auto* cnt = reinterpret_cast<unsigned long long*>(iu_counts);
+        const unsigned ce_mask = (1u << V) - 1u;
+        const bool i64 = label_kind == CWT_LABEL_I64;
+        int rc;
+        if (V == 1) rc = i64 ? launch_logits_iou_stream<true, 1>(wts, f_q, q_label, normalize_mask, ce_mask, cnt, logits60_or_null, ce_or_null, E, C, h, w, H, W, ignore_index, st)
+                             : launch_logits_iou_stream<false, 1>(wts, f_q, q_label, normalize_mask, ce_mask, cnt, logits60_or_null, ce_or_null, E, C, h, w, H, W, ignore_index, st);
+        else        rc = i64 ? launch_logits_iou_stream<true, 2>(wts, f_q, q_label, normalize_mask, ce_mask, cnt, logits60_or_null, ce_or_null, E, C, h, w, H, W, ignore_index, st)
+                             : launch_logits_iou_stream<false, 2>(wts, f_q, q_label, normalize_mask, ce_mask, cnt, logits60_or_null, ce_or_null, E, C, h, w, H, W, ignore_index, st);
+        if (rc != CWT_ERR_UNSUPPORTED) return rc;
+    }
+    // fused band kernel whenever the band loads can be vectorised; otherwise logits pass + histogram pass
     if (HWl % 4 == 0 && V <= 4 && w <= IOU_MAXW && H == 8 * (h - 1) + 1 && W == 8 * (w - 1) + 1 &&
         (size_t)C * 2 * V * 4 <= 96 * 1024) {
         CWT_CUDA(cudaMemsetAsync(iu_counts, 0, sizeof(long long) * 6 * (size_t)E * V, st));

@@ -313,6 +313,53 @@ def test_batch_intersection_and_union_dropin(cuda_device, geom, dtype):
     assert abs(float(got) - float(ce_ref)) < 1e-5 * max(1.0, float(ce_ref))
 
 
+@pytest.mark.parametrize("algo", ["stream", "band"])
+@pytest.mark.parametrize("case", [
+    # E, V, C, h, w, label dtype
+    (3, 2, 64, 12, 12, torch.uint8),
+    (5, 1, 96, 9, 12, torch.int64),        # non-square, single weight set
+    (2, 2, 512, 60, 60, torch.uint8),      # the head geometry
+    (37, 2, 32, 12, 16, torch.uint8),      # more episodes than cell rows per CTA range: ranges cross episode boundaries
+    (1, 2, 64, 5, 8, torch.int64),         # fewer cell rows than one chunk
+    (200, 2, 32, 4, 4, torch.uint8),       # ranges shorter than an episode AND spanning several tiny episodes
+])
+def test_logits_iou_fused_kernels(cuda_device, monkeypatch, case, algo):
+    """(c) logits -> up-sample -> argmax -> I/U/T (+CE) in one pass: the streaming kernel (bulk-TMA ring, default) and the
+    band kernel (CWT_LOGITS_IOU=band) against torch: logits within 2e-6, counts bit-exact given the kernel's own logits
+    (F.interpolate / argmax / histc of src/util.py:237-308 on the CPU), CE within 1e-5."""
+    E, V, C, h, w, dtype = case
+    H, W = 8 * (h - 1) + 1, 8 * (w - 1) + 1
+    if algo == "band":
+        monkeypatch.setenv("CWT_LOGITS_IOU", "band")
+    g = torch.Generator().manual_seed(E * 1000 + C)
+    f_q = torch.relu(torch.randn(E, C, h, w, generator=g))
+    f_q[0, :, 0, 0] = 0.0                                          # F.normalize clamps the norm at 1e-12
+    wts = torch.randn(E, V, 2, C, generator=g) * 0.1
+    tgt = torch.randint(0, 3, (E, H, W), generator=g)
+    tgt[tgt == 2] = 255
+    tgt[E - 1, : H // 2] = 255
+    n0 = L.launch_count()
+    counts, ce, logits = ops.logits_iou(wts.to(cuda_device), f_q.to(cuda_device), tgt.to(dtype).to(cuda_device),
+                                        normalize_mask=0b01, return_logits=True)
+    counts2, ce2, none = ops.logits_iou(wts.to(cuda_device), f_q.to(cuda_device), tgt.to(dtype).to(cuda_device),
+                                        normalize_mask=0b01, return_logits=False)
+    assert L.launch_count() > n0 and none is None
+    counts, ce, logits = counts.cpu(), ce.cpu(), logits.cpu()
+    assert torch.equal(counts, counts2.cpu())                      # deterministic, with and without the logits output
+    X = f_q.reshape(E, C, h * w).double()
+    Xn = F.normalize(f_q, dim=1).reshape(E, C, h * w).double()
+    for v in range(V):
+        ref = torch.einsum("erc,ecp->erp", wts[:, v].double(), Xn if v == 0 else X).reshape(E, 2, h, w)
+        assert rel_err(logits[:, v], ref) < 2e-6
+        I, U, T = O.batch_intersection_and_union_ref(logits[:, v].unsqueeze(1), tgt.unsqueeze(1), 2)
+        assert torch.equal(counts[:, v, :, 0].float(), I[:, 0]) and torch.equal(counts[:, v, :, 1].float(), U[:, 0])
+        assert torch.equal(counts[:, v, :, 2].float(), T[:, 0])
+        up = F.interpolate(logits[:, v], size=(H, W), mode="bilinear", align_corners=True)
+        ce_ref = F.cross_entropy(up, tgt, ignore_index=255, reduction="sum")
+        assert abs(float(ce[:, v, 0].sum()) - float(ce_ref)) < 1e-5 * max(1.0, float(ce_ref))
+        assert int(ce[:, v, 1].sum()) == int((tgt != 255).sum())
+
+
 def test_argmax_ties_and_empty(cuda_device):
     lg = torch.zeros(1, 1, 2, 3, 3, device=cuda_device)                      # exact tie everywhere
     tgt = torch.zeros(1, 1, 17, 17, dtype=torch.long, device=cuda_device)
