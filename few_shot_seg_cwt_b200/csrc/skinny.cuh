@@ -234,7 +234,7 @@ static int launch_feat_times_cols(const float* f, const float* P, float* out, in
     if (r_actual <= 1) return launch_ftc_t<1, 4>(f, P, E, S, C, HW, r_actual, epi, st);
     if (r_actual <= 2) return launch_ftc_t<2, 4>(f, P, E, S, C, HW, r_actual, epi, st);
     if (r_actual <= 4) return launch_ftc_t<4, 4>(f, P, E, S, C, HW, r_actual, epi, st);
-    if (r_actual <= 8) return launch_ftc_t<8, 2>(f, P, E, S, C, HW, r_actual, epi, st);
+    if (r_actual <= 8) return launch_ftc_t<8, 2>(f, P, E, S, C, HW, r_actual, epi, st);     // (4 channels per warp: 168 registers, measured slower)
     return launch_ftc_t<16, 2>(f, P, E, S, C, HW, r_actual, epi, st);
 }
 

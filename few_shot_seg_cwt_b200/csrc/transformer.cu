@@ -45,24 +45,39 @@ __global__ void __launch_bounds__(256) k_sgemm_small(GemmP p) {
     const float* B = p.B + (size_t)blockIdx.z * p.b_bs;
     float* C = p.C + (size_t)blockIdx.z * p.c_bs;
     float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-    for (int k0 = 0; k0 < p.K; k0 += G_TK) {
+    // the next k-tile is fetched into registers while the current one is multiplied (the CTA is alone on its SM for the
+    // small problems of this path, so nothing else hides the L2 latency)
+    float ra[2], rb[4];
+    auto fetch = [&](int k0) {
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
             int idx = tid + i * 256, m, k;
             if (p.a_ks == 1) { k = idx % G_TK; m = idx / G_TK; } else { m = idx % G_TM; k = idx / G_TM; }
-            float v = 0.f;
-            if (m0 + m < p.M && k0 + k < p.K) v = A[(size_t)(m0 + m) * p.a_ms + (size_t)(k0 + k) * p.a_ks];
-            As[k][m] = v;
+            ra[i] = (m0 + m < p.M && k0 + k < p.K) ? A[(size_t)(m0 + m) * p.a_ms + (size_t)(k0 + k) * p.a_ks] : 0.f;
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             int idx = tid + i * 256, n, k;
             if (p.b_ns == 1) { n = idx % G_TN; k = idx / G_TN; } else { k = idx % G_TK; n = idx / G_TK; }
-            float v = 0.f;
-            if (n0 + n < p.N && k0 + k < p.K) v = B[(size_t)(k0 + k) * p.b_ks + (size_t)(n0 + n) * p.b_ns];
-            Bs[k][n] = v;
+            rb[i] = (n0 + n < p.N && k0 + k < p.K) ? B[(size_t)(k0 + k) * p.b_ks + (size_t)(n0 + n) * p.b_ns] : 0.f;
+        }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < p.K; k0 += G_TK) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            int idx = tid + i * 256, m, k;
+            if (p.a_ks == 1) { k = idx % G_TK; m = idx / G_TK; } else { m = idx % G_TM; k = idx / G_TM; }
+            As[k][m] = ra[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int idx = tid + i * 256, n, k;
+            if (p.b_ns == 1) { n = idx % G_TN; k = idx / G_TN; } else { k = idx % G_TK; n = idx / G_TK; }
+            Bs[k][n] = rb[i];
         }
         __syncthreads();
+        if (k0 + G_TK < p.K) fetch(k0 + G_TK);
 #pragma unroll
         for (int k = 0; k < G_TK; ++k) {
             const float a0 = As[k][ty * 2], a1 = As[k][ty * 2 + 1];
@@ -151,7 +166,8 @@ k_softmax_rows(const float* __restrict__ sraw, const float* __restrict__ n2, con
 
 // Rr = Z*keep/(1-p) + q ; LayerNorm over C (eps 1e-5, biased variance)   grid (rows)
 __global__ void __launch_bounds__(128)
-k_residual_layernorm(const float* __restrict__ Z, const float* __restrict__ q, const uint8_t* __restrict__ keep,
+k_residual_layernorm(const float* __restrict__ Z, int nparts, size_t part_stride, const float* __restrict__ zbias,
+                     const float* __restrict__ q, const uint8_t* __restrict__ keep,
                      float drop_scale, const float* __restrict__ g, const float* __restrict__ b,
                      float* __restrict__ out, float* __restrict__ xhat, float* __restrict__ rstd_out, int C) {
     extern __shared__ float rbuf[];            // [C]
@@ -161,7 +177,9 @@ k_residual_layernorm(const float* __restrict__ Z, const float* __restrict__ q, c
     const int tid = threadIdx.x;
     float s = 0.f;
     for (int c = tid; c < C; c += 128) {
-        float z = Z[row * C + c];
+        float z = Z[row * C + c];                           // Z = sum over heads of the per-head fc partials (+ bias), fixed order
+        for (int h2 = 1; h2 < nparts; ++h2) z += Z[(size_t)h2 * part_stride + row * C + c];
+        if (zbias) z += zbias[c];
         if (keep) z = keep[row * C + c] ? z * drop_scale : 0.f;
         float v = z + q[row * C + c];
         rbuf[c] = v;
@@ -284,7 +302,7 @@ static size_t carve_fwd(Carver& cv, TFwdWs& w, int E, int Lq, int nH, int C, int
     w.sraw = cv.take<float>((size_t)E * R * HW);
     w.n2 = cv.take<float>((size_t)E * HW);
     w.Pm = cv.take<float>((size_t)E * R * HW);
-    w.Z = cv.take<float>((size_t)E * Lq * C);
+    w.Z = cv.take<float>((size_t)nH * E * Lq * C);          // per-head partials of fc
     w.tc_bytes = (algo == CWT_ATTN_TCGEN05) ? kproj_tcgen05_workspace_bytes(E, Lq, nH, C, HW) : 0;
     w.tc = cv.take<char>(w.tc_bytes);
     return align_up(cv.off);
@@ -372,9 +390,11 @@ extern "C" int cwt_transformer_fwd_f32(const float* q, const float* k, int norma
     rc = gemm(sv.aX, NC, 1, w_qkvs, 1, C, sv.O, NC, ML, C, C, 1.f, false, nullptr, nH, C, (long long)C * C, C, st);
     if (rc) return rc;
     // Z = O Fc^T + b
-    rc = gemm(sv.O, NC, 1, fc_w, 1, NC, w.Z, C, ML, C, NC, 1.f, false, fc_b, 1, 0, 0, 0, st);
+    //   one GEMM per head (K = C instead of nH*C, nH times the CTAs): Z_h = O_h Fc_h^T; the partials are summed, with the bias,
+    //   by the LayerNorm kernel in a fixed order
+    rc = gemm(sv.O, NC, 1, fc_w, 1, NC, w.Z, C, ML, C, C, 1.f, false, nullptr, nH, C, C, (long long)ML * C, st);
     if (rc) return rc;
-    k_residual_layernorm<<<ML, 128, sizeof(float) * C, st>>>(w.Z, q, keep_out, keep_out ? 1.f / (1.f - p_out) : 1.f,
+    k_residual_layernorm<<<ML, 128, sizeof(float) * C, st>>>(w.Z, nH, (size_t)ML * C, fc_b, q, keep_out, keep_out ? 1.f / (1.f - p_out) : 1.f,
                                                              ln_g, ln_b, out, sv.xhat, sv.rstd, C);
     CWT_LAUNCHED("residual_layernorm");
     return CWT_OK;
