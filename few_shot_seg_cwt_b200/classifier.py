@@ -13,8 +13,10 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
+import torch.nn.functional as F
+
 from . import _lib as L
-from .ops import fit_classifier
+from .ops import fit_classifier, normalize_features
 
 
 def get_classifier(bottleneck_dim: int = 512, num_classes: int = 2, device=None) -> nn.Conv2d:
@@ -31,18 +33,70 @@ def draw_initial_weights(n_episodes: int, C: int = 512, generator: Optional[torc
     return w.to(device) if device is not None else w
 
 
-def inner_loop(classifier: nn.Conv2d, f_s: torch.Tensor, s_label: torch.Tensor, cls_lr: float,
-               adapt_iter: int, reset: bool = True, check: bool = True, algo: int = L.FIT_AUTO) -> None:
-    """``PSPNet.inner_loop`` drop-in (src/model/pspnet.py:189-205, loss 'wt_ce'): re-initialise the
-    classifier, fit it on (f_s [S,C,h,w], s_label [S,H,W]) and write the result into
-    ``classifier.weight`` in place. The class weight bg_cnt/fg_cnt of model_util.py:27-37 equals
-    n0/n1 for labels in {0,1,255}."""
-    if classifier.bias is not None or classifier.weight.shape[0] != 2 or classifier.kernel_size != (1, 1):
+class CosCls(nn.Module):
+    """Cosine classifier with the reference's constructor and parameter names (``CosCls``,
+    src/model/pspnet.py:290-315): ``cls`` is the 1x1 conv, ``scale_factor`` the temperature (2.0).
+    ``cls_type`` = four flags [weight-norm reparametrisation 'r', weight normalisation 'n', bias 'b', learnable
+    temperature 't']; '0' / 'o' switch a flag off. ``forward`` is plain torch (it is not on the episodic hot path);
+    :func:`inner_loop` fits the flag-free form ('oooo' / '0000') with the fused CUDA fit."""
+
+    def __init__(self, in_dim: int = 512, n_classes: int = 2, cls_type: str = "0000"):
+        super().__init__()
+        if len(cls_type) != 4 or any(ch not in ok for ch, ok in zip(cls_type, ("r0o", "n0o", "b0o", "t0o"))):
+            raise KeyError(f"cls_type {cls_type!r}")                 # parse_param_coscls raises KeyError on unknown flags
+        self.WeightNormR, self.weight_norm, self.bias, self.temp = (cls_type[0] == "r", cls_type[1] == "n",
+                                                                    cls_type[2] == "b", cls_type[3] == "t")
+        self.cls = nn.Conv2d(in_dim, n_classes, kernel_size=1, bias=self.bias)
+        if self.WeightNormR:
+            nn.utils.weight_norm(self.cls, "weight", dim=0)
+        self.scale_factor = nn.Parameter(torch.tensor(2.0)) if self.temp else 2.0
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        x_norm = F.normalize(x, p=2, dim=1, eps=0.00001)
+        if self.weight_norm:
+            self.cls.weight.data = F.normalize(self.cls.weight.data, p=2, dim=1, eps=0.00001)
+        return self.scale_factor * self.cls(x_norm)
+
+    def reset_parameters(self) -> None:
+        self.cls.reset_parameters()
+
+    @property
+    def plain(self) -> bool:
+        return not (self.WeightNormR or self.weight_norm or self.bias or self.temp)
+
+
+def inner_loop(classifier, f_s: torch.Tensor, s_label: torch.Tensor, cls_lr: float,
+               adapt_iter: int, reset: bool = True, check: bool = True, algo: int = L.FIT_AUTO,
+               loss_type: str = "wt_ce") -> None:
+    """``PSPNet.inner_loop`` drop-in (src/model/pspnet.py:189-205): re-initialise the classifier, fit it on
+    (f_s [S,C,h,w], s_label [S,H,W]) and write the result into its weight in place.
+
+    ``loss_type`` is ``args.inner_loss_type`` (SegLoss, src/model/model_util.py:9-24):
+      * ``'wt_ce'`` — class-weighted CE; the weight bg_cnt/fg_cnt of model_util.py:27-37 equals n0/n1 for labels
+        in {0,1,255};
+      * ``'ce'``    — plain ``nn.CrossEntropyLoss(ignore_index=255)`` (class weight [1, 1]);
+      * ``'wt_dc'`` / ``'dc'`` (per-channel sigmoid dice) are not built — NotImplementedError.
+    ``classifier`` is the reference's ``nn.Conv2d(C, 2, 1, bias=False)`` (``dist == 'dot'``) or a flag-free
+    :class:`CosCls` (``dist == 'cos'``, cls_type 'oooo'): ``scale_factor * conv(F.normalize(x, eps=1e-5))`` is the same
+    bias-free classifier on the features ``2 * x_norm``, which one extra kernel prepares."""
+    if loss_type in ("wt_dc", "dc"):
+        raise NotImplementedError("cwt_b200 inner_loop: the dice losses of SegLoss ('wt_dc', 'dc') are not built")
+    if loss_type not in ("wt_ce", "ce"):
+        loss_type = "wt_ce"                                     # SegLoss falls through to weighted CE for any other string
+    if isinstance(classifier, CosCls):
+        if not classifier.plain:
+            raise NotImplementedError("cwt_b200 inner_loop fits CosCls without weight-norm / bias / learnable temperature "
+                                      "(cls_type 'oooo' or '0000')")
+        conv, feat = classifier.cls, normalize_features(f_s, eps=1e-5, scale=float(classifier.scale_factor))
+    else:
+        conv, feat = classifier, f_s
+    if conv.bias is not None or conv.weight.shape[0] != 2 or conv.kernel_size != (1, 1):
         raise NotImplementedError("cwt_b200 inner_loop fits the reference's 2-class bias-free 1x1 classifier")
     if reset:
         classifier.reset_parameters()                      # CPU/GPU generator order as in the reference
-    C = classifier.weight.shape[1]
-    w0 = classifier.weight.detach().reshape(2, C).to(f_s.device, torch.float32)
-    w = fit_classifier(f_s, s_label, w0, cls_lr, adapt_iter, check=check, algo=algo)
+    C = conv.weight.shape[1]
+    w0 = conv.weight.detach().reshape(2, C).to(f_s.device, torch.float32)
+    cw = torch.ones(2, dtype=torch.float32, device=f_s.device) if loss_type == "ce" else None
+    w = fit_classifier(feat, s_label, w0, cls_lr, adapt_iter, class_weight=cw, check=check, algo=algo)
     with torch.no_grad():
-        classifier.weight.copy_(w.reshape(2, C, 1, 1))
+        conv.weight.copy_(w.reshape(2, C, 1, 1))

@@ -296,6 +296,21 @@ def feat_times_rows(P: torch.Tensor, f: torch.Tensor, normalize: bool = False) -
     return out
 
 
+def normalize_features(f: torch.Tensor, eps: float = 1e-5, scale: float = 1.0) -> torch.Tensor:
+    """scale * F.normalize(f, p=2, dim=-3, eps=eps) for f [..., C, h, w]: the feature side of the cosine classifier
+    (CosCls.forward, src/model/pspnet.py:302-310, with scale = scale_factor = 2.0)."""
+    dev = L.require_cuda(f)
+    fc = _f32c(f, "f")
+    Cc, h, w = fc.shape[-3:]
+    n_img = fc.numel() // max(Cc * h * w, 1)
+    out = torch.empty_like(fc)
+    lib = L.load()
+    with torch.cuda.device(dev):
+        rc = lib.cwt_normalize_features_f32(L.ptr(fc), L.ptr(out), n_img, Cc, h * w, float(eps), float(scale), L.stream_ptr(dev))
+    L.check(rc, "cwt_normalize_features_f32")
+    return out
+
+
 # ----------------------------------------------------------------------------------------
 # torch.ops.cwt_b200.* registration (PyTorch custom ops in front of the C ABI)
 # ----------------------------------------------------------------------------------------

@@ -174,6 +174,15 @@ int cwt_rows_times_feat(const float* M, const float* f, int normalize, float* ou
 int cwt_feat_times_rows(const float* P, const float* f, int normalize, float* out,
                         int E, int R, int C, int HW, void* workspace, size_t ws_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Feature side of the cosine classifier: out[i][c][p] = scale * f[i][c][p] / max(|f[i,:,p]|_2, eps).
+ * Replaces `x_norm = F.normalize(x, p=2, dim=1, eps=0.00001)` and the constant `scale_factor = 2.0` of
+ * CosCls.forward (src/model/pspnet.py:302-310): with cls_type 'oooo'/'0000' (no weight-norm, bias or learnable
+ * temperature) the cosine classifier is the bias-free 1x1 classifier of cwt_fit_classifier_f32 on these features.
+ * f, out: [n_img][C][HW] fp32 (out may not alias f).
+ * ------------------------------------------------------------------------------------- */
+int cwt_normalize_features_f32(const float* f, float* out, int n_img, int C, int HW, float eps, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

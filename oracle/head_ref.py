@@ -80,6 +80,43 @@ def fit_classifier_ref(f_s: torch.Tensor, s_label: torch.Tensor, w0: torch.Tenso
     return (w, losses) if return_losses else w
 
 
+# --------------------------------------------------------------------------------------
+# PSPNet.inner_loop variants                      src/model/pspnet.py:189-205, 290-334
+#   SegLoss 'wt_ce' / 'ce' (src/model/model_util.py:9-37); classifier 'dot' or CosCls 'oooo'
+# --------------------------------------------------------------------------------------
+def inner_loop_ref(f_s: torch.Tensor, s_label: torch.Tensor, w0: torch.Tensor, lr: float, n_iter: int,
+                   loss_type: str = "wt_ce", dist: str = "dot") -> torch.Tensor:
+    """The inner loop with its two switches: ``args.inner_loss_type`` ('wt_ce': weight[fg] = bg_cnt / fg_cnt from
+    torch.bincount, model_util.py:27-37; 'ce': plain CE, ignore 255) and ``args.dist`` ('dot': nn.Conv2d;
+    'cos': CosCls with cls_type 'oooo' — scores = 2.0 * conv(F.normalize(x, p=2, dim=1, eps=1e-5)),
+    pspnet.py:302-310). f_s [S,C,h,w]; s_label [S,H,W]; w0 [2,C] -> fitted weight [2,C]."""
+    S, C = f_s.shape[:2]
+    tgt = s_label.long()
+    conv = nn.Conv2d(C, 2, kernel_size=1, bias=False)
+    with torch.no_grad():
+        conv.weight.copy_(w0.reshape(2, C, 1, 1))
+    opt = torch.optim.SGD(conv.parameters(), lr=lr)
+    for _ in range(n_iter):
+        if dist == "dot":
+            out = conv(f_s)
+        else:
+            out = 2.0 * conv(F.normalize(f_s, p=2, dim=1, eps=0.00001))
+        out = F.interpolate(out, size=tgt.shape[-2:], mode="bilinear", align_corners=True)
+        if loss_type == "ce":
+            loss = nn.CrossEntropyLoss(ignore_index=IGNORE)(out, tgt)
+        else:
+            count = torch.bincount(tgt.view(-1))
+            fg = count[1]
+            bg = (torch.sum(count) - fg) if len(count) <= 255 else (torch.sum(count) - count[255] - fg)
+            weight = torch.tensor([1.0, 1.0])
+            weight[1] = bg / fg
+            loss = nn.CrossEntropyLoss(weight=weight, ignore_index=IGNORE)(out, tgt)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+    return conv.weight.detach().reshape(2, C).clone()
+
+
 def bilinear_matrix(n_in: int, n_out: int, dtype=torch.float64) -> torch.Tensor:
     """Dense [n_out, n_in] align_corners=True interpolation matrix (2 non-zeros per row).
     ATen: scale = (n_in-1)/(n_out-1); src = scale*dst; i0 = floor(src); l1 = src - i0."""

@@ -54,6 +54,12 @@ CASES = {
     # configs[1]: 5-shot, pooled class weight and pooled mean
     "full_5shot_h4":         dict(idx=7, shot=5, C=512, h=60, w=60, H=473, W=473, style="unit", n_head=4, lr=0.1, n_iter=200),
 }
+# PSPNet.inner_loop variants (src/model/pspnet.py:189-205): SegLoss type x classifier kind
+INNER_CASES = {
+    "inner_small_dot_ce":   dict(idx=21, shot=1, C=64, h=12, w=12, H=89, W=89, style="unit", lr=0.1, n_iter=50, loss_type="ce", dist="dot"),
+    "inner_small_cos_wtce": dict(idx=22, shot=2, C=64, h=12, w=12, H=89, W=89, style="backbone", lr=0.1, n_iter=50, loss_type="wt_ce", dist="cos"),
+    "inner_full_cos_ce":    dict(idx=23, shot=1, C=512, h=60, w=60, H=473, W=473, style="backbone", lr=0.1, n_iter=100, loss_type="ce", dist="cos"),
+}
 TRAIN_CASES = {
     "train_small_h2": dict(idx=11, shot=1, C=64, h=12, w=12, H=89, W=89, style="unit", n_head=2, lr=0.1, n_iter=20, p_attn=0.1, p_out=0.5),
     "train_full_h1":  dict(idx=12, shot=1, C=512, h=60, w=60, H=473, W=473, style="unit", n_head=1, lr=0.1, n_iter=20, p_attn=0.1, p_out=0.5),
@@ -135,6 +141,42 @@ def episode_via_reference(ep, params, n_head, lr, n_iter, MHA, batch_iou):
         "tie_margin": (logits[0, 1] - logits[0, 0]).abs(),
         "tie_margin0": (logits0[0, 1] - logits0[0, 0]).abs(),
     }
+
+
+def inner_loop_via_reference(ep, case):
+    """src/model/pspnet.py:189-205 with the reference's own ``CosCls`` / ``nn.Conv2d`` classifier (get_classifier,
+    pspnet.py:326-334) and its own ``SegLoss`` (model_util.py:9-24) doing the work."""
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from src.model.pspnet import CosCls
+        from src.model.model_util import SegLoss
+    C = ep.f_s.shape[1]
+    if case["dist"] == "dot":
+        classifier = nn.Conv2d(C, 2, kernel_size=1, bias=False)
+        conv = classifier
+    else:
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):          # parse_param_coscls prints its flags
+            classifier = CosCls(in_dim=C, n_classes=2, cls_type="oooo")
+        conv = classifier.cls
+    with torch.no_grad():
+        conv.weight.copy_(ep.w0.reshape(2, C, 1, 1))
+    optimizer = torch.optim.SGD(classifier.parameters(), lr=case["lr"])
+    criterion = SegLoss(loss_type=case["loss_type"])
+    f_s, s_label = ep.f_s, ep.s_label.long()
+    cuda_avail = torch.cuda.is_available
+    torch.cuda.is_available = lambda: False                       # weighted_ce_loss moves its weight with .cuda() when it can
+    try:
+        for _ in range(case["n_iter"]):
+            pred_s_label = classifier(f_s)
+            pred_s_label = F.interpolate(pred_s_label, size=s_label.size()[1:], mode="bilinear", align_corners=True)
+            s_loss = criterion(pred_s_label, s_label)
+            optimizer.zero_grad()
+            s_loss.backward()
+            optimizer.step()
+    finally:
+        torch.cuda.is_available = cuda_avail
+    return conv.weight.detach().reshape(2, C).clone(), float(s_loss)
 
 
 def relerr(a, b):
@@ -276,6 +318,20 @@ def main():
                 tie_counts=np.array([[int((tm <= t).sum()) for t in (1e-6, 1e-5, 1e-4)],
                                      [int((tm0 <= t).sum()) for t in (1e-6, 1e-5, 1e-4)]]))
 
+    for name, case in INNER_CASES.items():
+        if a.only and a.only not in name:
+            continue
+        ep = syn.make_episode(case["idx"], **gen_kwargs(case))
+        w_ref, last_loss = inner_loop_via_reference(ep, case)
+        w_ora = O.inner_loop_ref(ep.f_s, ep.s_label, ep.w0, case["lr"], case["n_iter"], case["loss_type"], case["dist"])
+        err = relerr(w_ora, w_ref)
+        print(f"[pin] {name}: oracle vs reference inner_loop rel {err:.2e} last loss {last_loss:.6f}")
+        assert err < 1e-6, err
+        report["cases"][name] = {"errs": {"W_fit": err}, "loss": last_loss}
+        if a.write:
+            np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), case=json.dumps(case), checksum=input_checksum(ep),
+                                torch_version=torch.__version__, W_fit=w_ref.numpy(), loss=last_loss)
+
     for name, case in TRAIN_CASES.items():
         if a.only and a.only not in name:
             continue
@@ -303,7 +359,12 @@ def main():
             np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **out)
 
     if a.write:
-        with open(os.path.join(GOLDEN_DIR, "PIN_REPORT.json"), "w") as f:
+        rp = os.path.join(GOLDEN_DIR, "PIN_REPORT.json")
+        if a.only and os.path.exists(rp):                        # partial run: keep the other cases of the stored report
+            old = json.load(open(rp))
+            old["cases"].update(report["cases"])
+            report["cases"] = old["cases"]
+        with open(rp, "w") as f:
             json.dump(report, f, indent=1)
     print("[pin] done")
 

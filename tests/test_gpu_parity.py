@@ -225,6 +225,41 @@ def test_inner_loop_dropin(cuda_device):
     assert rel_err(clf.weight.detach().view(2, 64), w_ref) < TIGHT
 
 
+@pytest.mark.parametrize("name", golden_names("inner_"))
+def test_inner_loop_variants_vs_golden(cuda_device, name):
+    """PSPNet.inner_loop with its two switches (src/model/pspnet.py:189-205): SegLoss 'ce' / 'wt_ce'
+    (model_util.py:9-37) and the dot / cosine classifier (CosCls 'oooo', pspnet.py:290-315); goldens recorded from
+    the live reference's own CosCls and SegLoss objects."""
+    g = load_golden(name)
+    case = g["case"]
+    ep = syn.make_episode(case["idx"], **gen_kwargs(case))
+    C = case["C"]
+    clf = cwt.CosCls(C, 2, "oooo") if case["dist"] == "cos" else cwt.get_classifier(C, 2)
+    clf = clf.to(cuda_device)
+    conv = clf.cls if case["dist"] == "cos" else clf
+    with torch.no_grad():
+        conv.weight.copy_(ep.w0.reshape(2, C, 1, 1))
+    cwt.inner_loop(clf, ep.f_s.to(cuda_device), ep.s_label.to(cuda_device), case["lr"], case["n_iter"], reset=False,
+                   loss_type=case["loss_type"])
+    assert rel_err(conv.weight.reshape(2, C), g["W_fit"]) < TIGHT
+    if case["dist"] == "cos":                                # the module's own forward is the reference's formula
+        x = ep.f_s.to(cuda_device)
+        ref = 2.0 * F.conv2d(F.normalize(x, p=2, dim=1, eps=1e-5), conv.weight)
+        assert torch.allclose(clf(x), ref)
+        assert rel_err(ops.normalize_features(x, 1e-5, 2.0), 2.0 * F.normalize(x.cpu(), p=2, dim=1, eps=1e-5)) < 1e-6
+
+
+def test_inner_loop_unsupported_variants_raise(cuda_device):
+    ep = syn.make_episode(1, **SMALL)
+    f, lab = ep.f_s.to(cuda_device), ep.s_label.to(cuda_device)
+    with pytest.raises(NotImplementedError):                 # dice losses of SegLoss
+        cwt.inner_loop(cwt.get_classifier(64, 2).to(cuda_device), f, lab, 0.1, 5, loss_type="wt_dc")
+    with pytest.raises(NotImplementedError):                 # weight-normalised cosine classifier
+        cwt.inner_loop(cwt.CosCls(64, 2, "0n00").to(cuda_device), f, lab, 0.1, 5)
+    with pytest.raises(KeyError):                            # parse_param_coscls
+        cwt.CosCls(64, 2, "xxxx")
+
+
 # ---------------------------------------------------------------------------- (b) transformer
 @pytest.mark.parametrize("algo", [L.ATTN_REASSOC, L.ATTN_TCGEN05])
 @pytest.mark.parametrize("n_head,C,hw", [(1, 64, (12, 12)), (4, 64, (12, 12)), (2, 128, (9, 14)), (4, 512, (60, 60))])
@@ -395,7 +430,7 @@ def test_intersection_and_union_dropin(cuda_device, dtype):
 
 
 # ---------------------------------------------------------------------------- whole episode
-@pytest.mark.parametrize("name", [n for n in golden_names() if not n.startswith("train_")])
+@pytest.mark.parametrize("name", [n for n in golden_names() if not n.startswith(("train_", "inner_"))])
 def test_episode_head_vs_golden(cuda_device, name):
     g = load_golden(name)
     case = g["case"]

@@ -20,7 +20,7 @@ def _checksum(ep):
     return h.hexdigest()
 
 
-EVAL_CASES = [n for n in golden_names() if not n.startswith("train_")]
+EVAL_CASES = [n for n in golden_names() if not n.startswith(("train_", "inner_"))]
 FAST = [n for n in EVAL_CASES if n.startswith("small")] + ["full_1shot_h1_yaml"]
 
 
@@ -37,6 +37,23 @@ def test_oracle_reproduces_reference_golden(name):
     assert np.array_equal(out["counts"].numpy(), g["counts"])
     assert np.array_equal(out["counts0"].numpy(), g["counts0"])
     assert abs(float(out["loss"]) - float(g["loss"])) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["inner_small_dot_ce", "inner_small_cos_wtce"])
+def test_oracle_inner_loop_variants_reproduce_reference_golden(name):
+    """PSPNet.inner_loop switches (SegLoss 'ce' / 'wt_ce', dot / cosine classifier) against the vectors recorded from the
+    live reference's CosCls and SegLoss objects; also: 'ce' is the weighted fit with class weight [1, 1], and the cosine
+    classifier is the dot classifier on 2 * F.normalize(f, eps=1e-5) — the two identities the CUDA path relies on."""
+    g = load_golden(name)
+    case = g["case"]
+    ep = syn.make_episode(case["idx"], **gen_kwargs(case))
+    assert _checksum(ep) == str(g["checksum"])
+    w = O.inner_loop_ref(ep.f_s, ep.s_label, ep.w0, case["lr"], case["n_iter"], case["loss_type"], case["dist"])
+    assert rel_err(w, g["W_fit"]) < 1e-6
+    feat = 2.0 * torch.nn.functional.normalize(ep.f_s, p=2, dim=1, eps=1e-5) if case["dist"] == "cos" else ep.f_s
+    cw = torch.ones(2) if case["loss_type"] == "ce" else None
+    w2 = O.fit_classifier_ref(feat, ep.s_label, ep.w0, case["lr"], case["n_iter"], class_weight=cw)
+    assert rel_err(w2, g["W_fit"]) < 2e-6
 
 
 @pytest.mark.parametrize("name", ["small_1shot_h4", "small_5shot_h4", "small_rect"])
