@@ -62,7 +62,13 @@ __device__ __forceinline__ void ls_tma_2d(void* dst, const CUtensorMap* map, int
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(ls_u32(dst)), "l"(map), "r"(ls_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
-struct LsMaps { CUtensorMap m[4]; };       // m[ns - 1]: box of ns low-res rows
+struct LsMaps { CUtensorMap m[4]; };
+// 128-bit shared-memory load as two packed fp32 pairs, from a 32-bit shared address
+__device__ __forceinline__ ulonglong2 ls_lds128(uint32_t saddr) {
+    ulonglong2 v;
+    asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "r"(saddr));
+    return v;
+}       // m[ns - 1]: box of ns low-res rows
 
 struct LsParams {
     const float* wts;          // [E][2V][C]
@@ -182,23 +188,23 @@ __global__ void __launch_bounds__(LS_THREADS, 1) k_logits_iou_stream(const __gri
             for (int r = 0; r < R2; ++r) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0ull; }
             n2[0] = n2[1] = n2[2] = n2[3] = 0ull;
             if (ck.ns > 0) {
-                // lane's two quads in channel row cl of a stage: byte offset (cl * npx + 4 * quad) * 4; weights of channel c at Ms[c * R2]
-                const unsigned rowb = (unsigned)npx * 4u;
-                const unsigned char* lane_base = ring + (size_t)cw * rowb + (size_t)lane * 16;
-                const f32x2* mrow = Ms + (size_t)cw * R2;
+                // lane's two quads in channel row cl of a stage: byte offset (cl * npx + 4 * quad) * 4; weights of channel c at
+                // Ms[c * R2]. 32-bit shared-memory addresses + explicit ld.shared keep the address arithmetic out of the loop.
+                const uint32_t rowb = (uint32_t)npx * 4u;
+                const uint32_t lane_base = ls_u32(ring) + (uint32_t)cw * rowb + (uint32_t)lane * 16u;
+                uint32_t maddr = ls_u32(Ms) + (uint32_t)cw * (R2 * 8u);
+                const ulonglong2 zero2 = make_ulonglong2(0ull, 0ull);
                 for (int s = 0; s < nstage; ++s) {
                     ls_wait(&full[slot], ph);
-                    const unsigned char* st = lane_base + (size_t)slot * L.stage_bytes;
+                    const uint32_t st = lane_base + slot * L.stage_bytes;
 #pragma unroll
                     for (int k = 0; k < CHT / LS_CW; ++k) {
-                        const ulonglong2* row = reinterpret_cast<const ulonglong2*>(st + (size_t)(k * LS_CW) * rowb);
-                        const ulonglong2* mp = reinterpret_cast<const ulonglong2*>(mrow + (size_t)(s * CHT + k * LS_CW) * R2);
-                        ulonglong2 d0 = make_ulonglong2(0ull, 0ull), d1 = make_ulonglong2(0ull, 0ull);
-                        if (q0) d0 = row[0];
-                        if (q1) d1 = row[32];
+                        const uint32_t row = st + (uint32_t)(k * LS_CW) * rowb;
+                        const ulonglong2 d0 = q0 ? ls_lds128(row) : zero2;
+                        const ulonglong2 d1 = q1 ? ls_lds128(row + 512u) : zero2;
 #pragma unroll
                         for (int r2 = 0; r2 < V; ++r2) {
-                            const ulonglong2 m = mp[r2];                        // {m_2r2, m_2r2, m_2r2+1, m_2r2+1}
+                            const ulonglong2 m = ls_lds128(maddr + (uint32_t)(k * LS_CW * R2 * 8 + r2 * 16));   // {m_2r2, m_2r2, m_2r2+1, m_2r2+1}
                             acc[2 * r2][0] = fma2(m.x, d0.x, acc[2 * r2][0]); acc[2 * r2][1] = fma2(m.x, d0.y, acc[2 * r2][1]);
                             acc[2 * r2][2] = fma2(m.x, d1.x, acc[2 * r2][2]); acc[2 * r2][3] = fma2(m.x, d1.y, acc[2 * r2][3]);
                             acc[2 * r2 + 1][0] = fma2(m.y, d0.x, acc[2 * r2 + 1][0]); acc[2 * r2 + 1][1] = fma2(m.y, d0.y, acc[2 * r2 + 1][1]);
@@ -207,6 +213,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) k_logits_iou_stream(const __gri
                         n2[0] = fma2(d0.x, d0.x, n2[0]); n2[1] = fma2(d0.y, d0.y, n2[1]);
                         n2[2] = fma2(d1.x, d1.x, n2[2]); n2[3] = fma2(d1.y, d1.y, n2[3]);
                     }
+                    maddr += (uint32_t)(CHT * R2 * 8);
                     __syncwarp();
                     if (lane == 0) ls_arrive(&empty[slot]);
                     if (++slot == (unsigned)NS) { slot = 0; ph ^= 1u; }
