@@ -368,10 +368,33 @@ class HostPipeline:
         self.fit_algo, self.attn_algo = fit_algo, attn_algo
         self.copy_stream = torch.cuda.Stream(self.device)
         self.table = IoUTable(num_classes_val, self.device)
+        # two device-resident staging slots, reused for the whole run: no allocator traffic (a cudaMalloc of ~1 GB
+        # synchronises the device) once the first two batches have been seen
+        self._slots: List[Optional[EpisodeBatch]] = [None, None]
+        self._slot_free: List[Optional[torch.cuda.Event]] = [None, None]
+        self._host_counts: List[Optional[torch.Tensor]] = []
 
-    def _stage(self, hb: EpisodeBatch):
+    @staticmethod
+    def _same_layout(a: EpisodeBatch, b: EpisodeBatch) -> bool:
+        return all(x.shape == y.shape and x.dtype == y.dtype for x, y in
+                   zip((a.f_s, a.s_label, a.f_q, a.q_label, a.w0, a.subcls, a.idx),
+                       (b.f_s, b.s_label, b.f_q, b.q_label, b.w0, b.subcls, b.idx)))
+
+    def _stage(self, hb: EpisodeBatch, slot: int):
+        """H2D copy of one host batch into staging slot ``slot`` on the copy stream."""
         with torch.cuda.stream(self.copy_stream):
-            db = hb.to(self.device, non_blocking=True)
+            db = self._slots[slot]
+            if db is None or not self._same_layout(db, hb):
+                alloc = lambda t: torch.empty(t.shape, dtype=t.dtype, device=self.device)
+                db = EpisodeBatch(*(alloc(t) for t in (hb.f_s, hb.s_label, hb.f_q, hb.q_label, hb.w0, hb.subcls, hb.idx)))
+                for t in (db.f_s, db.s_label, db.f_q, db.q_label, db.w0, db.subcls, db.idx):
+                    t.record_stream(self._main)                       # read by the head's stream
+                self._slots[slot] = db
+            elif self._slot_free[slot] is not None:
+                self.copy_stream.wait_event(self._slot_free[slot])      # the head that read this slot last has finished
+            for dst, src in zip((db.f_s, db.s_label, db.f_q, db.q_label, db.w0, db.subcls, db.idx),
+                                (hb.f_s, hb.s_label, hb.f_q, hb.q_label, hb.w0, hb.subcls, hb.idx)):
+                dst.copy_(src, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
         return db, ev
@@ -379,20 +402,25 @@ class HostPipeline:
     def run(self, host_batches: Iterable[EpisodeBatch], reduce_every_step: bool = True) -> List[torch.Tensor]:
         """Returns the per-batch count tensors (CPU, int64 [E,2,2,3]); ``self.table`` accumulates the sweep metrics."""
         main = torch.cuda.current_stream(self.device)
+        self._main = main
         it = iter(host_batches)
         results: List[torch.Tensor] = []
         nxt = next(it, None)
-        staged = self._stage(nxt) if nxt is not None else None
+        slot = 0
+        staged = self._stage(nxt, slot) if nxt is not None else None
         while staged is not None:
             db, ev = staged
+            cur = slot
             nxt = next(it, None)
-            staged = self._stage(nxt) if nxt is not None else None      # H2D of the next batch overlaps this head
+            slot ^= 1
+            staged = self._stage(nxt, slot) if nxt is not None else None      # H2D of the next batch overlaps this head
             main.wait_event(ev)
-            for t in (db.f_s, db.s_label, db.f_q, db.q_label, db.w0, db.subcls):
-                t.record_stream(main)
             out = episode_head(db.f_s, db.s_label, db.f_q, db.q_label, db.w0, self.params, self.n_head, self.lr,
                                self.n_iter, fit_algo=self.fit_algo, attn_algo=self.attn_algo)
             self.table.update(out.counts, db.subcls, out.ce)
+            done = torch.cuda.Event()
+            done.record(main)
+            self._slot_free[cur] = done
             if reduce_every_step:
                 self.table.all_reduce()
             host_counts = torch.empty(out.counts.shape, dtype=out.counts.dtype, pin_memory=True)
