@@ -183,6 +183,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        cwt.bind_host_to_gpu(dev)        # pinned staging buffers on the GPU's NUMA node (no-op when the CPUs are not visible)
     L.load()
 
     E = a.episodes

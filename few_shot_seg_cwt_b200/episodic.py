@@ -352,6 +352,35 @@ def do_epoch(args, train_loader, model, transformer, optimizer_trans, epoch: int
 # ----------------------------------------------------------------------------------------
 # host-resident episodes: double-buffered H2D staging in front of the head
 # ----------------------------------------------------------------------------------------
+def bind_host_to_gpu(device) -> Optional[List[int]]:
+    """Pin this process to the CPUs that are local to ``device`` (NVML's ideal CPU affinity) so that the pinned staging
+    buffers it allocates afterwards live on the GPU's NUMA node: with one process per GPU the H2D streams of a sharded
+    sweep then do not cross the socket interconnect. Returns the CPU list, or None when NVML / the CPUs are unavailable
+    (e.g. a container that only sees a slice of the host); never raises."""
+    try:
+        import os
+        import pynvml
+        pynvml.nvmlInit()
+        idx = torch.device(device).index or 0
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            tok = vis.split(",")[idx].strip()
+            h = pynvml.nvmlDeviceGetHandleByIndex(int(tok)) if tok.isdigit() else pynvml.nvmlDeviceGetHandleByUUID(tok)
+        else:
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1]
+        allowed = set(os.sched_getaffinity(0))
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus or len(cpus) == len(allowed):
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 class HostPipeline:
     """Evaluate batches of episodes that live in (pinned) HOST memory.
 
