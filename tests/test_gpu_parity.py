@@ -624,6 +624,25 @@ def test_meta_train_step_vs_golden(cuda_device, name):
         assert torch.allclose(p.detach().cpu(), new_ref[k], rtol=1e-5, atol=1e-7), k
 
 
+def test_host_pipeline_slots_and_sub_batches(cuda_device):
+    """HostPipeline (the e2e call of bench.py): staging slots are reused across batches of different sizes, cold-start
+    sub-batching gives the same per-episode counts, and the table equals a direct episode_head on the same episodes."""
+    kw = dict(shot=1, C=64, h=12, w=12, H=89, W=89, style="unit")
+    params = syn.make_transformer_params(2, 64)
+    batches = [syn.make_batch(list(range(0, 5)), **kw).pin_memory(), syn.make_batch(list(range(5, 8)), **kw).pin_memory(),
+               syn.make_batch(list(range(8, 13)), **kw).pin_memory()]
+    outs = []
+    for sub in (0, 2):
+        pipe = cwt.HostPipeline(cuda_device, params, 2, 0.1, 30, sub_batch=sub)
+        res = pipe.run(batches)
+        assert [tuple(r.shape) for r in res] == [(5, 2, 2, 3), (3, 2, 2, 3), (5, 2, 2, 3)]
+        outs.append((torch.cat(res), pipe.table.cls.cpu().clone(), int(pipe.table.n_episodes)))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and outs[0][2] == outs[1][2] == 13
+    allb = syn.make_batch(list(range(13)), **kw).to(cuda_device)
+    direct = cwt.episode_head(allb.f_s, allb.s_label, allb.f_q, allb.q_label, allb.w0, dev_params(params, cuda_device), 2, 0.1, 30)
+    assert torch.equal(direct.counts.cpu(), outs[0][0])
+
+
 def test_torch_custom_ops_registered(cuda_device):
     cwt.register_torch_ops()
     ep = syn.make_batch([40], **SMALL).to(cuda_device)
