@@ -21,8 +21,8 @@
 #pragma once
 #include "common.cuh"
 #include "hires.cuh"
+#include "tma_pipe.cuh"
 #include <type_traits>
-#include <cuda.h>
 
 namespace cwt {
 
@@ -31,44 +31,7 @@ constexpr int LS_UW = 8;                       // up-sample warps (measured: 8 +
 constexpr int LS_THREADS = 32 * (1 + LS_CW + LS_UW);
 constexpr int LS_CHT = 32;                     // channels per ring stage = per TMA tile copy
 constexpr int LS_MAXQ = 64;                    // pixel quads per chunk (two per lane)
-constexpr unsigned LS_SPIN = 1u << 27;
-
-__device__ __forceinline__ uint32_t ls_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void ls_mbar_init(uint64_t* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ls_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void ls_expect_tx(uint64_t* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ls_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void ls_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ls_u32(bar)) : "memory");
-}
-// bounded wait: a protocol bug traps (launch error) instead of hanging the GPU
-__device__ __forceinline__ void ls_wait(uint64_t* bar, unsigned parity) {
-    unsigned ok = 0, it = 0;
-    for (;;) {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok) : "r"(ls_u32(bar)), "r"(parity) : "memory");
-        if (ok) return;
-        if (++it > LS_SPIN) __trap();
-    }
-}
-__device__ __forceinline__ void ls_bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(ls_u32(dst)), "l"(src), "r"(bytes), "r"(ls_u32(bar)) : "memory");
-}
-// one TMA tile copy: box (ns * w pixels) x (LS_CHT channels) of the [E*C][h*w] feature matrix (SASS: UTMALDG.2D)
-__device__ __forceinline__ void ls_tma_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(ls_u32(dst)), "l"(map), "r"(ls_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-struct LsMaps { CUtensorMap m[4]; };
-// 128-bit shared-memory load as two packed fp32 pairs, from a 32-bit shared address
-__device__ __forceinline__ ulonglong2 ls_lds128(uint32_t saddr) {
-    ulonglong2 v;
-    asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "r"(saddr));
-    return v;
-}       // m[ns - 1]: box of ns low-res rows
+struct LsMaps { CUtensorMap m[4]; };       // m[ns - 1]: box of ns low-res rows
 
 struct LsParams {
     const float* wts;          // [E][2V][C]
@@ -408,21 +371,6 @@ __global__ void __launch_bounds__(LS_THREADS, 1) k_logits_iou_stream(const __gri
         }
         if (cur_e >= 0) flush(cur_e);
     }
-}
-
-typedef CUresult (*LsEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static LsEncodeFn ls_encode_fn() {
-    static LsEncodeFn fn = nullptr;
-    if (!fn) {
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<LsEncodeFn>(ptr);
-    }
-    return fn;
 }
 
 // returns CWT_ERR_UNSUPPORTED (without setting an error) when the shape does not suit the streaming kernel

@@ -2,6 +2,7 @@
 // step (a-13): logits = W' X^T (src/train.py:259-261) and its adjoint dW' = dlogits X.
 #include "common.cuh"
 #include "skinny.cuh"
+#include "skinny_stream.cuh"
 
 namespace cwt {
 
@@ -121,7 +122,7 @@ extern "C" int cwt_feat_times_rows(const float* P, const float* f, int normalize
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (E == 0) return CWT_OK;
     CWT_REQUIRE(P && f && out && E > 0 && R >= 1 && C >= 1 && HW >= 1, CWT_ERR_INVALID_ARG, "feat_times_rows: bad argument");
-    if (!normalize) return launch_feat_times_cols(f, P, out, E, 1, C, HW, R, st);
+    if (!normalize) return launch_feat_times_cols_auto(f, P, out, E, 1, C, HW, R, st);
     Carver cv(workspace, ws_bytes);
     float* n2 = cv.take<float>((size_t)E * HW);
     float* inv_n = cv.take<float>((size_t)E * HW);
@@ -138,5 +139,5 @@ extern "C" int cwt_feat_times_rows(const float* P, const float* f, int normalize
     CWT_CUDA(cudaMemcpyAsync(Pm, P, sizeof(float) * t2, cudaMemcpyDeviceToDevice, st));
     k_scale_rows<<<(unsigned)((t2 + 255) / 256), 256, 0, st>>>(Pm, inv_n, R, HW, t2);
     CWT_LAUNCHED("scale_rows");
-    return launch_feat_times_cols(f, Pm, out, E, 1, C, HW, R, st);
+    return launch_feat_times_cols_auto(f, Pm, out, E, 1, C, HW, R, st);
 }

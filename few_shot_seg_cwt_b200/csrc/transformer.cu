@@ -17,6 +17,7 @@
 // The backward uses the same re-association (SURVEY.md §8 math block): no dense HW x C x C GEMM.
 #include "common.cuh"
 #include "skinny.cuh"
+#include "skinny_stream.cuh"
 
 namespace cwt {
 
@@ -384,7 +385,7 @@ extern "C" int cwt_transformer_fwd_f32(const float* q, const float* k, int norma
                                                keep_attn ? 1.f / (1.f - p_attn) : 1.f, sv.P, w.Pm, sv.inv_n,
                                                E, Lq, nH, HW);
     CWT_LAUNCHED("softmax_rows");
-    rc = launch_feat_times_cols(k, w.Pm, sv.aX, E, 1, C, HW, R, st);
+    rc = launch_feat_times_cols_auto(k, w.Pm, sv.aX, E, 1, C, HW, R, st);
     if (rc) return rc;
     // O[(e,l)][h*C+n] = aX[e][l*nH+h][:] . A_h[n][:]
     rc = gemm(sv.aX, NC, 1, w_qkvs, 1, C, sv.O, NC, ML, C, C, 1.f, false, nullptr, nH, C, (long long)C * C, C, st);
@@ -446,7 +447,7 @@ extern "C" int cwt_transformer_bwd_f32(const float* d_out, const float* q, const
                                                    keep_attn ? 1.f / (1.f - p_attn) : 1.f, inv_tau, E, Lq, nH, HW);
     CWT_LAUNCHED("softmax_bwd_rows");
     // dSX = (dS X)/tau ; dQ_h = dSX_h A_h^T
-    rc = launch_feat_times_cols(k, w.dP, w.dSX, E, 1, C, HW, R, st);
+    rc = launch_feat_times_cols_auto(k, w.dP, w.dSX, E, 1, C, HW, R, st);
     if (rc) return rc;
     rc = gemm(w.dSX, NC, 1, w_qkvs, 1, C, w.dQ, NC, ML, C, C, 1.f, false, nullptr, nH, C, (long long)C * C, C, st);
     if (rc) return rc;
