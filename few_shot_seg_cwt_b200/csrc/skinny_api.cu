@@ -104,7 +104,7 @@ extern "C" int cwt_rows_times_feat(const float* M, const float* f, int normalize
     float* n2 = cv.take<float>((size_t)E * HW);
     float* inv_n = cv.take<float>((size_t)E * HW);
     CWT_REQUIRE(!normalize || (workspace && cv.ok()), CWT_ERR_WORKSPACE, "rows_times_feat: workspace too small");
-    int rc = launch_rows_times_feat(f, M, out, normalize ? n2 : nullptr, E, C, HW, 1, R, st);
+    int rc = launch_rows_times_feat_auto(f, M, out, normalize ? n2 : nullptr, E, C, HW, 1, R, st);
     if (rc) return rc;
     if (normalize) {
         size_t t1 = (size_t)E * HW, t2 = (size_t)E * R * HW;

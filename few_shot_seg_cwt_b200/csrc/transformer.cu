@@ -378,7 +378,7 @@ extern "C" int cwt_transformer_fwd_f32(const float* q, const float* k, int norma
         // QA[e][l*nH+h][:] = Q_h[e,l,:] A_h        (batch over heads)
         rc = gemm(sv.Qp, NC, 1, w_qkvs, C, 1, w.QA, NC, ML, C, C, 1.f, false, nullptr, nH, C, (long long)C * C, C, st);
         if (rc) return rc;
-        rc = launch_rows_times_feat(k, w.QA, w.sraw, normalize_k ? w.n2 : nullptr, E, C, HW, 1, R, st);
+        rc = launch_rows_times_feat_auto(k, w.QA, w.sraw, normalize_k ? w.n2 : nullptr, E, C, HW, 1, R, st);
         if (rc) return rc;
     }
     k_softmax_rows<<<dim3(R, E), 256, 0, st>>>(w.sraw, normalize_k ? w.n2 : nullptr, keep_attn, inv_tau,
@@ -441,7 +441,7 @@ extern "C" int cwt_transformer_bwd_f32(const float* d_out, const float* q, const
     // dPt_h = dO_h K_h^T = (dO_h A_h) X^T
     rc = gemm(w.dO, NC, 1, w_qkvs, C, 1, w.dOA, NC, ML, C, C, 1.f, false, nullptr, nH, C, (long long)C * C, C, st);
     if (rc) return rc;
-    rc = launch_rows_times_feat(k, w.dOA, w.dP, nullptr, E, C, HW, 1, R, st);
+    rc = launch_rows_times_feat_auto(k, w.dOA, w.dP, nullptr, E, C, HW, 1, R, st);
     if (rc) return rc;
     k_softmax_bwd_rows<<<dim3(R, E), 256, 0, st>>>(w.dP, sv.P, sv.inv_n, keep_attn,
                                                    keep_attn ? 1.f / (1.f - p_attn) : 1.f, inv_tau, E, Lq, nH, HW);
