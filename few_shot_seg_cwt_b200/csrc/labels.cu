@@ -64,22 +64,28 @@ k_pack_label_cells(const void* __restrict__ labels, int h, int w, int H, int W, 
     int c[4] = {0, 0, 0, 0};
     for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < h * w; cell += gridDim.x * blockDim.x) {
         const int a = cell / w, b = cell - a * w;
+        // branch-free: all 64 loads are unconditional (coordinates clamped into the image) and issued per row before use;
+        // pixels outside the image are coded 2 and masked out of the counts
+        const int nx = min(max(W - 8 * b, 0), 8);                       // in-image pixels of this cell's rows
+        const uint32_t xmask = ((1u << (2 * nx)) - 1u) & 0x5555u;
         uint32_t rows[8];
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
             const int Y = 8 * a + r;
-            uint32_t bits = 0;
+            const size_t rb = base + (size_t)min(Y, H - 1) * W;
+            uint32_t raw[8];
 #pragma unroll
             for (int s = 0; s < 8; ++s) {
-                const int X = 8 * b + s;
-                int code = 2;
-                if (Y < H && X < W) {
-                    code = load_label_code<I64>(labels, base + (size_t)Y * W + X, ignore_index);
-                    c[0] += (code == 0); c[1] += (code == 1); c[2] += (code == 2); c[3] += (code == 3);
-                }
-                bits |= (uint32_t)code << (2 * s);
+                const size_t i = rb + min(8 * b + s, W - 1);
+                long long v = I64 ? reinterpret_cast<const long long*>(labels)[i] : (long long)reinterpret_cast<const uint8_t*>(labels)[i];
+                raw[s] = (v == 0) ? 0u : ((v == 1) ? 1u : ((v == (long long)ignore_index) ? 2u : 3u));
             }
+            uint32_t bits = 0;
+#pragma unroll
+            for (int s = 0; s < 8; ++s) bits |= ((s < nx && Y < H) ? raw[s] : 2u) << (2 * s);
             rows[r] = bits;
+            const uint32_t m = (Y < H) ? xmask : 0u, lo = bits & 0x5555u, hi = (bits >> 1) & 0x5555u;
+            c[0] += __popc(~lo & ~hi & m); c[1] += __popc(lo & ~hi & m); c[2] += __popc(~lo & hi & m); c[3] += __popc(lo & hi & m);
         }
         cells[(size_t)img * h * w + cell] = make_uint4(rows[0] | (rows[1] << 16), rows[2] | (rows[3] << 16),
                                                        rows[4] | (rows[5] << 16), rows[6] | (rows[7] << 16));
