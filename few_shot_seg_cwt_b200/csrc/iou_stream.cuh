@@ -406,7 +406,7 @@ static int launch_logits_iou_stream(const float* wts, const float* f_q, const vo
         cuuint32_t box[2] = {(cuuint32_t)(ns * w), (cuuint32_t)p.CHT};
         cuuint32_t estr[2] = {1, 1};
         CUresult r = enc(&maps.m[ns - 1], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(f_q), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, ls_l2_promotion(),
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         CWT_REQUIRE(r == CUDA_SUCCESS, CWT_ERR_CUDA, "logits_iou: cuTensorMapEncodeTiled failed (%d)", (int)r);
     }

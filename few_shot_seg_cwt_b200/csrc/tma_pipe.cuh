@@ -3,10 +3,11 @@
 #pragma once
 #include "common.cuh"
 #include <cuda.h>
+#include <cstdlib>
 
 namespace cwt {
 
-constexpr unsigned LS_SPIN = 1u << 27;
+constexpr unsigned LS_SPIN = 1u << 22;      // try_wait suspends for a while itself: this is seconds, not milliseconds
 
 __device__ __forceinline__ uint32_t ls_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void ls_mbar_init(uint64_t* bar, unsigned count) {
@@ -59,6 +60,15 @@ static LsEncodeFn ls_encode_fn() {
     return fn;
 }
 
+// L2 promotion of the feature tensor maps; CWT_TMA_L2=0|64|128|256 overrides (measured DRAM reads of the logits kernel at
+// E = 64: 545 MB with 256 B, 526 MB with 128 B or none, 513 MB with 64 B — the 960-byte tile rows start at 240-byte multiples)
+static inline CUtensorMapL2promotion ls_l2_promotion() {
+    const char* s = getenv("CWT_TMA_L2");
+    const int v = s ? atoi(s) : 64;       // measured: 64 B gives the fewest DRAM bytes (513 vs 545 MB for the logits kernel)
+    return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+         : v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+}
+
 // fp32 matrix [rows][cols] row-major (cols * 4 a multiple of 16 B), box [box_rows][box_cols <= 256], no swizzle;
 // elements outside the matrix read as zero and count towards the transaction bytes
 static inline int ls_make_map_f32(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
@@ -70,7 +80,7 @@ static inline int ls_make_map_f32(CUtensorMap* m, const float* base, uint64_t ro
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, ls_l2_promotion(),
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     CWT_REQUIRE(r == CUDA_SUCCESS, CWT_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed (%d)", what, (int)r);
     return CWT_OK;
