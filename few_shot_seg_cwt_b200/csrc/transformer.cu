@@ -35,12 +35,12 @@ struct GemmP {
     float alpha; int accumulate;
 };
 
-constexpr int G_TM = 32, G_TN = 64, G_TK = 16, G_KG = 4;
+constexpr int G_TM = 32, G_TN = 32, G_TK = 16, G_KG = 4;
 
 // The GEMMs of this path are small (M = 2 E rows, N, K = 512 .. 2048): at most ~128 CTAs, one per SM, so a CTA's serial
 // K loop is what takes the time. The CTA therefore splits K over G_KG = 4 groups of 64 threads: group g multiplies the
-// k-tiles g, g + 4, ... of the same 32 x 64 output tile (own shared-memory tiles, own named barrier, next tile prefetched
-// into registers), thread = 4 x 8 outputs (three LDS.128 per 32 FMAs); the four partial tiles are added in a fixed order.
+// k-tiles g, g + 4, ... of the same 32 x 32 output tile (own shared-memory tiles, own named barrier, next tile prefetched
+// into registers), thread = 4 x 4 outputs; the four partial tiles are added in a fixed order.
 // (Measured at E = 64: one group per CTA 37 us per GEMM; a 64 x 64 tile with 4 x 4 outputs per thread and half the CTAs 47 us.)
 __global__ void __launch_bounds__(64 * G_KG) k_sgemm_small(GemmP p) {
     __shared__ __align__(16) float smem[G_KG * G_TK * (G_TM + 4 + G_TN + 4)];
@@ -51,12 +51,12 @@ __global__ void __launch_bounds__(64 * G_KG) k_sgemm_small(GemmP p) {
     const float* A = p.A + (size_t)blockIdx.z * p.a_bs;
     const float* B = p.B + (size_t)blockIdx.z * p.b_bs;
     float* C = p.C + (size_t)blockIdx.z * p.c_bs;
-    float acc[4][8];
+    float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-    float ra[8], rb[16];
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    float ra[8], rb[8];
     auto a_idx = [&](int i, int& m, int& k) {
         const int idx = gt + i * 64;
         if (p.a_ks == 1) { k = idx % G_TK; m = idx / G_TK; } else { m = idx % G_TM; k = idx / G_TM; }
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(64 * G_KG) k_sgemm_small(GemmP p) {
             ra[i] = (m0 + m < p.M && k0 + k < p.K) ? A[(size_t)(m0 + m) * p.a_ms + (size_t)(k0 + k) * p.a_ks] : 0.f;
         }
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 8; ++i) {
             int n, k;
             b_idx(i, n, k);
             rb[i] = (n0 + n < p.N && k0 + k < p.K) ? B[(size_t)(k0 + k) * p.b_ks + (size_t)(n0 + n) * p.b_ns] : 0.f;
@@ -85,30 +85,29 @@ __global__ void __launch_bounds__(64 * G_KG) k_sgemm_small(GemmP p) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) { int m, k; a_idx(i, m, k); As[k * (G_TM + 4) + m] = ra[i]; }
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { int n, k; b_idx(i, n, k); Bs[k * (G_TN + 4) + n] = rb[i]; }
+        for (int i = 0; i < 8; ++i) { int n, k; b_idx(i, n, k); Bs[k * (G_TN + 4) + n] = rb[i]; }
         asm volatile("bar.sync %0, 64;" ::"r"(1 + g) : "memory");
         if (k0 + kstep < p.K) fetch(k0 + kstep);
 #pragma unroll
         for (int k = 0; k < G_TK; ++k) {
             const float4 a = *reinterpret_cast<const float4*>(&As[k * (G_TM + 4) + ty * 4]);
-            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k * (G_TN + 4) + tx * 8]);
-            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[k * (G_TN + 4) + tx * 8 + 4]);
-            const float av[4] = {a.x, a.y, a.z, a.w}, bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k * (G_TN + 4) + tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b0.x, b0.y, b0.z, b0.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
         }
         asm volatile("bar.sync %0, 64;" ::"r"(1 + g) : "memory");
     }
     // groups 1..3 park their partial tiles in shared memory; group 0 adds them in order and stores
     __syncthreads();
-    float* part = smem;                                           // [G_KG - 1][G_TM][G_TN]  (24 KB <= the tile storage)
+    float* part = smem;                                           // [G_KG - 1][G_TM][G_TN]  (12 KB <= the tile storage)
     if (g > 0) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) part[((g - 1) * G_TM + ty * 4 + i) * G_TN + tx * 8 + j] = acc[i][j];
+            for (int j = 0; j < 4; ++j) part[((g - 1) * G_TM + ty * 4 + i) * G_TN + tx * 4 + j] = acc[i][j];
     }
     __syncthreads();
     if (g > 0) return;
@@ -117,12 +116,12 @@ __global__ void __launch_bounds__(64 * G_KG) k_sgemm_small(GemmP p) {
         const int m = m0 + ty * 4 + i;
         if (m >= p.M) continue;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int n = n0 + tx * 8 + j;
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
             if (n >= p.N) continue;
             float v = acc[i][j];
 #pragma unroll
-            for (int g2 = 0; g2 < G_KG - 1; ++g2) v += part[(g2 * G_TM + ty * 4 + i) * G_TN + tx * 8 + j];
+            for (int g2 = 0; g2 < G_KG - 1; ++g2) v += part[(g2 * G_TM + ty * 4 + i) * G_TN + tx * 4 + j];
             v *= p.alpha;
             if (p.bias) v += p.bias[n];
             float* dst = C + (size_t)m * p.ldc + n;
