@@ -265,6 +265,8 @@ def main():
     label_bytes = devb.s_label.element_size()
     bytes_fit = E * ((2 * a.adapt_iter + 1) * a.shot * F_bytes + a.shot * P * label_bytes + 2 * (2 * 512 * 4))
     bytes_iou = E * (F_bytes + P * label_bytes + 2 * 6 * 8)
+    # bytes_transformer(E) = E*F + nH*(2*C*C*4) + E*(2*2*C*4)  (f_q once; the re-associated path reads it twice)
+    bytes_tr = E * F_bytes + a.heads * (2 * 512 * 512 * 4) + E * (2 * 2 * 512 * 4)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -294,6 +296,8 @@ def main():
                        if resident else None),
         "stages_ms": {"fit": fit_ms, "transformer": tr_ms, "logits_iou": iou_ms},
         "logits_iou": {"achieved": bytes_iou / (iou_ms / 1e3) / 1e9, "frac": bytes_iou / (iou_ms / 1e3) / 1e9 / hbm_peak},
+        "transformer": {"achieved": bytes_tr / (tr_ms / 1e3) / 1e9, "frac": bytes_tr / (tr_ms / 1e3) / 1e9 / hbm_peak,
+                        "note": "algorithmic bytes count f_q once; the re-associated attention needs two passes over it"},
     }
 
     # ---- end to end through the public API with host buffers ("e2e") ----
