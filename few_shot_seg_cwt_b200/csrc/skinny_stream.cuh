@@ -23,6 +23,8 @@ constexpr int SS_THREADS = 32 * (1 + SS_W);
 constexpr int SS_PX = 256;              // pixels per stage (TMA box width; 64 quads = two per lane)
 constexpr int SS_CB = 32;               // channels per work item / per stage (four per consumer warp)
 constexpr int SS_NS = 4;                // ring stages
+// (no lower bound on the number of work items: even at E = 1 — 15 / 16 items — the streaming kernels beat the LDG ones,
+//  transformer forward + backward + optimizer of the training step 0.83 ms vs 1.12 ms)
 
 // CWT_SKINNY=ldg forces the LDG kernels of skinny.cuh (tests run both)
 static inline bool skinny_stream_enabled() {

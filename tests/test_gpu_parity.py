@@ -60,12 +60,13 @@ def test_label_counts(cuda_device, dtype):
 
 
 @pytest.mark.parametrize("shape", [(3, 2, 64, 12, 12), (2, 5, 40, 9, 14), (1, 10, 512, 60, 60), (2, 16, 96, 7, 5),
-                                   (2, 8, 64, 16, 20), (3, 5, 96, 20, 20), (4, 2, 32, 16, 17), (2, 8, 512, 60, 60)])
+                                   (2, 8, 64, 16, 20), (40, 5, 96, 20, 20), (70, 2, 32, 16, 17), (8, 8, 512, 60, 60)])
 @pytest.mark.parametrize("normalize", [False, True])
 @pytest.mark.parametrize("mode", ["stream", "ldg"])
 def test_skinny_contractions(cuda_device, monkeypatch, shape, normalize, mode):
     """rows_times_feat / feat_times_rows against fp64 einsum. mode 'stream': the TMA-ring kernels (skinny_stream.cuh) where
-    the shape allows (<= 8 rows, C % 32 == 0, h*w % 4 == 0, h*w >= 256), else the LDG kernels; 'ldg' forces the latter."""
+    the shape allows (<= 8 rows, C % 32 == 0, h*w % 4 == 0, h*w >= 256: the last four shapes), else the LDG kernels; 'ldg'
+    forces the latter."""
     if mode == "ldg":
         monkeypatch.setenv("CWT_SKINNY", "ldg")
     E, R, C, h, w = shape
