@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--fit-algo", type=int, default=0)
     ap.add_argument("--attn-algo", type=int, default=0)
     ap.add_argument("--cpu-baseline-episodes", type=int, default=8)
+    ap.add_argument("--ref-episodes", type=int, default=2, help="--impl reference: episodes per step (bounded CPU sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic episodes generated per rank (tiled to E)")
@@ -135,7 +136,7 @@ def run_reference(a, rank):
     Python and cannot travel to the GPU box). Rank 0 only."""
     if rank != 0:
         return
-    per_step = 2
+    per_step = max(1, a.ref_episodes)
     use_all_host_threads()
     from few_shot_seg_cwt_b200 import synthetic as syn
     from oracle import head_ref as O

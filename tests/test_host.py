@@ -96,6 +96,43 @@ def test_module_loads_reference_checkpoint_format():
     assert torch.equal(m.fc.weight, ref.fc.weight)
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference checkout not present")
+def test_coscls_mirror_matches_reference_module():
+    """few_shot_seg_cwt_b200.CosCls vs the reference's CosCls (src/model/pspnet.py:290-315): same state-dict keys and the
+    same forward for every flag combination that does not re-parametrise the weight."""
+    sys.path.insert(0, "/root/reference")
+    import contextlib, io, warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from src.model.pspnet import CosCls as RefCosCls
+    x = torch.relu(torch.randn(2, 16, 5, 6, generator=torch.Generator().manual_seed(3)))
+    for cls_type in ("oooo", "0000", "00b0", "000t", "0n00", "0nbt"):
+        with contextlib.redirect_stdout(io.StringIO()):
+            ref = RefCosCls(in_dim=16, n_classes=2, cls_type=cls_type)
+        mine = cwt.CosCls(16, 2, cls_type)
+        assert set(mine.state_dict().keys()) == set(ref.state_dict().keys())
+        mine.load_state_dict(ref.state_dict())
+        assert torch.equal(mine(x), ref(x)), cls_type
+        assert mine.plain == (cls_type in ("oooo", "0000"))
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = RefCosCls(in_dim=16, n_classes=2, cls_type="r000")            # WeightNorm: weight_g / weight_v
+    assert set(cwt.CosCls(16, 2, "r000").state_dict().keys()) == set(ref.state_dict().keys())
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) needs no GPU and prints one JSON line with the
+    keys of the contract."""
+    import json, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--ref-episodes", "1"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["unit"] == "episodes/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["kind"] in ("port", "reference")
+    assert d["metric"] == "episodes_per_sec_head_pascal_1shot_60x60x512" and "workload" in d["config"]
+
+
 def test_synthetic_generator_deterministic_and_well_formed():
     a = syn.make_episode(5, shot=2, C=32, h=12, w=12, H=89, W=89)
     b = syn.make_episode(5, shot=2, C=32, h=12, w=12, H=89, W=89)
