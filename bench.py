@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--ref-episodes", type=int, default=2, help="--impl reference: episodes per step (bounded CPU sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-sub-batch", type=int, default=32, help="HostPipeline sub-batch size (0 = whole batches)")
     ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic episodes generated per rank (tiled to E)")
     return ap.parse_args()
 
@@ -306,7 +307,8 @@ def main():
     # the previous step's head) and reads the step's int64 counts back to the host.
     e2e = None
     if not a.no_e2e:
-        pipe = cwt.HostPipeline(dev, params, a.heads, a.cls_lr, a.adapt_iter, fit_algo=a.fit_algo, attn_algo=a.attn_algo)
+        pipe = cwt.HostPipeline(dev, params, a.heads, a.cls_lr, a.adapt_iter, fit_algo=a.fit_algo, attn_algo=a.attn_algo,
+                                sub_batch=a.e2e_sub_batch, sub_batch_all=True)
         pipe.run([host] * max(1, a.warmup))
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -317,7 +319,7 @@ def main():
         ms_e = max_over_ranks(e0.elapsed_time(e1))
         e2e = {"value": world * E * a.steps / (ms_e / 1e3), "unit": UNIT, "h2d_bytes_per_step": host.nbytes() + host.subcls.numel() * 8,
                "d2h_bytes_per_step": res[0].numel() * res[0].element_size(), "ms_per_step": ms_e / a.steps,
-               "api": "few_shot_seg_cwt_b200.HostPipeline.run (double-buffered H2D, async D2H of the counts)"}
+               "api": "few_shot_seg_cwt_b200.HostPipeline.run (H2D in sub-batches of %d episodes through three device slots, async D2H of the counts)" % a.e2e_sub_batch}
 
     # ---- CPU baseline on the box's host cores (rank 0, N = 1 only) ----
     cpu = None

@@ -391,22 +391,23 @@ class HostPipeline:
 
     def __init__(self, device, params: Dict[str, torch.Tensor], n_head: int, lr: float, n_iter: int,
                  fit_algo: int = L.FIT_AUTO, attn_algo: int = L.ATTN_REASSOC, num_classes_val: int = 5, n_slots: int = 3,
-                 sub_batch: int = 0):
+                 sub_batch: int = 32, sub_batch_all: bool = True):
         self.device = torch.device(device)
         self.params = {k: v.to(self.device) for k, v in params.items()}
         self.n_head, self.lr, self.n_iter = n_head, lr, n_iter
         self.fit_algo, self.attn_algo = fit_algo, attn_algo
         self.copy_stream = torch.cuda.Stream(self.device)
         self.table = IoUTable(num_classes_val, self.device)
-        # ``sub_batch`` > 0 sends the FIRST host batch of a run through the pipeline in sub-batches so that the first head
-        # starts after 4.4 ms of PCIe instead of 17.5 ms (lower latency to the first result). It does not raise the
-        # throughput of a 10-step run: copy (17.5 ms per 64 episodes at 55.6 GB/s) and head (17.7 ms) are balanced, so the
-        # run lasts (K + 1) x 17.6 ms either way — one copy or one head is always exposed — and a 16-episode head costs
-        # 7 % more per episode than a 64-episode one. Measured: 19.5 ms per step at K = 10 with and without. Default off.
+        # Host batches go through the pipeline in SUB-BATCHES of ``sub_batch`` episodes (0 = whole batches; ``sub_batch_all`` False
+        # = only the first batch of a run). Copy (17.5 ms per 64 episodes at 55.6 GB/s) and head (17.7 ms) are balanced, so a
+        # K-batch run costs about one exposed copy plus K heads: with whole batches the exposed copy is 17.5 ms, with halves
+        # 8.8 ms, while a 32-episode head costs only ~1 % more per episode than a 64-episode one (a 16-episode head 7 %).
+        # Measured (bench.py, 10 steps of 64 episodes): whole 19.31 ms per step, sub-batches of 32: 18.87 ms, of 16: 18.99 ms.
         # Device-resident staging slots are reused for the whole run: no allocator traffic (a cudaMalloc of ~1 GB
         # synchronises the device). Three slots: the copy of sub-batch i+2 may start as soon as the copy of i+1 has
         # finished (its slot was released by head i-1 long ago), so the copy engine never waits for the head.
         self.sub_batch = max(0, int(sub_batch))
+        self.sub_batch_all = bool(sub_batch_all)            # sub-batch every host batch, not only the first
         self._slots: List[Optional[EpisodeBatch]] = [None] * n_slots
         self._slot_free: List[Optional[torch.cuda.Event]] = [None] * n_slots
 
@@ -443,7 +444,7 @@ class HostPipeline:
         """(batch number, first episode, is-last, host sub-batch): slices of a pinned tensor along dim 0 stay pinned."""
         for bi, hb in enumerate(host_batches):
             E = hb.n_episodes
-            step = self.sub_batch if (bi == 0 and self.sub_batch > 0) else max(E, 1)     # cold start only (see __init__)
+            step = self.sub_batch if (self.sub_batch > 0 and (bi == 0 or self.sub_batch_all)) else max(E, 1)
             for lo in range(0, max(E, 1), step):
                 hi = min(E, lo + step)
                 yield bi, lo, hi >= E, EpisodeBatch(*(t[lo:hi] for t in self._fields(hb))), E

@@ -639,12 +639,13 @@ def test_host_pipeline_slots_and_sub_batches(cuda_device):
     batches = [syn.make_batch(list(range(0, 5)), **kw).pin_memory(), syn.make_batch(list(range(5, 8)), **kw).pin_memory(),
                syn.make_batch(list(range(8, 13)), **kw).pin_memory()]
     outs = []
-    for sub in (0, 2):
-        pipe = cwt.HostPipeline(cuda_device, params, 2, 0.1, 30, sub_batch=sub)
+    for sub, every in ((0, False), (2, False), (2, True)):
+        pipe = cwt.HostPipeline(cuda_device, params, 2, 0.1, 30, sub_batch=sub, sub_batch_all=every)
         res = pipe.run(batches)
         assert [tuple(r.shape) for r in res] == [(5, 2, 2, 3), (3, 2, 2, 3), (5, 2, 2, 3)]
         outs.append((torch.cat(res), pipe.table.cls.cpu().clone(), int(pipe.table.n_episodes)))
-    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and outs[0][2] == outs[1][2] == 13
+    for o in outs[1:]:
+        assert torch.equal(outs[0][0], o[0]) and torch.equal(outs[0][1], o[1]) and outs[0][2] == o[2] == 13
     allb = syn.make_batch(list(range(13)), **kw).to(cuda_device)
     direct = cwt.episode_head(allb.f_s, allb.s_label, allb.f_q, allb.q_label, allb.w0, dev_params(params, cuda_device), 2, 0.1, 30)
     assert torch.equal(direct.counts.cpu(), outs[0][0])
