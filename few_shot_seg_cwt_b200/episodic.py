@@ -403,6 +403,9 @@ class HostPipeline:
         # K-batch run costs about one exposed copy plus K heads: with whole batches the exposed copy is 17.5 ms, with halves
         # 8.8 ms, while a 32-episode head costs only ~1 % more per episode than a 64-episode one (a 16-episode head 7 %).
         # Measured (bench.py, 10 steps of 64 episodes): whole 19.31 ms per step, sub-batches of 32: 18.87 ms, of 16: 18.99 ms.
+        # (A ramp — quarter sub-batches at the very start and end of a run — was measured too: 18.79 ms, no gain: a head can
+        # only start when everything before it has been copied, so the exposed time is one steady-state sub-batch copy
+        # whatever the first pieces are.)
         # Device-resident staging slots are reused for the whole run: no allocator traffic (a cudaMalloc of ~1 GB
         # synchronises the device). Three slots: the copy of sub-batch i+2 may start as soon as the copy of i+1 has
         # finished (its slot was released by head i-1 long ago), so the copy engine never waits for the head.
