@@ -1,20 +1,20 @@
 """Sharded evaluation sweep over synthetic episodes (BASELINE.json configs[3]).
 
-    python -m few_shot_seg_cwt_b200.sweep --episodes 10000 --batch 32 --workers 8 [--oracle-sample 16]
+    python -m few_shot_seg_cwt_b200.sweep --episodes 10000 --batch 32 --workers 8
     torchrun --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 -m few_shot_seg_cwt_b200.sweep --episodes 10000
 
 Episode i goes to rank i mod world; every rank generates its own episodes with DataLoader
 workers (the reference uses ``DataLoader(workers=2)``, pascal.yaml:12), stages them through pinned memory and
 ``HostPipeline``; the only collective is the int64 all-reduce of the IoU table. Rank 0 prints one JSON line
-with mIoU (adapted / baseline classifier), FB-IoU, mean loss and episodes/s; ``--oracle-sample K`` re-runs K of
-the episodes through the CPU oracle and reports the per-episode count differences and the mIoU gap.
+with mIoU (adapted / baseline classifier), FB-IoU, mean loss and episodes/s. ``--dump-counts PATH --dump-sample K``
+saves the per-episode counts of K episodes; the checker that re-runs them through the CPU oracle lives with the
+tests (``python tests/sweep_oracle_check.py``) — this package never imports ``oracle/``.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
-import sys
 import time
 
 import torch
@@ -52,7 +52,8 @@ def main(argv=None):
     ap.add_argument("--adapt-iter", type=int, default=200)
     ap.add_argument("--style", default="unit")
     ap.add_argument("--num-classes-val", type=int, default=5)
-    ap.add_argument("--oracle-sample", type=int, default=0)
+    ap.add_argument("--dump-counts", default="", help="torch.save the per-episode counts of the first --dump-sample episodes here")
+    ap.add_argument("--dump-sample", type=int, default=0)
     ap.add_argument("--small", action="store_true", help="64-channel 12x12 -> 89x89 episodes (quick checks)")
     a = ap.parse_args(argv)
 
@@ -79,9 +80,9 @@ def main(argv=None):
 
     def batches():
         for b in loader:
-            if a.oracle_sample and rank == 0 and len(kept) < a.oracle_sample:
+            if a.dump_counts and rank == 0 and len(kept) < a.dump_sample:
                 for j in range(b.n_episodes):
-                    if len(kept) < a.oracle_sample:
+                    if len(kept) < a.dump_sample:
                         kept[int(b.idx[j])] = None
             yield b.pin_memory()
 
@@ -97,36 +98,23 @@ def main(argv=None):
            "FBIoU_baseline": pipe.table.fb_iou(1), "loss_adapted": pipe.table.mean_loss(0),
            "class_iou_adapted": pipe.table.class_iou(0), "config": {**kw, "heads": a.heads, "cls_lr": a.cls_lr, "adapt_iter": a.adapt_iter}}
 
-    if a.oracle_sample and rank == 0:
-        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-        from oracle import head_ref as O                       # checker only (never on the product path)
-        counts_by_idx = {}
-        pos = 0
+    if a.dump_counts and rank == 0:
+        # per-episode counts of the first --dump-sample episodes of rank 0, for tests/sweep_oracle_check.py
+        counts_by_idx, pos = {}, 0
         for r in results:
             for j in range(r.shape[0]):
-                counts_by_idx[mine[pos]] = r[j]
+                if mine[pos] in kept:
+                    counts_by_idx[mine[pos]] = r[j].clone()
                 pos += 1
-        tg, to = IoUTable(a.num_classes_val, "cpu"), IoUTable(a.num_classes_val, "cpu")
-        max_diff, n_tie = 0, 0
-        for idx in kept:
-            ep = syn.make_episode(idx, **kw)
-            o = O.episode_ref(ep.f_s, ep.s_label, ep.f_q, ep.q_label, ep.w0, params, a.heads, a.cls_lr, a.adapt_iter)
-            ref = torch.stack([o["counts"], o["counts0"]]).unsqueeze(0)
-            got = counts_by_idx[idx].unsqueeze(0)
-            max_diff = max(max_diff, int((got - ref).abs().max()))
-            n_tie += int((o["tie_margin"] <= 1e-5 * max(1.0, float(o["logits60"].abs().max()))).sum())
-            sub = torch.tensor([ep.subcls])
-            tg.update(got, sub)
-            to.update(ref, sub)
-        out["oracle_check"] = {"episodes": len(kept), "max_count_diff": max_diff, "tie_set_pixels": n_tie,
-                               "mIoU_gpu": tg.miou(0), "mIoU_oracle": to.miou(0),
-                               "mIoU_gap_points": abs(tg.miou(0) - to.miou(0)) * 100,
-                               "FBIoU_gap_points": abs(tg.fb_iou(0) - to.fb_iou(0)) * 100}
+        torch.save({"counts": counts_by_idx, "kw": kw, "heads": a.heads, "cls_lr": a.cls_lr, "adapt_iter": a.adapt_iter,
+                    "num_classes_val": a.num_classes_val}, a.dump_counts)
+        out["dumped_counts"] = {"path": a.dump_counts, "episodes": len(counts_by_idx)}
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+    return out
 
 
 if __name__ == "__main__":

@@ -662,14 +662,15 @@ def test_torch_custom_ops_registered(cuda_device):
 
 
 def test_sweep_cli_small_with_oracle_check(cuda_device, capsys):
-    """few_shot_seg_cwt_b200.sweep: loader workers -> pinned host -> HostPipeline -> IoU table, oracle spot-check."""
+    """few_shot_seg_cwt_b200.sweep: loader workers -> pinned host -> HostPipeline -> IoU table; the oracle
+    spot-check of its per-episode counts is test infrastructure (tests/sweep_oracle_check.py)."""
     import json
-    from few_shot_seg_cwt_b200 import sweep
-    sweep.main(["--small", "--episodes", "24", "--batch", "8", "--workers", "0", "--oracle-sample", "6",
-                "--adapt-iter", "40", "--heads", "2"])
-    out = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
-    assert out["episodes"] == 24
-    chk = out["oracle_check"]
+    import sweep_oracle_check
+    sweep_oracle_check.main(["--sample", "6", "--", "--small", "--episodes", "24", "--batch", "8", "--workers", "0",
+                             "--adapt-iter", "40", "--heads", "2"])
+    lines = [json.loads(l) for l in capsys.readouterr().out.strip().splitlines() if l.startswith("{")]
+    out, chk = lines[-2], lines[-1]["oracle_check"]
+    assert out["episodes"] == 24 and out["dumped_counts"]["episodes"] == 6
     assert chk["episodes"] == 6
     assert chk["max_count_diff"] <= chk["tie_set_pixels"]
     assert chk["mIoU_gap_points"] < 0.05 and chk["FBIoU_gap_points"] < 0.05

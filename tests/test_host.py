@@ -215,21 +215,21 @@ def test_header_is_plain_c():
 
 
 def test_product_never_imports_the_oracle():
-    """The oracle is test infrastructure: no module of the product package may import it at import time,
-    and the only mention allowed is the sweep tool's opt-in --oracle-sample checker."""
+    """The oracle is test infrastructure: no module of the product package (nor tools/) may import it anywhere
+    — module level or inside a function; the sweep's oracle spot-check lives in tests/sweep_oracle_check.py."""
     import ast
-    pkg = os.path.join(ROOT, "few_shot_seg_cwt_b200")
-    for fn in sorted(os.listdir(pkg)):
-        if not fn.endswith(".py"):
-            continue
-        tree = ast.parse(open(os.path.join(pkg, fn)).read())
-        for node in tree.body:                      # module level only
-            names = []
-            if isinstance(node, ast.Import):
-                names = [a.name for a in node.names]
-            elif isinstance(node, ast.ImportFrom):
-                names = [node.module or ""]
-            assert not any(n.split(".")[0] == "oracle" for n in names), f"{fn} imports the oracle at module level"
+    for sub in ("few_shot_seg_cwt_b200", "tools"):
+        pkg = os.path.join(ROOT, sub)
+        for fn in sorted(os.listdir(pkg)):
+            if not fn.endswith(".py"):
+                continue
+            for node in ast.walk(ast.parse(open(os.path.join(pkg, fn)).read())):
+                names = []
+                if isinstance(node, ast.Import):
+                    names = [a.name for a in node.names]
+                elif isinstance(node, ast.ImportFrom):
+                    names = [node.module or ""]
+                assert not any(n.split(".")[0] == "oracle" for n in names), f"{sub}/{fn} imports the oracle"
     code = "import sys, few_shot_seg_cwt_b200; assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules)"
     r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
