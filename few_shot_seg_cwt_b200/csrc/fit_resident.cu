@@ -766,9 +766,12 @@ static ResidentPlan plan_resident_cfg(int E, int C, int h, int w, int n_sm, size
             const int CPG = HW / NP;
             if (CPG > n_sm * bps) continue;
             int G = n_sm * bps / CPG;
-            if (G > E) G = E;
-            // most concurrent episodes per on-chip byte first, then the largest tile, then the fewest cells
+            // most concurrent episodes per on-chip byte first, then the largest tile, then the fewest cells. The score uses
+            // the groups the chip could hold, not min(that, E): a small batch must NOT fall to a smaller tile with more CTAs
+            // per episode — measured on B200 at E = 1 (60x60x512, 200 steps): 20x5 (36 CTAs) 1.09 ms, 12x3 (100 CTAs) 1.68 ms,
+            // 20x3 (60 CTAs) 1.60 ms (tools/resident_small_e.py): the exchange latencies grow with the CTAs per group.
             const double score = (double)G / NP + 1e-9 * NP - 1e-12 * (TW + 1) * (TH + 1);
+            if (G > E) G = E;
             if (score > best_score) { best_score = score; best = ResidentPlan{TW, TH, NP, CPG, G, CT, bps, sm, true}; }
         }
     }
