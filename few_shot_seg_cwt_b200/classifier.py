@@ -16,7 +16,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib as L
-from .ops import fit_classifier, normalize_features
+from .ops import fit_classifier, fit_classifier_dice, label_counts, normalize_features
 
 
 def get_classifier(bottleneck_dim: int = 512, num_classes: int = 2, device=None) -> nn.Conv2d:
@@ -75,13 +75,12 @@ def inner_loop(classifier, f_s: torch.Tensor, s_label: torch.Tensor, cls_lr: flo
       * ``'wt_ce'`` — class-weighted CE; the weight bg_cnt/fg_cnt of model_util.py:27-37 equals n0/n1 for labels
         in {0,1,255};
       * ``'ce'``    — plain ``nn.CrossEntropyLoss(ignore_index=255)`` (class weight [1, 1]);
-      * ``'wt_dc'`` / ``'dc'`` (per-channel sigmoid dice) are not built — NotImplementedError.
+      * ``'wt_dc'`` / ``'dc'`` — the per-channel sigmoid dice loss (weighted_dice_loss, model_util.py:40-73; both
+        strings select the same function, model_util.py:18-19): :func:`fit_classifier_dice` (streaming kernels).
     ``classifier`` is the reference's ``nn.Conv2d(C, 2, 1, bias=False)`` (``dist == 'dot'``) or a flag-free
     :class:`CosCls` (``dist == 'cos'``, cls_type 'oooo'): ``scale_factor * conv(F.normalize(x, eps=1e-5))`` is the same
     bias-free classifier on the features ``2 * x_norm``, which one extra kernel prepares."""
-    if loss_type in ("wt_dc", "dc"):
-        raise NotImplementedError("cwt_b200 inner_loop: the dice losses of SegLoss ('wt_dc', 'dc') are not built")
-    if loss_type not in ("wt_ce", "ce"):
+    if loss_type not in ("wt_ce", "ce", "wt_dc", "dc"):
         loss_type = "wt_ce"                                     # SegLoss falls through to weighted CE for any other string
     if isinstance(classifier, CosCls):
         if not classifier.plain:
@@ -96,7 +95,34 @@ def inner_loop(classifier, f_s: torch.Tensor, s_label: torch.Tensor, cls_lr: flo
         classifier.reset_parameters()                      # CPU/GPU generator order as in the reference
     C = conv.weight.shape[1]
     w0 = conv.weight.detach().reshape(2, C).to(f_s.device, torch.float32)
-    cw = torch.ones(2, dtype=torch.float32, device=f_s.device) if loss_type == "ce" else None
-    w = fit_classifier(feat, s_label, w0, cls_lr, adapt_iter, class_weight=cw, check=check, algo=algo)
+    if loss_type in ("wt_dc", "dc"):
+        w = fit_classifier_dice(feat, s_label, w0, cls_lr, adapt_iter, check=check)
+    else:
+        cw = torch.ones(2, dtype=torch.float32, device=f_s.device) if loss_type == "ce" else None
+        w = fit_classifier(feat, s_label, w0, cls_lr, adapt_iter, class_weight=cw, check=check, algo=algo)
     with torch.no_grad():
         conv.weight.copy_(w.reshape(2, C, 1, 1))
+
+
+def increment_inner_loop(classifier: nn.Conv2d, f_s: torch.Tensor, s_label: torch.Tensor, cls_idx: int, cls_lr: float,
+                         adapt_iter: int, tp: float = 1.0, check: bool = True, algo: int = L.FIT_AUTO) -> None:
+    """``PSPNet.increment_inner_loop`` drop-in (src/model/pspnet.py:207-221) for a 2-class classifier: continue fitting
+    ``classifier`` (NO parameter reset, unlike :func:`inner_loop`) with ``Adapt_SegLoss(num_cls=2, fg_idx=cls_idx, tp)``
+    -> weighted_adpt_ce_loss (src/model/model_util.py:76-98): CE with ``weight[cls_idx] = (bg_cnt / fg_cnt) ** tp``,
+    bg_cnt = every non-ignored pixel that is not ``cls_idx``. The weight is computed on the device (no host sync; a
+    support mask without ``cls_idx`` pixels gives an infinite weight exactly as the reference's tensor division does).
+    Classifiers with more than two classes (the incremental multi-way setting of src/train_cca.py) are not built."""
+    if not isinstance(classifier, nn.Conv2d) or classifier.bias is not None or classifier.weight.shape[0] != 2 \
+            or classifier.kernel_size != (1, 1):
+        raise NotImplementedError("cwt_b200 increment_inner_loop fits the 2-class bias-free 1x1 classifier")
+    if cls_idx not in (0, 1):
+        raise IndexError(f"index {cls_idx} is out of bounds for dimension 0 with size 2")     # weight[fg_idx] in the reference
+    C = classifier.weight.shape[1]
+    n = label_counts(s_label).reshape(-1, 4).sum(0)                  # (#0, #1, #ignored, #invalid) over all shots
+    fg, bg = n[cls_idx].float(), n[1 - cls_idx].float()
+    cw = torch.ones(2, dtype=torch.float32, device=f_s.device)
+    cw[cls_idx] = (bg / fg) ** tp
+    w0 = classifier.weight.detach().reshape(2, C).to(f_s.device, torch.float32)
+    w = fit_classifier(f_s, s_label, w0, cls_lr, adapt_iter, class_weight=cw, check=check, algo=algo)
+    with torch.no_grad():
+        classifier.weight.copy_(w.reshape(2, C, 1, 1))

@@ -101,6 +101,42 @@ def fit_classifier(f_s: torch.Tensor, s_label: torch.Tensor, w0: torch.Tensor, l
     return (out, losses) if return_losses else out
 
 
+def fit_classifier_dice(f_s: torch.Tensor, s_label: torch.Tensor, w0: torch.Tensor, lr: float, n_iter: int,
+                        ignore_index: int = IGNORE, return_losses: bool = False, check: bool = True):
+    """The inner loop of :func:`fit_classifier` with the reference's dice loss, ``SegLoss('wt_dc' | 'dc')``
+    (src/model/model_util.py:18-19 -> weighted_dice_loss, :40-73): a sigmoid per logit channel, one dice term per
+    (support image, channel), summed and divided by the number of support images. Same shapes as
+    :func:`fit_classifier`; there is no class weight and an episode without foreground is legal (the dice term of an
+    empty target is 1). ``check``: one host sync to raise ValueError on labels outside {0, 1, ignore_index}."""
+    dev = L.require_cuda(f_s, s_label, w0)
+    if f_s.dim() == 4:
+        f_s, s_label = f_s.unsqueeze(0), s_label.unsqueeze(0)
+    if f_s.dim() != 5 or s_label.dim() != 4:
+        raise ValueError(f"f_s must be [E,S,C,h,w] and s_label [E,S,H,W]; got {tuple(f_s.shape)}, {tuple(s_label.shape)}")
+    E, S, Cc, h, w = f_s.shape
+    H, W = s_label.shape[-2:]
+    if s_label.shape[0] != E or s_label.shape[1] != S:
+        raise ValueError("f_s and s_label disagree on E or S")
+    w0_shape = w0.shape
+    w0v = _f32c(w0, "w0").reshape(E, 2, Cc)
+    f_s = _f32c(f_s, "f_s")
+    lab = s_label.contiguous()
+    w_out = torch.empty(E, 2, Cc, dtype=torch.float32, device=dev)
+    losses = torch.empty(n_iter, E, dtype=torch.float32, device=dev) if return_losses else None
+    lib = L.load()
+    nbytes = lib.cwt_fit_dice_workspace_bytes(E, S, Cc, h, w, H, W)
+    ws = L.WORKSPACE.get(nbytes, dev, "fit_dice")
+    with torch.cuda.device(dev):
+        rc = lib.cwt_fit_classifier_dice_f32(L.ptr(f_s), L.ptr(lab), L.label_kind(lab), L.ptr(w0v), L.ptr(w_out),
+                                             L.ptr(losses), E, S, Cc, h, w, H, W, int(n_iter), float(lr),
+                                             int(ignore_index), L.ptr(ws), ws.numel(), L.stream_ptr(dev))
+    L.check(rc, "cwt_fit_classifier_dice_f32")
+    if check and int(label_counts(lab.reshape(E * S, H, W), ignore_index)[:, 3].sum()) > 0:
+        raise ValueError("s_label holds values outside {0, 1, ignore_index}")
+    out = w_out.reshape(w0_shape)
+    return (out, losses) if return_losses else out
+
+
 # ----------------------------------------------------------------------------------------
 # (a-5, a-6, a-13) transformer forward / backward
 # ----------------------------------------------------------------------------------------

@@ -92,6 +92,23 @@ int cwt_fit_classifier_f32(const float* f_s, const void* s_label, int label_kind
                            void* workspace, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * (f-3) the same inner loop with SegLoss('wt_dc' | 'dc'), the per-channel sigmoid dice loss:
+ * PSPNet.inner_loop, src/model/pspnet.py:189-205, with criterion = SegLoss(args.inner_loss_type),
+ * src/model/model_util.py:18-19 -> weighted_dice_loss, model_util.py:40-73 (weighted_val 1,
+ * reduction 'sum', input_type 'lg'):  n_iter x { 1x1 conv 2xC, bilinear up to HxW, sigmoid per
+ * channel, sum over (image, channel) rows of 1 - 2 sum(t p) / clamp(sum p^2 + sum t^2, 1e-8),
+ * divided by S, backward, SGD }.  Arguments as cwt_fit_classifier_f32 (no class weight: the dice
+ * loss has none; labels equal to ignore_index are in neither target but their p^2 counts).
+ *   loss_trace_or_null [n_iter,E]: the dice loss of every step
+ * ------------------------------------------------------------------------------------- */
+size_t cwt_fit_dice_workspace_bytes(int E, int S, int C, int h, int w, int H, int W);
+int cwt_fit_classifier_dice_f32(const float* f_s, const void* s_label, int label_kind, const float* w0,
+                                float* w_out, float* loss_trace_or_null,
+                                int E, int S, int C, int h, int w, int H, int W,
+                                int n_iter, float lr, int ignore_index,
+                                void* workspace, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * (a-5, a-6) MultiHeadAttentionOne forward.  Replaces src/model/transformer.py:54-83
  * (+ ScaledDotProductAttention :23-30) for the call transformer(W, f_q, f_q) of
  * src/test.py:197 / src/train.py:257 (k is v, one shared projection w_qkvs).

@@ -82,14 +82,31 @@ def fit_classifier_ref(f_s: torch.Tensor, s_label: torch.Tensor, w0: torch.Tenso
 
 # --------------------------------------------------------------------------------------
 # PSPNet.inner_loop variants                      src/model/pspnet.py:189-205, 290-334
-#   SegLoss 'wt_ce' / 'ce' (src/model/model_util.py:9-37); classifier 'dot' or CosCls 'oooo'
+#   SegLoss 'wt_ce' / 'ce' / 'wt_dc' / 'dc' (src/model/model_util.py:9-73); classifier 'dot' or CosCls 'oooo'
 # --------------------------------------------------------------------------------------
+def weighted_dice_loss_ref(prediction: torch.Tensor, target_seg: torch.Tensor, eps: float = 1e-8) -> torch.Tensor:
+    """SegLoss 'wt_dc' / 'dc' (model_util.py:18-19 -> weighted_dice_loss, :40-73, weighted_val 1.0, reduction 'sum',
+    input_type 'lg'): every (image, channel) row is a sigmoid dice, 1 - 2 sum(t p) / clamp(sum p^2 + sum t^2, eps), with
+    targets [label == 0, label == 1] (255 is in neither, but its p^2 counts); the rows are summed and divided by the
+    number of images. prediction [S,2,H,W] logits, target_seg [S,H,W]."""
+    tgt = torch.stack([target_seg == 0, target_seg == 1], dim=1).float()
+    n, _, h, w = tgt.shape
+    p = torch.sigmoid(prediction.reshape(-1, h, w)).reshape(-1, h * w)
+    t = tgt.reshape(-1, h * w)
+    part = (p ** 2).sum(dim=-1) + (t ** 2).sum(dim=-1)
+    loss = 1 - 2 * (t * p).sum(dim=-1) / torch.clamp(part, min=eps)
+    return loss.sum() / n
+
+
 def inner_loop_ref(f_s: torch.Tensor, s_label: torch.Tensor, w0: torch.Tensor, lr: float, n_iter: int,
-                   loss_type: str = "wt_ce", dist: str = "dot") -> torch.Tensor:
+                   loss_type: str = "wt_ce", dist: str = "dot", fg_idx: int = 1, tp: float = 1.0) -> torch.Tensor:
     """The inner loop with its two switches: ``args.inner_loss_type`` ('wt_ce': weight[fg] = bg_cnt / fg_cnt from
-    torch.bincount, model_util.py:27-37; 'ce': plain CE, ignore 255) and ``args.dist`` ('dot': nn.Conv2d;
+    torch.bincount, model_util.py:27-37; 'ce': plain CE, ignore 255; 'wt_dc' / 'dc': per-channel sigmoid dice) and ``args.dist`` ('dot': nn.Conv2d;
     'cos': CosCls with cls_type 'oooo' — scores = 2.0 * conv(F.normalize(x, p=2, dim=1, eps=1e-5)),
-    pspnet.py:302-310). f_s [S,C,h,w]; s_label [S,H,W]; w0 [2,C] -> fitted weight [2,C]."""
+    pspnet.py:302-310). f_s [S,C,h,w]; s_label [S,H,W]; w0 [2,C] -> fitted weight [2,C].
+    ``loss_type == 'adapt_ce'`` is ``PSPNet.increment_inner_loop`` (pspnet.py:207-221) for a 2-class classifier: the same
+    loop (no parameter reset) with Adapt_SegLoss -> weighted_adpt_ce_loss (model_util.py:76-98):
+    weight[fg_idx] = (bg_cnt / fg_cnt) ** tp."""
     S, C = f_s.shape[:2]
     tgt = s_label.long()
     conv = nn.Conv2d(C, 2, kernel_size=1, bias=False)
@@ -102,14 +119,21 @@ def inner_loop_ref(f_s: torch.Tensor, s_label: torch.Tensor, w0: torch.Tensor, l
         else:
             out = 2.0 * conv(F.normalize(f_s, p=2, dim=1, eps=0.00001))
         out = F.interpolate(out, size=tgt.shape[-2:], mode="bilinear", align_corners=True)
-        if loss_type == "ce":
+        if loss_type in ("wt_dc", "dc"):
+            loss = weighted_dice_loss_ref(out, tgt)
+        elif loss_type == "ce":
             loss = nn.CrossEntropyLoss(ignore_index=IGNORE)(out, tgt)
         else:
             count = torch.bincount(tgt.view(-1))
             fg = count[1]
             bg = (torch.sum(count) - fg) if len(count) <= 255 else (torch.sum(count) - count[255] - fg)
             weight = torch.tensor([1.0, 1.0])
-            weight[1] = bg / fg
+            if loss_type == "adapt_ce":
+                fg = count[fg_idx]
+                bg = (torch.sum(count) - fg) if len(count) <= 255 else (torch.sum(count) - count[255] - fg)
+                weight[fg_idx] = (bg / fg) ** tp
+            else:
+                weight[1] = bg / fg
             loss = nn.CrossEntropyLoss(weight=weight, ignore_index=IGNORE)(out, tgt)
         opt.zero_grad()
         loss.backward()

@@ -58,6 +58,12 @@ CASES = {
 INNER_CASES = {
     "inner_small_dot_ce":   dict(idx=21, shot=1, C=64, h=12, w=12, H=89, W=89, style="unit", lr=0.1, n_iter=50, loss_type="ce", dist="dot"),
     "inner_small_cos_wtce": dict(idx=22, shot=2, C=64, h=12, w=12, H=89, W=89, style="backbone", lr=0.1, n_iter=50, loss_type="wt_ce", dist="cos"),
+    "inner_small_dot_wtdc": dict(idx=24, shot=2, C=64, h=12, w=12, H=89, W=89, style="unit", lr=0.1, n_iter=50, loss_type="wt_dc", dist="dot"),
+    "inner_small_cos_dc":   dict(idx=25, shot=1, C=64, h=12, w=12, H=89, W=89, style="backbone", lr=0.1, n_iter=50, loss_type="dc", dist="cos"),
+    "inner_full_dot_dc":    dict(idx=26, shot=1, C=512, h=60, w=60, H=473, W=473, style="unit", lr=0.1, n_iter=100, loss_type="dc", dist="dot"),
+    # PSPNet.increment_inner_loop (pspnet.py:207-221) on a 2-class classifier: Adapt_SegLoss(num_cls=2, fg_idx, tp)
+    "inner_incr_small_tp05": dict(idx=27, shot=1, C=64, h=12, w=12, H=89, W=89, style="unit", lr=0.1, n_iter=50, loss_type="adapt_ce", dist="dot", fg_idx=1, tp=0.5),
+    "inner_incr_small_fg0":  dict(idx=28, shot=2, C=64, h=12, w=12, H=89, W=89, style="unit", lr=0.1, n_iter=50, loss_type="adapt_ce", dist="dot", fg_idx=0, tp=1.0),
     "inner_full_cos_ce":    dict(idx=23, shot=1, C=512, h=60, w=60, H=473, W=473, style="backbone", lr=0.1, n_iter=100, loss_type="ce", dist="cos"),
 }
 TRAIN_CASES = {
@@ -149,7 +155,7 @@ def inner_loop_via_reference(ep, case):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         from src.model.pspnet import CosCls
-        from src.model.model_util import SegLoss
+        from src.model.model_util import SegLoss, Adapt_SegLoss
     C = ep.f_s.shape[1]
     if case["dist"] == "dot":
         classifier = nn.Conv2d(C, 2, kernel_size=1, bias=False)
@@ -162,7 +168,10 @@ def inner_loop_via_reference(ep, case):
     with torch.no_grad():
         conv.weight.copy_(ep.w0.reshape(2, C, 1, 1))
     optimizer = torch.optim.SGD(classifier.parameters(), lr=case["lr"])
-    criterion = SegLoss(loss_type=case["loss_type"])
+    if case["loss_type"] == "adapt_ce":                           # increment_inner_loop's criterion (pspnet.py:213)
+        criterion = Adapt_SegLoss(num_cls=2, fg_idx=case["fg_idx"], tp=case["tp"])
+    else:
+        criterion = SegLoss(loss_type=case["loss_type"])
     f_s, s_label = ep.f_s, ep.s_label.long()
     cuda_avail = torch.cuda.is_available
     torch.cuda.is_available = lambda: False                       # weighted_ce_loss moves its weight with .cuda() when it can
@@ -323,7 +332,8 @@ def main():
             continue
         ep = syn.make_episode(case["idx"], **gen_kwargs(case))
         w_ref, last_loss = inner_loop_via_reference(ep, case)
-        w_ora = O.inner_loop_ref(ep.f_s, ep.s_label, ep.w0, case["lr"], case["n_iter"], case["loss_type"], case["dist"])
+        w_ora = O.inner_loop_ref(ep.f_s, ep.s_label, ep.w0, case["lr"], case["n_iter"], case["loss_type"], case["dist"],
+                                 case.get("fg_idx", 1), case.get("tp", 1.0))
         err = relerr(w_ora, w_ref)
         print(f"[pin] {name}: oracle vs reference inner_loop rel {err:.2e} last loss {last_loss:.6f}")
         assert err < 1e-6, err

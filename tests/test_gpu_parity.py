@@ -234,8 +234,8 @@ def test_inner_loop_dropin(cuda_device):
 
 @pytest.mark.parametrize("name", golden_names("inner_"))
 def test_inner_loop_variants_vs_golden(cuda_device, name):
-    """PSPNet.inner_loop with its two switches (src/model/pspnet.py:189-205): SegLoss 'ce' / 'wt_ce'
-    (model_util.py:9-37) and the dot / cosine classifier (CosCls 'oooo', pspnet.py:290-315); goldens recorded from
+    """PSPNet.inner_loop with its two switches (src/model/pspnet.py:189-205): SegLoss 'ce' / 'wt_ce' / 'wt_dc' / 'dc'
+    (model_util.py:9-73) and the dot / cosine classifier (CosCls 'oooo', pspnet.py:290-315); goldens recorded from
     the live reference's own CosCls and SegLoss objects."""
     g = load_golden(name)
     case = g["case"]
@@ -246,8 +246,12 @@ def test_inner_loop_variants_vs_golden(cuda_device, name):
     conv = clf.cls if case["dist"] == "cos" else clf
     with torch.no_grad():
         conv.weight.copy_(ep.w0.reshape(2, C, 1, 1))
-    cwt.inner_loop(clf, ep.f_s.to(cuda_device), ep.s_label.to(cuda_device), case["lr"], case["n_iter"], reset=False,
-                   loss_type=case["loss_type"])
+    if case["loss_type"] == "adapt_ce":                      # PSPNet.increment_inner_loop (pspnet.py:207-221), 2-class
+        cwt.increment_inner_loop(clf, ep.f_s.to(cuda_device), ep.s_label.to(cuda_device), case["fg_idx"], case["lr"],
+                                 case["n_iter"], tp=case["tp"])
+    else:
+        cwt.inner_loop(clf, ep.f_s.to(cuda_device), ep.s_label.to(cuda_device), case["lr"], case["n_iter"], reset=False,
+                       loss_type=case["loss_type"])
     assert rel_err(conv.weight.reshape(2, C), g["W_fit"]) < TIGHT
     if case["dist"] == "cos":                                # the module's own forward is the reference's formula
         x = ep.f_s.to(cuda_device)
@@ -256,15 +260,46 @@ def test_inner_loop_variants_vs_golden(cuda_device, name):
         assert rel_err(ops.normalize_features(x, 1e-5, 2.0), 2.0 * F.normalize(x.cpu(), p=2, dim=1, eps=1e-5)) < 1e-6
 
 
+def test_fit_dice_loss_trace_batch_and_label_dtypes(cuda_device):
+    """SegLoss 'wt_dc' (weighted_dice_loss, model_util.py:40-73): loss of every step and the weights against the
+    oracle's autograd loop, a batch equals its episodes one by one, uint8 == int64 labels, an episode without any
+    foreground pixel is legal (the reference's dice has no division by the foreground count)."""
+    eps = [syn.make_episode(i, **{**SMALL, "shot": 2}) for i in (50, 51, 52)]
+    f = torch.stack([e.f_s for e in eps]).to(cuda_device)
+    lab = torch.stack([e.s_label for e in eps]).to(cuda_device)
+    w0 = torch.stack([e.w0 for e in eps]).to(cuda_device)
+    lab[2][lab[2] == 1] = 0                                   # no foreground at all
+    w, losses = ops.fit_classifier_dice(f, lab, w0, 0.1, 30, return_losses=True)
+    for j, e in enumerate(eps):
+        conv = torch.nn.Conv2d(64, 2, 1, bias=False)
+        with torch.no_grad():
+            conv.weight.copy_(e.w0.reshape(2, 64, 1, 1))
+        opt = torch.optim.SGD(conv.parameters(), lr=0.1)
+        tgt = lab[j].cpu().long()
+        trace = []
+        for _ in range(30):
+            out = F.interpolate(conv(e.f_s), size=tgt.shape[-2:], mode="bilinear", align_corners=True)
+            loss = O.weighted_dice_loss_ref(out, tgt)
+            trace.append(float(loss))
+            opt.zero_grad(); loss.backward(); opt.step()
+        assert rel_err(w[j], conv.weight.detach().reshape(2, 64)) < TIGHT
+        assert rel_err(losses[:, j], torch.tensor(trace)) < TIGHT
+        w1 = ops.fit_classifier_dice(f[j], lab[j].long(), w0[j], 0.1, 30)
+        assert torch.equal(w1, w[j])
+    with pytest.raises(ValueError):
+        bad = lab.clone(); bad[0, 0, 0, 0] = 7
+        ops.fit_classifier_dice(f, bad, w0, 0.1, 2)
+
+
 def test_inner_loop_unsupported_variants_raise(cuda_device):
     ep = syn.make_episode(1, **SMALL)
     f, lab = ep.f_s.to(cuda_device), ep.s_label.to(cuda_device)
-    with pytest.raises(NotImplementedError):                 # dice losses of SegLoss
-        cwt.inner_loop(cwt.get_classifier(64, 2).to(cuda_device), f, lab, 0.1, 5, loss_type="wt_dc")
     with pytest.raises(NotImplementedError):                 # weight-normalised cosine classifier
         cwt.inner_loop(cwt.CosCls(64, 2, "0n00").to(cuda_device), f, lab, 0.1, 5)
     with pytest.raises(KeyError):                            # parse_param_coscls
         cwt.CosCls(64, 2, "xxxx")
+    with pytest.raises(NotImplementedError):                 # multi-way incremental classifier
+        cwt.increment_inner_loop(cwt.get_classifier(64, 3).to(cuda_device), f, lab, 1, 0.1, 5)
 
 
 # ---------------------------------------------------------------------------- (b) transformer

@@ -39,7 +39,27 @@ def test_oracle_reproduces_reference_golden(name):
     assert abs(float(out["loss"]) - float(g["loss"])) < 1e-6
 
 
-@pytest.mark.parametrize("name", ["inner_small_dot_ce", "inner_small_cos_wtce"])
+def _dice_fit_closed_form(f_s, s_label, w0, lr, n_iter):
+    """weighted_dice_loss (model_util.py:40-73) + SGD without autograd, in float64: explicit bilinear matrices and the
+    hand-derived gradient dl/du = (-2 t / D + 4 N p / D^2) p (1 - p) / S the CUDA kernels implement."""
+    S, C, h, w = f_s.shape
+    H, W = s_label.shape[-2:]
+    By, Bx = O.bilinear_matrix(h, H), O.bilinear_matrix(w, W)
+    Fm = f_s.double().reshape(S, C, h * w)
+    t = torch.stack([s_label == 0, s_label == 1], dim=1).double()                     # [S,2,H,W]
+    Wt = w0.double().clone()
+    for _ in range(n_iter):
+        lg = torch.einsum("rc,scp->srp", Wt, Fm).reshape(S, 2, h, w)
+        p = torch.sigmoid(torch.einsum("Yy,sryx,Xx->srYX", By, lg, Bx))
+        N, D = (t * p).sum((-1, -2), keepdim=True), ((p * p).sum((-1, -2), keepdim=True) + t.sum((-1, -2), keepdim=True)).clamp_min(1e-8)
+        du = (-2 * t / D + 4 * N * p / D ** 2) * p * (1 - p) / S
+        g60 = torch.einsum("Yy,srYX,Xx->sryx", By, du, Bx).reshape(S, 2, h * w)
+        Wt -= lr * torch.einsum("srp,scp->rc", g60, Fm)
+    return Wt.float()
+
+
+@pytest.mark.parametrize("name", ["inner_small_dot_ce", "inner_small_cos_wtce", "inner_small_dot_wtdc", "inner_small_cos_dc",
+                                  "inner_incr_small_tp05", "inner_incr_small_fg0"])
 def test_oracle_inner_loop_variants_reproduce_reference_golden(name):
     """PSPNet.inner_loop switches (SegLoss 'ce' / 'wt_ce', dot / cosine classifier) against the vectors recorded from the
     live reference's CosCls and SegLoss objects; also: 'ce' is the weighted fit with class weight [1, 1], and the cosine
@@ -48,10 +68,19 @@ def test_oracle_inner_loop_variants_reproduce_reference_golden(name):
     case = g["case"]
     ep = syn.make_episode(case["idx"], **gen_kwargs(case))
     assert _checksum(ep) == str(g["checksum"])
-    w = O.inner_loop_ref(ep.f_s, ep.s_label, ep.w0, case["lr"], case["n_iter"], case["loss_type"], case["dist"])
+    w = O.inner_loop_ref(ep.f_s, ep.s_label, ep.w0, case["lr"], case["n_iter"], case["loss_type"], case["dist"],
+                         case.get("fg_idx", 1), case.get("tp", 1.0))
     assert rel_err(w, g["W_fit"]) < 1e-6
+    if case["loss_type"] in ("wt_dc", "dc"):                  # dice: no CE identity to check; an independent restatement instead
+        feat = 2.0 * torch.nn.functional.normalize(ep.f_s, p=2, dim=1, eps=1e-5) if case["dist"] == "cos" else ep.f_s
+        assert rel_err(_dice_fit_closed_form(feat, ep.s_label, ep.w0, case["lr"], case["n_iter"]), g["W_fit"]) < 2e-5
+        return
     feat = 2.0 * torch.nn.functional.normalize(ep.f_s, p=2, dim=1, eps=1e-5) if case["dist"] == "cos" else ep.f_s
     cw = torch.ones(2) if case["loss_type"] == "ce" else None
+    if case["loss_type"] == "adapt_ce":                       # increment_inner_loop == the weighted fit with weight[fg] = (bg/fg)^tp
+        n = [int((ep.s_label == k).sum()) for k in (0, 1)]
+        cw = torch.ones(2)
+        cw[case["fg_idx"]] = (torch.tensor(n[1 - case["fg_idx"]]) / torch.tensor(n[case["fg_idx"]])) ** case["tp"]
     w2 = O.fit_classifier_ref(feat, ep.s_label, ep.w0, case["lr"], case["n_iter"], class_weight=cw)
     assert rel_err(w2, g["W_fit"]) < 2e-6
 
