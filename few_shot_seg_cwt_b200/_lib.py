@@ -32,6 +32,8 @@ SIGNATURES = {
     "cwt_prep_labels": (_i, [_vp, _i, _i, _ll, _i, _vp, _vp, _vp]),
     "cwt_fit_workspace_bytes": (_sz, [_i] * 7),
     "cwt_fit_classifier_f32": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp] + [_i] * 8 + [_f, _i, _i, _vp, _sz, _vp]),
+    "cwt_fit_bias_workspace_bytes": (_sz, [_i] * 7),
+    "cwt_fit_classifier_bias_f32": (_i, [_vp, _vp, _i] + [_vp] * 7 + [_i] * 8 + [_f, _f, _i, _vp, _sz, _vp]),
     "cwt_fit_dice_workspace_bytes": (_sz, [_i] * 7),
     "cwt_fit_classifier_dice_f32": (_i, [_vp, _vp, _i, _vp, _vp, _vp] + [_i] * 8 + [_f, _i, _vp, _sz, _vp]),
     "cwt_transformer_workspace_bytes": (_sz, [_i] * 6),

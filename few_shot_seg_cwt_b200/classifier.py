@@ -16,7 +16,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib as L
-from .ops import fit_classifier, fit_classifier_dice, label_counts, normalize_features
+from .ops import fit_classifier, fit_classifier_bias, fit_classifier_dice, label_counts, normalize_features
 
 
 def get_classifier(bottleneck_dim: int = 512, num_classes: int = 2, device=None) -> nn.Conv2d:
@@ -38,7 +38,8 @@ class CosCls(nn.Module):
     src/model/pspnet.py:290-315): ``cls`` is the 1x1 conv, ``scale_factor`` the temperature (2.0).
     ``cls_type`` = four flags [weight-norm reparametrisation 'r', weight normalisation 'n', bias 'b', learnable
     temperature 't']; '0' / 'o' switch a flag off. ``forward`` is plain torch (it is not on the episodic hot path);
-    :func:`inner_loop` fits the flag-free form ('oooo' / '0000') with the fused CUDA fit."""
+    :func:`inner_loop` fits the flag-free form ('oooo' / '0000') with the fused CUDA fit and the form with a bias
+    ('oobo') with the streaming kernels."""
 
     def __init__(self, in_dim: int = 512, n_classes: int = 2, cls_type: str = "0000"):
         super().__init__()
@@ -77,25 +78,35 @@ def inner_loop(classifier, f_s: torch.Tensor, s_label: torch.Tensor, cls_lr: flo
       * ``'ce'``    — plain ``nn.CrossEntropyLoss(ignore_index=255)`` (class weight [1, 1]);
       * ``'wt_dc'`` / ``'dc'`` — the per-channel sigmoid dice loss (weighted_dice_loss, model_util.py:40-73; both
         strings select the same function, model_util.py:18-19): :func:`fit_classifier_dice` (streaming kernels).
-    ``classifier`` is the reference's ``nn.Conv2d(C, 2, 1, bias=False)`` (``dist == 'dot'``) or a flag-free
-    :class:`CosCls` (``dist == 'cos'``, cls_type 'oooo'): ``scale_factor * conv(F.normalize(x, eps=1e-5))`` is the same
-    bias-free classifier on the features ``2 * x_norm``, which one extra kernel prepares."""
+    ``classifier`` is the reference's ``nn.Conv2d(C, 2, 1, bias=False)`` (``dist == 'dot'``) or a :class:`CosCls`
+    (``dist == 'cos'``) with cls_type 'oooo' or 'oobo': ``scale_factor * conv(F.normalize(x, eps=1e-5))`` is the same
+    classifier on the features ``2 * x_norm``, which one extra kernel prepares (a bias is then scaled by 2 as well);
+    a classifier with a bias is fitted by :func:`fit_classifier_bias` (weights and bias updated by the same SGD)."""
     if loss_type not in ("wt_ce", "ce", "wt_dc", "dc"):
         loss_type = "wt_ce"                                     # SegLoss falls through to weighted CE for any other string
     if isinstance(classifier, CosCls):
-        if not classifier.plain:
-            raise NotImplementedError("cwt_b200 inner_loop fits CosCls without weight-norm / bias / learnable temperature "
-                                      "(cls_type 'oooo' or '0000')")
-        conv, feat = classifier.cls, normalize_features(f_s, eps=1e-5, scale=float(classifier.scale_factor))
+        if classifier.WeightNormR or classifier.weight_norm or classifier.temp:
+            raise NotImplementedError("cwt_b200 inner_loop fits CosCls without weight-norm / learnable temperature "
+                                      "(cls_type 'oooo' / '0000' / 'oobo')")
+        scale = float(classifier.scale_factor)
+        conv, feat = classifier.cls, normalize_features(f_s, eps=1e-5, scale=scale)
     else:
-        conv, feat = classifier, f_s
-    if conv.bias is not None or conv.weight.shape[0] != 2 or conv.kernel_size != (1, 1):
-        raise NotImplementedError("cwt_b200 inner_loop fits the reference's 2-class bias-free 1x1 classifier")
+        conv, feat, scale = classifier, f_s, 1.0
+    if conv.weight.shape[0] != 2 or conv.kernel_size != (1, 1):
+        raise NotImplementedError("cwt_b200 inner_loop fits the reference's 2-class 1x1 classifier")
     if reset:
         classifier.reset_parameters()                      # CPU/GPU generator order as in the reference
     C = conv.weight.shape[1]
     w0 = conv.weight.detach().reshape(2, C).to(f_s.device, torch.float32)
-    if loss_type in ("wt_dc", "dc"):
+    if conv.bias is not None:                              # CosCls cls_type[2] == 'b' (or any nn.Conv2d(C, 2, 1, bias=True))
+        if loss_type in ("wt_dc", "dc"):
+            raise NotImplementedError("cwt_b200 inner_loop: the dice losses are built for the bias-free classifier")
+        cw = torch.ones(2, dtype=torch.float32, device=f_s.device) if loss_type == "ce" else None
+        b0 = conv.bias.detach().to(f_s.device, torch.float32)
+        w, b = fit_classifier_bias(feat, s_label, w0, b0, cls_lr, adapt_iter, class_weight=cw, bias_scale=scale, check=check)
+        with torch.no_grad():
+            conv.bias.copy_(b)
+    elif loss_type in ("wt_dc", "dc"):
         w = fit_classifier_dice(feat, s_label, w0, cls_lr, adapt_iter, check=check)
     else:
         cw = torch.ones(2, dtype=torch.float32, device=f_s.device) if loss_type == "ce" else None

@@ -145,5 +145,99 @@ extern "C" int cwt_fit_classifier_f32(const float* f_s, const void* s_label, int
     return CWT_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same fit for a classifier WITH a bias (nn.Conv2d(C, 2, 1, bias=True); the reference builds one inside CosCls when
+// cls_type[2] == 'b', src/model/pspnet.py:294,319): logits l_c = W_c . F + bias_scale * b_c, so the logit difference is
+// zd + bias_scale * (b1 - b0) and  db1 = bias_scale * sum_p g60[p] = -db0  (plain SGD on both, like the weights).
+// bias_scale = 1 for the dot classifier; CosCls multiplies conv(x_norm) INCLUDING its bias by scale_factor, and the
+// caller folds scale_factor into the features, so it passes bias_scale = scale_factor. Streaming algorithm.
+// ---------------------------------------------------------------------------------------------------------------
+namespace cwt {
+// one CTA per episode: b <- b0 (or, with g60, one SGD step on the bias from the step's logit gradient); bd = scale (b1 - b0)
+__global__ void __launch_bounds__(256)
+k_fit_bias_update(const float* __restrict__ g60, const float* __restrict__ b_init, float* __restrict__ b, float* __restrict__ bd,
+                  float lr, float bias_scale, int n /* S*h*w */) {
+    __shared__ float red[8];
+    const int e = blockIdx.x, tid = threadIdx.x;
+    float s = 0.f;
+    if (g60) for (int i = tid; i < n; i += 256) s += g60[(size_t)e * n + i];
+    s = warp_sum(s);
+    if ((tid & 31) == 0) red[tid >> 5] = s;
+    __syncthreads();
+    if (tid == 0) {
+        float tot = 0.f;
+        for (int k = 0; k < 8; ++k) tot += red[k];                         // fixed order
+        const float db1 = bias_scale * tot;
+        const float o0 = b_init ? b_init[e * 2] : b[e * 2], o1 = b_init ? b_init[e * 2 + 1] : b[e * 2 + 1];
+        const float n0 = fmaf(lr, db1, o0), n1 = fmaf(-lr, db1, o1);      // db0 = -db1
+        b[e * 2] = n0; b[e * 2 + 1] = n1;
+        bd[e] = bias_scale * (n1 - n0);
+    }
+}
+}  // namespace cwt
+
+extern "C" size_t cwt_fit_bias_workspace_bytes(int E, int S, int C, int h, int w, int H, int W) {
+    Carver cv(nullptr, 0);
+    FitWs ws;
+    carve_fit(cv, ws, E, S, C, h, w, H, W);
+    cv.take<float>((size_t)E);
+    return align_up(cv.off);
+}
+
+extern "C" int cwt_fit_classifier_bias_f32(const float* f_s, const void* s_label, int label_kind, const float* w0,
+                                           const float* b0, const float* class_weight_or_null, float* w_out, float* b_out,
+                                           float* loss_trace_or_null, int32_t* label_counts_or_null,
+                                           int E, int S, int C, int h, int w, int H, int W,
+                                           int n_iter, float lr, float bias_scale, int ignore_index,
+                                           void* workspace, size_t ws_bytes, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CWT_REQUIRE(E >= 0 && S >= 1 && C >= 1 && h >= 1 && w >= 1 && n_iter >= 0, CWT_ERR_INVALID_ARG,
+                "fit_bias: bad sizes E=%d S=%d C=%d h=%d w=%d n_iter=%d", E, S, C, h, w, n_iter);
+    if (E == 0) return CWT_OK;
+    CWT_REQUIRE(f_s && s_label && w0 && b0 && w_out && b_out, CWT_ERR_INVALID_ARG, "fit_bias: null pointer");
+    CWT_REQUIRE(H == 8 * (h - 1) + 1 && W == 8 * (w - 1) + 1, CWT_ERR_UNSUPPORTED,
+                "fit_bias: label size %dx%d is not 8*(%dx%d - 1) + 1 (align_corners scale must be 1/8)", H, W, h, w);
+    CWT_REQUIRE(w <= HIRES_MAXW, CWT_ERR_UNSUPPORTED, "fit_bias: w=%d exceeds the supported width (%d)", w, HIRES_MAXW);
+    CWT_REQUIRE(label_kind == CWT_LABEL_U8 || label_kind == CWT_LABEL_I64, CWT_ERR_INVALID_ARG,
+                "fit_bias: label_kind %d", label_kind);
+    Carver cv(workspace, ws_bytes);
+    FitWs ws;
+    carve_fit(cv, ws, E, S, C, h, w, H, W);
+    float* bd = cv.take<float>((size_t)E);
+    const size_t need = align_up(cv.off);
+    CWT_REQUIRE(workspace && ws_bytes >= need, CWT_ERR_WORKSPACE, "fit_bias: workspace %zu < %zu bytes", ws_bytes, need);
+
+    const int HWl = h * w;
+    int rc = pack_label_cells(s_label, label_kind, E * S, h, w, H, W, ignore_index, ws.cells, ws.counts_img, st);
+    if (rc != CWT_OK) return rc;
+    k_class_consts<<<(E + 127) / 128, 128, 0, st>>>(ws.counts_img, class_weight_or_null, 0.0, ws.cw,
+                                                    label_counts_or_null, E, S);
+    CWT_LAUNCHED("class_consts");
+    k_fit_init_weights<<<E, 256, 0, st>>>(w0, w_out, ws.wd, C);
+    CWT_LAUNCHED("fit_init_weights");
+    k_fit_bias_update<<<E, 256, 0, st>>>(nullptr, b0, b_out, bd, 0.f, bias_scale, 0);
+    CWT_LAUNCHED("fit_bias_init");
+
+    FitUpdateEpilogue epi{w_out, ws.wd, lr, C};
+    for (int it = 0; it < n_iter; ++it) {
+        rc = launch_rows_times_feat(f_s, ws.wd, ws.zd, nullptr, E * S, C, HWl, S, 1, st);
+        if (rc != CWT_OK) return rc;
+        if (loss_trace_or_null) {
+            rc = launch_fit_hires<true>(ws.zd, ws.cells, ws.cw, ws.g60, ws.loss_part, E * S, h, w, S, st, bd);
+            if (rc != CWT_OK) return rc;
+            k_reduce_loss<<<E, 32, 0, st>>>(ws.loss_part, loss_trace_or_null + (size_t)it * E, S * ws.nblk);
+            CWT_LAUNCHED("reduce_loss");
+        } else {
+            rc = launch_fit_hires<false>(ws.zd, ws.cells, ws.cw, ws.g60, nullptr, E * S, h, w, S, st, bd);
+            if (rc != CWT_OK) return rc;
+        }
+        rc = launch_ftc_t<1, 4>(f_s, ws.g60, E, S, C, HWl, 1, epi, st);
+        if (rc != CWT_OK) return rc;
+        k_fit_bias_update<<<E, 256, 0, st>>>(ws.g60, nullptr, b_out, bd, lr, bias_scale, S * HWl);
+        CWT_LAUNCHED("fit_bias_update");
+    }
+    return CWT_OK;
+}
+
 // debug hook: device buffer [grid][8] int64 receiving the resident kernel's per-phase cycle counters
 extern "C" void cwt_debug_set_prof_buffer(void* dev_buffer) { cwt::g_prof_buffer = static_cast<long long*>(dev_buffer); }

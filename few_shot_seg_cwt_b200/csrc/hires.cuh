@@ -100,12 +100,14 @@ constexpr int HIRES_RROWS = 4;
 template <int RROWS, bool LOSS>
 __global__ void __launch_bounds__((RROWS + 1) * HIRES_MAXW > 1024 ? 1024 : 512)
 k_fit_hires(const float* __restrict__ zd, const uint4* __restrict__ cells, const float2* __restrict__ cw,
-            float* __restrict__ g60, float* __restrict__ loss_part, int h, int w, int S) {
+            float* __restrict__ g60, float* __restrict__ loss_part, int h, int w, int S,
+            const float* __restrict__ zbias) {        // zbias (nullable) [E]: classifier bias difference added to z
     extern __shared__ float hsm[];
     float* zs = hsm;                                  // [(RROWS+2)][w]   rows a_first-1 .. a_last+1
     float* cc = zs + (RROWS + 2) * w;                 // [4][(RROWS+1)][w] corner contributions
     __shared__ float lred[32];
     const int img = blockIdx.y, e = img / S;
+    const float zb = zbias ? zbias[e] : 0.f;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int a_first = blockIdx.x * RROWS;
     const int a_last = min(a_first + RROWS - 1, h - 1);
@@ -114,7 +116,7 @@ k_fit_hires(const float* __restrict__ zd, const uint4* __restrict__ cells, const
     for (int i = tid; i < (RROWS + 2) * w; i += nthr) {
         const int ar = i / w, b = i - ar * w;
         const int a = min(max(a_first - 1 + ar, 0), h - 1);       // clamped (out-of-range rows carry zero weight)
-        zs[i] = zimg[a * w + b];
+        zs[i] = zimg[a * w + b] + zb;
     }
     __syncthreads();
     float loss = 0.f;
@@ -168,9 +170,9 @@ static inline int hires_bands(int h) { return (h + HIRES_RROWS - 1) / HIRES_RROW
 
 template <bool LOSS>
 static int launch_fit_hires(const float* zd, const uint4* cells, const float2* cw, float* g60, float* loss_part,
-                            int n_img, int h, int w, int S, cudaStream_t st) {
+                            int n_img, int h, int w, int S, cudaStream_t st, const float* zbias = nullptr) {
     dim3 grid(hires_bands(h), n_img);
-    k_fit_hires<HIRES_RROWS, LOSS><<<grid, hires_threads(w), hires_smem(w), st>>>(zd, cells, cw, g60, loss_part, h, w, S);
+    k_fit_hires<HIRES_RROWS, LOSS><<<grid, hires_threads(w), hires_smem(w), st>>>(zd, cells, cw, g60, loss_part, h, w, S, zbias);
     CWT_LAUNCHED("fit_hires");
     return CWT_OK;
 }

@@ -175,6 +175,27 @@ def validate_transformer(args, val_loader, model, transformer, verbose: bool = T
         IoU: Dict[int, float] = {}
         IoU0: Dict[int, float] = {}
         loss_sum, loss_cnt, iter_num, runtime = 0.0, 0, 0, 0.0
+        pending = None                       # results of the previous batch, still on their way to the host
+
+        def finish(p):
+            """Account one batch: the reference's per-class accumulation (src/test.py:225-234) and progress line."""
+            nonlocal loss_sum, loss_cnt
+            counts, ce, ev, classes, n_seen = p
+            ev.synchronize()
+            loss = float(ce[:, 0, 0].sum() / ce[:, 0, 1].sum().clamp_min(1.0))     # CE over the batch's valid pixels
+            loss_sum += loss; loss_cnt += 1
+            for i, task_classes in enumerate(classes):
+                for j, class_ in enumerate(task_classes):
+                    cls_I[class_] += int(counts[i, 0, j + 1, 0]); cls_U[class_] += int(counts[i, 0, j + 1, 1])
+                    cls_I0[class_] += int(counts[i, 1, j + 1, 0]); cls_U0[class_] += int(counts[i, 1, j + 1, 1])
+            for class_ in cls_U:
+                IoU[class_] = cls_I[class_] / (cls_U[class_] + 1e-10)
+                IoU0[class_] = cls_I0[class_] / (cls_U0[class_] + 1e-10)
+            if verbose and n_seen % 200 == 0:
+                print('Test: [{}/{}] mIoU {:.4f} mIoU0 {:.4f} Loss {:.4f} ({:.4f}) '.format(
+                    n_seen, args.test_num, np.mean(list(IoU.values())), np.mean(list(IoU0.values())),
+                    loss, loss_sum / loss_cnt))
+
         for e in range(nb_episodes):
             t0 = time.time()
             fs_l, sl_l, fq_l, ql_l, w0_l, classes = [], [], [], [], [], []
@@ -198,22 +219,23 @@ def validate_transformer(args, val_loader, model, transformer, verbose: bool = T
                 classes.append([int(c.item()) if torch.is_tensor(c) else int(c) for c in subcls])
             out = episode_head(torch.stack(fs_l), torch.stack(sl_l), torch.stack(fq_l), torch.stack(ql_l),
                                torch.stack(w0_l).to(device), params, n_head, args.cls_lr, args.adapt_iter)
-            counts = out.counts.cpu()
-            ce = out.ce.cpu()
+            # No device sync per batch (the reference has one per EPISODE, src/test.py:169-171): the counts travel to
+            # pinned host memory asynchronously and are accounted one batch later, after the next batch's backbone and
+            # head have been queued — the GPU never waits for the Python side.
+            counts = torch.empty(out.counts.shape, dtype=out.counts.dtype, pin_memory=True)
+            ce = torch.empty(out.ce.shape, dtype=out.ce.dtype, pin_memory=True)
+            counts.copy_(out.counts, non_blocking=True)
+            ce.copy_(out.ce, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(device))
+            if pending is not None:
+                finish(pending)
+            pending = (counts, ce, ev, classes, iter_num)
             runtime += time.time() - t0
-            loss = float(ce[:, 0, 0].sum() / ce[:, 0, 1].sum().clamp_min(1.0))     # CE over the batch's valid pixels
-            loss_sum += loss; loss_cnt += 1
-            for i, task_classes in enumerate(classes):
-                for j, class_ in enumerate(task_classes):
-                    cls_I[class_] += int(counts[i, 0, j + 1, 0]); cls_U[class_] += int(counts[i, 0, j + 1, 1])
-                    cls_I0[class_] += int(counts[i, 1, j + 1, 0]); cls_U0[class_] += int(counts[i, 1, j + 1, 1])
-            for class_ in cls_U:
-                IoU[class_] = cls_I[class_] / (cls_U[class_] + 1e-10)
-                IoU0[class_] = cls_I0[class_] / (cls_U0[class_] + 1e-10)
-            if verbose and iter_num % 200 == 0:
-                print('Test: [{}/{}] mIoU {:.4f} mIoU0 {:.4f} Loss {:.4f} ({:.4f}) '.format(
-                    iter_num, args.test_num, np.mean(list(IoU.values())), np.mean(list(IoU0.values())),
-                    loss, loss_sum / loss_cnt))
+        if pending is not None:
+            t0 = time.time()
+            finish(pending)
+            runtime += time.time() - t0
         runtimes[run] = runtime
         mIoU = float(np.mean(list(IoU.values()))) if IoU else 0.0
         if verbose:

@@ -101,6 +101,57 @@ def fit_classifier(f_s: torch.Tensor, s_label: torch.Tensor, w0: torch.Tensor, l
     return (out, losses) if return_losses else out
 
 
+def fit_classifier_bias(f_s: torch.Tensor, s_label: torch.Tensor, w0: torch.Tensor, b0: torch.Tensor, lr: float,
+                        n_iter: int, class_weight: Optional[torch.Tensor] = None, bias_scale: float = 1.0,
+                        ignore_index: int = IGNORE, return_losses: bool = False, check: bool = True):
+    """:func:`fit_classifier` for a classifier with a bias (``nn.Conv2d(C, 2, 1, bias=True)``, built by the reference's
+    CosCls with cls_type[2] == 'b', src/model/pspnet.py:294,319): logits = W . f + bias_scale * b, plain SGD on both.
+    b0 [E,2] (or [2]). Returns (W [E,2,C], b [E,2]) with the leading shapes given (+ losses [n_iter,E] if requested)."""
+    dev = L.require_cuda(f_s, s_label, w0, b0)
+    if f_s.dim() == 4:
+        f_s, s_label = f_s.unsqueeze(0), s_label.unsqueeze(0)
+    if f_s.dim() != 5 or s_label.dim() != 4:
+        raise ValueError(f"f_s must be [E,S,C,h,w] and s_label [E,S,H,W]; got {tuple(f_s.shape)}, {tuple(s_label.shape)}")
+    E, S, Cc, h, w = f_s.shape
+    H, W = s_label.shape[-2:]
+    if s_label.shape[0] != E or s_label.shape[1] != S:
+        raise ValueError("f_s and s_label disagree on E or S")
+    w0_shape, b0_shape = w0.shape, b0.shape
+    w0v = _f32c(w0, "w0").reshape(E, 2, Cc)
+    b0v = _f32c(b0, "b0").reshape(E, 2)
+    f_s = _f32c(f_s, "f_s")
+    lab = s_label.contiguous()
+    cw = None
+    if class_weight is not None:
+        cw = _f32c(class_weight.to(dev), "class_weight").reshape(-1, 2)
+        if cw.shape[0] == 1 and E > 1:
+            cw = cw.expand(E, 2).contiguous()
+        if cw.shape[0] != E:
+            raise ValueError("class_weight must be [2] or [E,2]")
+    w_out = torch.empty(E, 2, Cc, dtype=torch.float32, device=dev)
+    b_out = torch.empty(E, 2, dtype=torch.float32, device=dev)
+    losses = torch.empty(n_iter, E, dtype=torch.float32, device=dev) if return_losses else None
+    counts = torch.empty(E, 4, dtype=torch.int32, device=dev)
+    lib = L.load()
+    nbytes = lib.cwt_fit_bias_workspace_bytes(E, S, Cc, h, w, H, W)
+    ws = L.WORKSPACE.get(nbytes, dev, "fit_bias")
+    with torch.cuda.device(dev):
+        rc = lib.cwt_fit_classifier_bias_f32(L.ptr(f_s), L.ptr(lab), L.label_kind(lab), L.ptr(w0v), L.ptr(b0v), L.ptr(cw),
+                                             L.ptr(w_out), L.ptr(b_out), L.ptr(losses), L.ptr(counts),
+                                             E, S, Cc, h, w, H, W, int(n_iter), float(lr), float(bias_scale),
+                                             int(ignore_index), L.ptr(ws), ws.numel(), L.stream_ptr(dev))
+    L.check(rc, "cwt_fit_classifier_bias_f32")
+    if check:
+        c = counts.cpu()
+        if int(c[:, 3].sum()) > 0:
+            raise ValueError("s_label holds values outside {0, 1, ignore_index}")
+        if class_weight is None and bool((c[:, 1] == 0).any()):
+            raise ZeroDivisionError("division by zero: an episode's support mask has no foreground pixel "
+                                    "(reference: len(back_pix[0]) / len(target_pix[0]), src/test.py:174)")
+    out = (w_out.reshape(w0_shape), b_out.reshape(b0_shape))
+    return out + (losses,) if return_losses else out
+
+
 def fit_classifier_dice(f_s: torch.Tensor, s_label: torch.Tensor, w0: torch.Tensor, lr: float, n_iter: int,
                         ignore_index: int = IGNORE, return_losses: bool = False, check: bool = True):
     """The inner loop of :func:`fit_classifier` with the reference's dice loss, ``SegLoss('wt_dc' | 'dc')``

@@ -92,6 +92,22 @@ int cwt_fit_classifier_f32(const float* f_s, const void* s_label, int label_kind
                            void* workspace, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * (a-3 / f-3) the same fit for a classifier WITH a bias: nn.Conv2d(C, 2, 1, bias=True), which the
+ * reference builds inside CosCls when cls_type[2] == 'b' (src/model/pspnet.py:294,319; fitted by
+ * PSPNet.inner_loop, pspnet.py:189-205).  logits = W . F + bias_scale * b  (bias_scale = 1 for the
+ * dot classifier; CosCls multiplies conv(x_norm) including its bias by scale_factor — the caller
+ * folds scale_factor into the features and passes bias_scale = scale_factor).  Plain SGD on W and b.
+ *   b0 [E,2] initial bias, b_out [E,2]; everything else as cwt_fit_classifier_f32 (streaming algorithm)
+ * ------------------------------------------------------------------------------------- */
+size_t cwt_fit_bias_workspace_bytes(int E, int S, int C, int h, int w, int H, int W);
+int cwt_fit_classifier_bias_f32(const float* f_s, const void* s_label, int label_kind, const float* w0,
+                                const float* b0, const float* class_weight_or_null, float* w_out, float* b_out,
+                                float* loss_trace_or_null, int32_t* label_counts_or_null,
+                                int E, int S, int C, int h, int w, int H, int W,
+                                int n_iter, float lr, float bias_scale, int ignore_index,
+                                void* workspace, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * (f-3) the same inner loop with SegLoss('wt_dc' | 'dc'), the per-channel sigmoid dice loss:
  * PSPNet.inner_loop, src/model/pspnet.py:189-205, with criterion = SegLoss(args.inner_loss_type),
  * src/model/model_util.py:18-19 -> weighted_dice_loss, model_util.py:40-73 (weighted_val 1,

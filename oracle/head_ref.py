@@ -84,6 +84,13 @@ def fit_classifier_ref(f_s: torch.Tensor, s_label: torch.Tensor, w0: torch.Tenso
 # PSPNet.inner_loop variants                      src/model/pspnet.py:189-205, 290-334
 #   SegLoss 'wt_ce' / 'ce' / 'wt_dc' / 'dc' (src/model/model_util.py:9-73); classifier 'dot' or CosCls 'oooo'
 # --------------------------------------------------------------------------------------
+def initial_bias(idx: int, C: int) -> torch.Tensor:
+    """Deterministic initial bias [2] ~ U(-1/sqrt(C), 1/sqrt(C)) — the distribution nn.Conv2d.reset_parameters draws a
+    bias from (fan_in = C) — for the golden cases of classifiers with a bias."""
+    g = torch.Generator().manual_seed(977 + idx)
+    return (torch.rand(2, generator=g) * 2.0 - 1.0) / math.sqrt(C)
+
+
 def weighted_dice_loss_ref(prediction: torch.Tensor, target_seg: torch.Tensor, eps: float = 1e-8) -> torch.Tensor:
     """SegLoss 'wt_dc' / 'dc' (model_util.py:18-19 -> weighted_dice_loss, :40-73, weighted_val 1.0, reduction 'sum',
     input_type 'lg'): every (image, channel) row is a sigmoid dice, 1 - 2 sum(t p) / clamp(sum p^2 + sum t^2, eps), with
@@ -99,19 +106,24 @@ def weighted_dice_loss_ref(prediction: torch.Tensor, target_seg: torch.Tensor, e
 
 
 def inner_loop_ref(f_s: torch.Tensor, s_label: torch.Tensor, w0: torch.Tensor, lr: float, n_iter: int,
-                   loss_type: str = "wt_ce", dist: str = "dot", fg_idx: int = 1, tp: float = 1.0) -> torch.Tensor:
+                   loss_type: str = "wt_ce", dist: str = "dot", fg_idx: int = 1, tp: float = 1.0,
+                   bias0: Optional[torch.Tensor] = None):
     """The inner loop with its two switches: ``args.inner_loss_type`` ('wt_ce': weight[fg] = bg_cnt / fg_cnt from
     torch.bincount, model_util.py:27-37; 'ce': plain CE, ignore 255; 'wt_dc' / 'dc': per-channel sigmoid dice) and ``args.dist`` ('dot': nn.Conv2d;
     'cos': CosCls with cls_type 'oooo' — scores = 2.0 * conv(F.normalize(x, p=2, dim=1, eps=1e-5)),
     pspnet.py:302-310). f_s [S,C,h,w]; s_label [S,H,W]; w0 [2,C] -> fitted weight [2,C].
     ``loss_type == 'adapt_ce'`` is ``PSPNet.increment_inner_loop`` (pspnet.py:207-221) for a 2-class classifier: the same
     loop (no parameter reset) with Adapt_SegLoss -> weighted_adpt_ce_loss (model_util.py:76-98):
-    weight[fg_idx] = (bg_cnt / fg_cnt) ** tp."""
+    weight[fg_idx] = (bg_cnt / fg_cnt) ** tp.
+    ``bias0`` [2]: the classifier has a bias (CosCls cls_type[2] == 'b', pspnet.py:294; its bias sits inside ``cls`` and
+    is therefore multiplied by scale_factor too, pspnet.py:307-308); returns (weight [2,C], bias [2]) then."""
     S, C = f_s.shape[:2]
     tgt = s_label.long()
-    conv = nn.Conv2d(C, 2, kernel_size=1, bias=False)
+    conv = nn.Conv2d(C, 2, kernel_size=1, bias=bias0 is not None)
     with torch.no_grad():
         conv.weight.copy_(w0.reshape(2, C, 1, 1))
+        if bias0 is not None:
+            conv.bias.copy_(bias0)
     opt = torch.optim.SGD(conv.parameters(), lr=lr)
     for _ in range(n_iter):
         if dist == "dot":
@@ -138,6 +150,8 @@ def inner_loop_ref(f_s: torch.Tensor, s_label: torch.Tensor, w0: torch.Tensor, l
         opt.zero_grad()
         loss.backward()
         opt.step()
+    if bias0 is not None:
+        return conv.weight.detach().reshape(2, C).clone(), conv.bias.detach().clone()
     return conv.weight.detach().reshape(2, C).clone()
 
 

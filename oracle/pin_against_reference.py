@@ -64,6 +64,10 @@ INNER_CASES = {
     # PSPNet.increment_inner_loop (pspnet.py:207-221) on a 2-class classifier: Adapt_SegLoss(num_cls=2, fg_idx, tp)
     "inner_incr_small_tp05": dict(idx=27, shot=1, C=64, h=12, w=12, H=89, W=89, style="unit", lr=0.1, n_iter=50, loss_type="adapt_ce", dist="dot", fg_idx=1, tp=0.5),
     "inner_incr_small_fg0":  dict(idx=28, shot=2, C=64, h=12, w=12, H=89, W=89, style="unit", lr=0.1, n_iter=50, loss_type="adapt_ce", dist="dot", fg_idx=0, tp=1.0),
+    # classifier with a bias: CosCls cls_type 'oobo' (pspnet.py:294) and nn.Conv2d(C, 2, 1, bias=True); b0 ~ U(+-1/sqrt(C)) from seed idx
+    "inner_small_cosb_wtce": dict(idx=29, shot=2, C=64, h=12, w=12, H=89, W=89, style="backbone", lr=0.1, n_iter=50, loss_type="wt_ce", dist="cos", bias=True),
+    "inner_small_dotb_ce":   dict(idx=30, shot=1, C=64, h=12, w=12, H=89, W=89, style="unit", lr=0.1, n_iter=50, loss_type="ce", dist="dot", bias=True),
+    "inner_full_cosb_wtce":  dict(idx=31, shot=1, C=512, h=60, w=60, H=473, W=473, style="backbone", lr=0.1, n_iter=100, loss_type="wt_ce", dist="cos", bias=True),
     "inner_full_cos_ce":    dict(idx=23, shot=1, C=512, h=60, w=60, H=473, W=473, style="backbone", lr=0.1, n_iter=100, loss_type="ce", dist="cos"),
 }
 TRAIN_CASES = {
@@ -157,16 +161,19 @@ def inner_loop_via_reference(ep, case):
         from src.model.pspnet import CosCls
         from src.model.model_util import SegLoss, Adapt_SegLoss
     C = ep.f_s.shape[1]
+    with_bias = bool(case.get("bias"))
     if case["dist"] == "dot":
-        classifier = nn.Conv2d(C, 2, kernel_size=1, bias=False)
+        classifier = nn.Conv2d(C, 2, kernel_size=1, bias=with_bias)
         conv = classifier
     else:
         import contextlib, io
         with contextlib.redirect_stdout(io.StringIO()):          # parse_param_coscls prints its flags
-            classifier = CosCls(in_dim=C, n_classes=2, cls_type="oooo")
+            classifier = CosCls(in_dim=C, n_classes=2, cls_type="oobo" if with_bias else "oooo")
         conv = classifier.cls
     with torch.no_grad():
         conv.weight.copy_(ep.w0.reshape(2, C, 1, 1))
+        if with_bias:
+            conv.bias.copy_(O.initial_bias(case["idx"], C))
     optimizer = torch.optim.SGD(classifier.parameters(), lr=case["lr"])
     if case["loss_type"] == "adapt_ce":                           # increment_inner_loop's criterion (pspnet.py:213)
         criterion = Adapt_SegLoss(num_cls=2, fg_idx=case["fg_idx"], tp=case["tp"])
@@ -185,6 +192,8 @@ def inner_loop_via_reference(ep, case):
             optimizer.step()
     finally:
         torch.cuda.is_available = cuda_avail
+    if with_bias:
+        return (conv.weight.detach().reshape(2, C).clone(), conv.bias.detach().clone()), float(s_loss)
     return conv.weight.detach().reshape(2, C).clone(), float(s_loss)
 
 
@@ -332,15 +341,21 @@ def main():
             continue
         ep = syn.make_episode(case["idx"], **gen_kwargs(case))
         w_ref, last_loss = inner_loop_via_reference(ep, case)
+        b0 = O.initial_bias(case["idx"], case["C"]) if case.get("bias") else None
         w_ora = O.inner_loop_ref(ep.f_s, ep.s_label, ep.w0, case["lr"], case["n_iter"], case["loss_type"], case["dist"],
-                                 case.get("fg_idx", 1), case.get("tp", 1.0))
+                                 case.get("fg_idx", 1), case.get("tp", 1.0), b0)
+        extra = {}
+        if b0 is not None:
+            (w_ref, b_ref), (w_ora, b_ora) = w_ref, w_ora
+            assert relerr(b_ora, b_ref) < 1e-6
+            extra = dict(b_fit=b_ref.numpy(), b0=b0.numpy())
         err = relerr(w_ora, w_ref)
         print(f"[pin] {name}: oracle vs reference inner_loop rel {err:.2e} last loss {last_loss:.6f}")
         assert err < 1e-6, err
         report["cases"][name] = {"errs": {"W_fit": err}, "loss": last_loss}
         if a.write:
             np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), case=json.dumps(case), checksum=input_checksum(ep),
-                                torch_version=torch.__version__, W_fit=w_ref.numpy(), loss=last_loss)
+                                torch_version=torch.__version__, W_fit=w_ref.numpy(), loss=last_loss, **extra)
 
     for name, case in TRAIN_CASES.items():
         if a.only and a.only not in name:

@@ -241,11 +241,18 @@ def test_inner_loop_variants_vs_golden(cuda_device, name):
     case = g["case"]
     ep = syn.make_episode(case["idx"], **gen_kwargs(case))
     C = case["C"]
-    clf = cwt.CosCls(C, 2, "oooo") if case["dist"] == "cos" else cwt.get_classifier(C, 2)
+    with_bias = bool(case.get("bias"))                       # CosCls 'oobo' / nn.Conv2d(C, 2, 1, bias=True)
+    if case["dist"] == "cos":
+        clf = cwt.CosCls(C, 2, "oobo" if with_bias else "oooo")
+    else:
+        clf = torch.nn.Conv2d(C, 2, 1, bias=True) if with_bias else cwt.get_classifier(C, 2)
     clf = clf.to(cuda_device)
     conv = clf.cls if case["dist"] == "cos" else clf
     with torch.no_grad():
         conv.weight.copy_(ep.w0.reshape(2, C, 1, 1))
+        if with_bias:
+            assert np.array_equal(O.initial_bias(case["idx"], C).numpy(), g["b0"])
+            conv.bias.copy_(torch.from_numpy(g["b0"]))
     if case["loss_type"] == "adapt_ce":                      # PSPNet.increment_inner_loop (pspnet.py:207-221), 2-class
         cwt.increment_inner_loop(clf, ep.f_s.to(cuda_device), ep.s_label.to(cuda_device), case["fg_idx"], case["lr"],
                                  case["n_iter"], tp=case["tp"])
@@ -253,9 +260,11 @@ def test_inner_loop_variants_vs_golden(cuda_device, name):
         cwt.inner_loop(clf, ep.f_s.to(cuda_device), ep.s_label.to(cuda_device), case["lr"], case["n_iter"], reset=False,
                        loss_type=case["loss_type"])
     assert rel_err(conv.weight.reshape(2, C), g["W_fit"]) < TIGHT
+    if with_bias:
+        assert rel_err(conv.bias, g["b_fit"]) < TIGHT
     if case["dist"] == "cos":                                # the module's own forward is the reference's formula
         x = ep.f_s.to(cuda_device)
-        ref = 2.0 * F.conv2d(F.normalize(x, p=2, dim=1, eps=1e-5), conv.weight)
+        ref = 2.0 * F.conv2d(F.normalize(x, p=2, dim=1, eps=1e-5), conv.weight, conv.bias)
         assert torch.allclose(clf(x), ref)
         assert rel_err(ops.normalize_features(x, 1e-5, 2.0), 2.0 * F.normalize(x.cpu(), p=2, dim=1, eps=1e-5)) < 1e-6
 

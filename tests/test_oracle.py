@@ -59,7 +59,7 @@ def _dice_fit_closed_form(f_s, s_label, w0, lr, n_iter):
 
 
 @pytest.mark.parametrize("name", ["inner_small_dot_ce", "inner_small_cos_wtce", "inner_small_dot_wtdc", "inner_small_cos_dc",
-                                  "inner_incr_small_tp05", "inner_incr_small_fg0"])
+                                  "inner_incr_small_tp05", "inner_incr_small_fg0", "inner_small_cosb_wtce", "inner_small_dotb_ce"])
 def test_oracle_inner_loop_variants_reproduce_reference_golden(name):
     """PSPNet.inner_loop switches (SegLoss 'ce' / 'wt_ce', dot / cosine classifier) against the vectors recorded from the
     live reference's CosCls and SegLoss objects; also: 'ce' is the weighted fit with class weight [1, 1], and the cosine
@@ -68,8 +68,12 @@ def test_oracle_inner_loop_variants_reproduce_reference_golden(name):
     case = g["case"]
     ep = syn.make_episode(case["idx"], **gen_kwargs(case))
     assert _checksum(ep) == str(g["checksum"])
+    b0 = O.initial_bias(case["idx"], case["C"]) if case.get("bias") else None
     w = O.inner_loop_ref(ep.f_s, ep.s_label, ep.w0, case["lr"], case["n_iter"], case["loss_type"], case["dist"],
-                         case.get("fg_idx", 1), case.get("tp", 1.0))
+                         case.get("fg_idx", 1), case.get("tp", 1.0), b0)
+    if b0 is not None:                                        # classifier with a bias (CosCls 'oobo'): weight and bias
+        assert rel_err(w[0], g["W_fit"]) < 1e-6 and rel_err(w[1], g["b_fit"]) < 1e-6
+        return
     assert rel_err(w, g["W_fit"]) < 1e-6
     if case["loss_type"] in ("wt_dc", "dc"):                  # dice: no CE identity to check; an independent restatement instead
         feat = 2.0 * torch.nn.functional.normalize(ep.f_s, p=2, dim=1, eps=1e-5) if case["dist"] == "cos" else ep.f_s
