@@ -152,7 +152,7 @@ def run_reference(a, rank):
     dt = time.perf_counter() - t0
     v = per_step * a.steps / dt
     cores = torch.get_num_threads()
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -161,12 +161,30 @@ def run_reference(a, rank):
                          "sample": f"{per_step} episodes/step x {a.steps} steps, torch {torch.__version__} CPU fp32, "
                                    f"oracle/head_ref.episode_ref (restatement of src/test.py:162-234)"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    }))
 
 
 # ------------------------------------------------------------------------------------------------
+_JSON_FD = None
+
+
+def emit(line: str) -> None:
+    """The ONE JSON line goes to the process's original stdout."""
+    data = (line + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line + "\n"); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
     a = parse()
+    # stdout carries exactly one JSON line: anything native libraries print on fd 1 during the run (NCCL's
+    # "NCCL version ..." banner when NCCL_DEBUG=VERSION is set in the environment) is sent to stderr instead
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -330,7 +348,7 @@ def main():
                          f"oracle/head_ref.episode_ref, torch {torch.__version__} CPU fp32"}
 
     if rank == 0:
-        print(json.dumps({
+        emit(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
@@ -340,7 +358,7 @@ def main():
                        "fit_algo": a.fit_algo, "attn_algo": a.attn_algo},
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "miou_adapted": table.miou(0), "miou_baseline": table.miou(1),
-        }), flush=True)
+        }))
     if world > 1:
         dist.destroy_process_group()
 
