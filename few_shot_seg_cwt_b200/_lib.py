@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libcwt_b200.so")
 OK = 0
 LABEL_U8, LABEL_I64 = 0, 1
 FIT_AUTO, FIT_STREAM, FIT_RESIDENT = 0, 1, 2
+COSCLS_R, COSCLS_N, COSCLS_T = 1, 2, 4          # cwt_fit_coscls_f32 flags (CosCls cls_type 'r', 'n', 't')
 ATTN_REASSOC, ATTN_TCGEN05 = 0, 1
 
 _lib: Optional[C.CDLL] = None
@@ -34,6 +35,8 @@ SIGNATURES = {
     "cwt_fit_classifier_f32": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp] + [_i] * 8 + [_f, _i, _i, _vp, _sz, _vp]),
     "cwt_fit_bias_workspace_bytes": (_sz, [_i] * 7),
     "cwt_fit_classifier_bias_f32": (_i, [_vp, _vp, _i] + [_vp] * 7 + [_i] * 8 + [_f, _f, _i, _vp, _sz, _vp]),
+    "cwt_fit_coscls_workspace_bytes": (_sz, [_i] * 7),
+    "cwt_fit_coscls_f32": (_i, [_vp, _vp, _i] + [_vp] * 7 + [_i] * 9 + [_f, _i, _vp, _sz, _vp]),
     "cwt_fit_dice_workspace_bytes": (_sz, [_i] * 7),
     "cwt_fit_classifier_dice_f32": (_i, [_vp, _vp, _i, _vp, _vp, _vp] + [_i] * 8 + [_f, _i, _vp, _sz, _vp]),
     "cwt_transformer_workspace_bytes": (_sz, [_i] * 6),

@@ -16,7 +16,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib as L
-from .ops import fit_classifier, fit_classifier_bias, fit_classifier_dice, label_counts, normalize_features
+from .ops import fit_classifier, fit_classifier_bias, fit_classifier_dice, fit_coscls, label_counts, normalize_features
 
 
 def get_classifier(bottleneck_dim: int = 512, num_classes: int = 2, device=None) -> nn.Conv2d:
@@ -38,8 +38,8 @@ class CosCls(nn.Module):
     src/model/pspnet.py:290-315): ``cls`` is the 1x1 conv, ``scale_factor`` the temperature (2.0).
     ``cls_type`` = four flags [weight-norm reparametrisation 'r', weight normalisation 'n', bias 'b', learnable
     temperature 't']; '0' / 'o' switch a flag off. ``forward`` is plain torch (it is not on the episodic hot path);
-    :func:`inner_loop` fits the flag-free form ('oooo' / '0000') with the fused CUDA fit and the form with a bias
-    ('oobo') with the streaming kernels."""
+    :func:`inner_loop` fits the flag-free form ('oooo' / '0000') with the fused CUDA fit, the form with a bias ('oobo') and
+    every other flag combination ('r', 'n', 't') with the streaming kernels."""
 
     def __init__(self, in_dim: int = 512, n_classes: int = 2, cls_type: str = "0000"):
         super().__init__()
@@ -79,15 +79,16 @@ def inner_loop(classifier, f_s: torch.Tensor, s_label: torch.Tensor, cls_lr: flo
       * ``'wt_dc'`` / ``'dc'`` — the per-channel sigmoid dice loss (weighted_dice_loss, model_util.py:40-73; both
         strings select the same function, model_util.py:18-19): :func:`fit_classifier_dice` (streaming kernels).
     ``classifier`` is the reference's ``nn.Conv2d(C, 2, 1, bias=False)`` (``dist == 'dot'``) or a :class:`CosCls`
-    (``dist == 'cos'``) with cls_type 'oooo' or 'oobo': ``scale_factor * conv(F.normalize(x, eps=1e-5))`` is the same
+    (``dist == 'cos'``) with any cls_type. 'oooo' / 'oobo': ``scale_factor * conv(F.normalize(x, eps=1e-5))`` is the same
     classifier on the features ``2 * x_norm``, which one extra kernel prepares (a bias is then scaled by 2 as well);
-    a classifier with a bias is fitted by :func:`fit_classifier_bias` (weights and bias updated by the same SGD)."""
+    a classifier with a bias is fitted by :func:`fit_classifier_bias` (weights and bias updated by the same SGD). With
+    'r' / 'n' / 't' every parameter of ``classifier.parameters()`` (weight or weight_g + weight_v, bias, scale_factor) is
+    fitted by :func:`fit_coscls`."""
     if loss_type not in ("wt_ce", "ce", "wt_dc", "dc"):
         loss_type = "wt_ce"                                     # SegLoss falls through to weighted CE for any other string
+    if isinstance(classifier, CosCls) and (classifier.WeightNormR or classifier.weight_norm or classifier.temp):
+        return _inner_loop_coscls(classifier, f_s, s_label, cls_lr, adapt_iter, reset, check, loss_type)
     if isinstance(classifier, CosCls):
-        if classifier.WeightNormR or classifier.weight_norm or classifier.temp:
-            raise NotImplementedError("cwt_b200 inner_loop fits CosCls without weight-norm / learnable temperature "
-                                      "(cls_type 'oooo' / '0000' / 'oobo')")
         scale = float(classifier.scale_factor)
         conv, feat = classifier.cls, normalize_features(f_s, eps=1e-5, scale=scale)
     else:
@@ -113,6 +114,38 @@ def inner_loop(classifier, f_s: torch.Tensor, s_label: torch.Tensor, cls_lr: flo
         w = fit_classifier(feat, s_label, w0, cls_lr, adapt_iter, class_weight=cw, check=check, algo=algo)
     with torch.no_grad():
         conv.weight.copy_(w.reshape(2, C, 1, 1))
+
+
+def _inner_loop_coscls(classifier: CosCls, f_s, s_label, cls_lr, adapt_iter, reset, check, loss_type) -> None:
+    """CosCls with weight-norm ('r'), per-forward weight normalisation ('n') or a learnable temperature ('t'), with or
+    without a bias: every parameter of ``classifier.parameters()`` is updated by the same SGD (cwt_fit_coscls_f32)."""
+    if loss_type in ("wt_dc", "dc"):
+        raise NotImplementedError("cwt_b200 inner_loop: the dice losses are built for the flag-free classifier")
+    conv = classifier.cls
+    if conv.weight.shape[0] != 2 or conv.kernel_size != (1, 1):
+        raise NotImplementedError("cwt_b200 inner_loop fits the reference's 2-class 1x1 classifier")
+    if reset:
+        classifier.reset_parameters()       # with 'r' this re-draws only the derived .weight, not weight_g / weight_v — as in the reference
+    dev, C = f_s.device, conv.weight.shape[1]
+    if f_s.dim() != 4:
+        raise ValueError("inner_loop fits ONE classifier: pass f_s [S,C,h,w] and s_label [S,H,W]")
+    x, lab, E = normalize_features(f_s, eps=1e-5, scale=1.0).unsqueeze(0), s_label.unsqueeze(0), 1
+    rep = lambda t, shape: t.detach().to(dev, torch.float32).reshape(1, *shape).expand(E, *shape).contiguous()
+    flags = (L.COSCLS_R if classifier.WeightNormR else 0) | (L.COSCLS_N if classifier.weight_norm else 0) | \
+            (L.COSCLS_T if classifier.temp else 0)
+    wsrc = conv.weight_v if classifier.WeightNormR else conv.weight
+    out = fit_coscls(x, lab, rep(wsrc, (2, C)), torch.full((E,), float(classifier.scale_factor), device=dev), cls_lr, adapt_iter,
+                     weight_g=rep(conv.weight_g, (2,)) if classifier.WeightNormR else None,
+                     bias=rep(conv.bias, (2,)) if conv.bias is not None else None, flags=flags,
+                     class_weight=torch.ones(2, dtype=torch.float32, device=dev) if loss_type == "ce" else None, check=check)
+    with torch.no_grad():
+        wsrc.copy_(out["weight"][0].reshape(wsrc.shape))
+        if classifier.WeightNormR:
+            conv.weight_g.copy_(out["weight_g"][0].reshape(conv.weight_g.shape))
+        if conv.bias is not None:
+            conv.bias.copy_(out["bias"][0])
+        if classifier.temp:
+            classifier.scale_factor.copy_(out["scale"][0])
 
 
 def increment_inner_loop(classifier: nn.Conv2d, f_s: torch.Tensor, s_label: torch.Tensor, cls_idx: int, cls_lr: float,

@@ -152,6 +152,56 @@ def fit_classifier_bias(f_s: torch.Tensor, s_label: torch.Tensor, w0: torch.Tens
     return out + (losses,) if return_losses else out
 
 
+def fit_coscls(x_norm: torch.Tensor, s_label: torch.Tensor, weight: torch.Tensor, scale: torch.Tensor, lr: float,
+               n_iter: int, weight_g: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None, flags: int = 0,
+               class_weight: Optional[torch.Tensor] = None, ignore_index: int = IGNORE, return_losses: bool = False,
+               check: bool = True):
+    """The inner loop on the reference's cosine classifier ``CosCls`` with any ``cls_type`` (src/model/pspnet.py:290-323):
+    scores = scale * (weight . x_norm + bias), SGD over every parameter the flags switch on.
+
+    x_norm [E,S,C,h,w] = F.normalize(f_s, dim=1, eps=1e-5) (:func:`normalize_features`); weight [E,2,C] (``cls.weight``, or
+    ``cls.weight_v`` with flag 'r'); weight_g [E,2] (flag 'r'); bias [E,2] or None; scale [E]; flags = OR of L.COSCLS_R /
+    L.COSCLS_N / L.COSCLS_T. Returns a dict of the fitted parameters (new tensors; the inputs are not modified)."""
+    dev = L.require_cuda(x_norm, s_label, weight, scale)
+    if x_norm.dim() != 5 or s_label.dim() != 4:
+        raise ValueError(f"x_norm must be [E,S,C,h,w] and s_label [E,S,H,W]; got {tuple(x_norm.shape)}, {tuple(s_label.shape)}")
+    E, S, Cc, h, w = x_norm.shape
+    H, W = s_label.shape[-2:]
+    x_norm = _f32c(x_norm, "x_norm")
+    lab = s_label.contiguous()
+    wv = _f32c(weight, "weight").reshape(E, 2, Cc).clone()
+    sc = _f32c(scale, "scale").reshape(E).clone()
+    gv = _f32c(weight_g, "weight_g").reshape(E, 2).clone() if weight_g is not None else None
+    bv = _f32c(bias, "bias").reshape(E, 2).clone() if bias is not None else None
+    if (flags & L.COSCLS_R) and gv is None:
+        raise ValueError("flag 'r' needs weight_g")
+    cw = None
+    if class_weight is not None:
+        cw = _f32c(class_weight.to(dev), "class_weight").reshape(-1, 2)
+        if cw.shape[0] == 1 and E > 1:
+            cw = cw.expand(E, 2).contiguous()
+    losses = torch.empty(n_iter, E, dtype=torch.float32, device=dev) if return_losses else None
+    counts = torch.empty(E, 4, dtype=torch.int32, device=dev)
+    lib = L.load()
+    nbytes = lib.cwt_fit_coscls_workspace_bytes(E, S, Cc, h, w, H, W)
+    ws = L.WORKSPACE.get(nbytes, dev, "fit_coscls")
+    with torch.cuda.device(dev):
+        rc = lib.cwt_fit_coscls_f32(L.ptr(x_norm), L.ptr(lab), L.label_kind(lab), L.ptr(wv), L.ptr(gv), L.ptr(bv), L.ptr(sc),
+                                    L.ptr(cw), L.ptr(losses), L.ptr(counts), int(flags), E, S, Cc, h, w, H, W,
+                                    int(n_iter), float(lr), int(ignore_index), L.ptr(ws), ws.numel(), L.stream_ptr(dev))
+    L.check(rc, "cwt_fit_coscls_f32")
+    if check:
+        c = counts.cpu()
+        if int(c[:, 3].sum()) > 0:
+            raise ValueError("s_label holds values outside {0, 1, ignore_index}")
+        if class_weight is None and bool((c[:, 1] == 0).any()):
+            raise ZeroDivisionError("division by zero: an episode's support mask has no foreground pixel")
+    out = {"weight": wv, "weight_g": gv, "bias": bv, "scale": sc}
+    if return_losses:
+        out["losses"] = losses
+    return out
+
+
 def fit_classifier_dice(f_s: torch.Tensor, s_label: torch.Tensor, w0: torch.Tensor, lr: float, n_iter: int,
                         ignore_index: int = IGNORE, return_losses: bool = False, check: bool = True):
     """The inner loop of :func:`fit_classifier` with the reference's dice loss, ``SegLoss('wt_dc' | 'dc')``

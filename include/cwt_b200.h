@@ -108,6 +108,27 @@ int cwt_fit_classifier_bias_f32(const float* f_s, const void* s_label, int label
                                 void* workspace, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * (f-3) PSPNet.inner_loop (src/model/pspnet.py:189-205) on the reference's cosine classifier CosCls
+ * with any cls_type (src/model/pspnet.py:290-323): scores = scale_factor * (weight . x^ + bias) on
+ * x^ = F.normalize(x, dim=1, eps=1e-5) (the caller passes x^, cwt_normalize_features_f32), SGD over
+ * classifier.parameters().  flags: CWT_COSCLS_R 'r' weight-norm reparametrisation (weight = weight_v,
+ * weight_g_or_null = weight_g [E,2]), CWT_COSCLS_N 'n' weight rows re-normalised in place at every
+ * forward, CWT_COSCLS_T 't' scale_factor is learned; a bias exists iff bias_or_null != NULL ('b').
+ * weight [E,2,C], weight_g [E,2], bias [E,2], scale [E] are IN/OUT (initial values in, fitted out).
+ * Everything else as cwt_fit_classifier_f32 (streaming algorithm).
+ * ------------------------------------------------------------------------------------- */
+#define CWT_COSCLS_R 1
+#define CWT_COSCLS_N 2
+#define CWT_COSCLS_T 4
+size_t cwt_fit_coscls_workspace_bytes(int E, int S, int C, int h, int w, int H, int W);
+int cwt_fit_coscls_f32(const float* x_norm, const void* s_label, int label_kind,
+                       float* weight, float* weight_g_or_null, float* bias_or_null, float* scale,
+                       const float* class_weight_or_null, float* loss_trace_or_null, int32_t* label_counts_or_null,
+                       int flags, int E, int S, int C, int h, int w, int H, int W,
+                       int n_iter, float lr, int ignore_index,
+                       void* workspace, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * (f-3) the same inner loop with SegLoss('wt_dc' | 'dc'), the per-channel sigmoid dice loss:
  * PSPNet.inner_loop, src/model/pspnet.py:189-205, with criterion = SegLoss(args.inner_loss_type),
  * src/model/model_util.py:18-19 -> weighted_dice_loss, model_util.py:40-73 (weighted_val 1,

@@ -155,6 +155,48 @@ def inner_loop_ref(f_s: torch.Tensor, s_label: torch.Tensor, w0: torch.Tensor, l
     return conv.weight.detach().reshape(2, C).clone()
 
 
+def coscls_inner_loop_ref(f_s: torch.Tensor, s_label: torch.Tensor, w0: torch.Tensor, lr: float, n_iter: int,
+                          cls_type: str, loss_type: str = "wt_ce", bias0: Optional[torch.Tensor] = None,
+                          g0: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    """PSPNet.inner_loop (pspnet.py:189-205) on CosCls with any ``cls_type`` (pspnet.py:290-323), restated with explicit
+    parameters: 'r' -> WeightNorm.apply(cls, 'weight', dim=0) (parameters weight_g [2,1,1,1] = g0, weight_v = w0; the
+    pre-forward hook rebuilds cls.weight, which also undoes 'n'); 'n' -> cls.weight.data re-normalised (dim=1, eps 1e-5)
+    at every forward; 'b' -> bias (= bias0); 't' -> scale_factor is a parameter (2.0). SGD over classifier.parameters()."""
+    fr, fn, fb, ft = (cls_type[0] == "r", cls_type[1] == "n", cls_type[2] == "b", cls_type[3] == "t")
+    C = f_s.shape[1]
+    tgt = s_label.long()
+    W = w0.detach().clone().reshape(2, C, 1, 1).requires_grad_(True)              # cls.weight, or cls.weight_v with 'r'
+    g = g0.detach().clone().reshape(2, 1, 1, 1).requires_grad_(True) if fr else None
+    b = bias0.detach().clone().requires_grad_(True) if fb else None
+    s = torch.tensor(2.0, requires_grad=ft)
+    params = [p for p in (g, W, b, s if ft else None) if p is not None]
+    opt = torch.optim.SGD(params, lr=lr)
+    for _ in range(n_iter):
+        x_norm = F.normalize(f_s, p=2, dim=1, eps=0.00001)
+        if fr:
+            weight = torch._weight_norm(W, g, 0)
+        else:
+            if fn:
+                W.data = F.normalize(W.data, p=2, dim=1, eps=0.00001)
+            weight = W
+        out = s * F.conv2d(x_norm, weight, b)
+        out = F.interpolate(out, size=tgt.shape[-2:], mode="bilinear", align_corners=True)
+        if loss_type == "ce":
+            loss = nn.CrossEntropyLoss(ignore_index=IGNORE)(out, tgt)
+        else:
+            count = torch.bincount(tgt.view(-1))
+            fg = count[1]
+            bg = (torch.sum(count) - fg) if len(count) <= 255 else (torch.sum(count) - count[255] - fg)
+            wt = torch.tensor([1.0, 1.0])
+            wt[1] = bg / fg
+            loss = nn.CrossEntropyLoss(weight=wt, ignore_index=IGNORE)(out, tgt)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+    return {"weight": W.detach().reshape(2, C).clone(), "weight_g": g.detach().reshape(2).clone() if fr else None,
+            "bias": b.detach().clone() if fb else None, "scale": s.detach().clone()}
+
+
 def bilinear_matrix(n_in: int, n_out: int, dtype=torch.float64) -> torch.Tensor:
     """Dense [n_out, n_in] align_corners=True interpolation matrix (2 non-zeros per row).
     ATen: scale = (n_in-1)/(n_out-1); src = scale*dst; i0 = floor(src); l1 = src - i0."""

@@ -70,6 +70,18 @@ INNER_CASES = {
     "inner_full_cosb_wtce":  dict(idx=31, shot=1, C=512, h=60, w=60, H=473, W=473, style="backbone", lr=0.1, n_iter=100, loss_type="wt_ce", dist="cos", bias=True),
     "inner_full_cos_ce":    dict(idx=23, shot=1, C=512, h=60, w=60, H=473, W=473, style="backbone", lr=0.1, n_iter=100, loss_type="ce", dist="cos"),
 }
+# CosCls with the remaining cls_type flags (pspnet.py:290-323): 'r' weight-norm reparametrisation, 'n' per-forward weight
+# normalisation, 'b' bias, 't' learnable temperature. weight_v / weight = w0, weight_g = [0.9, 1.2] * row norms of w0,
+# bias = O.initial_bias(idx, C), scale_factor = 2.0.
+COSCLS_CASES = {
+    "coscls_small_onoo": dict(idx=32, shot=1, C=64, h=12, w=12, H=89, W=89, style="unit", lr=0.1, n_iter=50, loss_type="wt_ce", cls_type="onoo"),
+    "coscls_small_ooot": dict(idx=33, shot=2, C=64, h=12, w=12, H=89, W=89, style="backbone", lr=0.1, n_iter=50, loss_type="wt_ce", cls_type="ooot"),
+    "coscls_small_rooo": dict(idx=34, shot=1, C=64, h=12, w=12, H=89, W=89, style="unit", lr=0.1, n_iter=50, loss_type="ce", cls_type="rooo"),
+    "coscls_small_robt": dict(idx=35, shot=1, C=64, h=12, w=12, H=89, W=89, style="backbone", lr=0.1, n_iter=50, loss_type="wt_ce", cls_type="robt"),
+    "coscls_small_onbt": dict(idx=36, shot=2, C=64, h=12, w=12, H=89, W=89, style="unit", lr=0.1, n_iter=50, loss_type="wt_ce", cls_type="onbt"),
+    "coscls_full_rnbt":  dict(idx=37, shot=1, C=512, h=60, w=60, H=473, W=473, style="backbone", lr=0.1, n_iter=100, loss_type="wt_ce", cls_type="rnbt"),
+}
+
 TRAIN_CASES = {
     "train_small_h2": dict(idx=11, shot=1, C=64, h=12, w=12, H=89, W=89, style="unit", n_head=2, lr=0.1, n_iter=20, p_attn=0.1, p_out=0.5),
     "train_full_h1":  dict(idx=12, shot=1, C=512, h=60, w=60, H=473, W=473, style="unit", n_head=1, lr=0.1, n_iter=20, p_attn=0.1, p_out=0.5),
@@ -195,6 +207,53 @@ def inner_loop_via_reference(ep, case):
     if with_bias:
         return (conv.weight.detach().reshape(2, C).clone(), conv.bias.detach().clone()), float(s_loss)
     return conv.weight.detach().reshape(2, C).clone(), float(s_loss)
+
+
+def coscls_g0(w0):
+    return w0.reshape(2, -1).norm(dim=1) * torch.tensor([0.9, 1.2])
+
+
+def coscls_via_reference(ep, case):
+    """inner_loop (pspnet.py:189-205) with the reference's own CosCls(cls_type) and SegLoss objects."""
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from src.model.pspnet import CosCls
+        from src.model.model_util import SegLoss
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):
+            classifier = CosCls(in_dim=ep.f_s.shape[1], n_classes=2, cls_type=case["cls_type"])
+    C = ep.f_s.shape[1]
+    ct = case["cls_type"]
+    with torch.no_grad():
+        if ct[0] == "r":
+            classifier.cls.weight_v.copy_(ep.w0.reshape(2, C, 1, 1))
+            classifier.cls.weight_g.copy_(coscls_g0(ep.w0).reshape(2, 1, 1, 1))
+        else:
+            classifier.cls.weight.copy_(ep.w0.reshape(2, C, 1, 1))
+        if ct[2] == "b":
+            classifier.cls.bias.copy_(O.initial_bias(case["idx"], C))
+    optimizer = torch.optim.SGD(classifier.parameters(), lr=case["lr"])
+    criterion = SegLoss(loss_type=case["loss_type"])
+    f_s, s_label = ep.f_s, ep.s_label.long()
+    cuda_avail = torch.cuda.is_available
+    torch.cuda.is_available = lambda: False
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for _ in range(case["n_iter"]):
+                pred = classifier(f_s)
+                pred = F.interpolate(pred, size=s_label.size()[1:], mode="bilinear", align_corners=True)
+                s_loss = criterion(pred, s_label)
+                optimizer.zero_grad()
+                s_loss.backward()
+                optimizer.step()
+    finally:
+        torch.cuda.is_available = cuda_avail
+    cls = classifier.cls
+    return {"weight": (cls.weight_v if ct[0] == "r" else cls.weight).detach().reshape(2, C).clone(),
+            "weight_g": cls.weight_g.detach().reshape(2).clone() if ct[0] == "r" else None,
+            "bias": cls.bias.detach().clone() if ct[2] == "b" else None,
+            "scale": torch.as_tensor(classifier.scale_factor).detach().clone().float()}, float(s_loss)
 
 
 def relerr(a, b):
@@ -356,6 +415,25 @@ def main():
         if a.write:
             np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), case=json.dumps(case), checksum=input_checksum(ep),
                                 torch_version=torch.__version__, W_fit=w_ref.numpy(), loss=last_loss, **extra)
+
+    for name, case in COSCLS_CASES.items():
+        if a.only and a.only not in name:
+            continue
+        ep = syn.make_episode(case["idx"], **gen_kwargs(case))
+        ref, last_loss = coscls_via_reference(ep, case)
+        ct = case["cls_type"]
+        ora = O.coscls_inner_loop_ref(ep.f_s, ep.s_label, ep.w0, case["lr"], case["n_iter"], ct, case["loss_type"],
+                                      O.initial_bias(case["idx"], case["C"]) if ct[2] == "b" else None,
+                                      coscls_g0(ep.w0) if ct[0] == "r" else None)
+        errs = {k: relerr(ora[k], ref[k]) for k in ref if ref[k] is not None}
+        print(f"[pin] {name}: oracle vs reference CosCls('{ct}') inner_loop " + " ".join(f"{k} {v:.1e}" for k, v in errs.items())
+              + f" last loss {last_loss:.6f} scale {float(ref['scale']):.4f}")
+        assert max(errs.values()) < 1e-6, errs
+        report["cases"][name] = {"errs": errs, "loss": last_loss}
+        if a.write:
+            np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), case=json.dumps(case), checksum=input_checksum(ep),
+                                torch_version=torch.__version__, loss=last_loss, g0=coscls_g0(ep.w0).numpy(),
+                                **{k: v.numpy() for k, v in ref.items() if v is not None})
 
     for name, case in TRAIN_CASES.items():
         if a.only and a.only not in name:

@@ -300,11 +300,47 @@ def test_fit_dice_loss_trace_batch_and_label_dtypes(cuda_device):
         ops.fit_classifier_dice(f, bad, w0, 0.1, 2)
 
 
+@pytest.mark.parametrize("name", golden_names("coscls_"))
+def test_coscls_flag_variants_vs_golden(cuda_device, name):
+    """PSPNet.inner_loop on CosCls with the cls_type flags 'r' (weight-norm reparametrisation), 'n' (per-forward weight
+    normalisation), 'b' (bias), 't' (learnable temperature) — src/model/pspnet.py:290-323; goldens recorded from the live
+    reference's own CosCls(cls_type) object: every parameter of classifier.parameters() after the fit."""
+    g = load_golden(name)
+    case = g["case"]
+    ep = syn.make_episode(case["idx"], **gen_kwargs(case))
+    C, ct = case["C"], case["cls_type"]
+    clf = cwt.CosCls(C, 2, ct).to(cuda_device)
+    with torch.no_grad():
+        if ct[0] == "r":
+            clf.cls.weight_v.copy_(ep.w0.reshape(2, C, 1, 1))
+            clf.cls.weight_g.copy_(torch.from_numpy(g["g0"]).reshape(2, 1, 1, 1))
+        else:
+            clf.cls.weight.copy_(ep.w0.reshape(2, C, 1, 1))
+        if ct[2] == "b":
+            clf.cls.bias.copy_(O.initial_bias(case["idx"], C))
+    cwt.inner_loop(clf, ep.f_s.to(cuda_device), ep.s_label.to(cuda_device), case["lr"], case["n_iter"], reset=False,
+                   loss_type=case["loss_type"])
+    w = clf.cls.weight_v if ct[0] == "r" else clf.cls.weight
+    assert rel_err(w.reshape(2, C), g["weight"]) < TIGHT
+    if ct[0] == "r":
+        assert rel_err(clf.cls.weight_g.reshape(2), g["weight_g"]) < TIGHT
+    if ct[2] == "b":
+        assert rel_err(clf.cls.bias, g["bias"]) < TIGHT
+    assert abs(float(clf.scale_factor) - float(g["scale"])) < TIGHT * 2.0
+    # the module's own forward with the fitted parameters is the reference's formula
+    x = ep.f_s.to(cuda_device)
+    with torch.no_grad():
+        weight = torch._weight_norm(clf.cls.weight_v, clf.cls.weight_g, 0) if ct[0] == "r" else \
+            (F.normalize(clf.cls.weight, p=2, dim=1, eps=1e-5) if ct[1] == "n" else clf.cls.weight)
+        ref = clf.scale_factor * F.conv2d(F.normalize(x, p=2, dim=1, eps=1e-5), weight, clf.cls.bias)
+        assert torch.allclose(clf(x), ref, rtol=1e-5, atol=1e-6)
+
+
 def test_inner_loop_unsupported_variants_raise(cuda_device):
     ep = syn.make_episode(1, **SMALL)
     f, lab = ep.f_s.to(cuda_device), ep.s_label.to(cuda_device)
-    with pytest.raises(NotImplementedError):                 # weight-normalised cosine classifier
-        cwt.inner_loop(cwt.CosCls(64, 2, "0n00").to(cuda_device), f, lab, 0.1, 5)
+    with pytest.raises(NotImplementedError):                 # dice loss on a flagged cosine classifier
+        cwt.inner_loop(cwt.CosCls(64, 2, "0n00").to(cuda_device), f, lab, 0.1, 5, loss_type="wt_dc")
     with pytest.raises(KeyError):                            # parse_param_coscls
         cwt.CosCls(64, 2, "xxxx")
     with pytest.raises(NotImplementedError):                 # multi-way incremental classifier
@@ -481,7 +517,7 @@ def test_intersection_and_union_dropin(cuda_device, dtype):
 
 
 # ---------------------------------------------------------------------------- whole episode
-@pytest.mark.parametrize("name", [n for n in golden_names() if not n.startswith(("train_", "inner_"))])
+@pytest.mark.parametrize("name", [n for n in golden_names() if not n.startswith(("train_", "inner_", "coscls_"))])
 def test_episode_head_vs_golden(cuda_device, name):
     g = load_golden(name)
     case = g["case"]

@@ -20,7 +20,7 @@ def _checksum(ep):
     return h.hexdigest()
 
 
-EVAL_CASES = [n for n in golden_names() if not n.startswith(("train_", "inner_"))]
+EVAL_CASES = [n for n in golden_names() if not n.startswith(("train_", "inner_", "coscls_"))]
 FAST = [n for n in EVAL_CASES if n.startswith("small")] + ["full_1shot_h1_yaml"]
 
 
@@ -153,3 +153,20 @@ def test_pin_against_live_reference_small():
     g = load_golden("small_1shot_h4")
     assert rel_err(ref["W_adapted"], g["W_adapted"]) < 1e-6
     assert np.array_equal(ref["counts"].numpy(), g["counts"])
+
+
+@pytest.mark.parametrize("name", ["coscls_small_onoo", "coscls_small_robt", "coscls_small_onbt"])
+def test_oracle_coscls_flag_variants_reproduce_reference_golden(name):
+    """CosCls with cls_type flags 'r' / 'n' / 'b' / 't' (pspnet.py:290-323): the explicit-parameter restatement against the
+    parameters recorded from the live reference's CosCls object after inner_loop."""
+    g = load_golden(name)
+    case = g["case"]
+    ep = syn.make_episode(case["idx"], **gen_kwargs(case))
+    assert _checksum(ep) == str(g["checksum"])
+    ct = case["cls_type"]
+    out = O.coscls_inner_loop_ref(ep.f_s, ep.s_label, ep.w0, case["lr"], case["n_iter"], ct, case["loss_type"],
+                                  O.initial_bias(case["idx"], case["C"]) if ct[2] == "b" else None,
+                                  torch.from_numpy(g["g0"]) if ct[0] == "r" else None)
+    for k in ("weight", "weight_g", "bias", "scale"):
+        if out[k] is not None:
+            assert rel_err(out[k], g[k]) < 1e-6
