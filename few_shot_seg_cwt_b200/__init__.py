@@ -20,13 +20,13 @@ from .episodic import (HeadOutput, HostPipeline, IoUTable, bind_host_to_gpu, do_
                        transformer_params, validate_transformer)
 from .metrics import (batch_intersection_union_int, batch_intersectionAndUnionGPU,  # noqa: F401
                       intersection_union_int, intersectionAndUnionGPU)
-from .ops import (feat_times_rows, normalize_features, fit_classifier, fit_classifier_bias, fit_classifier_dice, fit_coscls, intersection_union, label_counts, logits_iou,  # noqa: F401
+from .ops import (feat_times_rows, normalize_features, fit_classifier, fit_classifier_bias, fit_classifier_dice, fit_coscls, fit_multiclass, intersection_union, label_counts, logits_iou,  # noqa: F401
                   query_loss_grad, rows_times_feat, transformer_backward, transformer_forward,
                   upsample_argmax_iou)
 from .transformer import MultiHeadAttentionOne  # noqa: F401
 
 __all__ = [
-    "MultiHeadAttentionOne", "fit_classifier", "fit_classifier_bias", "fit_classifier_dice", "fit_coscls", "inner_loop", "increment_inner_loop", "get_classifier", "CosCls", "draw_initial_weights",
+    "MultiHeadAttentionOne", "fit_classifier", "fit_classifier_bias", "fit_classifier_dice", "fit_coscls", "fit_multiclass", "inner_loop", "increment_inner_loop", "get_classifier", "CosCls", "draw_initial_weights",
     "batch_intersectionAndUnionGPU", "intersectionAndUnionGPU", "batch_intersection_union_int",
     "intersection_union_int", "validate_transformer", "episode_head", "run_sweep", "IoUTable", "HostPipeline", "bind_host_to_gpu",
     "meta_train_step", "do_epoch", "query_loss", "transformer_forward", "transformer_backward", "logits_iou",

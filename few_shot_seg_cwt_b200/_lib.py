@@ -37,6 +37,8 @@ SIGNATURES = {
     "cwt_fit_classifier_bias_f32": (_i, [_vp, _vp, _i] + [_vp] * 7 + [_i] * 8 + [_f, _f, _i, _vp, _sz, _vp]),
     "cwt_fit_coscls_workspace_bytes": (_sz, [_i] * 7),
     "cwt_fit_coscls_f32": (_i, [_vp, _vp, _i] + [_vp] * 7 + [_i] * 9 + [_f, _i, _vp, _sz, _vp]),
+    "cwt_fit_multiclass_workspace_bytes": (_sz, [_i] * 7),
+    "cwt_fit_multiclass_f32": (_i, [_vp, _vp, _i, _vp, _vp, _vp] + [_i] * 8 + [_f, _i, _vp, _sz, _vp]),
     "cwt_fit_dice_workspace_bytes": (_sz, [_i] * 7),
     "cwt_fit_classifier_dice_f32": (_i, [_vp, _vp, _i, _vp, _vp, _vp] + [_i] * 8 + [_f, _i, _vp, _sz, _vp]),
     "cwt_transformer_workspace_bytes": (_sz, [_i] * 6),

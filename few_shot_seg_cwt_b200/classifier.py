@@ -16,7 +16,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib as L
-from .ops import fit_classifier, fit_classifier_bias, fit_classifier_dice, fit_coscls, label_counts, normalize_features
+from .ops import fit_classifier, fit_classifier_bias, fit_classifier_dice, fit_coscls, fit_multiclass, label_counts, normalize_features
 
 
 def get_classifier(bottleneck_dim: int = 512, num_classes: int = 2, device=None) -> nn.Conv2d:
@@ -150,23 +150,33 @@ def _inner_loop_coscls(classifier: CosCls, f_s, s_label, cls_lr, adapt_iter, res
 
 def increment_inner_loop(classifier: nn.Conv2d, f_s: torch.Tensor, s_label: torch.Tensor, cls_idx: int, cls_lr: float,
                          adapt_iter: int, tp: float = 1.0, check: bool = True, algo: int = L.FIT_AUTO) -> None:
-    """``PSPNet.increment_inner_loop`` drop-in (src/model/pspnet.py:207-221) for a 2-class classifier: continue fitting
-    ``classifier`` (NO parameter reset, unlike :func:`inner_loop`) with ``Adapt_SegLoss(num_cls=2, fg_idx=cls_idx, tp)``
-    -> weighted_adpt_ce_loss (src/model/model_util.py:76-98): CE with ``weight[cls_idx] = (bg_cnt / fg_cnt) ** tp``,
+    """``PSPNet.increment_inner_loop`` drop-in (src/model/pspnet.py:207-221): continue fitting ``classifier`` (NO
+    parameter reset, unlike :func:`inner_loop`) with ``Adapt_SegLoss(num_cls, fg_idx=cls_idx, tp)`` ->
+    weighted_adpt_ce_loss (src/model/model_util.py:76-98): CE with ``weight[cls_idx] = (bg_cnt / fg_cnt) ** tp``,
     bg_cnt = every non-ignored pixel that is not ``cls_idx``. The weight is computed on the device (no host sync; a
     support mask without ``cls_idx`` pixels gives an infinite weight exactly as the reference's tensor division does).
-    Classifiers with more than two classes (the incremental multi-way setting of src/train_cca.py) are not built."""
-    if not isinstance(classifier, nn.Conv2d) or classifier.bias is not None or classifier.weight.shape[0] != 2 \
-            or classifier.kernel_size != (1, 1):
-        raise NotImplementedError("cwt_b200 increment_inner_loop fits the 2-class bias-free 1x1 classifier")
-    if cls_idx not in (0, 1):
-        raise IndexError(f"index {cls_idx} is out of bounds for dimension 0 with size 2")     # weight[fg_idx] in the reference
-    C = classifier.weight.shape[1]
-    n = label_counts(s_label).reshape(-1, 4).sum(0)                  # (#0, #1, #ignored, #invalid) over all shots
-    fg, bg = n[cls_idx].float(), n[1 - cls_idx].float()
-    cw = torch.ones(2, dtype=torch.float32, device=f_s.device)
-    cw[cls_idx] = (bg / fg) ** tp
-    w0 = classifier.weight.detach().reshape(2, C).to(f_s.device, torch.float32)
-    w = fit_classifier(f_s, s_label, w0, cls_lr, adapt_iter, class_weight=cw, check=check, algo=algo)
+    ``classifier`` = ``self.classifier`` (``meta_train``) or ``self.val_classifier``: 2 classes run on the fused binary
+    fit; more classes (the multi-way setting of src/train_cca.py, 16 / 17 on PASCAL, 61 / 62 on COCO) on
+    :func:`fit_multiclass`."""
+    if not isinstance(classifier, nn.Conv2d) or classifier.bias is not None or classifier.kernel_size != (1, 1):
+        raise NotImplementedError("cwt_b200 increment_inner_loop fits a bias-free 1x1 classifier")
+    K, C = classifier.weight.shape[:2]
+    if not 0 <= cls_idx < K:
+        raise IndexError(f"index {cls_idx} is out of bounds for dimension 0 with size {K}")     # weight[fg_idx] in the reference
+    dev = f_s.device
+    if K == 2:
+        n = label_counts(s_label).reshape(-1, 4).sum(0)              # (#0, #1, #ignored, #invalid) over all shots
+        fg, bg = n[cls_idx].float(), n[1 - cls_idx].float()
+        cw = torch.ones(2, dtype=torch.float32, device=dev)
+        cw[cls_idx] = (bg / fg) ** tp
+        w0 = classifier.weight.detach().reshape(2, C).to(dev, torch.float32)
+        w = fit_classifier(f_s, s_label, w0, cls_lr, adapt_iter, class_weight=cw, check=check, algo=algo)
+    else:
+        lab = s_label.long()
+        fg = (lab == cls_idx).sum()
+        bg = (lab != 255).sum() - fg                                   # model_util.py:90: everything that is not cls_idx nor 255
+        cw = torch.ones(K, dtype=torch.float32, device=dev)
+        cw[cls_idx] = (bg / fg) ** tp
+        w = fit_multiclass(f_s, s_label, classifier.weight.detach().to(dev, torch.float32), cw, cls_lr, adapt_iter, check=check)
     with torch.no_grad():
-        classifier.weight.copy_(w.reshape(2, C, 1, 1))
+        classifier.weight.copy_(w.reshape(K, C, 1, 1))

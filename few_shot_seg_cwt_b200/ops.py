@@ -202,6 +202,39 @@ def fit_coscls(x_norm: torch.Tensor, s_label: torch.Tensor, weight: torch.Tensor
     return out
 
 
+def fit_multiclass(f_s: torch.Tensor, s_label: torch.Tensor, weight: torch.Tensor, class_weight: torch.Tensor, lr: float,
+                   n_iter: int, ignore_index: int = IGNORE, check: bool = True) -> torch.Tensor:
+    """``n_iter`` plain-SGD steps on ONE K-class bias-free 1x1 classifier with ``CrossEntropyLoss(class_weight,
+    ignore_index)`` of the logits up-sampled to the label size — the loop of ``PSPNet.increment_inner_loop``
+    (src/model/pspnet.py:207-221) for K > 2. f_s [S,C,h,w], s_label [S,H,W] in [0,K) or ignore_index, weight [K,C] (or
+    [K,C,1,1]), class_weight [K]. Returns the fitted weight (new tensor, same shape as given)."""
+    dev = L.require_cuda(f_s, s_label, weight, class_weight)
+    if f_s.dim() != 4 or s_label.dim() != 3:
+        raise ValueError(f"f_s must be [S,C,h,w] and s_label [S,H,W]; got {tuple(f_s.shape)}, {tuple(s_label.shape)}")
+    S, Cc, h, w = f_s.shape
+    H, W = s_label.shape[-2:]
+    K = weight.shape[0]
+    f_s = _f32c(f_s, "f_s")
+    lab = s_label.contiguous()
+    wv = _f32c(weight, "weight").reshape(K, Cc).clone()
+    cw = _f32c(class_weight, "class_weight").reshape(K)
+    valid = lab != ignore_index
+    if check and bool(((lab.long() >= K) & valid).any()):
+        raise ValueError(f"s_label holds values outside [0, {K}) and ignore_index")
+    # sum_i w[y_i] over the non-ignored pixels, on the device (no host sync)
+    sumw = cw[lab.long().clamp(0, K - 1)][valid].sum(dtype=torch.float32)
+    inv_sumw = (1.0 / sumw).reshape(1).contiguous()
+    lib = L.load()
+    nbytes = lib.cwt_fit_multiclass_workspace_bytes(K, S, Cc, h, w, H, W)
+    ws = L.WORKSPACE.get(nbytes, dev, "fit_multiclass")
+    with torch.cuda.device(dev):
+        rc = lib.cwt_fit_multiclass_f32(L.ptr(f_s), L.ptr(lab), L.label_kind(lab), L.ptr(wv), L.ptr(cw), L.ptr(inv_sumw),
+                                        K, S, Cc, h, w, H, W, int(n_iter), float(lr), int(ignore_index),
+                                        L.ptr(ws), ws.numel(), L.stream_ptr(dev))
+    L.check(rc, "cwt_fit_multiclass_f32")
+    return wv.reshape(weight.shape)
+
+
 def fit_classifier_dice(f_s: torch.Tensor, s_label: torch.Tensor, w0: torch.Tensor, lr: float, n_iter: int,
                         ignore_index: int = IGNORE, return_losses: bool = False, check: bool = True):
     """The inner loop of :func:`fit_classifier` with the reference's dice loss, ``SegLoss('wt_dc' | 'dc')``

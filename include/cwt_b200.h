@@ -129,6 +129,22 @@ int cwt_fit_coscls_f32(const float* x_norm, const void* s_label, int label_kind,
                        void* workspace, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * (f-3) PSPNet.increment_inner_loop with more than two classes (src/model/pspnet.py:207-221; the
+ * multi-way incremental setting of src/train_cca.py:146,322): n_iter plain-SGD steps on ONE K-class
+ * bias-free 1x1 classifier with CrossEntropyLoss(weight[K], ignore_index) of the logits up-sampled
+ * to HxW (Adapt_SegLoss -> weighted_adpt_ce_loss, src/model/model_util.py:76-98).
+ *   f_s [S,C,h,w]   s_label [S,H,W] values in [0,K) or ignore_index   weight [K,C] IN/OUT
+ *   class_weight [K] (ones, weight[fg_idx] = (bg_cnt/fg_cnt)^tp)   inv_sum_weight [1] = 1 / sum_i w[y_i]
+ *   (both device pointers: the caller counts the labels on the device, no host sync)
+ * ------------------------------------------------------------------------------------- */
+size_t cwt_fit_multiclass_workspace_bytes(int K, int S, int C, int h, int w, int H, int W);
+int cwt_fit_multiclass_f32(const float* f_s, const void* s_label, int label_kind, float* weight,
+                           const float* class_weight, const float* inv_sum_weight,
+                           int K, int S, int C, int h, int w, int H, int W,
+                           int n_iter, float lr, int ignore_index,
+                           void* workspace, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * (f-3) the same inner loop with SegLoss('wt_dc' | 'dc'), the per-channel sigmoid dice loss:
  * PSPNet.inner_loop, src/model/pspnet.py:189-205, with criterion = SegLoss(args.inner_loss_type),
  * src/model/model_util.py:18-19 -> weighted_dice_loss, model_util.py:40-73 (weighted_val 1,

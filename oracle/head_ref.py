@@ -197,6 +197,50 @@ def coscls_inner_loop_ref(f_s: torch.Tensor, s_label: torch.Tensor, w0: torch.Te
             "bias": b.detach().clone() if fb else None, "scale": s.detach().clone()}
 
 
+def multiclass_labels(s_label: torch.Tensor, K: int, fg_idx: int) -> torch.Tensor:
+    """Deterministic K-way labels for the multi-way inner loop from a {0,1,255} support mask: foreground -> fg_idx,
+    255 stays, background -> a block pattern over the other classes (what reset_spt_label, model_util.py:120-128,
+    produces from the base classifier's prediction: pseudo-labels of the base classes on the background)."""
+    H, W = s_label.shape[-2:]
+    yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    pat = ((yy // 11) + 2 * (xx // 13)) % K
+    pat = torch.where(pat == fg_idx, torch.zeros_like(pat) if fg_idx != 0 else torch.ones_like(pat), pat)
+    lab = s_label.long()
+    out = torch.where(lab == 1, torch.full_like(lab, fg_idx), torch.where(lab == 0, pat.expand_as(lab), torch.full_like(lab, IGNORE)))
+    return out
+
+
+def multiclass_w0(idx: int, K: int, C: int) -> torch.Tensor:
+    """Deterministic initial K-class weights ~ U(-1/sqrt(C), 1/sqrt(C)) (nn.Conv2d's init) for the golden cases."""
+    g = torch.Generator().manual_seed(4409 + idx)
+    return (torch.rand(K, C, generator=g) * 2.0 - 1.0) / math.sqrt(C)
+
+
+def increment_inner_loop_ref(f_s: torch.Tensor, s_label: torch.Tensor, w0: torch.Tensor, lr: float, n_iter: int,
+                             fg_idx: int, tp: float = 1.0) -> torch.Tensor:
+    """PSPNet.increment_inner_loop (pspnet.py:207-221) for a K-class classifier: SGD on Adapt_SegLoss ->
+    weighted_adpt_ce_loss (model_util.py:87-98), weight = ones(K) with weight[fg_idx] = (bg_cnt / fg_cnt) ** tp.
+    f_s [S,C,h,w]; s_label [S,H,W] in [0,K) or 255; w0 [K,C] -> fitted weight [K,C]."""
+    K, C = w0.shape
+    tgt = s_label.long()
+    conv = nn.Conv2d(C, K, kernel_size=1, bias=False)
+    with torch.no_grad():
+        conv.weight.copy_(w0.reshape(K, C, 1, 1))
+    opt = torch.optim.SGD(conv.parameters(), lr=lr)
+    for _ in range(n_iter):
+        out = F.interpolate(conv(f_s), size=tgt.shape[-2:], mode="bilinear", align_corners=True)
+        count = torch.bincount(tgt.view(-1))
+        fg = count[fg_idx]
+        bg = (torch.sum(count) - fg) if len(count) <= 255 else (torch.sum(count) - count[255] - fg)
+        weight = torch.tensor([1.0] * K)
+        weight[fg_idx] = (bg / fg) ** tp
+        loss = nn.CrossEntropyLoss(weight=weight, ignore_index=IGNORE)(out, tgt)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+    return conv.weight.detach().reshape(K, C).clone()
+
+
 def bilinear_matrix(n_in: int, n_out: int, dtype=torch.float64) -> torch.Tensor:
     """Dense [n_out, n_in] align_corners=True interpolation matrix (2 non-zeros per row).
     ATen: scale = (n_in-1)/(n_out-1); src = scale*dst; i0 = floor(src); l1 = src - i0."""

@@ -82,6 +82,15 @@ COSCLS_CASES = {
     "coscls_full_rnbt":  dict(idx=37, shot=1, C=512, h=60, w=60, H=473, W=473, style="backbone", lr=0.1, n_iter=100, loss_type="wt_ce", cls_type="rnbt"),
 }
 
+# PSPNet.increment_inner_loop with more than two classes (pspnet.py:207-221; train_cca.py's multi-way setting)
+INCRMC_CASES = {
+    "incrmc_small_k5":  dict(idx=38, shot=2, C=64, h=12, w=12, H=89, W=89, style="unit", lr=0.1, n_iter=40, K=5, fg_idx=3, tp=1.1),
+    # ("backbone"-scale features at lr 0.1 make the 17-way trajectory chaotic — a 2e-7 difference after one step grows
+    #  tenfold every five steps on ANY implementation, measured — so the multi-way vectors use the O(1)-scale features)
+    "incrmc_small_k17": dict(idx=39, shot=1, C=64, h=12, w=12, H=89, W=89, style="unit", lr=0.1, n_iter=40, K=17, fg_idx=16, tp=1.0),
+    "incrmc_full_k16":  dict(idx=40, shot=1, C=512, h=60, w=60, H=473, W=473, style="unit", lr=0.1, n_iter=30, K=16, fg_idx=7, tp=1.1),
+}
+
 TRAIN_CASES = {
     "train_small_h2": dict(idx=11, shot=1, C=64, h=12, w=12, H=89, W=89, style="unit", n_head=2, lr=0.1, n_iter=20, p_attn=0.1, p_out=0.5),
     "train_full_h1":  dict(idx=12, shot=1, C=512, h=60, w=60, H=473, W=473, style="unit", n_head=1, lr=0.1, n_iter=20, p_attn=0.1, p_out=0.5),
@@ -254,6 +263,33 @@ def coscls_via_reference(ep, case):
             "weight_g": cls.weight_g.detach().reshape(2).clone() if ct[0] == "r" else None,
             "bias": cls.bias.detach().clone() if ct[2] == "b" else None,
             "scale": torch.as_tensor(classifier.scale_factor).detach().clone().float()}, float(s_loss)
+
+
+def incr_multiclass_via_reference(ep, case):
+    """The loop of PSPNet.increment_inner_loop (pspnet.py:207-221) with the reference's own Adapt_SegLoss doing the work."""
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from src.model.model_util import Adapt_SegLoss
+    K, C = case["K"], ep.f_s.shape[1]
+    classifier = nn.Conv2d(C, K, kernel_size=1, bias=False)
+    with torch.no_grad():
+        classifier.weight.copy_(O.multiclass_w0(case["idx"], K, C).reshape(K, C, 1, 1))
+    optimizer = torch.optim.SGD(classifier.parameters(), lr=case["lr"])
+    criterion = Adapt_SegLoss(num_cls=K, fg_idx=case["fg_idx"], tp=case["tp"])
+    f_s, s_label = ep.f_s, O.multiclass_labels(ep.s_label, K, case["fg_idx"])
+    cuda_avail = torch.cuda.is_available
+    torch.cuda.is_available = lambda: False
+    try:
+        for _ in range(case["n_iter"]):
+            pred_s_label = classifier(f_s)
+            pred_s_label = F.interpolate(pred_s_label, size=s_label.size()[1:], mode="bilinear", align_corners=True)
+            s_loss = criterion(pred_s_label, s_label)
+            optimizer.zero_grad()
+            s_loss.backward()
+            optimizer.step()
+    finally:
+        torch.cuda.is_available = cuda_avail
+    return classifier.weight.detach().reshape(K, C).clone(), float(s_loss)
 
 
 def relerr(a, b):
@@ -434,6 +470,22 @@ def main():
             np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), case=json.dumps(case), checksum=input_checksum(ep),
                                 torch_version=torch.__version__, loss=last_loss, g0=coscls_g0(ep.w0).numpy(),
                                 **{k: v.numpy() for k, v in ref.items() if v is not None})
+
+    for name, case in INCRMC_CASES.items():
+        if a.only and a.only not in name:
+            continue
+        ep = syn.make_episode(case["idx"], **gen_kwargs(case))
+        w_ref, last_loss = incr_multiclass_via_reference(ep, case)
+        w_ora = O.increment_inner_loop_ref(ep.f_s, O.multiclass_labels(ep.s_label, case["K"], case["fg_idx"]),
+                                           O.multiclass_w0(case["idx"], case["K"], case["C"]), case["lr"], case["n_iter"],
+                                           case["fg_idx"], case["tp"])
+        err = relerr(w_ora, w_ref)
+        print(f"[pin] {name}: oracle vs reference increment_inner_loop (K={case['K']}) rel {err:.2e} last loss {last_loss:.6f}")
+        assert err < 1e-6, err
+        report["cases"][name] = {"errs": {"W_fit": err}, "loss": last_loss}
+        if a.write:
+            np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), case=json.dumps(case), checksum=input_checksum(ep),
+                                torch_version=torch.__version__, W_fit=w_ref.numpy(), loss=last_loss)
 
     for name, case in TRAIN_CASES.items():
         if a.only and a.only not in name:

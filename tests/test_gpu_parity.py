@@ -336,6 +336,27 @@ def test_coscls_flag_variants_vs_golden(cuda_device, name):
         assert torch.allclose(clf(x), ref, rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("name", golden_names("incrmc_"))
+def test_increment_inner_loop_multiclass_vs_golden(cuda_device, name):
+    """PSPNet.increment_inner_loop with K > 2 classes (src/model/pspnet.py:207-221, the multi-way setting of
+    src/train_cca.py): goldens recorded with the reference's own Adapt_SegLoss; K = 17 exercises two row chunks."""
+    g = load_golden(name)
+    case = g["case"]
+    ep = syn.make_episode(case["idx"], **gen_kwargs(case))
+    K, C = case["K"], case["C"]
+    lab = O.multiclass_labels(ep.s_label, K, case["fg_idx"])
+    for dtype in (torch.int64, torch.uint8):
+        clf = torch.nn.Conv2d(C, K, 1, bias=False).to(cuda_device)
+        with torch.no_grad():
+            clf.weight.copy_(O.multiclass_w0(case["idx"], K, C).reshape(K, C, 1, 1))
+        cwt.increment_inner_loop(clf, ep.f_s.to(cuda_device), lab.to(dtype).to(cuda_device), case["fg_idx"], case["lr"],
+                                 case["n_iter"], tp=case["tp"])
+        assert rel_err(clf.weight.reshape(K, C), g["W_fit"]) < TIGHT
+    with pytest.raises(ValueError):                          # a label outside [0, K)
+        bad = lab.clone(); bad[0, 0, 0] = K
+        cwt.increment_inner_loop(clf, ep.f_s.to(cuda_device), bad.to(cuda_device), case["fg_idx"], case["lr"], 2)
+
+
 def test_inner_loop_unsupported_variants_raise(cuda_device):
     ep = syn.make_episode(1, **SMALL)
     f, lab = ep.f_s.to(cuda_device), ep.s_label.to(cuda_device)
@@ -343,8 +364,8 @@ def test_inner_loop_unsupported_variants_raise(cuda_device):
         cwt.inner_loop(cwt.CosCls(64, 2, "0n00").to(cuda_device), f, lab, 0.1, 5, loss_type="wt_dc")
     with pytest.raises(KeyError):                            # parse_param_coscls
         cwt.CosCls(64, 2, "xxxx")
-    with pytest.raises(NotImplementedError):                 # multi-way incremental classifier
-        cwt.increment_inner_loop(cwt.get_classifier(64, 3).to(cuda_device), f, lab, 1, 0.1, 5)
+    with pytest.raises(NotImplementedError):                 # incremental classifier with a bias
+        cwt.increment_inner_loop(torch.nn.Conv2d(64, 3, 1, bias=True).to(cuda_device), f, lab, 1, 0.1, 5)
 
 
 # ---------------------------------------------------------------------------- (b) transformer
@@ -517,7 +538,7 @@ def test_intersection_and_union_dropin(cuda_device, dtype):
 
 
 # ---------------------------------------------------------------------------- whole episode
-@pytest.mark.parametrize("name", [n for n in golden_names() if not n.startswith(("train_", "inner_", "coscls_"))])
+@pytest.mark.parametrize("name", [n for n in golden_names() if not n.startswith(("train_", "inner_", "coscls_", "incrmc_"))])
 def test_episode_head_vs_golden(cuda_device, name):
     g = load_golden(name)
     case = g["case"]

@@ -20,7 +20,7 @@ def _checksum(ep):
     return h.hexdigest()
 
 
-EVAL_CASES = [n for n in golden_names() if not n.startswith(("train_", "inner_", "coscls_"))]
+EVAL_CASES = [n for n in golden_names() if not n.startswith(("train_", "inner_", "coscls_", "incrmc_"))]
 FAST = [n for n in EVAL_CASES if n.startswith("small")] + ["full_1shot_h1_yaml"]
 
 
@@ -170,3 +170,17 @@ def test_oracle_coscls_flag_variants_reproduce_reference_golden(name):
     for k in ("weight", "weight_g", "bias", "scale"):
         if out[k] is not None:
             assert rel_err(out[k], g[k]) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["incrmc_small_k5", "incrmc_small_k17"])
+def test_oracle_increment_inner_loop_multiclass_reproduces_reference_golden(name):
+    """PSPNet.increment_inner_loop with K > 2 (pspnet.py:207-221) against weights recorded with the reference's Adapt_SegLoss."""
+    g = load_golden(name)
+    case = g["case"]
+    ep = syn.make_episode(case["idx"], **gen_kwargs(case))
+    assert _checksum(ep) == str(g["checksum"])
+    lab = O.multiclass_labels(ep.s_label, case["K"], case["fg_idx"])
+    assert int(lab[lab != 255].max()) < case["K"] and bool((lab == case["fg_idx"]).any())
+    w = O.increment_inner_loop_ref(ep.f_s, lab, O.multiclass_w0(case["idx"], case["K"], case["C"]), case["lr"],
+                                   case["n_iter"], case["fg_idx"], case["tp"])
+    assert rel_err(w, g["W_fit"]) < 1e-6
