@@ -253,6 +253,20 @@ int cwt_feat_times_rows(const float* P, const float* f, int normalize, float* ou
  * ------------------------------------------------------------------------------------- */
 int cwt_normalize_features_f32(const float* f, float* out, int n_img, int C, int HW, float eps, float scale, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * (f-4) the reference's validation transform on the device, one fused kernel per image:
+ * Resize (src/dataset/transform.py:109-163: aspect-preserving cv2.resize INTER_LINEAR to new_h x new_w,
+ * padded to size x size; label cv2.INTER_NEAREST, padded with pad_label) -> ToTensor (/255, transform.py:58-82)
+ * -> Normalize ((x - mean) / std, transform.py:85-107), composed in src/dataset/dataset.py:78-84.
+ *   image_hwc [ori_h,ori_w,3] fp32 RGB in [0,255] (device)   label_or_null [ori_h,ori_w] uint8 (device)
+ *   mean3 / std3 / pad3_or_null: HOST pointers (3 floats; pad in [0,255] units, NULL = zero padding)
+ *   out_chw [3,size,size] fp32   label_out [size,size] uint8 or int64 (label_out_kind)
+ * ------------------------------------------------------------------------------------- */
+int cwt_resize_pad_normalize_f32(const float* image_hwc, const uint8_t* label_or_null, int ori_h, int ori_w,
+                                 int new_h, int new_w, int size, const float* mean3, const float* std3,
+                                 const float* pad3_or_null, int pad_label, float* out_chw, void* label_out_or_null,
+                                 int label_out_kind, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -448,3 +448,68 @@ def sgd_nesterov_step_ref(params, grads, bufs, lr, momentum=0.9, weight_decay=1e
         new_b[k] = b
         new_p[k] = params[k] - lr * (g + momentum * b)
     return new_p, new_b
+
+
+# --------------------------------------------------------------------------------------
+# (f-4) validation transform                      src/dataset/transform.py:58-163, dataset.py:78-84
+# --------------------------------------------------------------------------------------
+def synthetic_image(idx: int, h: int, w: int):
+    """Deterministic test image [h,w,3] float32 in [0,255] (integers, as np.float32(cv2.imread(...)) delivers,
+    dataset.py:138-140) and label [h,w] uint8 in {0,1,255}."""
+    g = np.random.RandomState(7000 + idx)
+    base = g.randint(0, 256, size=(h // 7 + 2, w // 7 + 2, 3)).astype(np.float32)
+    img = np.kron(base, np.ones((7, 7, 1), np.float32))[:h, :w] + g.randint(-9, 10, size=(h, w, 3))
+    img = np.clip(img, 0, 255).astype(np.float32)
+    lab = np.zeros((h, w), np.uint8)
+    lab[h // 4: h // 4 + h // 3, w // 5: w // 5 + w // 2] = 1
+    lab[h // 4 - 2: h // 4, :] = 255
+    return img, lab
+
+
+def val_transform_ref(image: np.ndarray, label: np.ndarray, size: int, mean, std, padding=None, plain_cv2: bool = False):
+    """Resize -> ToTensor -> Normalize exactly as the reference composes them (dataset.py:78-84), with cv2 doing the
+    resampling as in transform.py:143-157 (cv2 = the reference's third-party dependency for this step).
+    ``plain_cv2``: run cv2.resize with ``cv2.setUseOptimized(False)`` — OpenCV's portable C++ resampler instead of its
+    IPP / SIMD one. The two differ by up to 0.0044 grey levels (of 255) on PASCAL-sized images [measured, cv2 4.13]; the
+    CUDA kernel reproduces the portable path bit for bit."""
+    import cv2
+    was_optimized = cv2.useOptimized()
+    if plain_cv2:
+        cv2.setUseOptimized(False)
+    try:
+        return _val_transform_ref(cv2, image, label, size, mean, std, padding)
+    finally:
+        cv2.setUseOptimized(was_optimized)
+
+
+def _val_transform_ref(cv2, image, label, size, mean, std, padding):
+
+    def find_new_hw(ori_h, ori_w, test_size):                     # transform.py:117-137
+        if ori_h >= ori_w:
+            ratio = test_size * 1.0 / ori_h
+            new_h, new_w = test_size, int(ori_w * ratio)
+        else:
+            ratio = test_size * 1.0 / ori_w
+            new_h, new_w = int(ori_h * ratio), test_size
+        if new_h % 8 != 0:
+            new_h = (int(new_h / 8)) * 8
+        if new_w % 8 != 0:
+            new_w = (int(new_w / 8)) * 8
+        return new_h, new_w
+
+    new_h, new_w = find_new_hw(image.shape[0], image.shape[1], size)
+    image_crop = cv2.resize(image, dsize=(int(new_w), int(new_h)), interpolation=cv2.INTER_LINEAR)      # :143-144
+    back_crop = np.zeros((size, size, 3))                                                                # :147 (float64)
+    if padding:
+        back_crop[:, :, 0], back_crop[:, :, 1], back_crop[:, :, 2] = padding[0], padding[1], padding[2]
+    back_crop[:new_h, :new_w, :] = image_crop
+    s_mask = cv2.resize(label.astype(np.float32), dsize=(int(new_w), int(new_h)), interpolation=cv2.INTER_NEAREST)  # :156-157
+    back_mask = np.ones((size, size)) * 255
+    back_mask[:new_h, :new_w] = s_mask
+    img = torch.from_numpy(back_crop.transpose((2, 0, 1)))                                               # ToTensor :70-72
+    if not isinstance(img, torch.FloatTensor):
+        img = img.float().div(255)
+    lab = torch.from_numpy(back_mask).long()
+    for t, m, s in zip(img, mean, std):                                                                  # Normalize :101-102
+        t.sub_(m).div_(s)
+    return img, lab

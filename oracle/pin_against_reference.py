@@ -91,6 +91,15 @@ INCRMC_CASES = {
     "incrmc_full_k16":  dict(idx=40, shot=1, C=512, h=60, w=60, H=473, W=473, style="unit", lr=0.1, n_iter=30, K=16, fg_idx=7, tp=1.1),
 }
 
+# validation transform (src/dataset/transform.py Resize -> ToTensor -> Normalize): source sizes x target size
+TRANSFORM_CASES = {
+    "transform_land_97":   dict(idx=1, h=75, w=120, size=97, padding=None),
+    "transform_port_97":   dict(idx=2, h=131, w=88, size=97, padding="avg"),
+    "transform_up_97":     dict(idx=3, h=40, w=52, size=97, padding=None),
+    "transform_half_96":   dict(idx=4, h=192, w=192, size=96, padding=None),        # exact 2x down-scale (cv2's area fast path)
+}
+PASCAL_MEAN, PASCAL_STD = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]               # config_files/pascal.yaml:15-16
+
 TRAIN_CASES = {
     "train_small_h2": dict(idx=11, shot=1, C=64, h=12, w=12, H=89, W=89, style="unit", n_head=2, lr=0.1, n_iter=20, p_attn=0.1, p_out=0.5),
     "train_full_h1":  dict(idx=12, shot=1, C=512, h=60, w=60, H=473, W=473, style="unit", n_head=1, lr=0.1, n_iter=20, p_attn=0.1, p_out=0.5),
@@ -486,6 +495,26 @@ def main():
         if a.write:
             np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), case=json.dumps(case), checksum=input_checksum(ep),
                                 torch_version=torch.__version__, W_fit=w_ref.numpy(), loss=last_loss)
+
+    for name, case in TRANSFORM_CASES.items():
+        if a.only and a.only not in name:
+            continue
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            from src.dataset import transform as RT
+        img, lab = O.synthetic_image(case["idx"], case["h"], case["w"])
+        padding = [v * 255 for v in PASCAL_MEAN] if case["padding"] == "avg" else None                    # dataset.py:82
+        compose = RT.Compose([RT.Resize(case["size"], padding=padding), RT.ToTensor(),
+                              RT.Normalize(mean=PASCAL_MEAN, std=PASCAL_STD)])                            # dataset.py:78-84
+        ref_img, ref_lab = compose(img.copy(), lab.copy())
+        ora_img, ora_lab = O.val_transform_ref(img, lab, case["size"], PASCAL_MEAN, PASCAL_STD, padding)
+        err = float((ora_img - ref_img).abs().max())
+        print(f"[pin] {name}: oracle vs reference Compose(Resize, ToTensor, Normalize) max abs {err:.1e} labels equal {bool(torch.equal(ora_lab, ref_lab))}")
+        assert err == 0.0 and torch.equal(ora_lab, ref_lab)
+        report["cases"][name] = {"errs": {"image": err}}
+        if a.write:
+            np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), case=json.dumps(case), torch_version=torch.__version__,
+                                image=ref_img.numpy().astype(np.float32), label=ref_lab.numpy().astype(np.uint8))
 
     for name, case in TRAIN_CASES.items():
         if a.only and a.only not in name:

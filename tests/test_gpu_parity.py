@@ -538,7 +538,7 @@ def test_intersection_and_union_dropin(cuda_device, dtype):
 
 
 # ---------------------------------------------------------------------------- whole episode
-@pytest.mark.parametrize("name", [n for n in golden_names() if not n.startswith(("train_", "inner_", "coscls_", "incrmc_"))])
+@pytest.mark.parametrize("name", [n for n in golden_names() if not n.startswith(("train_", "inner_", "coscls_", "incrmc_", "transform_"))])
 def test_episode_head_vs_golden(cuda_device, name):
     g = load_golden(name)
     case = g["case"]
@@ -775,3 +775,43 @@ def test_sweep_cli_small_with_oracle_check(cuda_device, capsys):
     assert chk["episodes"] == 6
     assert chk["max_count_diff"] <= chk["tie_set_pixels"]
     assert chk["mIoU_gap_points"] < 0.05 and chk["FBIoU_gap_points"] < 0.05
+
+
+# ---------------------------------------------------------------------------- (f-4) validation transform
+PASCAL_MEAN, PASCAL_STD = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+TRANSFORM_ATOL = 2e-4     # normalised units, against cv2's DEFAULT (IPP / SIMD) resampler: that one differs from OpenCV's own portable
+                          # C++ resampler by up to 0.005 grey levels = 8.6e-5 normalised [measured]; against the portable path
+                          # (cv2.setUseOptimized(False)) the kernel is BIT-EXACT, and labels are identical either way
+
+
+@pytest.mark.parametrize("name", golden_names("transform_"))
+def test_val_transform_vs_golden(cuda_device, name):
+    """The fused Resize -> ToTensor -> Normalize kernel against tensors recorded from the reference's own transform classes
+    (src/dataset/transform.py, composed as in dataset.py:78-84): land-/portrait, up-scaling, exact 2x down-scaling, zero and
+    mean padding; int64 and uint8 label outputs."""
+    g = load_golden(name)
+    case = g["case"]
+    img, lab = O.synthetic_image(case["idx"], case["h"], case["w"])
+    padding = [v * 255 for v in PASCAL_MEAN] if case["padding"] == "avg" else None
+    ti, tl = torch.from_numpy(img).to(cuda_device), torch.from_numpy(lab).to(cuda_device)
+    for dtype in (torch.int64, torch.uint8):
+        o_img, o_lab = cwt.resize_pad_normalize(ti, tl, case["size"], PASCAL_MEAN, PASCAL_STD, padding, label_dtype=dtype)
+        assert float((o_img.cpu() - torch.from_numpy(g["image"])).abs().max()) <= TRANSFORM_ATOL
+        assert torch.equal(o_lab.cpu().long(), torch.from_numpy(g["label"]).long())
+    only_img, nh, nw = cwt.resize_pad_normalize(ti, None, case["size"], PASCAL_MEAN, PASCAL_STD, padding)
+    assert torch.equal(only_img, o_img) and (nh, nw) == cwt.find_new_hw(case["h"], case["w"], case["size"])
+
+
+@pytest.mark.parametrize("hw", [(375, 500), (500, 333), (473, 473), (281, 500)])
+def test_val_transform_full_size_vs_oracle(cuda_device, hw):
+    """PASCAL-sized images to 473 x 473 through the ValTransform callable, against the oracle (cv2 on the host)."""
+    img, lab = O.synthetic_image(hw[0] + hw[1], *hw)
+    r_img, r_lab = O.val_transform_ref(img, lab, 473, PASCAL_MEAN, PASCAL_STD, None)
+    o_img, o_lab = cwt.ValTransform(473, PASCAL_MEAN, PASCAL_STD, device=cuda_device)(img, lab)
+    assert o_img.shape == (3, 473, 473) and o_lab.dtype == torch.int64
+    assert float((o_img.cpu() - r_img).abs().max()) <= TRANSFORM_ATOL
+    assert torch.equal(o_lab.cpu(), r_lab)
+    p_img, p_lab = O.val_transform_ref(img, lab, 473, PASCAL_MEAN, PASCAL_STD, None, plain_cv2=True)
+    assert torch.equal(o_img.cpu(), p_img) and torch.equal(o_lab.cpu(), p_lab)       # bit-exact vs OpenCV's portable resampler
+    with pytest.raises(ValueError):
+        cwt.resize_pad_normalize(torch.zeros(4, 4, 3, dtype=torch.float64, device=cuda_device), None, 16, PASCAL_MEAN, PASCAL_STD)

@@ -20,7 +20,7 @@ def _checksum(ep):
     return h.hexdigest()
 
 
-EVAL_CASES = [n for n in golden_names() if not n.startswith(("train_", "inner_", "coscls_", "incrmc_"))]
+EVAL_CASES = [n for n in golden_names() if not n.startswith(("train_", "inner_", "coscls_", "incrmc_", "transform_"))]
 FAST = [n for n in EVAL_CASES if n.startswith("small")] + ["full_1shot_h1_yaml"]
 
 
@@ -184,3 +184,23 @@ def test_oracle_increment_inner_loop_multiclass_reproduces_reference_golden(name
     w = O.increment_inner_loop_ref(ep.f_s, lab, O.multiclass_w0(case["idx"], case["K"], case["C"]), case["lr"],
                                    case["n_iter"], case["fg_idx"], case["tp"])
     assert rel_err(w, g["W_fit"]) < 1e-6
+
+
+PASCAL_MEAN, PASCAL_STD = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+
+
+@pytest.mark.parametrize("name", golden_names("transform_"))
+def test_oracle_val_transform_reproduces_reference_golden(name):
+    """Resize -> ToTensor -> Normalize (src/dataset/transform.py:58-163 as composed in dataset.py:78-84): the restatement
+    (cv2 does the resampling, as in the reference) against tensors recorded from the reference's own transform classes."""
+    g = load_golden(name)
+    case = g["case"]
+    img, lab = O.synthetic_image(case["idx"], case["h"], case["w"])
+    padding = [v * 255 for v in PASCAL_MEAN] if case["padding"] == "avg" else None
+    o_img, o_lab = O.val_transform_ref(img, lab, case["size"], PASCAL_MEAN, PASCAL_STD, padding)
+    assert float((o_img - torch.from_numpy(g["image"])).abs().max()) <= 2e-6          # same cv2 build: identical in practice
+    assert torch.equal(o_lab, torch.from_numpy(g["label"]).long())
+    from few_shot_seg_cwt_b200.transforms import find_new_hw
+    nh, nw = find_new_hw(case["h"], case["w"], case["size"])
+    assert nh % 8 == 0 and nw % 8 == 0 and max(nh, nw) <= case["size"]
+    assert bool((o_lab[nh:, :] == 255).all()) and bool((o_lab[:, nw:] == 255).all())
