@@ -17,7 +17,6 @@ from typing import Dict, Iterable, List, Optional, Tuple
 import numpy as np
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import _lib as L
 from . import ops

@@ -5,7 +5,7 @@ Each function is also registered as a PyTorch custom op (``torch.ops.cwt_b200.*`
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Optional
 
 import torch
 

@@ -20,7 +20,7 @@ import time
 import torch
 
 from . import synthetic as syn
-from .episodic import HostPipeline, IoUTable
+from .episodic import HostPipeline
 
 
 class _Episodes(torch.utils.data.Dataset):
