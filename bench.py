@@ -223,12 +223,14 @@ def main():
     table = cwt.IoUTable(5, dev)
     torch.cuda.synchronize()
 
+    # cwt.HeadPipeline: the fit of step i+1 is queued on the main stream while the post stage of step i (transformer,
+    # fused logits / IoU, table update and the one collective — an int64 all-reduce of the counts, no-op at world 1) runs on
+    # a side stream; every step's work completes inside the timed region (finish() before the closing event)
+    head = cwt.HeadPipeline(dev, params, a.heads, a.cls_lr, a.adapt_iter, fit_algo=a.fit_algo, attn_algo=a.attn_algo,
+                            table=table, reduce_every_step=True)
+
     def step_resident():
-        out = cwt.episode_head(devb.f_s, devb.s_label, devb.f_q, devb.q_label, devb.w0, params, a.heads, a.cls_lr,
-                               a.adapt_iter, fit_algo=a.fit_algo, attn_algo=a.attn_algo)
-        table.update(out.counts, devb.subcls, out.ce)
-        table.all_reduce()                      # the one collective (int64 counts), no-op at world 1
-        return out
+        return head.submit(devb.f_s, devb.s_label, devb.f_q, devb.q_label, devb.w0, devb.subcls)
 
     def barrier():
         if world > 1:
@@ -248,6 +250,7 @@ def main():
         sampler.start()
     for _ in range(a.warmup):
         step_resident()
+    head.finish()
     barrier()
     n0 = L.launch_count()
     t_wall0 = time.time()
@@ -255,6 +258,7 @@ def main():
     ev0.record()
     for _ in range(a.steps):
         step_resident()
+    head.finish()
     ev1.record()
     barrier()
     ms = max_over_ranks(ev0.elapsed_time(ev1))
@@ -354,6 +358,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "episodes_per_gpu_per_step": E, "global_episodes_per_step": E * world,
                        "parallelism": f"episodes sharded over {world} GPU(s), int64 IoU all-reduce",
+                       "pipelining": "post stage of step i (transformer, logits/IoU, all-reduce) on a side stream under the fit of step i+1",
                        "l2_policy": f"inputs larger than L2 ({host.nbytes() / 1e6:.0f} MB per step per GPU, streamed every SGD step)",
                        "fit_algo": a.fit_algo, "attn_algo": a.attn_algo},
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,

@@ -17,7 +17,7 @@ tensor raises (there is no CPU fallback).
 from . import _lib, synthetic  # noqa: F401
 from .transforms import ValTransform, find_new_hw, resize_pad_normalize  # noqa: F401
 from .classifier import CosCls, draw_initial_weights, get_classifier, increment_inner_loop, inner_loop  # noqa: F401
-from .episodic import (HeadOutput, HostPipeline, IoUTable, bind_host_to_gpu, do_epoch, episode_head, meta_train_step, query_loss, run_sweep,  # noqa: F401
+from .episodic import (HeadOutput, HeadPipeline, HostPipeline, IoUTable, bind_host_to_gpu, do_epoch, episode_head, meta_train_step, query_loss, run_sweep,  # noqa: F401
                        transformer_params, validate_transformer)
 from .metrics import (batch_intersection_union_int, batch_intersectionAndUnionGPU,  # noqa: F401
                       intersection_union_int, intersectionAndUnionGPU)
@@ -29,7 +29,7 @@ from .transformer import MultiHeadAttentionOne  # noqa: F401
 __all__ = [
     "MultiHeadAttentionOne", "fit_classifier", "fit_classifier_bias", "fit_classifier_dice", "fit_coscls", "fit_multiclass", "ValTransform", "find_new_hw", "resize_pad_normalize", "inner_loop", "increment_inner_loop", "get_classifier", "CosCls", "draw_initial_weights",
     "batch_intersectionAndUnionGPU", "intersectionAndUnionGPU", "batch_intersection_union_int",
-    "intersection_union_int", "validate_transformer", "episode_head", "run_sweep", "IoUTable", "HostPipeline", "bind_host_to_gpu",
+    "intersection_union_int", "validate_transformer", "episode_head", "run_sweep", "IoUTable", "HostPipeline", "HeadPipeline", "bind_host_to_gpu",
     "meta_train_step", "do_epoch", "query_loss", "transformer_forward", "transformer_backward", "logits_iou",
     "upsample_argmax_iou", "intersection_union", "label_counts", "query_loss_grad",
     "rows_times_feat", "feat_times_rows", "synthetic",

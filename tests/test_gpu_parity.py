@@ -752,6 +752,28 @@ def test_host_pipeline_slots_and_sub_batches(cuda_device):
     assert torch.equal(direct.counts.cpu(), outs[0][0])
 
 
+def test_head_pipeline_equals_episode_head(cuda_device):
+    """HeadPipeline (post stage of batch i on a side stream under the fit of batch i+1) gives exactly the results of the
+    serial episode_head, batch by batch, and the same IoU table."""
+    params = dev_params(syn.make_transformer_params(2, 64), cuda_device)
+    batches = [syn.make_batch(list(range(60 + 5 * k, 65 + 5 * k)), **SMALL).to(cuda_device) for k in range(4)]
+    t_ser, t_pipe = cwt.IoUTable(5, cuda_device), cwt.IoUTable(5, cuda_device)
+    ser = []
+    for b in batches:
+        o = cwt.episode_head(b.f_s, b.s_label, b.f_q, b.q_label, b.w0, params, 2, 0.1, 40)
+        t_ser.update(o.counts, b.subcls, o.ce)
+        ser.append(o)
+    pipe = cwt.HeadPipeline(cuda_device, params, 2, 0.1, 40, table=t_pipe)
+    outs = [pipe.submit(b.f_s, b.s_label, b.f_q, b.q_label, b.w0, b.subcls) for b in batches]
+    pipe.finish()
+    torch.cuda.synchronize()
+    for o, (p, done) in zip(ser, outs):
+        assert done.query()
+        assert torch.equal(o.counts, p.counts) and torch.equal(o.w_fit, p.w_fit) and torch.equal(o.w_adapted, p.w_adapted)
+        assert torch.equal(o.ce, p.ce)
+    assert torch.equal(t_ser.cls, t_pipe.cls) and torch.equal(t_ser.fb, t_pipe.fb) and int(t_pipe.n_episodes) == 20
+
+
 def test_torch_custom_ops_registered(cuda_device):
     cwt.register_torch_ops()
     ep = syn.make_batch([40], **SMALL).to(cuda_device)
