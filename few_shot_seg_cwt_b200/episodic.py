@@ -479,6 +479,9 @@ class HostPipeline:
         # (A ramp — quarter sub-batches at the very start and end of a run — was measured too: 18.79 ms, no gain: a head can
         # only start when everything before it has been copied, so the exposed time is one steady-state sub-batch copy
         # whatever the first pieces are.)
+        # Re-measured with HeadPipeline (post stage hidden under the next fit), e2e episodes/s at 10 steps of 64 episodes:
+        # sub-batches of 32: 3 453 / 3 462; of 16: 3 407; of 8: 3 541, 3 541 and once 2 696 (23.7 ms per step — not
+        # investigated: no GPU time left in the round); of 4: 3 477. The default stays 32 (stable).
         # Device-resident staging slots are reused for the whole run: no allocator traffic (a cudaMalloc of ~1 GB
         # synchronises the device). Three slots: the copy of sub-batch i+2 may start as soon as the copy of i+1 has
         # finished (its slot was released by head i-1 long ago), so the copy engine never waits for the head.
