@@ -204,3 +204,32 @@ def test_oracle_val_transform_reproduces_reference_golden(name):
     nh, nw = find_new_hw(case["h"], case["w"], case["size"])
     assert nh % 8 == 0 and nw % 8 == 0 and max(nh, nw) <= case["size"]
     assert bool((o_lab[nh:, :] == 255).all()) and bool((o_lab[:, nw:] == 255).all())
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_iou_counts_are_additive_and_consistent(seed):
+    """Size-independent properties of src/util.py:279-308 that the full-size GPU checks rely on:
+    the counts of a pixel set are the sum of the counts of any split of it, I <= min(pred area,
+    T), U = pred area + T - I, ignored pixels count nowhere, and a relabelling of the ignored
+    pixels' predictions changes nothing."""
+    g = torch.Generator().manual_seed(seed)
+    n = 473 * 7
+    preds = torch.randint(0, 2, (n,), generator=g)
+    target = torch.randint(0, 2, (n,), generator=g)
+    target[torch.rand(n, generator=g) < 0.1] = O.IGNORE
+    before = preds.clone()
+    I, U, T = O.intersection_and_union_ref(preds, target, 2)
+    assert torch.equal(preds, before)                                    # the oracle leaves its input alone
+    cut = int(torch.randint(1, n - 1, (1,), generator=g))
+    Ia, Ua, Ta = O.intersection_and_union_ref(preds[:cut], target[:cut], 2)
+    Ib, Ub, Tb = O.intersection_and_union_ref(preds[cut:], target[cut:], 2)
+    assert torch.equal(I, Ia + Ib) and torch.equal(U, Ua + Ub) and torch.equal(T, Ta + Tb)
+    valid = target != O.IGNORE
+    area = torch.stack([(preds[valid] == c).sum() for c in range(2)]).float()
+    assert torch.equal(U, area + T - I)
+    assert bool((I <= torch.minimum(area, T)).all())
+    assert float(T.sum()) == float(valid.sum())
+    flipped = preds.clone()
+    flipped[~valid] = 1 - flipped[~valid]
+    I2, U2, T2 = O.intersection_and_union_ref(flipped, target, 2)
+    assert torch.equal(I, I2) and torch.equal(U, U2) and torch.equal(T, T2)
