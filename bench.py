@@ -49,7 +49,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-sub-batch", type=int, default=32, help="HostPipeline sub-batch size (0 = whole batches)")
-    ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic episodes generated per rank (tiled to E)")
+    ap.add_argument("--distinct", type=int, default=64, help="distinct synthetic episodes generated per rank (tiled to E)")
+    ap.add_argument("--attn-both", action="store_true", help="also time the tcgen05 K-projection path of the transformer block "
+                                                             "(reported under roofline.transformer_tcgen05; used by the ncu capture)")
     return ap.parse_args()
 
 
@@ -106,6 +108,21 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def load_kernel_counters():
+    """Latest profiles/*_kernel_counters.json (written by tools/ncu_counters_to_json.py from an ncu capture of this very
+    command) -> (dict, file name, whether its build fingerprint equals the build that is running)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_kernel_counters.json")))
+    if not files:
+        return None, None, False
+    try:
+        d = json.load(open(files[-1]))
+        from few_shot_seg_cwt_b200 import build as B
+        return d, os.path.relpath(files[-1], ROOT), d.get("build_fingerprint") == B.fingerprint()
+    except Exception:
+        return None, None, False
+
+
 def use_all_host_threads() -> int:
     """torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every core this process may run on."""
     try:
@@ -116,34 +133,51 @@ def use_all_host_threads() -> int:
     return torch.get_num_threads()
 
 
-def cpu_reference_rate(a, n_episodes: int, warm: int = 1):
-    """The reference algorithm (oracle port, torch CPU, all host threads) on the same workload."""
-    use_all_host_threads()
+def cpu_episode_runner(a):
+    """The reference head for one episode on the host CPU -> (callable(ep) -> outputs, kind, description).
+    kind "reference": the episode body of src/test.py:162-234 around the reference's OWN MultiHeadAttentionOne and
+    batch_intersectionAndUnionGPU (oracle/_ref, the verbatim copy made by oracle/make_ref.py — it travels to the GPU box);
+    kind "port": the line-by-line restatement oracle/head_ref.episode_ref, when oracle/_ref has not been made."""
     from few_shot_seg_cwt_b200 import synthetic as syn
     from oracle import head_ref as O
+    from oracle import ref_episode as R
     params = syn.make_transformer_params(a.heads, 512)
-    eps = [syn.make_episode(i, shot=a.shot, style=a.style, **GEOM) for i in range(warm + n_episodes)]
-    for ep in eps[:warm]:
-        O.episode_ref(ep.f_s, ep.s_label, ep.f_q, ep.q_label, ep.w0, params, a.heads, a.cls_lr, a.adapt_iter)
+    mods = R.load_reference_modules(prefer_live=False)          # never reads /root/reference at run time
+    if mods is not None:
+        MHA, batch_iou = mods[0], mods[1]
+        return (lambda ep: R.episode_via_reference(ep, params, a.heads, a.cls_lr, a.adapt_iter, MHA, batch_iou), "reference",
+                "src/test.py:162-234 episode body with the reference's own src/model/transformer.py + src/util.py (oracle/_ref)")
+    return (lambda ep: O.episode_ref(ep.f_s, ep.s_label, ep.f_q, ep.q_label, ep.w0, params, a.heads, a.cls_lr, a.adapt_iter), "port",
+            "oracle/head_ref.episode_ref (restatement of src/test.py:162-234)")
+
+
+def cpu_reference_rate(a, n_episodes: int, warm: int = 1, first_index: int = 0):
+    """The reference head on the host CPU (all host threads) on the same workload: episodes ``first_index ...`` of the
+    synthetic generator, i.e. the very episodes of the GPU batch. Returns (episodes/s, seconds, the outputs of the first
+    episode — what `parity_check` compares the GPU result with —, kind, description)."""
+    use_all_host_threads()
+    from few_shot_seg_cwt_b200 import synthetic as syn
+    run, kind, desc = cpu_episode_runner(a)
+    eps = [syn.make_episode(first_index + i, shot=a.shot, style=a.style, **GEOM) for i in range(warm + n_episodes)]
+    outs = [run(ep) for ep in eps[:warm]]
     t0 = time.perf_counter()
     for ep in eps[warm:]:
-        O.episode_ref(ep.f_s, ep.s_label, ep.f_q, ep.q_label, ep.w0, params, a.heads, a.cls_lr, a.adapt_iter)
+        outs.append(run(ep))
     dt = time.perf_counter() - t0
-    return n_episodes / dt, dt
+    return n_episodes / dt, dt, outs[0], kind, desc
 
 
 def run_reference(a, rank):
-    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference is pure
-    Python and cannot travel to the GPU box). Rank 0 only."""
+    """--impl reference: the reference's CPU implementation of the path on the box's host cores (the reference's own
+    modules from oracle/_ref when present, else the oracle port). Rank 0 only."""
     if rank != 0:
         return
     per_step = max(1, a.ref_episodes)
     use_all_host_threads()
     from few_shot_seg_cwt_b200 import synthetic as syn
-    from oracle import head_ref as O
-    params = syn.make_transformer_params(a.heads, 512)
+    run_ep, kind, desc = cpu_episode_runner(a)
     eps = [syn.make_episode(i, shot=a.shot, style=a.style, **GEOM) for i in range(per_step)]
-    run = lambda: [O.episode_ref(ep.f_s, ep.s_label, ep.f_q, ep.q_label, ep.w0, params, a.heads, a.cls_lr, a.adapt_iter) for ep in eps]
+    run = lambda: [run_ep(ep) for ep in eps]
     for _ in range(a.warmup):
         run()
     t0 = time.perf_counter()
@@ -157,9 +191,8 @@ def run_reference(a, rank):
         "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "episodes_per_step": per_step},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{per_step} episodes/step x {a.steps} steps, torch {torch.__version__} CPU fp32, "
-                                   f"oracle/head_ref.episode_ref (restatement of src/test.py:162-234)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{per_step} episodes/step x {a.steps} steps, torch {torch.__version__} CPU fp32, {desc}"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -257,7 +290,7 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(a.steps):
-        step_resident()
+        last_out, _ = step_resident()
     head.finish()
     ev1.record()
     barrier()
@@ -287,7 +320,8 @@ def main():
     wts = torch.stack([w_ad, w_fit], 1)
     iou_ms, _ = timed(lambda: cwt.logits_iou(wts, devb.f_q, devb.q_label, 0b01, return_logits=False))
     label_bytes = devb.s_label.element_size()
-    bytes_fit = E * ((2 * a.adapt_iter + 1) * a.shot * F_bytes + a.shot * P * label_bytes + 2 * (2 * 512 * 4))
+    T, S = a.adapt_iter, a.shot
+    bytes_fit = E * ((2 * T + 1) * S * F_bytes + S * P * label_bytes + 2 * (2 * 512 * 4))     # (2T+1) S F per episode
     bytes_iou = E * (F_bytes + P * label_bytes + 2 * 6 * 8)
     # bytes_transformer(E) = E*F + nH*(2*C*C*4) + E*(2*2*C*4)  (f_q once; the re-associated path reads it twice)
     bytes_tr = E * F_bytes + a.heads * (2 * 512 * 512 * 4) + E * (2 * 2 * 512 * 4)
@@ -299,30 +333,68 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     fit_gbs = bytes_fit / (fit_ms / 1e3) / 1e9
-    resident = (a.fit_algo != 1 and a.shot == 1)
-    # measured DRAM traffic of the dominant kernel per launch at E=64 (ncu --set full, profiles/r1_resident_E64_ncu.txt: dram__bytes_read + dram__bytes_write)
-    traffic = {True: 483.4e6, False: None}[resident and E == 64]
+    resident = (a.fit_algo != 1 and S == 1)
     sm_clk = (clocks or {}).get("sm_mhz") or 1965.0
-    steps_per_group = a.adapt_iter * ((E + 3) // 4)
-    smem_B_per_clk = (2 * 512 * 100 * 4) / (fit_ms * 1e-3 * sm_clk * 1e6 / max(steps_per_group, 1)) if resident else None
-    roofline = {
-        "kernel": ("k_fit_resident<512 compute threads, 1 CTA/SM, C=512, tile 20x5 of 60x60> (one cooperative launch: features "
-                   "staged once into shared memory by bulk-TMA, 200 SGD steps on chip, all-reduce through 64-bit L2 atomics)")
-                  if resident else
-                  "fit_classifier streaming: 200 x {rows_times_feat<1>, fit_hires, feat_times_cols<1>+SGD}",
-        "bound": "hbm", "achieved": fit_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": fit_gbs / hbm_peak,
-        "traffic": traffic, "peak_source": peak_src,
-        "note": ("achieved = ALGORITHMIC bytes (2T+1)*S*F per episode / time; > 1 x HBM peak because the resident kernel "
-                 "reads the features from HBM once (see traffic) and sweeps them 2T times from shared memory") if resident else
-                "achieved = algorithmic bytes (2T+1)*S*F per episode / time, features streamed from HBM every step",
+    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    counters, counters_file, counters_match = load_kernel_counters()
+    fit_kernel = "k_fit_resident" if resident else ("k_fit_l2" if a.fit_algo != 1 else None)
+    kc = (counters or {}).get("kernels", {}).get(fit_kernel or "", None)
+    # DRAM traffic of the dominant kernel per launch: ncu dram__bytes_read + dram__bytes_write of the SAME command
+    # (tools/ncu_bench_kernels.sh -> profiles/*_kernel_counters.json, with the fingerprint of the build it was taken on)
+    traffic = (kc["dram_bytes_read"] + kc["dram_bytes_write"]) if (kc and E == 64) else None
+    traffic_src = ({"file": counters_file, "build_fingerprint": counters["build_fingerprint"], "matches_this_build": counters_match}
+                   if traffic is not None else None)
+    if resident:
+        # On-chip roof: every SGD step sweeps the staged tile twice out of shared memory (P1 and P3): algorithmic
+        # shared-memory bytes = E * 2T * F; peak = 128 B/clk/SM x all SMs x the SM clock sampled in the timed region.
+        smem_bytes = E * 2 * T * S * F_bytes
+        smem_gbs = smem_bytes / (fit_ms / 1e3) / 1e9
+        smem_peak = 128.0 * n_sm * sm_clk * 1e6 / 1e9
+        steps_per_group = T * ((E + 3) // 4)
+        roofline = {
+            "kernel": ("k_fit_resident<512 compute threads, 1 CTA/SM, C=512, tile 20x5 of 60x60> (one cooperative launch: features "
+                       "staged once into shared memory by bulk-TMA, 200 SGD steps on chip, all-reduce through 64-bit L2 atomics)"),
+            "bound": "smem", "achieved": smem_gbs, "peak": smem_peak, "unit": "GB/s", "frac": smem_gbs / smem_peak,
+            "traffic": traffic, "traffic_source": traffic_src,
+            "peak_source": f"128 B/clk/SM x {n_sm} SMs x {sm_clk:.0f} MHz (SM clock sampled during the timed region)",
+            "note": ("the step is two shared-memory sweeps of the resident tile; achieved = E*2T*F algorithmic shared-memory bytes / "
+                     "CUDA-event time of the fit call; the kernel occupies 144 of the SMs (4 groups x 36 CTAs)"),
+            "clk_per_step": fit_ms * 1e-3 * sm_clk * 1e6 / max(steps_per_group, 1),
+            "B_per_clk_per_active_SM": (2 * 512 * 100 * 4) / (fit_ms * 1e-3 * sm_clk * 1e6 / max(steps_per_group, 1)),
+            "hbm_equivalent": {"achieved": fit_gbs, "peak": hbm_peak, "unit": "GB/s", "x_of_hbm_peak": fit_gbs / hbm_peak,
+                               "peak_source": peak_src,
+                               "note": "SURVEY §8d's (2T+1)*S*F bytes per episode / time: what an HBM-streamed fit would have to move — "
+                                       "above 1 x the HBM peak by construction, because the bytes come from shared memory"},
+            "dram_frac": (traffic / (fit_ms / 1e3) / 1e9 / hbm_peak) if traffic else None,
+            "compulsory_dram_bytes": E * S * F_bytes,
+        }
+    else:
+        roofline = {
+            "kernel": ("k_fit_l2 (persistent cooperative kernel, features L2-resident across the SGD steps)" if fit_kernel == "k_fit_l2"
+                       else "fit_classifier streaming: 200 x {rows_times_feat<1>, fit_hires, feat_times_cols<1>+SGD}"),
+            "bound": "hbm", "achieved": fit_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": fit_gbs / hbm_peak,
+            "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+            "note": "achieved = algorithmic bytes (2T+1)*S*F per episode / CUDA-event time of the fit call (SURVEY §8d)",
+        }
+    roofline.update({
         "algorithmic_bytes_per_call": bytes_fit, "ms_per_call": fit_ms,
-        "smem_sweep": ({"achieved_B_per_clk_per_SM": smem_B_per_clk, "peak": 128.0, "frac": smem_B_per_clk / 128.0}
-                       if resident else None),
         "stages_ms": {"fit": fit_ms, "transformer": tr_ms, "logits_iou": iou_ms},
-        "logits_iou": {"achieved": bytes_iou / (iou_ms / 1e3) / 1e9, "frac": bytes_iou / (iou_ms / 1e3) / 1e9 / hbm_peak},
-        "transformer": {"achieved": bytes_tr / (tr_ms / 1e3) / 1e9, "frac": bytes_tr / (tr_ms / 1e3) / 1e9 / hbm_peak,
+        "logits_iou": {"bound": "hbm", "achieved": bytes_iou / (iou_ms / 1e3) / 1e9, "frac": bytes_iou / (iou_ms / 1e3) / 1e9 / hbm_peak},
+        "transformer": {"bound": "hbm", "achieved": bytes_tr / (tr_ms / 1e3) / 1e9, "frac": bytes_tr / (tr_ms / 1e3) / 1e9 / hbm_peak,
                         "note": "algorithmic bytes count f_q once; the re-associated attention needs two passes over it"},
-    }
+    })
+    if a.attn_both:
+        tc_ms, w_tc = timed(lambda: cwt.transformer_forward(w_fit, devb.f_q, params["w_qkvs.weight"], params["fc.weight"],
+                                                            params["fc.bias"], params["layer_norm.weight"],
+                                                            params["layer_norm.bias"], a.heads, normalize_k=True, algo=1))
+        flops = E * a.heads * 2.0 * 3600 * 512 * 512 * 3                  # 3 bf16 products (hi.hi + hi.lo + lo.hi) per fp32 product
+        tpeak = float(peaks.get("bf16_tflops", 1590.0))
+        roofline["transformer_tcgen05"] = {
+            "bound": "tensor", "ms_per_call": tc_ms, "achieved": flops / (tc_ms / 1e3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
+            "frac": flops / (tc_ms / 1e3) / 1e12 / tpeak,
+            "max_rel_diff_vs_reassoc": float((w_tc - w_ad).norm() / w_ad.norm()),
+            "note": "whole block with the K projection as a tcgen05 GEMM (3 x bf16 split); flops = E*nH*2*HW*C*C*3 over the time of "
+                    "the WHOLE block (pre-pass, GEMM, softmax, V side, fc, LayerNorm); the re-associated path (default) needs 127x fewer flops"}
 
     # ---- end to end through the public API with host buffers ("e2e") ----
     # few_shot_seg_cwt_b200.HostPipeline: every step copies its inputs from pinned host memory (side stream, overlapping
@@ -331,25 +403,42 @@ def main():
     if not a.no_e2e:
         pipe = cwt.HostPipeline(dev, params, a.heads, a.cls_lr, a.adapt_iter, fit_algo=a.fit_algo, attn_algo=a.attn_algo,
                                 sub_batch=a.e2e_sub_batch, sub_batch_all=True)
-        pipe.run([host] * max(1, a.warmup))
+        pipe.run([host] * max(1, a.warmup), reduce_every_step=True)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        res = pipe.run([host] * a.steps)
+        res = pipe.run([host] * a.steps, reduce_every_step=True)
         e1.record()
         barrier()
         ms_e = max_over_ranks(e0.elapsed_time(e1))
         e2e = {"value": world * E * a.steps / (ms_e / 1e3), "unit": UNIT, "h2d_bytes_per_step": host.nbytes() + host.subcls.numel() * 8,
-               "d2h_bytes_per_step": res[0].numel() * res[0].element_size(), "ms_per_step": ms_e / a.steps,
-               "api": "few_shot_seg_cwt_b200.HostPipeline.run (H2D in sub-batches of %d episodes through three device slots, async D2H of the counts)" % a.e2e_sub_batch}
+               "d2h_bytes_per_step": res[0].numel() * res[0].element_size() + 4 * E, "ms_per_step": ms_e / a.steps,
+               "api": "few_shot_seg_cwt_b200.HostPipeline.run (H2D in sub-batches of %d episodes through three device slots, async D2H of the counts and the fit status words)" % a.e2e_sub_batch,
+               "counts_equal_device_resident_run": bool(torch.equal(res[0].to(dev), last_out.counts))}
 
     # ---- CPU baseline on the box's host cores (rank 0, N = 1 only) ----
     cpu = None
+    parity = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        rate, dt = cpu_reference_rate(a, a.cpu_baseline_episodes)
-        cpu = {"value": rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+        # the CPU leg runs the oracle on the first episodes of THIS rank's batch (outside every timed region); its result for
+        # episode 0 doubles as the parity check of the numbers above
+        rate, dt, ora, kind, desc = cpu_reference_rate(a, a.cpu_baseline_episodes, warm=1, first_index=int(host.idx[0]))
+        cpu = {"value": rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
                "sample": f"{a.cpu_baseline_episodes} episodes of the same workload after 1 warm-up ({dt:.1f} s), "
-                         f"oracle/head_ref.episode_ref, torch {torch.__version__} CPU fp32"}
+                         f"{desc}, torch {torch.__version__} CPU fp32"}
+        got = last_out.counts[0].cpu()
+        rel = lambda x, y: float((x.double().cpu() - y.double()).norm() / y.double().norm())
+        scale = max(1.0, float(ora["logits60"].abs().max()))
+        tie = int((ora["tie_margin"] <= 1e-5 * scale).sum())
+        tie0 = int((ora["tie_margin0"] <= 1e-5 * max(1.0, float(ora["logits60_0"].abs().max()))).sum())
+        d_ad = int((got[0] - ora["counts"]).abs().max())
+        d_bl = int((got[1] - ora["counts0"]).abs().max())
+        parity = {"episode": int(host.idx[0]), "w_fit_rel_err": rel(last_out.w_fit[0], ora["W_fit"]),
+                  "w_adapted_rel_err": rel(last_out.w_adapted[0], ora["W_adapted"]),
+                  "counts_max_abs_diff": {"adapted": d_ad, "baseline": d_bl}, "tie_set_pixels": {"adapted": tie, "baseline": tie0},
+                  "ok": bool(rel(last_out.w_fit[0], ora["W_fit"]) < 1e-4 and rel(last_out.w_adapted[0], ora["W_adapted"]) < 1e-4
+                             and d_ad <= tie and d_bl <= tie0),
+                  "against": f"{desc} on the same synthetic episode (checked outside the timed regions)"}
 
     if rank == 0:
         emit(json.dumps({
@@ -360,9 +449,12 @@ def main():
                        "parallelism": f"episodes sharded over {world} GPU(s), int64 IoU all-reduce",
                        "pipelining": "post stage of step i (transformer, logits/IoU, all-reduce) on a side stream under the fit of step i+1",
                        "l2_policy": f"inputs larger than L2 ({host.nbytes() / 1e6:.0f} MB per step per GPU, streamed every SGD step)",
-                       "fit_algo": a.fit_algo, "attn_algo": a.attn_algo},
+                       "distinct_episodes_per_gpu": nd,
+                       "fit_algo": a.fit_algo,
+                       "attn_algo": f"{a.attn_algo} ({'re-associated scores on CUDA cores (default: 127x fewer flops)' if a.attn_algo == 0 else 'K projection as a tcgen05/TMEM GEMM'})"},
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-            "miou_adapted": table.miou(0), "miou_baseline": table.miou(1),
+            "parity_check": parity, "miou_adapted": table.miou(0), "miou_baseline": table.miou(1),
+            "bad_episodes": int(table.n_bad),
         }))
     if world > 1:
         dist.destroy_process_group()

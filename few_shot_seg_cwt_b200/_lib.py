@@ -11,7 +11,8 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcwt_b200.so")
+# CWT_LIB_PATH: developer hook (tools/build_variants.py) to time an alternative build of the same C ABI
+LIB_PATH = os.environ.get("CWT_LIB_PATH") or os.path.join(_HERE, "lib", "libcwt_b200.so")
 
 OK = 0
 LABEL_U8, LABEL_I64 = 0, 1
@@ -28,11 +29,10 @@ SIGNATURES = {
     "cwt_version": (_i, []),
     "cwt_last_error": (C.c_char_p, []),
     "cwt_launch_count": (_ll, []),
-    "cwt_debug_set_prof_buffer": (None, [_vp]),
-    "cwt_debug_l2_read": (_i, [_vp, _sz, _i, _i, _vp, _vp]),
     "cwt_prep_labels": (_i, [_vp, _i, _i, _ll, _i, _vp, _vp, _vp]),
     "cwt_fit_workspace_bytes": (_sz, [_i] * 7),
     "cwt_fit_classifier_f32": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp] + [_i] * 8 + [_f, _i, _i, _vp, _sz, _vp]),
+    "cwt_fit_status": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp]),
     "cwt_fit_bias_workspace_bytes": (_sz, [_i] * 7),
     "cwt_fit_classifier_bias_f32": (_i, [_vp, _vp, _i] + [_vp] * 7 + [_i] * 8 + [_f, _f, _i, _vp, _sz, _vp]),
     "cwt_fit_coscls_workspace_bytes": (_sz, [_i] * 7),
@@ -59,6 +59,14 @@ SIGNATURES = {
 }
 
 
+# developer-only entry points declared in include/cwt_b200_debug.h (tools/ only; never on the product path)
+DEBUG_SIGNATURES = {
+    "cwt_debug_fit_classifier_prof_f32": (_i, [_vp, _vp, _i, _vp, _vp, _vp] + [_i] * 7 + [_f, _i, _vp, _sz, _vp, _vp]),
+    "cwt_debug_l2_read": (_i, [_vp, _sz, _i, _i, _vp, _vp]),
+}
+FIT_BAD_LABEL, FIT_NO_FG, FIT_NONFINITE = 1, 2, 4      # bits of cwt_fit_status
+
+
 def load() -> C.CDLL:
     """Load the shared object (built in-tree by ``python -m few_shot_seg_cwt_b200.build``)."""
     global _lib
@@ -69,7 +77,7 @@ def load() -> C.CDLL:
             f"{LIB_PATH} is missing: the CUDA extension has not been built "
             "(run `python -m few_shot_seg_cwt_b200.build`). There is no CPU fallback.")
     lib = C.CDLL(LIB_PATH)
-    for name, (res, args) in SIGNATURES.items():
+    for name, (res, args) in list(SIGNATURES.items()) + list(DEBUG_SIGNATURES.items()):
         fn = getattr(lib, name)        # AttributeError if the .so does not export it
         fn.restype = res
         fn.argtypes = args

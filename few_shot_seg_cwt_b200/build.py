@@ -65,5 +65,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def fingerprint() -> str:
+    """sha256 over every CUDA source, header and the compiler flags: names the build a profile was taken on."""
+    return _fingerprint()
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--fingerprint" in sys.argv:
+        print(_fingerprint())
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

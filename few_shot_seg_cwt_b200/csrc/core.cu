@@ -1,6 +1,6 @@
 // Error reporting, launch bookkeeping, version.
 #include "common.cuh"
-#include <atomic>
+#include "../../include/cwt_b200_debug.h"
 #include <cstdarg>
 #include <cstdio>
 
@@ -9,7 +9,7 @@ namespace cwt {
 void count_launch(int n);
 int check_cuda(cudaError_t e, const char* what);
 static thread_local char g_err[512] = "";
-static std::atomic<long long> g_launches{0};
+static thread_local long long g_launches = 0;     // per calling thread, like the error string
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -18,7 +18,7 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
-void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+void count_launch(int n) { g_launches += n; }
 
 int check_cuda(cudaError_t e, const char* what) {
     if (e == cudaSuccess) return CWT_OK;
@@ -53,4 +53,4 @@ extern "C" int cwt_debug_l2_read(const void* buf, size_t bytes, int iters, int c
 
 extern "C" int cwt_version(void) { return 100; }
 extern "C" const char* cwt_last_error(void) { return cwt::g_err; }
-extern "C" long long cwt_launch_count(void) { return cwt::g_launches.load(std::memory_order_relaxed); }
+extern "C" long long cwt_launch_count(void) { return cwt::g_launches; }

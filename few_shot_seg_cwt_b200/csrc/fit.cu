@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "skinny.cuh"
 #include "hires.cuh"
+#include "../../include/cwt_b200_debug.h"
 
 namespace cwt {
 
@@ -23,7 +24,6 @@ int pack_label_cells(const void* labels, int label_kind, int n_img, int h, int w
 size_t fit_resident_workspace_bytes(int E, int C, int h, int w);
 int fit_resident(const float* f_s, const uint4* cells, const float2* cw, float* w_io, int E, int C, int h, int w,
                  int n_iter, float lr, void* ws, size_t ws_bytes, long long* prof_out, cudaStream_t st);
-static long long* g_prof_buffer = nullptr;   // debug: per-CTA phase cycle counters of the resident kernel
 
 // one CTA per episode: W <- W0, Wd = W1 - W0
 __global__ void __launch_bounds__(256)
@@ -81,12 +81,12 @@ extern "C" size_t cwt_fit_workspace_bytes(int E, int S, int C, int h, int w, int
     return carve_fit(cv, ws, E, S, C, h, w, H, W);
 }
 
-extern "C" int cwt_fit_classifier_f32(const float* f_s, const void* s_label, int label_kind, const float* w0,
-                                      const float* class_weight_or_null, float* w_out,
-                                      float* loss_trace_or_null, int32_t* label_counts_or_null,
-                                      int E, int S, int C, int h, int w, int H, int W,
-                                      int n_iter, float lr, int ignore_index, int algo,
-                                      void* workspace, size_t ws_bytes, void* stream) {
+static int fit_classifier_impl(const float* f_s, const void* s_label, int label_kind, const float* w0,
+                               const float* class_weight_or_null, float* w_out,
+                               float* loss_trace_or_null, int32_t* label_counts_or_null,
+                               int E, int S, int C, int h, int w, int H, int W,
+                               int n_iter, float lr, int ignore_index, int algo,
+                               void* workspace, size_t ws_bytes, long long* prof_out, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CWT_REQUIRE(E >= 0 && S >= 1 && C >= 1 && h >= 1 && w >= 1 && n_iter >= 0, CWT_ERR_INVALID_ARG,
                 "fit: bad sizes E=%d S=%d C=%d h=%d w=%d n_iter=%d", E, S, C, h, w, n_iter);
@@ -117,7 +117,7 @@ extern "C" int cwt_fit_classifier_f32(const float* f_s, const void* s_label, int
     if (algo != CWT_FIT_STREAM && n_iter > 0) {
         if (S == 1 && !loss_trace_or_null && HWl % 4 == 0) {
             rc = fit_resident(f_s, ws.cells, ws.cw, w_out, E, C, h, w, n_iter, lr, ws.resident, ws.resident_bytes,
-                              g_prof_buffer, st);
+                              prof_out, st);
             if (rc == CWT_OK) return CWT_OK;
             if (rc != CWT_ERR_UNSUPPORTED || algo == CWT_FIT_RESIDENT) return rc;
         } else if (algo == CWT_FIT_RESIDENT) {
@@ -142,6 +142,54 @@ extern "C" int cwt_fit_classifier_f32(const float* f_s, const void* s_label, int
         rc = launch_ftc_t<1, 4>(f_s, ws.g60, E, S, C, HWl, 1, epi, st);
         if (rc != CWT_OK) return rc;
     }
+    return CWT_OK;
+}
+
+extern "C" int cwt_fit_classifier_f32(const float* f_s, const void* s_label, int label_kind, const float* w0,
+                                      const float* class_weight_or_null, float* w_out,
+                                      float* loss_trace_or_null, int32_t* label_counts_or_null,
+                                      int E, int S, int C, int h, int w, int H, int W,
+                                      int n_iter, float lr, int ignore_index, int algo,
+                                      void* workspace, size_t ws_bytes, void* stream) {
+    return fit_classifier_impl(f_s, s_label, label_kind, w0, class_weight_or_null, w_out, loss_trace_or_null,
+                               label_counts_or_null, E, S, C, h, w, H, W, n_iter, lr, ignore_index, algo, workspace, ws_bytes,
+                               nullptr, stream);
+}
+
+// developer entry point (include/cwt_b200_debug.h): the same fit on the instrumented resident kernel
+extern "C" int cwt_debug_fit_classifier_prof_f32(const float* f_s, const void* s_label, int label_kind, const float* w0,
+                                                 const float* class_weight_or_null, float* w_out,
+                                                 int E, int C, int h, int w, int H, int W,
+                                                 int n_iter, float lr, int ignore_index,
+                                                 void* workspace, size_t ws_bytes, long long* prof_out, void* stream) {
+    CWT_REQUIRE(prof_out, CWT_ERR_INVALID_ARG, "debug_fit_prof: null profile buffer");
+    return fit_classifier_impl(f_s, s_label, label_kind, w0, class_weight_or_null, w_out, nullptr, nullptr,
+                               E, 1, C, h, w, H, W, n_iter, lr, ignore_index, CWT_FIT_RESIDENT, workspace, ws_bytes,
+                               prof_out, stream);
+}
+
+namespace cwt {
+// one warp per episode: deferred error word of a fit (see cwt_fit_status in include/cwt_b200.h)
+__global__ void __launch_bounds__(128)
+k_fit_status(const int32_t* __restrict__ counts, const float* __restrict__ w, int has_cw, int32_t* __restrict__ status, int E, int C) {
+    const int e = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (e >= E) return;
+    bool bad = false;
+    for (int i = lane; i < 2 * C; i += 32) bad |= (__float_as_uint(w[(size_t)e * 2 * C + i]) & 0x7f800000u) == 0x7f800000u;
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0)
+        status[e] = (counts[e * 4 + 3] > 0 ? CWT_FIT_BAD_LABEL : 0) | ((!has_cw && counts[e * 4 + 1] == 0) ? CWT_FIT_NO_FG : 0) |
+                    (bad ? CWT_FIT_NONFINITE : 0);
+}
+}  // namespace cwt
+
+extern "C" int cwt_fit_status(const int32_t* label_counts, const float* w_fit, int has_class_weight, int32_t* status,
+                              int E, int C, void* stream) {
+    CWT_REQUIRE(E >= 0 && C >= 1, CWT_ERR_INVALID_ARG, "fit_status: bad sizes E=%d C=%d", E, C);
+    if (E == 0) return CWT_OK;
+    CWT_REQUIRE(label_counts && w_fit && status, CWT_ERR_INVALID_ARG, "fit_status: null pointer");
+    k_fit_status<<<(E + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(label_counts, w_fit, has_class_weight, status, E, C);
+    CWT_LAUNCHED("fit_status");
     return CWT_OK;
 }
 
@@ -238,6 +286,3 @@ extern "C" int cwt_fit_classifier_bias_f32(const float* f_s, const void* s_label
     }
     return CWT_OK;
 }
-
-// debug hook: device buffer [grid][8] int64 receiving the resident kernel's per-phase cycle counters
-extern "C" void cwt_debug_set_prof_buffer(void* dev_buffer) { cwt::g_prof_buffer = static_cast<long long*>(dev_buffer); }

@@ -52,6 +52,15 @@
 #include <cstdio>
 #include <cstdlib>
 
+// Developer builds only (tools/build_variants.py): bit mask of ablations / alternative phase implementations that are timed
+// against the product kernel (RES_VARIANT == 0). 0x01 compute warps do not wait for the halo, 0x02 no full-resolution
+// arithmetic, 0x04 compute warps do not wait for the all-reduce, 0x08 no P3 sweep, 0x10 no P1 sweep (0x01..0x10 give wrong
+// results on purpose: they measure what a phase costs), 0x20 P3 with all quads at once, 0x40 P3 with lane = pixel quad,
+// 0x80 one applier warp per channel chunk, 0x100 / 0x200 the applier / halo warps do not poll (wrong results).
+#ifndef RES_VARIANT
+#define RES_VARIANT 0
+#endif
+
 namespace cwt {
 
 // A CTA has CT compute threads + the applier warp + the halo warp. Two configurations are built:
@@ -59,7 +68,18 @@ namespace cwt {
 //   CT = 256, two CTAs per SM  (tile 4 x 10: while one CTA waits for the halo / the all-reduce or runs the ALU-bound
 //                               full-resolution stage, the other one could keep the shared-memory pipe busy — measured
 //                               25.4 ms vs 17 ms at E = 64: the exchange latencies grow with the 90 CTAs per episode)
-constexpr int RES_HELPER_THREADS = 64;
+// helper warps: the applier warp(s) + the halo warp. With one CTA per SM every channel chunk of the all-reduce has its OWN
+// applier warp (RES_VARIANT 0x80): a chunk's words are polled from the moment the step starts, instead of only after the
+// previous chunk has been applied (one L2 round trip per chunk in series).
+// RES_VARIANT 0x400 (PSPNet head geometry only): Wd is kept in shared memory in the order the P1 threads consume it —
+// position(c) = 128 j + 8 grp + u for channel c = grp + 16 (8 j + u) — so that a thread fetches the 8 weights of a chunk with
+// two 128-bit loads instead of eight 32-bit ones (the sweeps are bound by the shared-memory pipe: 40 -> 34 wavefronts per warp
+// and chunk).
+__host__ __device__ constexpr int res_wd_pos(int c, bool permute) {
+    return permute ? ((c >> 7) << 7) + ((c & 15) << 3) + ((c >> 4) & 7) : c;
+}
+constexpr int res_appliers(int CT) { return ((RES_VARIANT & 0x80) && CT == 512) ? 4 : 1; }
+constexpr int res_helper_threads(int CT) { return 32 * (res_appliers(CT) + 1); }
 constexpr unsigned RES_SPIN_LIMIT = 1u << 24;
 constexpr int RES_KCH = 4;        // channel chunks of the pipelined all-reduce
 constexpr int RES_AW = 4;         // accumulator words an applier lane keeps in flight
@@ -226,30 +246,31 @@ __device__ __forceinline__ size_t acc_offset(int e, int group, int G, int SPL, i
 }
 
 struct ResSmem {
-    size_t F, W0, W1, Wd, zt, g, scratch, mbar, cum, total;
+    size_t F, W0, W1, Wd, zt, g, scratch, mbar, cum, poll, total;
 };
 static __host__ __device__ inline ResSmem res_smem_layout(int C, int TW, int TH, int CT) {
     ResSmem s;
     const int NP = TW * TH, NQ = NP / 4, NG = CT / NQ, NCELL = (TW + 1) * (TH + 1);
     size_t o = 0;
-    size_t sz[9];
+    size_t sz[10];
     sz[0] = (size_t)C * NP * 4; sz[1] = sz[2] = sz[3] = (size_t)C * 4;
     sz[4] = (size_t)(TW + 2) * (TH + 2) * 4; sz[5] = (size_t)NP * 4;
     const size_t sc1 = (size_t)NG * NP * 4, sc2 = (size_t)16 * NCELL * 4;
     sz[6] = sc1 > sc2 ? sc1 : sc2;
-    sz[7] = 8 * (2 + RES_KCH) + 16;                                  // mbarriers + two words of the max|F| exchange
+    sz[7] = 8 * (2 + RES_KCH) + 16 + 16;                             // mbarriers + two words of the max|F| exchange + poll mbarrier
     sz[8] = (size_t)C * 16;                                          // previous cumulative dW per channel and step parity (applier warp)
-    size_t off[9];
-    for (int i = 0; i < 9; ++i) { off[i] = o; o = (o + sz[i] + 127) / 128 * 128; }
+    sz[9] = (RES_VARIANT & 0x800) ? 1024 : 0;                        // landing zone of the applier's bulk-copy polls
+    size_t off[10];
+    for (int i = 0; i < 10; ++i) { off[i] = o; o = (o + sz[i] + 127) / 128 * 128; }
     s.F = off[0]; s.W0 = off[1]; s.W1 = off[2]; s.Wd = off[3]; s.zt = off[4]; s.g = off[5];
-    s.scratch = off[6]; s.mbar = off[7]; s.cum = off[8]; s.total = o;
+    s.scratch = off[6]; s.mbar = off[7]; s.cum = off[8]; s.poll = off[9]; s.total = o;
     return s;
 }
 
 // CT: compute threads, MINB: CTAs per SM. TC / TTW / TTH / TWL / THL > 0: compile-time shape (C, tile width / height,
 // low-res width / height); 0: run-time shape.
 template <int CT, int MINB, int TC, int TTW, int TTH, int TWL, int THL, bool PROF>
-__global__ void __launch_bounds__(CT + RES_HELPER_THREADS, MINB) k_fit_resident(ResidentParams p) {
+__global__ void __launch_bounds__(CT + res_helper_threads(CT), MINB) k_fit_resident(ResidentParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int C = TC ? TC : p.C, TW = TTW ? TTW : p.TW, TH = TTH ? TTH : p.TH, wl = TWL ? TWL : p.w_lo, h = THL ? THL : p.h;
     const int NP = TW * TH, HW = wl * h, TPR = wl / TW, CPG = HW / NP;
@@ -274,6 +295,8 @@ __global__ void __launch_bounds__(CT + RES_HELPER_THREADS, MINB) k_fit_resident(
     uint64_t* halo_ready = mbar + 1 + RES_KCH;        // the ring of this step is in zt
     unsigned* smax = reinterpret_cast<unsigned*>(mbar + 2 + RES_KCH);   // [0] tile max|F| bits, [1] episode max|F| bits
     long long* cum = reinterpret_cast<long long*>(smem_raw + L.cum);
+    uint64_t* pollbar = mbar + 4 + RES_KCH;           // completion of the applier's bulk-copy poll (RES_VARIANT 0x800)
+    unsigned long long* pollbuf = reinterpret_cast<unsigned long long*>(smem_raw + L.poll);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int group = blockIdx.x / CPG, k = blockIdx.x - group * CPG;
@@ -288,6 +311,7 @@ __global__ void __launch_bounds__(CT + RES_HELPER_THREADS, MINB) k_fit_resident(
         mbar_init(mbar, 1);
         for (int j = 0; j < RES_KCH; ++j) mbar_init(&applied[j], 1);
         mbar_init(halo_ready, 1);
+        mbar_init(pollbar, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
@@ -309,6 +333,7 @@ __global__ void __launch_bounds__(CT + RES_HELPER_THREADS, MINB) k_fit_resident(
 
         // chunk j of global step gs has been folded into W0 / W1 / Wd by the applier warp
         auto wait_applied = [&](int j, unsigned gs) {
+            if (RES_VARIANT & 0x04) return;
             unsigned it = 0;
             if (PROF && tid == 0 && !mbar_try_wait(&applied[j], gs & 1u)) {      // had to wait: latency = now - store time
                 while (!mbar_try_wait(&applied[j], gs & 1u)) { if (++it > RES_SPIN_LIMIT) break; }
@@ -336,7 +361,7 @@ __global__ void __launch_bounds__(CT + RES_HELPER_THREADS, MINB) k_fit_resident(
             }
             for (int c = tid; c < C; c += CT) {
                 const float a = p.w[((size_t)e * 2) * C + c], b = p.w[((size_t)e * 2 + 1) * C + c];
-                W0[c] = a; W1[c] = b; Wd[c] = b - a;
+                W0[c] = a; W1[c] = b; Wd[res_wd_pos(c, kStatic && (RES_VARIANT & 0x400))] = b - a;
             }
             if (tid < 2) smax[tid] = 0u;
             // HR task descriptors (static for the episode): task = (cell, row r); 8 adjacent lanes = one cell. Interior cells
@@ -414,15 +439,23 @@ __global__ void __launch_bounds__(CT + RES_HELPER_THREADS, MINB) k_fit_resident(
 #pragma unroll
                     for (int j = 0; j < RES_KCH; ++j) {
                         if (t > 0) wait_applied(j, gstep - 1u);
-                        if (p1_active) {
+                        if (p1_active && !(RES_VARIANT & 0x10)) {
                             if constexpr (kStatic) {
                                 // chunk j = channels grp + 16*(8j .. 8j+7): 8 independent LDS.128 + 8 broadcast LDS.32, immediate offsets
                                 const float4* Fj = reinterpret_cast<const float4*>(F) + tid + j * (8 * 400);
                                 const float* Wj = Wd + grp + j * 128;
                                 float4 f[8];
                                 float wd[8];
+                                if constexpr ((RES_VARIANT & 0x400) != 0) {
+                                    const float4 wa = *reinterpret_cast<const float4*>(Wd + j * 128 + grp * 8);
+                                    const float4 wb = *reinterpret_cast<const float4*>(Wd + j * 128 + grp * 8 + 4);
+                                    wd[0] = wa.x; wd[1] = wa.y; wd[2] = wa.z; wd[3] = wa.w; wd[4] = wb.x; wd[5] = wb.y; wd[6] = wb.z; wd[7] = wb.w;
+#pragma unroll
+                                    for (int u = 0; u < 8; ++u) f[u] = Fj[u * 400];
+                                } else {
 #pragma unroll
                                 for (int u = 0; u < 8; ++u) { f[u] = Fj[u * 400]; wd[u] = Wj[u * 16]; }
+                                }
 #pragma unroll
                                 for (int u = 0; u < 8; ++u) {
                                     za.x = fmaf(wd[u], f[u].x, za.x); za.y = fmaf(wd[u], f[u].y, za.y);
@@ -459,7 +492,7 @@ __global__ void __launch_bounds__(CT + RES_HELPER_THREADS, MINB) k_fit_resident(
 #pragma unroll
                 for (int m = 0; m < RES_MAXTASK; ++m) {
                     if (m * CT < 8 * NCELL) {                     // uniform: does this round have tasks at all
-                        if (m == (round0_interior ? 1 : 0)) {
+                        if (!(RES_VARIANT & 0x01) && m == (round0_interior ? 1 : 0)) {
                             long long tw0 = 0;
                             if (PROF && tid == 0) tw0 = clock64();
                             unsigned it = 0;
@@ -475,7 +508,9 @@ __global__ void __launch_bounds__(CT + RES_HELPER_THREADS, MINB) k_fit_resident(
                         if (d >> 31) {
                             const int ci = (d >> 19) & 0xff, r = tid & 7;
                             float gl = 0.f, gr = 0.f;
-                            if (d & (1u << 18)) {
+                            if ((RES_VARIANT & 0x02) && (d & (1u << 18))) {
+                                gl = zt[ci + (int)((d >> 27) & 0xfu)] * 1e-6f;
+                            } else if (d & (1u << 18)) {
                                 const int zi = ci + (int)((d >> 27) & 0xfu);     // cy * ZW + cx = ci + cy
                                 const int dx = (d >> 16) & 1, dy = (d & (1u << 17)) ? ZW : 0;
                                 const float z00 = zt[zi], z01 = zt[zi + dx], z10 = zt[zi + dy], z11 = zt[zi + dy + dx];
@@ -516,7 +551,36 @@ __global__ void __launch_bounds__(CT + RES_HELPER_THREADS, MINB) k_fit_resident(
                 // ------------ P3: dW = g . F^T chunk by chunk; every partial goes straight to the channel's accumulator word,
                 // so chunk j's all-reduce runs under the rest of P3 and the next P1 ------------
                 unsigned long long* acc_t = acc_ep + (t & 1) * C;          // even / odd steps use different words (see header)
-                if constexpr (kStatic) {
+                if constexpr (kStatic && (RES_VARIANT & 0x40) != 0) {
+                    // lane = pixel quad (25 of 32 lanes), warp = 8 channels of the chunk: all 16 warps sweep chunk j together, g stays
+                    // in registers, the 8 per-lane partials are summed over the lanes by a transposing butterfly (9 shuffles)
+                    const float4 g4 = lane < 25 ? reinterpret_cast<const float4*>(gsm)[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const uint32_t base = smem_u32(F) + (uint32_t)(warp * 8 * 400 + lane * 16);
+#pragma unroll
+                    for (int j = 0; j < RES_KCH; ++j) {
+                        float s8[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const float4 f = lds128_v(base + (uint32_t)((j * 128 + u) * 400));
+                            s8[u] = (RES_VARIANT & 0x08) ? g4.x : fmaf(g4.x, f.x, fmaf(g4.y, f.y, fmaf(g4.z, f.z, g4.w * f.w)));
+                        }
+                        float r4[4], q2[2];
+                        const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            r4[u] = (h16 ? s8[u + 4] : s8[u]) + __shfl_xor_sync(0xffffffffu, h16 ? s8[u] : s8[u + 4], 16);
+#pragma unroll
+                        for (int u = 0; u < 2; ++u)
+                            q2[u] = (h8 ? r4[u + 2] : r4[u]) + __shfl_xor_sync(0xffffffffu, h8 ? r4[u] : r4[u + 2], 8);
+                        float d = (h4 ? q2[1] : q2[0]) + __shfl_xor_sync(0xffffffffu, h4 ? q2[0] : q2[1], 4);
+                        d += __shfl_xor_sync(0xffffffffu, d, 2);
+                        d += __shfl_xor_sync(0xffffffffu, d, 1);
+                        const int u_own = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                        if ((lane & 3) == 0)
+                            red_add_u64(acc_t + j * 128 + warp * 8 + u_own, ((unsigned long long)__float2ll_rn(d * fx_inv) << KB) + 1ull);
+                        if (PROF && tid == 0) *reinterpret_cast<volatile long long*>(&tstore_sm[j]) = clock64();
+                    }
+                } else if constexpr (kStatic) {
                     // One thread per channel, no cross-thread reduction; g is broadcast from shared memory. The four warp
                     // quads take turns (quad j = channel chunk j, handed over through named barriers 2..4): the sweep of a
                     // quad is latency-bound anyway, a finished quad moves on to the next step's P1 at once, and chunk j's
@@ -524,20 +588,24 @@ __global__ void __launch_bounds__(CT + RES_HELPER_THREADS, MINB) k_fit_resident(
                     // (Measured alternatives at E = 64: all quads at once 20.3 ms, 4 threads per channel + shuffles 18.8 ms,
                     // two channels per thread 18.0 ms, this 17.5 ms.)
                     const int j = warp >> 2;
-                    if (j > 0) asm volatile("bar.sync %0, 256;" ::"r"(1 + j) : "memory");
+                    if (!(RES_VARIANT & 0x20) && j > 0) asm volatile("bar.sync %0, 256;" ::"r"(1 + j) : "memory");
                     const uint32_t row = smem_u32(F) + (uint32_t)tid * 400u, gad = smem_u32(gsm);
                     constexpr int D = RES_P3_DEPTH;                 // quads in flight per operand
                     float4 fb[D], gb[D];
+                    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+                    if (RES_VARIANT & 0x08) {
+                        d0 = gsm[tid & 63];
+                    } else {
 #pragma unroll
                     for (int i = 0; i < D; ++i) { fb[i] = lds128_v(row + 16 * i); gb[i] = lds128_v(gad + 16 * i); }
-                    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
                     for (int i = 0; i < 25; ++i) {
                         const float4 f = fb[i % D], g = gb[i % D];
                         if (i + D < 25) { fb[i % D] = lds128_v(row + 16 * (i + D)); gb[i % D] = lds128_v(gad + 16 * (i + D)); }
                         d0 = fmaf(g.x, f.x, d0); d1 = fmaf(g.y, f.y, d1); d2 = fmaf(g.z, f.z, d2); d3 = fmaf(g.w, f.w, d3);
                     }
-                    if (j < RES_KCH - 1) asm volatile("bar.arrive %0, 256;" ::"r"(2 + j) : "memory");
+                    }
+                    if (!(RES_VARIANT & 0x20) && j < RES_KCH - 1) asm volatile("bar.arrive %0, 256;" ::"r"(2 + j) : "memory");
                     const float d = (d0 + d1) + (d2 + d3);
                     // value and arrival in ONE atomic: (fix(d) << K) + 1
                     red_add_u64(acc_t + tid, ((unsigned long long)__float2ll_rn(d * fx_inv) << KB) + 1ull);
@@ -612,15 +680,18 @@ __global__ void __launch_bounds__(CT + RES_HELPER_THREADS, MINB) k_fit_resident(
             p.prof[(size_t)blockIdx.x * RES_NPROF + 10] = t_acc[6];
         }
         if (tid == 0 && !ok) atomicExch(p.abort_flag, 1u);
-    } else if (warp == CT / 32) {
+    } else if (warp < CT / 32 + res_appliers(CT)) {
         // =====================================================================================================
         // applier warp: accumulator words -> SGD update in shared memory -> release the compute warps
         // =====================================================================================================
         long long a_acc[4] = {0, 0, 0, 0};               // PROF: poll rounds, cycles polling, sum(done - own store), chunks
         const unsigned long long cnt_mask = (1ull << KB) - 1ull;
+        constexpr int NAPPL = res_appliers(CT);
+        const int aw = warp - CT / 32;                   // applier number: owns chunks aw, aw + NAPPL, ...
+        unsigned poll_parity = 0u;
         for (int e = group; e < p.E; e += p.G) {
             __syncthreads();                                           // S1
-            for (int c = lane; c < 2 * C; c += 32) cum[c] = 0ll;
+            for (int c = aw * 32 + lane; c < 2 * C; c += 32 * NAPPL) cum[c] = 0ll;
             __syncthreads();                                           // S2
             __syncthreads();                                           // S3
             __syncthreads();                                           // S4
@@ -630,7 +701,7 @@ __global__ void __launch_bounds__(CT + RES_HELPER_THREADS, MINB) k_fit_resident(
             for (int t = 0; t < p.T; ++t) {
                 const unsigned long long expect = (unsigned long long)CPG * (unsigned)(t / 2 + 1);   // arrivals so far on every word of this parity
                 long long* cum_t = cum + (t & 1) * C;
-                for (int j = 0; j < RES_KCH; ++j) {
+                for (int j = aw; j < RES_KCH; j += NAPPL) {
                     const unsigned long long* sw = acc_ep + (t & 1) * C + j * CCH;
                     for (int c0 = 0; c0 < CCH; c0 += 32 * RES_AW) {
                         // every load of this lane is issued before any count is looked at (independent L2 round
@@ -641,18 +712,38 @@ __global__ void __launch_bounds__(CT + RES_HELPER_THREADS, MINB) k_fit_resident(
                         if (PROF) tp0 = clock64();
 #pragma unroll
                         for (int m = 0; m < RES_AW; ++m) { wv[m] = 0ull; if (c0 + m * 32 + lane < CCH) pending |= 1u << m; }
-                        while (pending) {
+                        if (RES_VARIANT & 0x100) pending = 0u;
+                        // (the bulk-copy poll is a warp-level operation: the loop condition must be warp-uniform)
+                        while ((kStatic && (RES_VARIANT & 0x800)) ? __any_sync(0xffffffffu, pending != 0u) : (pending != 0u)) {
+                            if constexpr (kStatic && (RES_VARIANT & 0x800) != 0) {
+                                // one 1 KB bulk copy (async proxy: straight from L2, not through the LSU queue the sweeps fill)
+                                if (lane == 0) { mbar_expect_tx(pollbar, 1024u); bulk_g2s(pollbuf, sw, 1024u, pollbar); }
+                                unsigned spin = 0;
+                                while (!mbar_try_wait(pollbar, poll_parity)) { if (++spin > RES_SPIN_LIMIT) break; }
+                                poll_parity ^= 1u;
+#pragma unroll
+                                for (int m = 0; m < RES_AW; ++m)
+                                    if (pending & (1u << m)) wv[m] = pollbuf[m * 32 + lane];
+                            } else {
 #pragma unroll
                             for (int m = 0; m < RES_AW; ++m)
                                 if (pending & (1u << m)) wv[m] = ld_relaxed_u64(&sw[c0 + m * 32 + lane]);
+                            }
 #pragma unroll
                             for (int m = 0; m < RES_AW; ++m)
-                                if ((pending & (1u << m)) && (wv[m] & cnt_mask) == expect) pending &= ~(1u << m);
-                            if (pending && (++it & 0xffu) == 0u) {
+                                if ((pending & (1u << m)) && ((RES_VARIANT & 0x1f) ? (wv[m] & cnt_mask) >= expect : (wv[m] & cnt_mask) == expect))
+                                    pending &= ~(1u << m);
+                            if constexpr (kStatic && (RES_VARIANT & 0x800) != 0) {
+                                if ((++it & 0xffu) == 0u) {                       // warp-uniform watchdog
+                                    if (*reinterpret_cast<volatile unsigned*>(p.abort_flag) != 0u) break;
+                                    if (it > (RES_SPIN_LIMIT >> 2)) { atomicExch(p.abort_flag, 1u); break; }
+                                }
+                            } else if (pending && (++it & 0xffu) == 0u) {
                                 if (*reinterpret_cast<volatile unsigned*>(p.abort_flag) != 0u) break;
                                 if (it > (RES_SPIN_LIMIT >> 2)) { atomicExch(p.abort_flag, 1u); break; }
                             }
                             if (PROF) ++a_acc[0];
+                            if constexpr (kStatic && (RES_VARIANT & 0x800) != 0) __syncwarp();
                         }
                         if (PROF) {
                             __syncwarp();
@@ -670,7 +761,7 @@ __global__ void __launch_bounds__(CT + RES_HELPER_THREADS, MINB) k_fit_resident(
                                 const float dw = __ll2float_rn(cur - cum_t[c]) * fx_unit;        // this step's all-reduced dW
                                 cum_t[c] = cur;
                                 const float n0 = fmaf(p.lr, dw, W0[c]), n1 = fmaf(-p.lr, dw, W1[c]);
-                                W0[c] = n0; W1[c] = n1; Wd[c] = n1 - n0;
+                                W0[c] = n0; W1[c] = n1; Wd[res_wd_pos(c, kStatic && (RES_VARIANT & 0x400))] = n1 - n0;
                             }
                         }
                     }
@@ -680,7 +771,7 @@ __global__ void __launch_bounds__(CT + RES_HELPER_THREADS, MINB) k_fit_resident(
             }
             __syncthreads();                                           // S5
         }
-        if (PROF && lane == 0 && p.prof) {
+        if (PROF && lane == 0 && aw == 0 && p.prof) {
             for (int i = 0; i < 4; ++i) p.prof[(size_t)blockIdx.x * RES_NPROF + 6 + i] = a_acc[i];
         }
     } else {
@@ -716,13 +807,14 @@ __global__ void __launch_bounds__(CT + RES_HELPER_THREADS, MINB) k_fit_resident(
                 unsigned pending = 0u, it = 0u;
 #pragma unroll
                 for (int m = 0; m < RES_HWORDS; ++m) { bits[m] = 0u; tag[m] = 0u; if (ring_q[m] >= 0) pending |= 1u << m; }
+                if (RES_VARIANT & 0x200) pending = 0u;
                 while (pending) {
 #pragma unroll
                     for (int m = 0; m < RES_HWORDS; ++m)
                         if (pending & (1u << m)) ld_tagged(&zsrc[ring_q[m]], bits[m], tag[m]);
 #pragma unroll
                     for (int m = 0; m < RES_HWORDS; ++m)
-                        if ((pending & (1u << m)) && tag[m] == gstep + 1u) pending &= ~(1u << m);
+                        if ((pending & (1u << m)) && ((RES_VARIANT & 0x1f) ? tag[m] >= gstep + 1u : tag[m] == gstep + 1u)) pending &= ~(1u << m);
                     if (pending && (++it & 0xffu) == 0u) {
                         if (*reinterpret_cast<volatile unsigned*>(p.abort_flag) != 0u) break;
                         if (it > (RES_SPIN_LIMIT >> 2)) { atomicExch(p.abort_flag, 1u); break; }
@@ -826,12 +918,12 @@ size_t fit_resident_workspace_bytes(int E, int C, int h, int w) {
 template <int CT, int MINB, int TC, int TTW, int TTH, int TWL, int THL>
 static int launch_resident(const ResidentParams& p, const ResidentPlan& pl, bool prof, cudaStream_t st) {
     void* args[] = {const_cast<ResidentParams*>(&p)};
-    dim3 grid(pl.G * pl.CPG), block(CT + RES_HELPER_THREADS);
+    dim3 grid(pl.G * pl.CPG), block(CT + res_helper_threads(CT));
     const void* fn = prof ? (const void*)k_fit_resident<CT, MINB, TC, TTW, TTH, TWL, THL, true>
                           : (const void*)k_fit_resident<CT, MINB, TC, TTW, TTH, TWL, THL, false>;
     CWT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     int resident_ctas = 0;
-    CWT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident_ctas, fn, CT + RES_HELPER_THREADS, pl.smem));
+    CWT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident_ctas, fn, CT + res_helper_threads(CT), pl.smem));
     CWT_REQUIRE(resident_ctas >= MINB, CWT_ERR_UNSUPPORTED, "fit_resident: only %d of %d CTAs per SM fit", resident_ctas, MINB);
     CWT_CUDA(cudaLaunchCooperativeKernel(fn, grid, block, args, pl.smem, st));
     count_launch();

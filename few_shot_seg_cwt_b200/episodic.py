@@ -41,6 +41,7 @@ class HeadOutput:
     counts: torch.Tensor       # int64 [E,2,2,3]  variant (0 adapted / 1 baseline) x class x (I,U,T)
     ce: torch.Tensor           # float64 [E,2,2]  variant x (sum -log p[y], #valid)
     logits60: Optional[torch.Tensor]   # [E,2,2,h,w] variant x class
+    status: Optional[torch.Tensor] = None   # int32 [E] deferred error word of the fit (ops.fit_status), still on the device
 
 
 def episode_head(f_s, s_label, f_q, q_label, w0, params: Dict[str, torch.Tensor], n_head: int, lr: float,
@@ -50,14 +51,16 @@ def episode_head(f_s, s_label, f_q, q_label, w0, params: Dict[str, torch.Tensor]
 
     f_s [E,S,C,h,w]; s_label [E,S,H,W]; f_q [E,C,h,w] (un-normalised backbone features);
     q_label [E,H,W]; w0 [E,2,C]."""
-    w_fit = ops.fit_classifier(f_s, s_label, w0, lr, n_iter, check=False, algo=fit_algo)       # :164-187
+    # no host sync: the reference's ZeroDivisionError (empty support mask, :174) / bad labels / non-finite weights travel as
+    # a per-episode status word that the caller reads back with the counts (ops.raise_for_status)
+    w_fit, status = ops.fit_classifier(f_s, s_label, w0, lr, n_iter, check=False, algo=fit_algo, return_status=True)   # :164-187
     w_ad = ops.transformer_forward(w_fit, f_q, params["w_qkvs.weight"], params["fc.weight"], params["fc.bias"],
                                    params["layer_norm.weight"], params["layer_norm.bias"], n_head,
                                    normalize_k=True, algo=attn_algo)                            # :194-197
     weights = torch.stack([w_ad, w_fit], dim=1)                                                 # [E,2,2,C]
     counts, ce, logits = ops.logits_iou(weights, f_q, q_label, normalize_mask=0b01,
                                         return_logits=return_logits)                            # :192,200-223
-    return HeadOutput(w_fit, w_ad, counts, ce, logits)
+    return HeadOutput(w_fit, w_ad, counts, ce, logits, status)
 
 
 class HeadPipeline:
@@ -85,20 +88,21 @@ class HeadPipeline:
         """Queue one batch. ``after(out)`` (optional) runs on the side stream right behind the post stage (e.g. the
         asynchronous copy of the counts to the host). Returns (HeadOutput, done event)."""
         main = torch.cuda.current_stream(self.device)
-        w_fit = ops.fit_classifier(f_s, s_label, w0, self.lr, self.n_iter, check=False, algo=self.fit_algo)
+        w_fit, status = ops.fit_classifier(f_s, s_label, w0, self.lr, self.n_iter, check=False, algo=self.fit_algo,
+                                           return_status=True)
         self.side.wait_stream(main)
         p = self.params
         with torch.cuda.stream(self.side):
-            for t in (w_fit, f_q, q_label) + ((subcls,) if subcls is not None else ()):
+            for t in (w_fit, status, f_q, q_label) + ((subcls,) if subcls is not None else ()):
                 t.record_stream(self.side)
             w_ad = ops.transformer_forward(w_fit, f_q, p["w_qkvs.weight"], p["fc.weight"], p["fc.bias"],
                                            p["layer_norm.weight"], p["layer_norm.bias"], self.n_head,
                                            normalize_k=True, algo=self.attn_algo)
             counts, ce, _ = ops.logits_iou(torch.stack([w_ad, w_fit], dim=1), f_q, q_label, normalize_mask=0b01,
                                            return_logits=False)
-            out = HeadOutput(w_fit, w_ad, counts, ce, None)
+            out = HeadOutput(w_fit, w_ad, counts, ce, None, status)
             if self.table is not None and subcls is not None:
-                self.table.update(counts, subcls, ce)
+                self.table.update(counts, subcls, ce, status)
                 if self.reduce_every_step if reduce is None else reduce:
                     self.table.all_reduce()
             if after is not None:
@@ -124,27 +128,54 @@ class IoUTable:
         self.fb = torch.zeros(n_variants, 2, 2, dtype=torch.int64, device=device)
         self.ce = torch.zeros(n_variants, 2, dtype=torch.float64, device=device)
         self.n_episodes = torch.zeros(1, dtype=torch.int64, device=device)
+        self.n_bad = torch.zeros(1, dtype=torch.int64, device=device)      # episodes whose fit status was non-zero
+        # What this rank accumulated since the last all_reduce (``_local_*``) is kept apart from the table the metrics
+        # read, so that all_reduce can be called any number of times (per step or once at the end): every call adds the
+        # sum over ranks of the not-yet-exchanged DELTAS to every rank's table — nothing is ever counted twice.
+        self._local = [torch.zeros_like(t) for t in self._fields()]
+        self._distributed = False
 
-    def update(self, counts: torch.Tensor, subcls: torch.Tensor, ce: Optional[torch.Tensor] = None) -> None:
-        """counts int64 [E,V,2,3]; subcls int64 [E] in 1..num_classes."""
+    def _fields(self):
+        return [self.cls, self.fb, self.n_episodes, self.n_bad, self.ce]
+
+    def update(self, counts: torch.Tensor, subcls: torch.Tensor, ce: Optional[torch.Tensor] = None,
+               status: Optional[torch.Tensor] = None) -> None:
+        """counts int64 [E,V,2,3]; subcls int64 [E] in 1..num_classes; status int32 [E] (episodes with a non-zero fit
+        status are counted in ``n_bad`` — their counts are still added, as the reference has no such episodes)."""
+        tgt = self._local if self._distributed else self._fields()
         fg = counts[:, :, 1, :2]                                   # [E,V,(I,U)]  "do not count background"
-        self.cls.index_add_(0, subcls.to(self.cls.device), fg)
-        self.fb += counts[:, :, :, :2].sum(0)
+        tgt[0].index_add_(0, subcls.to(self.cls.device), fg)
+        tgt[1] += counts[:, :, :, :2].sum(0)
+        tgt[2] += counts.shape[0]
+        if status is not None:
+            tgt[3] += (status != 0).sum()
         if ce is not None:
-            self.ce += ce.sum(0)
-        self.n_episodes += counts.shape[0]
+            tgt[4] += ce.sum(0)
 
     def all_reduce(self) -> None:
-        """The one collective of a sharded sweep: integer sum over ranks (NVLink / NVSwitch via NCCL)."""
+        """The one collective of a sharded sweep: integer sum over ranks (NVLink / NVSwitch via NCCL). Idempotent: only
+        what was accumulated since the previous call is exchanged, so per-step and end-of-sweep reductions give the same
+        table. Every rank must call it the same number of times."""
         import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            flat = torch.cat([self.cls.reshape(-1), self.fb.reshape(-1), self.n_episodes])
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-            a, b = self.cls.numel(), self.fb.numel()
-            self.cls.copy_(flat[:a].view_as(self.cls))
-            self.fb.copy_(flat[a:a + b].view_as(self.fb))
-            self.n_episodes.copy_(flat[a + b:])
-            dist.all_reduce(self.ce, op=dist.ReduceOp.SUM)
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        if not self._distributed:
+            # first call: everything accumulated so far is this rank's delta
+            self._distributed = True
+            for loc, t in zip(self._local, self._fields()):
+                loc.copy_(t)
+                t.zero_()
+        ints = self._local[:4]
+        flat = torch.cat([t.reshape(-1) for t in ints])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        dist.all_reduce(self._local[4], op=dist.ReduceOp.SUM)
+        off = 0
+        for loc, t in zip(ints, self._fields()[:4]):
+            t += flat[off:off + t.numel()].view_as(t)
+            off += t.numel()
+            loc.zero_()
+        self.ce += self._local[4]
+        self._local[4].zero_()
 
     def miou(self, variant: int = 0) -> float:
         """mean over classes seen of I_c / (U_c + 1e-10)   (src/test.py:232-243)."""
@@ -192,7 +223,8 @@ def run_sweep(n_episodes: int, params: Dict[str, torch.Tensor], n_head: int, lr:
 # ----------------------------------------------------------------------------------------
 # validate_transformer drop-in (src/test.py:103-254)
 # ----------------------------------------------------------------------------------------
-def validate_transformer(args, val_loader, model, transformer, verbose: bool = True) -> Tuple[float, float]:
+def validate_transformer(args, val_loader, model, transformer, verbose: bool = True,
+                         overlap_backbone: bool = True) -> Tuple[float, float]:
     """Same arguments and return value as the reference: ``(mean mIoU over runs, mean loss over runs)``.
 
     ``args`` needs test_num, batch_size_val, image_size, n_runs, bottleneck_dim, num_classes_tr, cls_lr,
@@ -200,7 +232,16 @@ def validate_transformer(args, val_loader, model, transformer, verbose: bool = T
     ``(qry_img, q_label, spprt_imgs, s_label, subcls, spprt_oris, qry_oris)`` with a leading batch
     dimension of 1 (src/dataset/dataset.py:326-327). The backbone ``model.extract_features`` stays the
     caller's PyTorch module; everything after it runs in the fused kernels, batch_size_val episodes
-    per launch."""
+    per launch.
+
+    Backbone -> head handoff. The reference calls ``extract_features`` twice per episode at batch
+    size ``shot`` and 1 (src/test.py:177-178,190-191). Here the ``batch_size_val`` episodes of a batch go through the
+    backbone as TWO calls (all support images, all query images; eval-mode BatchNorm makes the images independent),
+    on a side stream: the backbone of batch i+1 is queued before the head of batch i, so its launches, its H2D copies
+    and — whenever the cooperative fit leaves SMs free (post stage, launch gaps) — its kernels overlap the head; the
+    head waits on an event, never on the host. Results (counts, CE, the fit's status word) are read back one batch
+    late; an empty support mask still raises the reference's ``ZeroDivisionError`` (src/test.py:174), bad labels a
+    ``ValueError``, then."""
     if verbose:
         print('==> Start testing')
     model.eval()
@@ -212,12 +253,54 @@ def validate_transformer(args, val_loader, model, transformer, verbose: bool = T
     params = transformer_params(transformer)
     n_head = transformer.n_head
     C = args.bottleneck_dim
-    num_classes_val = int(getattr(args, "num_classes_val", 0) or 0)
+    B = int(args.batch_size_val)
+    main = torch.cuda.current_stream(device)
+    bb_stream = torch.cuda.Stream(device) if overlap_backbone else main
 
     runtimes = torch.zeros(args.n_runs)
     val_IoUs = np.zeros(args.n_runs)
     val_losses = np.zeros(args.n_runs)
     iter_loader = iter(val_loader)
+    iter_num = 0
+
+    def next_item():
+        nonlocal iter_loader
+        try:
+            return next(iter_loader)
+        except StopIteration:
+            iter_loader = iter(val_loader)
+            return next(iter_loader)
+
+    def stage_batch():
+        """Load ``B`` episodes, draw their classifier inits and queue the two backbone calls on the backbone stream."""
+        nonlocal iter_num
+        sp, sl, qi, ql, w0_l, classes = [], [], [], [], [], []
+        for _ in range(B):
+            qry_img, q_label, spprt_imgs, s_label, subcls = next_item()[:5]
+            iter_num += 1
+            # fresh classifier init, drawn like the reference's nn.Conv2d(...) (a-1); the reference draws a second Conv2d per
+            # episode (Pseudo_cls, src/test.py:200) whose init is overwritten — drawn too, to keep the RNG stream seed-for-seed
+            w0_l.append(nn.Conv2d(C, args.num_classes_tr, kernel_size=1, bias=False).weight.detach().view(2, C))
+            nn.Conv2d(C, args.num_classes_tr, kernel_size=1, bias=False)
+            sp.append(spprt_imgs.squeeze(0)); sl.append(s_label.squeeze(0))
+            qi.append(qry_img); ql.append(q_label.squeeze(0))
+            classes.append([int(c.item()) if torch.is_tensor(c) else int(c) for c in subcls])
+        S = sp[0].shape[0]
+        with torch.cuda.stream(bb_stream):
+            spprt = torch.cat(sp).to(device, non_blocking=True)                  # [B*S,3,H,W]
+            qry = torch.cat(qi).to(device, non_blocking=True)                    # [B,3,H,W]
+            s_lab = torch.stack(sl).to(device, non_blocking=True)
+            q_lab = torch.stack(ql).to(device, non_blocking=True)
+            w0 = torch.stack(w0_l).to(device, non_blocking=True)
+            with torch.no_grad():
+                f_s, _ = model.extract_features(spprt)                           # one call for all support images
+                f_q, _ = model.extract_features(qry)                             # one call for all query images
+            f_s = f_s.float().reshape(B, S, *f_s.shape[1:]).contiguous()
+            f_q = f_q.float().contiguous()
+            ready = torch.cuda.Event()
+            ready.record(bb_stream)
+        return (f_s, s_lab, f_q, q_lab, w0), ready, classes, iter_num
+
     for run in range(args.n_runs):
         cls_I: Dict[int, int] = defaultdict(int)
         cls_U: Dict[int, int] = defaultdict(int)
@@ -225,14 +308,15 @@ def validate_transformer(args, val_loader, model, transformer, verbose: bool = T
         cls_U0: Dict[int, int] = defaultdict(int)
         IoU: Dict[int, float] = {}
         IoU0: Dict[int, float] = {}
-        loss_sum, loss_cnt, iter_num, runtime = 0.0, 0, 0, 0.0
+        loss_sum, loss_cnt, runtime = 0.0, 0, 0.0
         pending = None                       # results of the previous batch, still on their way to the host
 
         def finish(p):
             """Account one batch: the reference's per-class accumulation (src/test.py:225-234) and progress line."""
             nonlocal loss_sum, loss_cnt
-            counts, ce, ev, classes, n_seen = p
+            counts, ce, status, ev, classes, n_seen = p
             ev.synchronize()
+            ops.raise_for_status(status, first_episode=n_seen - len(classes))     # the reference's errors, one batch late
             loss = float(ce[:, 0, 0].sum() / ce[:, 0, 1].sum().clamp_min(1.0))     # CE over the batch's valid pixels
             loss_sum += loss; loss_cnt += 1
             for i, task_classes in enumerate(classes):
@@ -247,46 +331,35 @@ def validate_transformer(args, val_loader, model, transformer, verbose: bool = T
                     n_seen, args.test_num, np.mean(list(IoU.values())), np.mean(list(IoU0.values())),
                     loss, loss_sum / loss_cnt))
 
+        # pinned result buffers, two sets (the batch being accounted and the batch in flight), allocated once per run
+        host = [(torch.empty((B, 2, 2, 3), dtype=torch.int64, pin_memory=True),
+                 torch.empty((B, 2, 2), dtype=torch.float64, pin_memory=True),
+                 torch.empty((B,), dtype=torch.int32, pin_memory=True)) for _ in range(2)]
+        t0 = time.time()
+        staged = stage_batch() if nb_episodes > 0 else None
         for e in range(nb_episodes):
-            t0 = time.time()
-            fs_l, sl_l, fq_l, ql_l, w0_l, classes = [], [], [], [], [], []
-            for i in range(args.batch_size_val):
-                try:
-                    item = next(iter_loader)
-                except StopIteration:
-                    iter_loader = iter(val_loader)
-                    item = next(iter_loader)
-                qry_img, q_label, spprt_imgs, s_label, subcls = item[:5]
-                iter_num += 1
-                spprt_imgs, s_label = spprt_imgs.to(device), s_label.to(device)
-                q_label, qry_img = q_label.to(device), qry_img.to(device)
-                # fresh classifier init, drawn like the reference's nn.Conv2d(...) (a-1)
-                w0_l.append(nn.Conv2d(C, args.num_classes_tr, kernel_size=1, bias=False).weight.detach().view(2, C))
-                with torch.no_grad():
-                    f_s, _ = model.extract_features(spprt_imgs.squeeze(0))
-                    f_q, _ = model.extract_features(qry_img)
-                fs_l.append(f_s.float()); fq_l.append(f_q[0].float())
-                sl_l.append(s_label.squeeze(0)); ql_l.append(q_label.squeeze(0))
-                classes.append([int(c.item()) if torch.is_tensor(c) else int(c) for c in subcls])
-            out = episode_head(torch.stack(fs_l), torch.stack(sl_l), torch.stack(fq_l), torch.stack(ql_l),
-                               torch.stack(w0_l).to(device), params, n_head, args.cls_lr, args.adapt_iter)
+            tensors, ready, classes, n_seen = staged
+            # queue the NEXT batch's backbone before this batch's head (it runs on the backbone stream)
+            staged = stage_batch() if e + 1 < nb_episodes else None
+            main.wait_event(ready)
+            for t in tensors:
+                t.record_stream(main)
+            f_s, s_lab, f_q, q_lab, w0 = tensors
+            out = episode_head(f_s, s_lab, f_q, q_lab, w0, params, n_head, args.cls_lr, args.adapt_iter)
             # No device sync per batch (the reference has one per EPISODE, src/test.py:169-171): the counts travel to
-            # pinned host memory asynchronously and are accounted one batch later, after the next batch's backbone and
-            # head have been queued — the GPU never waits for the Python side.
-            counts = torch.empty(out.counts.shape, dtype=out.counts.dtype, pin_memory=True)
-            ce = torch.empty(out.ce.shape, dtype=out.ce.dtype, pin_memory=True)
+            # pinned host memory asynchronously and are accounted one batch later — the GPU never waits for Python.
+            counts, ce, status = host[e % 2]
             counts.copy_(out.counts, non_blocking=True)
             ce.copy_(out.ce, non_blocking=True)
+            status.copy_(out.status, non_blocking=True)
             ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream(device))
+            ev.record(main)
             if pending is not None:
                 finish(pending)
-            pending = (counts, ce, ev, classes, iter_num)
-            runtime += time.time() - t0
+            pending = (counts, ce, status, ev, classes, n_seen)
         if pending is not None:
-            t0 = time.time()
             finish(pending)
-            runtime += time.time() - t0
+        runtime += time.time() - t0
         runtimes[run] = runtime
         mIoU = float(np.mean(list(IoU.values()))) if IoU else 0.0
         if verbose:
@@ -305,8 +378,9 @@ def validate_transformer(args, val_loader, model, transformer, verbose: bool = T
 # meta-training step (src/train.py:233-267)
 # ----------------------------------------------------------------------------------------
 class _QueryLoss(torch.autograd.Function):
-    """loss(W') = weighted CE( up( W' . normalize(f_q) ), q_label ), mean over the batch's episodes
-    (the reference trains with batch_size 1: config_files/pascal.yaml:25)."""
+    """loss(W') = weighted CE( up( W' . normalize(f_q) ), q_label ) per episode, SUMMED over the batch's episodes
+    (the reference trains with batch_size 1, config_files/pascal.yaml:25, where sum and mean coincide; with E > 1 the
+    transformer gradient is the sum of the per-episode gradients)."""
 
     @staticmethod
     def forward(ctx, w_ad, f_q, q_label):
@@ -361,8 +435,12 @@ def do_epoch(args, train_loader, model, transformer, optimizer_trans, epoch: int
     Per iteration: the backbone (the caller's PyTorch module, ``model.extract_features``) produces f_s in train mode
     and f_q in eval mode exactly as the reference does; the classifier fit, the transformer forward / backward, the
     weighted query CE and both IoU read-outs run in the fused kernels. In the 1-shot case the reference feeds the
-    support image twice (``expand(2, ...)``, so that train-mode BatchNorm sees a batch) and fits on the two identical
-    shots; the pooled-mean loss of two identical shots equals the 1-shot loss, so the fit runs on the first copy."""
+    support image twice (``expand(2, ...)``, so that train-mode BatchNorm sees a batch) and fits on BOTH feature maps
+    (S = 2, pooled loss): with the backbone in train mode (src/train.py:183) ``PSPNet.bottleneck`` ends in
+    ``nn.Dropout2d(p=args.dropout)`` (dropout 0.1 in pascal.yaml), so the two copies carry different channel masks and are
+    NOT identical. The fit therefore runs on both copies; only a backbone without any active dropout module (where the
+    two copies are bit-identical and the pooled-mean loss of two identical shots equals the 1-shot loss) takes the
+    single-copy shortcut onto the on-chip kernel."""
     device = next(transformer.parameters()).device
     if device.type != "cuda":
         raise RuntimeError("do_epoch (cwt_b200): the transformer must live on a CUDA device")
@@ -377,6 +455,7 @@ def do_epoch(args, train_loader, model, transformer, optimizer_trans, epoch: int
     it = iter(train_loader)
     model.train()
     transformer.train()
+    active_dropout = any(isinstance(m, nn.modules.dropout._DropoutNd) and m.p > 0 for m in model.modules())
     for i in range(iter_per_epoch):
         try:
             item = next(it)
@@ -394,8 +473,10 @@ def do_epoch(args, train_loader, model, transformer, optimizer_trans, epoch: int
         w0 = nn.Conv2d(C, args.num_classes_tr, kernel_size=1, bias=False).weight.detach().view(1, 2, C).to(device)
         with torch.no_grad():
             f_s, _ = model.extract_features(spprt)                     # [n_support, c, h, w], backbone in train mode
-        if one_shot:
-            f_s = f_s[:1]
+        if one_shot and not active_dropout:
+            f_s = f_s[:1]                                              # two bit-identical copies: fit on one
+        elif one_shot:
+            s_label = s_label.expand(1, 2, *s_label.shape[-2:])        # [1,2,H,W]: the label of both copies (src/train.py:201)
         model.eval()
         with torch.no_grad():
             f_q, _ = model.extract_features(qry_img)                   # [1, c, h, w]
@@ -489,6 +570,7 @@ class HostPipeline:
         self.sub_batch_all = bool(sub_batch_all)            # sub-batch every host batch, not only the first
         self._slots: List[Optional[EpisodeBatch]] = [None] * n_slots
         self._slot_free: List[Optional[torch.cuda.Event]] = [None] * n_slots
+        self._results: List[Optional[Tuple[torch.Tensor, torch.Tensor]]] = []   # pinned (counts, status) per host batch
 
     @staticmethod
     def _fields(b: EpisodeBatch):
@@ -528,12 +610,31 @@ class HostPipeline:
                 hi = min(E, lo + step)
                 yield bi, lo, hi >= E, EpisodeBatch(*(t[lo:hi] for t in self._fields(hb))), E
 
-    def run(self, host_batches: Iterable[EpisodeBatch], reduce_every_step: bool = True) -> List[torch.Tensor]:
-        """Returns the per-batch count tensors (CPU, int64 [E,2,2,3]); ``self.table`` accumulates the sweep metrics."""
+    def _result_buffers(self, bi: int, E: int):
+        """Pinned host buffers of host batch ``bi`` (counts int64 [E,2,2,3], fit status int32 [E]): owned by the pipeline and
+        reused by every run — no pinned allocation (a cudaHostAlloc synchronises) inside the loop after the first run."""
+        while len(self._results) <= bi:
+            self._results.append(None)
+        cur = self._results[bi]
+        if cur is None or cur[0].shape[0] < E:
+            cur = (torch.empty((max(E, 1), 2, 2, 3), dtype=torch.int64, pin_memory=True),
+                   torch.empty((max(E, 1),), dtype=torch.int32, pin_memory=True))
+            self._results[bi] = cur
+        return cur[0][:E], cur[1][:E]
+
+    def run(self, host_batches: Iterable[EpisodeBatch], reduce_every_step: bool = False, reduce: bool = True,
+            check: bool = True) -> List[torch.Tensor]:
+        """Returns the per-batch count tensors (CPU, int64 [E,2,2,3]; views of pipeline-owned pinned buffers, valid until the
+        next ``run``); ``self.table`` accumulates the sweep metrics. ``reduce_every_step``: all-reduce the table after
+        every host batch (every rank must then see the same number of batches); ``reduce``: all-reduce once at the end.
+        ``check``: raise the reference's errors (empty support mask -> ZeroDivisionError, bad labels -> ValueError,
+        non-finite fit -> FloatingPointError) from the status words that came back with the counts — after the run, so
+        the pipeline itself never waits for the host."""
         main = torch.cuda.current_stream(self.device)
         self._main = main
         it = self._sub_batches(host_batches)
         results: List[torch.Tensor] = []
+        statuses: List[torch.Tensor] = []
         n_slots = len(self._slots)
         queue = []                          # staged sub-batches, oldest first
         nslot = 0
@@ -551,20 +652,34 @@ class HostPipeline:
 
         head = HeadPipeline(self.device, self.params, self.n_head, self.lr, self.n_iter, self.fit_algo, self.attn_algo,
                             table=self.table)
+
+        def read_back(out, dst, dst_status):
+            dst.copy_(out.counts, non_blocking=True)
+            dst_status.copy_(out.status, non_blocking=True)
+
         prefetch()
         while queue:
             db, ev, cur, bi, lo, last, E = queue.pop(0)
             main.wait_event(ev)
-            if bi == len(results):                            # first sub-batch of host batch bi: its pinned result tensor
-                results.append(torch.empty((E, 2, 2, 3), dtype=torch.int64, pin_memory=True))
+            if bi == len(results):                            # first sub-batch of host batch bi: its pinned result buffers
+                r, st = self._result_buffers(bi, E)
+                results.append(r); statuses.append(st)
             dst = results[bi][lo:lo + db.n_episodes]
+            dst_status = statuses[bi][lo:lo + db.n_episodes]
             # fit on the main stream; transformer + logits/IoU, the table update, the (optional) all-reduce and the D2H read
             # of the step's result on the head's side stream, overlapping the NEXT sub-batch's fit
             _, done = head.submit(db.f_s, db.s_label, db.f_q, db.q_label, db.w0, db.subcls,
                                   reduce=bool(last and reduce_every_step),
-                                  after=lambda out, dst=dst: dst.copy_(out.counts, non_blocking=True))
+                                  after=lambda out, dst=dst, dst_status=dst_status: read_back(out, dst, dst_status))
             self._slot_free[cur] = done                       # the slot may be overwritten once its post stage has finished
             prefetch()                                        # H2D of the following sub-batches overlaps this and the next head
         head.finish()
+        if reduce and not reduce_every_step:
+            self.table.all_reduce()
         torch.cuda.current_stream(self.device).synchronize()
+        if check:
+            first = 0
+            for st in statuses:
+                ops.raise_for_status(st, first_episode=first)
+                first += st.shape[0]
         return results

@@ -20,6 +20,66 @@ def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
     return t.contiguous()
 
 
+def _episode_inputs(f_s: torch.Tensor, s_label: torch.Tensor, name: str = "f_s"):
+    """Common shape handling of the fit wrappers: ([E,]S,C,h,w) features + ([E,]S,H,W) labels -> contiguous 5-d / 4-d."""
+    if f_s.dim() == 4:
+        f_s, s_label = f_s.unsqueeze(0), s_label.unsqueeze(0)
+    if f_s.dim() != 5 or s_label.dim() != 4:
+        raise ValueError(f"{name} must be [E,S,C,h,w] and s_label [E,S,H,W]; got {tuple(f_s.shape)}, {tuple(s_label.shape)}")
+    if s_label.shape[0] != f_s.shape[0] or s_label.shape[1] != f_s.shape[1]:
+        raise ValueError(f"{name} and s_label disagree on E or S")
+    return _f32c(f_s, name), s_label.contiguous()
+
+
+def _class_weight(class_weight: Optional[torch.Tensor], E: int, dev) -> Optional[torch.Tensor]:
+    if class_weight is None:
+        return None
+    cw = _f32c(class_weight.to(dev), "class_weight").reshape(-1, 2)
+    if cw.shape[0] == 1 and E > 1:
+        cw = cw.expand(E, 2).contiguous()
+    if cw.shape[0] != E:
+        raise ValueError("class_weight must be [2] or [E,2]")
+    return cw
+
+
+def _raise_on_label_counts(counts: torch.Tensor, has_class_weight: bool) -> None:
+    """The synchronous ``check=True`` path: one host sync, the reference's own exceptions."""
+    c = counts.cpu()
+    if int(c[:, 3].sum()) > 0:
+        raise ValueError("s_label holds values outside {0, 1, ignore_index}")
+    if not has_class_weight and bool((c[:, 1] == 0).any()):
+        raise ZeroDivisionError("division by zero: an episode's support mask has no foreground pixel "
+                                "(reference: len(back_pix[0]) / len(target_pix[0]), src/test.py:174)")
+
+
+def fit_status(label_counts_: torch.Tensor, w_fit: torch.Tensor, has_class_weight: bool = False) -> torch.Tensor:
+    """Deferred error word per episode (int32 [E], device, no host sync): bits L.FIT_BAD_LABEL / L.FIT_NO_FG /
+    L.FIT_NONFINITE. Copy it to the host with the episode's results and hand it to :func:`raise_for_status`."""
+    dev = L.require_cuda(label_counts_, w_fit)
+    E = label_counts_.shape[0]
+    Cc = w_fit.shape[-1]
+    status = torch.empty(E, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.load().cwt_fit_status(L.ptr(label_counts_.contiguous()), L.ptr(_f32c(w_fit, "w_fit")), int(has_class_weight),
+                                     L.ptr(status), E, Cc, L.stream_ptr(dev))
+    L.check(rc, "cwt_fit_status")
+    return status
+
+
+def raise_for_status(status_host: torch.Tensor, first_episode: int = 0) -> None:
+    """Raise what the reference would have raised for the first bad episode of a (host) status vector."""
+    bad = torch.nonzero(status_host.reshape(-1)).reshape(-1)
+    if bad.numel() == 0:
+        return
+    i = int(bad[0]); code = int(status_host.reshape(-1)[i]); where = f"episode {first_episode + i}"
+    if code & L.FIT_BAD_LABEL:
+        raise ValueError(f"{where}: s_label holds values outside {{0, 1, ignore_index}}")
+    if code & L.FIT_NO_FG:
+        raise ZeroDivisionError(f"division by zero: {where}: the support mask has no foreground pixel "
+                                "(reference: len(back_pix[0]) / len(target_pix[0]), src/test.py:174)")
+    raise FloatingPointError(f"{where}: the fitted classifier is not finite (non-finite features, or the on-chip fit aborted)")
+
+
 # ----------------------------------------------------------------------------------------
 # (a-2) label statistics
 # ----------------------------------------------------------------------------------------
@@ -44,7 +104,7 @@ def label_counts(labels: torch.Tensor, ignore_index: int = IGNORE) -> torch.Tens
 # ----------------------------------------------------------------------------------------
 def fit_classifier(f_s: torch.Tensor, s_label: torch.Tensor, w0: torch.Tensor, lr: float, n_iter: int,
                    class_weight: Optional[torch.Tensor] = None, ignore_index: int = IGNORE,
-                   return_losses: bool = False, check: bool = True, algo: int = L.FIT_AUTO):
+                   return_losses: bool = False, check: bool = True, algo: int = L.FIT_AUTO, return_status: bool = False):
     """Fit a fresh 2-class 1x1-conv classifier per episode with ``n_iter`` plain-SGD steps
     (reference: src/test.py:164-187, src/train.py:206-231, PSPNet.inner_loop pspnet.py:189-205).
 
@@ -54,30 +114,18 @@ def fit_classifier(f_s: torch.Tensor, s_label: torch.Tensor, w0: torch.Tensor, l
     class_weight [E,2] or [2] or None (None => [1, n0/n1] counted on the device, all shots pooled)
     check    True: one host sync to raise ZeroDivisionError when an episode has no foreground
              pixel (what the reference's python division does) and ValueError on labels outside
-             {0,1,ignore}. False: fully asynchronous.
+             {0,1,ignore}. False: fully asynchronous — pass ``return_status=True`` to get the deferred error
+             word of every episode (int32 [E] on the device, :func:`fit_status`) and raise later with
+             :func:`raise_for_status` (what ``validate_transformer`` / ``HostPipeline`` do, one batch late).
 
     Returns W [E,2,C] (same leading shape as given), and losses [n_iter,E] if requested."""
     dev = L.require_cuda(f_s, s_label, w0)
-    single = f_s.dim() == 4
-    if single:
-        f_s, s_label = f_s.unsqueeze(0), s_label.unsqueeze(0)
-    if f_s.dim() != 5 or s_label.dim() != 4:
-        raise ValueError(f"f_s must be [E,S,C,h,w] and s_label [E,S,H,W]; got {tuple(f_s.shape)}, {tuple(s_label.shape)}")
+    f_s, lab = _episode_inputs(f_s, s_label)
     E, S, Cc, h, w = f_s.shape
-    H, W = s_label.shape[-2:]
-    if s_label.shape[0] != E or s_label.shape[1] != S:
-        raise ValueError("f_s and s_label disagree on E or S")
+    H, W = lab.shape[-2:]
     w0_shape = w0.shape
     w0v = _f32c(w0, "w0").reshape(E, 2, Cc)
-    f_s = _f32c(f_s, "f_s")
-    lab = s_label.contiguous()
-    cw = None
-    if class_weight is not None:
-        cw = _f32c(class_weight.to(dev), "class_weight").reshape(-1, 2)
-        if cw.shape[0] == 1 and E > 1:
-            cw = cw.expand(E, 2).contiguous()
-        if cw.shape[0] != E:
-            raise ValueError("class_weight must be [2] or [E,2]")
+    cw = _class_weight(class_weight, E, dev)
     w_out = torch.empty(E, 2, Cc, dtype=torch.float32, device=dev)
     losses = torch.empty(n_iter, E, dtype=torch.float32, device=dev) if return_losses else None
     counts = torch.empty(E, 4, dtype=torch.int32, device=dev)
@@ -91,14 +139,12 @@ def fit_classifier(f_s: torch.Tensor, s_label: torch.Tensor, w0: torch.Tensor, l
                                         L.ptr(ws), ws.numel(), L.stream_ptr(dev))
     L.check(rc, "cwt_fit_classifier_f32")
     if check:
-        c = counts.cpu()
-        if int(c[:, 3].sum()) > 0:
-            raise ValueError("s_label holds values outside {0, 1, ignore_index}")
-        if class_weight is None and bool((c[:, 1] == 0).any()):
-            raise ZeroDivisionError("division by zero: an episode's support mask has no foreground pixel "
-                                    "(reference: len(back_pix[0]) / len(target_pix[0]), src/test.py:174)")
+        _raise_on_label_counts(counts, cw is not None)
+    if return_status:
+        status = fit_status(counts, w_out, cw is not None)
     out = w_out.reshape(w0_shape)          # same leading shape as the w0 that was given
-    return (out, losses) if return_losses else out
+    res = (out,) + ((losses,) if return_losses else ()) + ((status,) if return_status else ())
+    return res if len(res) > 1 else out
 
 
 def fit_classifier_bias(f_s: torch.Tensor, s_label: torch.Tensor, w0: torch.Tensor, b0: torch.Tensor, lr: float,

@@ -80,18 +80,19 @@ class MultiHeadAttentionOne(nn.Module):
         """q [B,Lq,C]; k, v [B,C,h,w] -> [B,Lq,C].  ``v`` must be ``k`` (the only call pattern on the
         reference path: transformer(W, f_q, f_q))."""
         if v is not None and v is not k and not (v.data_ptr() == k.data_ptr() and v.shape == k.shape):
-            # distinct storage: accept only equal values (costs one comparison pass + a host sync)
-            if v.shape != k.shape or not torch.equal(v, k):
-                raise NotImplementedError("cwt_b200 MultiHeadAttentionOne requires v == k (shared K/V projection); "
-                                          "the reference only ever calls transformer(W, f_q, f_q)")
-        if self.training and keep_attn is None and keep_out is None:
+            # Distinct storage cannot be proven equal without a comparison pass and a host sync, which the hot path must not
+            # pay: refuse it. (The reference only ever calls transformer(W, f_q, f_q), src/test.py:197, src/train.py:257.)
+            raise NotImplementedError("cwt_b200 MultiHeadAttentionOne requires v to be k (shared K/V projection: pass the "
+                                      "same tensor twice, as the reference does: transformer(W, f_q, f_q))")
+        if self.training:
+            # each dropout draws its own mask unless the caller supplied it (a caller that passes only one mask still gets
+            # dropout on the other path, like nn.Dropout)
             B, Lq, C = q.shape
             HW = k.shape[2] * (k.shape[3] if k.dim() == 4 else 1)
-            keep_attn, keep_out = self.draw_masks(B, Lq, HW, C, q.device)
-            if self.p_attn == 0.0:
-                keep_attn = None
-            if self.p_out == 0.0:
-                keep_out = None
+            if keep_attn is None and self.p_attn > 0.0:
+                keep_attn = (torch.rand(self.n_head * B, Lq, HW, device=q.device) >= self.p_attn).to(torch.uint8)
+            if keep_out is None and self.p_out > 0.0:
+                keep_out = (torch.rand(B, Lq, C, device=q.device) >= self.p_out).to(torch.uint8)
         return _MHAOneFunction.apply(q, k, self.w_qkvs.weight, self.fc.weight, self.fc.bias,
                                      self.layer_norm.weight, self.layer_norm.bias, self.n_head,
                                      self.normalize_k, keep_attn, keep_out, self.p_attn, self.p_out, self.algo)

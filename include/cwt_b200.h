@@ -52,14 +52,10 @@ extern "C" {
 
 int         cwt_version(void);
 const char* cwt_last_error(void);
-/* number of kernels this library has launched from the calling process (bench bookkeeping) */
+/* number of kernels this library has launched from the CALLING THREAD (per-thread like the error string; bench / smoke
+ * bookkeeping: "gpu_launches") */
 long long   cwt_launch_count(void);
-/* debug: device buffer [grid][8] int64 that receives the resident fit kernel's per-phase cycle
- * counters (P1, X1, HR, P3, X2) on its next launches; NULL switches the instrumented build off */
-void        cwt_debug_set_prof_buffer(void* dev_buffer);
-/* debug: L2 read-bandwidth microbenchmark — `ctas` x 512 threads sweep `bytes` of `buf` `iters` times with
- * L1-bypassing 128-bit loads (time it with events; bytes * iters / time = bandwidth) */
-int         cwt_debug_l2_read(const void* buf, size_t bytes, int iters, int ctas, void* sink, void* stream);
+/* developer-only entry points (phase profile of the resident fit, L2 bandwidth probe) live in cwt_b200_debug.h */
 
 /* ---------------------------------------------------------------------------------------
  * (a-2) label statistics.  Replaces the per-episode D2H copy + numpy `where` of
@@ -90,6 +86,20 @@ int cwt_fit_classifier_f32(const float* f_s, const void* s_label, int label_kind
                            int E, int S, int C, int h, int w, int H, int W,
                            int n_iter, float lr, int ignore_index, int algo,
                            void* workspace, size_t ws_bytes, void* stream);
+
+/* Deferred error check of a fit (no host sync): status[e] = OR of
+ *   CWT_FIT_BAD_LABEL   a support label outside {0, 1, ignore_index}      (torch's CrossEntropyLoss raises)
+ *   CWT_FIT_NO_FG       no foreground pixel and no explicit class weight   (the reference's ZeroDivisionError,
+ *                       src/test.py:174: len(back_pix[0]) / len(target_pix[0]))
+ *   CWT_FIT_NONFINITE   a fitted weight is NaN / Inf (non-finite features, or the resident kernel's watchdog aborted)
+ * from the label counts the fit wrote and the fitted weights. The caller reads `status` back together with the
+ * episode's results (e.g. one batch late) and raises then.
+ *   label_counts [E,4] int32 (as written by the fit)   w_fit [E,2,C]   status [E] int32 out */
+#define CWT_FIT_BAD_LABEL  1
+#define CWT_FIT_NO_FG      2
+#define CWT_FIT_NONFINITE  4
+int cwt_fit_status(const int32_t* label_counts, const float* w_fit, int has_class_weight, int32_t* status,
+                   int E, int C, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * (a-3 / f-3) the same fit for a classifier WITH a bias: nn.Conv2d(C, 2, 1, bias=True), which the

@@ -166,6 +166,47 @@ def test_fit_resident_alternative_plans_long_run(cuda_device, monkeypatch, env):
     assert torch.equal(wr[:24], wr[24:])                          # integer all-reduce: bit-reproducible whatever the timing
 
 
+def test_fit_resident_default_plan_long_run_distinct_episodes(cuda_device):
+    """The plan behind every bench number (tile 20x5, one CTA per SM, 4 groups of 36 CTAs): 64 DISTINCT episodes x 200 steps,
+    16 episodes per group back to back — resident == streaming to rounding, bit-reproducible across two runs, and every
+    deferred status word is clean."""
+    E = 64
+    big = syn.make_batch(list(range(500, 500 + E)), shot=1, C=512, h=60, w=60, H=473, W=473).to(cuda_device)
+    wr, st = cwt.fit_classifier(big.f_s, big.s_label, big.w0, 0.1, 200, algo=L.FIT_RESIDENT, return_status=True)
+    wr2 = cwt.fit_classifier(big.f_s, big.s_label, big.w0, 0.1, 200, algo=L.FIT_RESIDENT)
+    ws = cwt.fit_classifier(big.f_s, big.s_label, big.w0, 0.1, 200, algo=L.FIT_STREAM)
+    assert torch.isfinite(wr).all() and int(st.abs().sum()) == 0
+    assert torch.equal(wr, wr2)                                   # integer all-reduce: bit-reproducible whatever the timing
+    for i in range(E):
+        assert rel_err(wr[i], ws[i]) < TIGHT, i
+
+
+def test_fit_status_words_and_deferred_errors(cuda_device):
+    """check=False + return_status: an empty support mask (the reference's ZeroDivisionError, src/test.py:174), a label outside
+    {0, 1, 255} and non-finite features are reported per episode without a host sync; episode_head carries the word."""
+    b = syn.make_batch([40, 41, 42, 43], **SMALL).to(cuda_device)
+    lab = b.s_label.clone()
+    lab[1][lab[1] == 1] = 0                     # no foreground
+    lab[2, 0, 0, 0] = 7                         # invalid value
+    f_s = b.f_s.clone()
+    f_s[3, 0, 2, 1, 1] = float("inf")
+    w, st = cwt.fit_classifier(f_s, lab, b.w0, 0.1, 10, check=False, return_status=True)
+    st = st.cpu()
+    assert int(st[0]) == 0
+    assert int(st[1]) & L.FIT_NO_FG and int(st[1]) & L.FIT_NONFINITE        # 0 * inf class weight -> NaN weights
+    assert int(st[2]) & L.FIT_BAD_LABEL
+    assert int(st[3]) == L.FIT_NONFINITE
+    with pytest.raises(ZeroDivisionError):
+        ops.raise_for_status(st[1:2])
+    with pytest.raises(ValueError):
+        ops.raise_for_status(st[2:3])
+    with pytest.raises(ZeroDivisionError):
+        ops.raise_for_status(st)                                        # the first bad episode (1: no foreground) decides
+    params = dev_params(syn.make_transformer_params(2, 64), cuda_device)
+    out = cwt.episode_head(b.f_s, lab, b.f_q, b.q_label, b.w0, params, 2, 0.1, 10)
+    assert out.status is not None and int(out.status[0]) == 0 and int(out.status[1]) & L.FIT_NO_FG
+
+
 def test_fit_resident_non_finite_features_give_nan_weights(cuda_device):
     """A NaN / Inf in the support features poisons that episode only (the reference's SGD would produce NaN weights too)."""
     b = syn.make_batch([30, 31, 32, 33, 34], **SMALL).to(cuda_device)
@@ -570,7 +611,16 @@ def test_episode_head_tcgen05_path_vs_golden(cuda_device):
                            case["n_head"], case["lr"], case["n_iter"], return_logits=True, attn_algo=L.ATTN_TCGEN05)
     assert rel_err(out.w_adapted[0], g["W_adapted"]) < REL
     assert rel_err(out.logits60[0, 0], g["logits60"]) < REL
-    assert int((out.counts[0, 0].cpu() - torch.from_numpy(g["counts"])).abs().max()) <= 8
+    # counts: bit-exact outside the oracle's stated near-tie set — with the tie threshold scaled to what the 3 x bf16 split of
+    # the K projection can move a logit by (its measured relative error on this episode), not a fixed pixel allowance
+    ep = syn.make_episode(case["idx"], **gen_kwargs(case))
+    ora = O.episode_ref(ep.f_s, ep.s_label, ep.f_q, ep.q_label, ep.w0, params, case["n_head"], case["lr"], case["n_iter"])
+    scale = float(ora["logits60"].abs().max())
+    moved = float((out.logits60[0, 0].cpu() - ora["logits60"]).abs().max())
+    allowed = int((ora["tie_margin"] <= max(TIE_TAU * scale, 2.0 * moved)).sum())
+    diff = int((out.counts[0, 0].cpu() - ora["counts"]).abs().max())
+    assert moved <= REL * scale
+    assert diff <= allowed, f"counts differ by {diff} with a tie set of {allowed} pixels (logits moved by {moved:.2e})"
 
 
 def test_sweep_miou_matches_oracle(cuda_device):
@@ -591,6 +641,39 @@ def test_sweep_miou_matches_oracle(cuda_device):
     assert int(table.n_episodes) == n
     assert abs(table.miou(0) - miou_ref) * 100 < 0.05
     assert abs(table.fb_iou(0) - fb_ref) * 100 < 0.05
+
+
+def test_coco20i_sweep_20_class_table(cuda_device):
+    """BASELINE config 3 (COCO-20i, config_files/coco.yaml:10 num_classes_val 20; accumulation src/test.py:225-243): the head
+    shapes equal PASCAL's, what changes is the 20-class table with subcls in 1..20. Per-class I/U bit-exact outside the tie
+    set, mIoU / FB-IoU within 0.05 pt of the oracle, through run_sweep AND through HostPipeline."""
+    kw = dict(shot=1, C=64, h=12, w=12, H=89, W=89, style="unit", num_classes_val=20)
+    n, n_head, lr, n_iter = 44, 2, 0.1, 40                      # every class at least twice
+    params = syn.make_transformer_params(n_head, 64)
+    table = cwt.run_sweep(n, dev_params(params, cuda_device), n_head, lr, n_iter, cuda_device, batch=16,
+                          num_classes_val=20, gen_kwargs=kw)
+    assert table.cls.shape[0] == 21 and int(table.n_episodes) == n and int(table.n_bad) == 0
+    cI, cU, fb, ties = {}, {}, torch.zeros(2, 2, dtype=torch.float64), {}
+    for i in range(n):
+        ep = syn.make_episode(i, **kw)
+        assert 1 <= ep.subcls <= 20
+        o = O.episode_ref(ep.f_s, ep.s_label, ep.f_q, ep.q_label, ep.w0, params, n_head, lr, n_iter)
+        cI[ep.subcls] = cI.get(ep.subcls, 0) + int(o["counts"][1, 0])
+        cU[ep.subcls] = cU.get(ep.subcls, 0) + int(o["counts"][1, 1])
+        ties[ep.subcls] = ties.get(ep.subcls, 0) + int((o["tie_margin"] <= TIE_TAU * max(1.0, float(o["logits60"].abs().max()))).sum())
+        fb += o["counts"][:, :2].double()
+    assert sorted(cU) == list(range(1, 21))
+    got = table.cls[:, 0].cpu()
+    for c in range(1, 21):
+        assert abs(int(got[c, 0]) - cI[c]) <= ties[c] and abs(int(got[c, 1]) - cU[c]) <= ties[c], c
+    assert abs(table.miou(0) - O.miou_from_counts(cI, cU)) * 100 < 0.05
+    assert abs(table.fb_iou(0) - float((fb[:, 0] / (fb[:, 1] + 1e-10)).mean())) * 100 < 0.05
+    assert len(table.class_iou(0)) == 20
+    # the same 44 episodes from pinned host memory (the e2e path) give the same table, bit for bit
+    pipe = cwt.HostPipeline(cuda_device, params, n_head, lr, n_iter, num_classes_val=20, sub_batch=8)
+    host = [syn.make_batch(list(range(lo, min(n, lo + 16))), **kw).pin_memory() for lo in range(0, n, 16)]
+    pipe.run(host)
+    assert torch.equal(pipe.table.cls, table.cls) and torch.equal(pipe.table.fb, table.fb)
 
 
 class _FakeBackbone(torch.nn.Module):
@@ -633,7 +716,11 @@ def test_validate_transformer_dropin(cuda_device):
     # oracle with the same RNG stream for the per-episode nn.Conv2d init
     torch.manual_seed(5)
     # (drawn up front: the oracle's own nn.Conv2d construction would otherwise advance the RNG in between)
-    w0s = [torch.nn.Conv2d(64, 2, 1, bias=False).weight.detach().view(2, 64).clone() for _ in eps]
+    # two nn.Conv2d draws per episode, like the reference (binary_classifier, src/test.py:166, and Pseudo_cls, :200)
+    w0s = []
+    for _ in eps:
+        w0s.append(torch.nn.Conv2d(64, 2, 1, bias=False).weight.detach().view(2, 64).clone())
+        torch.nn.Conv2d(64, 2, 1, bias=False)
     cI, cU, losses = {}, {}, []
     batch_ce = []
     for i, ep in enumerate(eps):

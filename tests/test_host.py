@@ -20,8 +20,8 @@ from few_shot_seg_cwt_b200 import _lib, synthetic as syn
 from few_shot_seg_cwt_b200.episodic import IoUTable
 
 
-def _header_functions():
-    src = open(os.path.join(ROOT, "include", "cwt_b200.h")).read()
+def _header_functions(name="cwt_b200.h"):
+    src = open(os.path.join(ROOT, "include", name)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(cwt_[a-z0-9_]+)\s*\(", src)))
 
@@ -34,6 +34,12 @@ def test_library_exports_every_header_symbol():
         assert hasattr(lib, n), f"{n} declared in include/cwt_b200.h but not exported"
     assert set(names) == set(_lib.SIGNATURES), "ctypes binding table and header disagree"
     assert _lib.load().cwt_version() >= 100
+    # the product header holds no developer entry points; those live in cwt_b200_debug.h (and are exported too)
+    assert not [n for n in names if n.startswith("cwt_debug_")]
+    dbg = _header_functions("cwt_b200_debug.h")
+    assert set(dbg) == set(_lib.DEBUG_SIGNATURES) and all(n.startswith("cwt_debug_") for n in dbg)
+    for n in dbg:
+        assert hasattr(lib, n), f"{n} declared in include/cwt_b200_debug.h but not exported"
 
 
 def test_library_is_blackwell_native():
@@ -179,39 +185,63 @@ def test_iou_table_matches_reference_accumulation():
     assert 0.0 < t.fb_iou(0) < 1.0 and int(t.n_episodes) == 23
 
 
-def _worker(rank, world, port, n, q):
+def _worker(rank, world, port, n, q, n_steps=1):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    t = _table_for(syn.shard_indices(n, rank, world))
-    t.all_reduce()
+    mine = syn.shard_indices(n, rank, world)
+    t = IoUTable(5, "cpu")
+    per = (len(mine) + n_steps - 1) // n_steps
+    for s_ in range(n_steps):                       # every rank reduces after every step (bench.py / HostPipeline pattern)
+        part = mine[s_ * per:(s_ + 1) * per]
+        if part:
+            counts = torch.stack([_fake_counts(i) for i in part])
+            t.update(counts, torch.tensor([i % 5 + 1 for i in part]), torch.ones(len(part), 2, 2, dtype=torch.float64))
+        t.all_reduce()
+    t.all_reduce()                                  # idempotent: a further reduce with nothing new changes nothing
     # plain lists: torch tensors in an mp.Queue travel through shared-memory files that vanish when the child exits
-    q.put((rank, t.cls.tolist(), t.fb.tolist(), int(t.n_episodes), t.miou(0), t.miou(1)))
+    q.put((rank, t.cls.tolist(), t.fb.tolist(), int(t.n_episodes), t.miou(0), t.miou(1), t.ce.tolist()))
     dist.destroy_process_group()
 
 
-def test_sharded_sweep_all_reduce_world2_gloo():
-    """episodes i -> rank i mod 2, one integer all-reduce: identical table on both ranks, equal to the
-    single-process table."""
+@pytest.mark.parametrize("n_steps", [1, 3])
+def test_sharded_sweep_all_reduce_world2_gloo(n_steps):
+    """episodes i -> rank i mod 2, integer all-reduce after every step (and once more at the end): identical table on both
+    ranks, equal to the single-process table — however many times the table is reduced."""
     n, world = 17, 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
+    port = 29500 + (os.getpid() % 2000) + n_steps
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, q, n_steps)) for r in range(world)]
     [p.start() for p in procs]
     res = [q.get(timeout=120) for _ in range(world)]
     [p.join(60) for p in procs]
     single = _table_for(list(range(n)))
-    for rank, cls, fb, ne, m0, m1 in res:
+    for rank, cls, fb, ne, m0, m1, ce in res:
         assert cls == single.cls.tolist() and fb == single.fb.tolist() and ne == n
         assert m0 == single.miou(0) and m1 == single.miou(1)
+        assert ce == single.ce.tolist()
+
+
+def test_fit_status_words_raise_the_reference_errors():
+    """ops.raise_for_status: the deferred form of the reference's ZeroDivisionError (src/test.py:174) / CrossEntropyLoss
+    target check, raised from the status words that travel with the counts."""
+    from few_shot_seg_cwt_b200 import ops
+    ops.raise_for_status(torch.zeros(4, dtype=torch.int32))
+    with pytest.raises(ZeroDivisionError, match="episode 6"):
+        ops.raise_for_status(torch.tensor([0, 0, _lib.FIT_NO_FG | _lib.FIT_NONFINITE, 0], dtype=torch.int32), first_episode=4)
+    with pytest.raises(ValueError):
+        ops.raise_for_status(torch.tensor([_lib.FIT_BAD_LABEL], dtype=torch.int32))
+    with pytest.raises(FloatingPointError):
+        ops.raise_for_status(torch.tensor([0, _lib.FIT_NONFINITE], dtype=torch.int32))
 
 
 def test_header_is_plain_c():
     """include/cwt_b200.h is a C ABI: it must compile as C (no C++/torch types in the signatures)."""
-    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c",
-                        os.path.join(ROOT, "include", "cwt_b200.h")], capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr
+    for name in ("cwt_b200.h", "cwt_b200_debug.h"):
+        r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c",
+                            os.path.join(ROOT, "include", name)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
 
 
 def test_product_never_imports_the_oracle():

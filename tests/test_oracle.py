@@ -155,6 +155,27 @@ def test_pin_against_live_reference_small():
     assert np.array_equal(ref["counts"].numpy(), g["counts"])
 
 
+def test_oracle_ref_copy_matches_restatement_and_golden():
+    """oracle/_ref (the reference's own transformer.py / util.py, copied verbatim by oracle/make_ref.py; what bench.py's CPU
+    legs run on the GPU box): the episode body around those modules equals the restatement and the golden vector."""
+    from oracle import ref_episode as R
+    mods = R.load_reference_modules(prefer_live=False)
+    if mods is None:
+        pytest.skip("oracle/_ref has not been made (python oracle/make_ref.py needs the reference checkout)")
+    MHA, biou, _siou, where = mods
+    assert where == "oracle/_ref"
+    g = load_golden("small_1shot_h4")
+    case = g["case"]
+    ep = syn.make_episode(case["idx"], **gen_kwargs(case))
+    params = syn.make_transformer_params(case["n_head"], case["C"])
+    ref = R.episode_via_reference(ep, params, case["n_head"], case["lr"], case["n_iter"], MHA, biou)
+    ora = O.episode_ref(ep.f_s, ep.s_label, ep.f_q, ep.q_label, ep.w0, params, case["n_head"], case["lr"], case["n_iter"])
+    for k in ("W_fit", "W_adapted", "logits60", "logits60_0"):
+        assert rel_err(ora[k], ref[k]) < 1e-6, k
+    assert torch.equal(ora["counts"], ref["counts"]) and torch.equal(ora["counts0"], ref["counts0"])
+    assert rel_err(ref["W_adapted"], g["W_adapted"]) < 1e-6 and np.array_equal(ref["counts"].numpy(), g["counts"])
+
+
 @pytest.mark.parametrize("name", ["coscls_small_onoo", "coscls_small_robt", "coscls_small_onbt"])
 def test_oracle_coscls_flag_variants_reproduce_reference_golden(name):
     """CosCls with cls_type flags 'r' / 'n' / 'b' / 't' (pspnet.py:290-323): the explicit-parameter restatement against the

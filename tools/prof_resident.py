@@ -30,10 +30,22 @@ wr, tr = run(L.FIT_RESIDENT); wr, tr = run(L.FIT_RESIDENT)
 err = float((wr - ws).norm() / ws.norm())
 print(f"E={E} iters={a.iters}: stream {ts:.2f} ms ({E/ts*1e3:.0f} ep/s)  resident {tr:.2f} ms ({E/tr*1e3:.0f} ep/s)  rel diff {err:.2e} finite={bool(torch.isfinite(wr).all())}")
 if a.prof:
-    buf = torch.zeros(160, 12, dtype=torch.int64, device=dev)
-    lib.cwt_debug_set_prof_buffer(ctypes.c_void_p(buf.data_ptr()))
-    wr, tp = run(L.FIT_RESIDENT)
-    lib.cwt_debug_set_prof_buffer(None)
+    buf = torch.zeros(320, 12, dtype=torch.int64, device=dev)
+    # developer entry point (include/cwt_b200_debug.h): the same fit on the instrumented kernel, profile buffer per call
+    nbytes = lib.cwt_fit_workspace_bytes(E, 1, 512, 60, 60, 473, 473)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    wr = torch.empty(E, 2, 512, device=dev)
+    def run_prof():
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = lib.cwt_debug_fit_classifier_prof_f32(L.ptr(f_s), L.ptr(s_label), L.label_kind(s_label), L.ptr(w0), None, L.ptr(wr),
+                                                   E, 512, 60, 60, 473, 473, a.iters, 0.1, 255, L.ptr(ws), ws.numel(),
+                                                   L.ptr(buf), L.stream_ptr(dev))
+        L.check(rc, "cwt_debug_fit_classifier_prof_f32")
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+    run_prof(); buf.zero_(); tp = run_prof()
     c = buf.cpu().double()
     used = c[:, 0] > 0
     G = 3 if os.environ.get("CWT_RESIDENT_BPS") == "2" else 4          # episode groups of the plan (60x60x512)
