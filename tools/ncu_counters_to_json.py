@@ -11,7 +11,7 @@ start = next(i for i, l in enumerate(lines) if l.startswith('"ID"'))
 rows = list(csv.DictReader(io.StringIO("\n".join(lines[start:]))))
 per = {}
 for r in rows:
-    name = re.sub(r"\(.*", "", r["Kernel Name"]).split("::")[-1].split("<")[0]
+    name = re.sub(r"\(.*", "", r["Kernel Name"]).split("::")[-1].split("<")[0].replace("void ", "").strip()
     key = (name, r["ID"])
     per.setdefault(key, {})[r["Metric Name"]] = float(r["Metric Value"].replace(",", ""))
     per[key]["_grid"] = r.get("Grid Size", "")
