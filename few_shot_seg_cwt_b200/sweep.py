@@ -88,12 +88,16 @@ def main(argv=None):
 
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    results = pipe.run(batches(), reduce_every_step=False)
-    pipe.table.all_reduce()
+    results = pipe.run(batches())                 # one integer all-reduce of the table at the end (every rank calls it once)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
 
-    out = {"episodes": int(pipe.table.n_episodes), "world": world, "seconds": dt, "episodes_per_s_incl_generation": a.episodes / dt,
+    import hashlib
+    tb = pipe.table
+    digest = hashlib.sha256(tb.cls.cpu().numpy().tobytes() + tb.fb.cpu().numpy().tobytes()).hexdigest()
+    out = {"episodes": int(pipe.table.n_episodes), "world": world, "bad_episodes": int(tb.n_bad),
+           # the whole int64 table: equal bit for bit for every world size (src/test.py:225-251 accumulates the same sums)
+           "table_sha256": digest, "table_cls_I_U": tb.cls.cpu().tolist(), "table_fb_I_U": tb.fb.cpu().tolist(), "seconds": dt, "episodes_per_s_incl_generation": a.episodes / dt,
            "mIoU_adapted": pipe.table.miou(0), "mIoU_baseline": pipe.table.miou(1), "FBIoU_adapted": pipe.table.fb_iou(0),
            "FBIoU_baseline": pipe.table.fb_iou(1), "loss_adapted": pipe.table.mean_loss(0),
            "class_iou_adapted": pipe.table.class_iou(0), "config": {**kw, "heads": a.heads, "cls_lr": a.cls_lr, "adapt_iter": a.adapt_iter}}
