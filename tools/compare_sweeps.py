@@ -1,7 +1,7 @@
 """Check that sweep lines (few_shot_seg_cwt_b200.sweep, one JSON line per file) taken at different world sizes hold the SAME
 int64 intersection/union table:   python tools/compare_sweeps.py profiles/r2_sweep_10000_n1.json profiles/r2_sweep_10000_n2.json ..."""
 import json, sys
-lines = [json.loads(open(f).read().strip().splitlines()[0]) for f in sys.argv[1:]]
+lines = [json.loads([l for l in open(f).read().splitlines() if l.startswith('{"episodes"')][-1]) for f in sys.argv[1:]]
 ref = lines[0]
 ok = True
 for f, d in zip(sys.argv[1:], lines):
