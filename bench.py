@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-sub-batch", type=int, default=32, help="HostPipeline sub-batch size (0 = whole batches)")
+    ap.add_argument("--e2e-format", default="zc", choices=["zc", "dense"], help="host format of the e2e leg: zero-compressed "
+                                                                               "features (default) or dense tensors")
     ap.add_argument("--distinct", type=int, default=64, help="distinct synthetic episodes generated per rank (tiled to E)")
     ap.add_argument("--attn-both", action="store_true", help="also time the tcgen05 K-projection path of the transformer block "
                                                              "(reported under roofline.transformer_tcgen05; used by the ncu capture)")
@@ -401,20 +403,36 @@ def main():
     # the previous step's head) and reads the step's int64 counts back to the host.
     e2e = None
     if not a.no_e2e:
-        pipe = cwt.HostPipeline(dev, params, a.heads, a.cls_lr, a.adapt_iter, fit_algo=a.fit_algo, attn_algo=a.attn_algo,
-                                sub_batch=a.e2e_sub_batch, sub_batch_all=True)
-        pipe.run([host] * max(1, a.warmup), reduce_every_step=True)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        res = pipe.run([host] * a.steps, reduce_every_step=True)
-        e1.record()
-        barrier()
-        ms_e = max_over_ranks(e0.elapsed_time(e1))
-        e2e = {"value": world * E * a.steps / (ms_e / 1e3), "unit": UNIT, "h2d_bytes_per_step": host.nbytes() + host.subcls.numel() * 8,
-               "d2h_bytes_per_step": res[0].numel() * res[0].element_size() + 4 * E, "ms_per_step": ms_e / a.steps,
-               "api": "few_shot_seg_cwt_b200.HostPipeline.run (H2D in sub-batches of %d episodes through three device slots, async D2H of the counts and the fit status words)" % a.e2e_sub_batch,
-               "counts_equal_device_resident_run": bool(torch.equal(res[0].to(dev), last_out.counts))}
+        def run_e2e(host_batch, tag):
+            pipe = cwt.HostPipeline(dev, params, a.heads, a.cls_lr, a.adapt_iter, fit_algo=a.fit_algo, attn_algo=a.attn_algo,
+                                    sub_batch=a.e2e_sub_batch, sub_batch_all=True)
+            pipe.run([host_batch] * max(1, a.warmup), reduce_every_step=True)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            res = pipe.run([host_batch] * a.steps, reduce_every_step=True)
+            e1.record()
+            barrier()
+            ms_e = max_over_ranks(e0.elapsed_time(e1))
+            return {"value": world * E * a.steps / (ms_e / 1e3), "unit": UNIT,
+                    "h2d_bytes_per_step": host_batch.nbytes() + host.subcls.numel() * 16,      # + subcls and idx (int64)
+                    "d2h_bytes_per_step": res[0].numel() * res[0].element_size() + 4 * E, "ms_per_step": ms_e / a.steps,
+                    "host_format": tag,
+                    "counts_equal_device_resident_run": bool(torch.equal(res[0].to(dev), last_out.counts))}
+        api = ("few_shot_seg_cwt_b200.HostPipeline.run (H2D in sub-batches of %d episodes through three device slots, "
+               "async D2H of the counts and the fit status words)" % a.e2e_sub_batch)
+        dense = run_e2e(host, "dense fp32 tensors in pinned host memory")
+        if a.e2e_format == "dense":
+            e2e = dict(dense, api=api)
+        else:
+            # lossless zero-compressed transport of the post-ReLU features (few_shot_seg_cwt_b200.hostformat): bit mask + prefix
+            # counts + packed non-zeros cross PCIe, cwt_expand_zero_compressed_f32 rebuilds the dense tensors on the device
+            # inside the timed region; the dense-format number is kept beside it
+            from few_shot_seg_cwt_b200 import hostformat
+            comp = hostformat.compress_batch(host).pin_memory()
+            e2e = dict(run_e2e(comp, "zero-compressed features (bit mask + prefix counts + packed non-zeros), expanded on the "
+                                     "device inside the timed region; labels / weights dense"), api=api)
+            e2e["dense_format"] = {k: dense[k] for k in ("value", "h2d_bytes_per_step", "ms_per_step", "counts_equal_device_resident_run")}
 
     # ---- CPU baseline on the box's host cores (rank 0, N = 1 only) ----
     cpu = None

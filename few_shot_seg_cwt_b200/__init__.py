@@ -24,6 +24,8 @@ from .metrics import (batch_intersection_union_int, batch_intersectionAndUnionGP
 from .ops import (feat_times_rows, normalize_features, fit_classifier, fit_classifier_bias, fit_classifier_dice, fit_coscls, fit_multiclass, intersection_union, label_counts, logits_iou,  # noqa: F401
                   query_loss_grad, rows_times_feat, transformer_backward, transformer_forward,
                   upsample_argmax_iou)
+from .ops import fit_status, raise_for_status  # noqa: F401
+from .hostformat import CompressedEpisodeBatch, compress_batch, compress_map, expand_map, expand_map_reference  # noqa: F401
 from .transformer import MultiHeadAttentionOne  # noqa: F401
 
 __all__ = [
@@ -32,7 +34,8 @@ __all__ = [
     "intersection_union_int", "validate_transformer", "episode_head", "run_sweep", "IoUTable", "HostPipeline", "HeadPipeline", "bind_host_to_gpu",
     "meta_train_step", "do_epoch", "query_loss", "transformer_forward", "transformer_backward", "logits_iou",
     "upsample_argmax_iou", "intersection_union", "label_counts", "query_loss_grad",
-    "rows_times_feat", "feat_times_rows", "synthetic",
+    "rows_times_feat", "feat_times_rows", "synthetic", "fit_status", "raise_for_status",
+    "CompressedEpisodeBatch", "compress_batch", "compress_map", "expand_map", "expand_map_reference",
 ]
 
 

@@ -21,6 +21,7 @@ import torch.nn as nn
 from . import _lib as L
 from . import ops
 from .synthetic import EpisodeBatch, make_batch, shard_indices
+from .hostformat import CompressedEpisodeBatch, CompressedMap, expand_map
 
 IGNORE = 255
 
@@ -571,44 +572,73 @@ class HostPipeline:
         self._slots: List[Optional[EpisodeBatch]] = [None] * n_slots
         self._slot_free: List[Optional[torch.cuda.Event]] = [None] * n_slots
         self._results: List[Optional[Tuple[torch.Tensor, torch.Tensor]]] = []   # pinned (counts, status) per host batch
+        self._cslots: List[Optional[dict]] = [None] * n_slots   # device staging of zero-compressed features (mask, prefix, values)
 
     @staticmethod
     def _fields(b: EpisodeBatch):
         return (b.f_s, b.s_label, b.f_q, b.q_label, b.w0, b.subcls, b.idx)
 
-    def _fits(self, slot_batch: EpisodeBatch, hb: EpisodeBatch) -> bool:
-        return all(x.shape[1:] == y.shape[1:] and x.dtype == y.dtype and x.shape[0] >= y.shape[0]
-                   for x, y in zip(self._fields(slot_batch), self._fields(hb)))
-
-    def _stage(self, hb: EpisodeBatch, slot: int, cap: int = 0):
-        """H2D copy of one host (sub-)batch into staging slot ``slot`` (capacity >= ``cap`` episodes) on the copy stream."""
-        n = hb.n_episodes
+    def _stage(self, hb, lo: int, hi: int, slot: int, cap: int = 0):
+        """H2D copy of episodes ``lo:hi`` of one host batch into staging slot ``slot`` (capacity >= ``cap`` episodes) on the
+        copy stream. ``hb`` is an :class:`EpisodeBatch` (dense pinned tensors) or a :class:`CompressedEpisodeBatch`
+        (zero-compressed features: mask / prefix / packed values are copied and the dense tensors are rebuilt on the device
+        by ``cwt_expand_zero_compressed_f32``, on the copy stream too)."""
+        n = hi - lo
+        compressed = isinstance(hb, CompressedEpisodeBatch)
+        shapes = [(tuple(hb.f_s.shape[1:]), torch.float32), (tuple(hb.s_label.shape[1:]), hb.s_label.dtype),
+                  (tuple(hb.f_q.shape[1:]), torch.float32), (tuple(hb.q_label.shape[1:]), hb.q_label.dtype),
+                  (tuple(hb.w0.shape[1:]), hb.w0.dtype), (tuple(hb.subcls.shape[1:]), hb.subcls.dtype),
+                  (tuple(hb.idx.shape[1:]), hb.idx.dtype)]
         with torch.cuda.stream(self.copy_stream):
             full = self._slots[slot]
-            if full is None or not self._fits(full, hb):
+            if full is None or not (all(tuple(x.shape[1:]) == sh and x.dtype == dt for x, (sh, dt) in zip(self._fields(full), shapes))
+                                    and full.f_s.shape[0] >= n):
                 cap = max(n, cap, 1)
-                alloc = lambda t: torch.empty((cap,) + tuple(t.shape[1:]), dtype=t.dtype, device=self.device)
-                full = EpisodeBatch(*(alloc(t) for t in self._fields(hb)))
+                full = EpisodeBatch(*(torch.empty((cap,) + sh, dtype=dt, device=self.device) for sh, dt in shapes))
                 for t in self._fields(full):
                     t.record_stream(self._main)                       # read by the head's stream
                 self._slots[slot] = full
+                self._cslots[slot] = None
             elif self._slot_free[slot] is not None:
                 self.copy_stream.wait_event(self._slot_free[slot])      # the head that read this slot last has finished
             db = EpisodeBatch(*(t.narrow(0, 0, n) for t in self._fields(full)))
-            for dst, src in zip(self._fields(db), self._fields(hb)):
-                dst.copy_(src, non_blocking=True)
+            if not compressed:
+                for dst, src in zip(self._fields(db), self._fields(hb)):
+                    dst.copy_(src[lo:hi], non_blocking=True)
+            else:
+                for dst, src in ((db.s_label, hb.s_label), (db.q_label, hb.q_label), (db.w0, hb.w0), (db.subcls, hb.subcls),
+                                 (db.idx, hb.idx)):
+                    dst.copy_(src[lo:hi], non_blocking=True)
+                cs = self._cslots[slot] or {}
+                for name, cm, dense in (("f_s", hb.f_s, db.f_s), ("f_q", hb.f_q, db.f_q)):
+                    W = cm.mask.shape[1]
+                    v0, v1 = cm.val_start[lo], cm.val_start[hi]
+                    st = cs.get(name)
+                    if st is None or st[0].shape[0] < n or st[0].shape[1] != W or st[2].numel() < v1 - v0:
+                        capn = max(n, full.f_s.shape[0])
+                        st = (torch.empty((capn, W), dtype=torch.int32, device=self.device),
+                              torch.empty((capn, W), dtype=torch.int32, device=self.device),
+                              torch.empty(max(int(1.25 * (v1 - v0)) + 1024, 1), dtype=torch.float32, device=self.device))
+                        cs[name] = st
+                    m, o, v = st[0][:n], st[1][:n], st[2][:max(v1 - v0, 1)]
+                    m.copy_(cm.mask[lo:hi], non_blocking=True)
+                    o.copy_(cm.woff[lo:hi], non_blocking=True)
+                    if v1 > v0:
+                        v[:v1 - v0].copy_(cm.vals[v0:v1], non_blocking=True)
+                    expand_map(m, o, v, dense, v0)
+                self._cslots[slot] = cs
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
         return db, ev
 
-    def _sub_batches(self, host_batches: Iterable[EpisodeBatch]):
-        """(batch number, first episode, is-last, host sub-batch): slices of a pinned tensor along dim 0 stay pinned."""
+    def _sub_batches(self, host_batches):
+        """(batch number, first episode, end episode, is-last, host batch, E): slices of a pinned tensor along dim 0 stay pinned."""
         for bi, hb in enumerate(host_batches):
             E = hb.n_episodes
             step = self.sub_batch if (self.sub_batch > 0 and (bi == 0 or self.sub_batch_all)) else max(E, 1)
             for lo in range(0, max(E, 1), step):
                 hi = min(E, lo + step)
-                yield bi, lo, hi >= E, EpisodeBatch(*(t[lo:hi] for t in self._fields(hb))), E
+                yield bi, lo, hi, hi >= E, hb, E
 
     def _result_buffers(self, bi: int, E: int):
         """Pinned host buffers of host batch ``bi`` (counts int64 [E,2,2,3], fit status int32 [E]): owned by the pipeline and
@@ -645,8 +675,8 @@ class HostPipeline:
                 item = next(it, None)
                 if item is None:
                     return
-                bi, lo, last, hb, E = item
-                db_, ev_ = self._stage(hb, nslot, E)
+                bi, lo, hi, last, hb, E = item
+                db_, ev_ = self._stage(hb, lo, hi, nslot, E)
                 queue.append((db_, ev_, nslot, bi, lo, last, E))
                 nslot = (nslot + 1) % n_slots
 

@@ -277,6 +277,18 @@ int cwt_resize_pad_normalize_f32(const float* image_hwc, const uint8_t* label_or
                                  const float* pad3_or_null, int pad_label, float* out_chw, void* label_out_or_null,
                                  int label_out_kind, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Zero-compressed transport of post-ReLU features (the host -> device leg in front of the path: the reference moves
+ * dense tensors with .cuda(), src/test.py:153-157; ~half of the elements are zeros). Lossless:
+ *   mask         [n_words] uint32   bit l of word w set <=> element 32 w + l has a non-zero BIT PATTERN
+ *   word_offsets [n_words] uint32   exclusive prefix count of set bits, base_offset = the count before word 0
+ *                                   (so that a slice of a larger compressed batch expands without re-basing)
+ *   vals         packed fp32 values of the set bits, in element order
+ *   out          [32 * n_words] fp32, 16-byte aligned: the dense tensor, bit-identical to the original
+ * ------------------------------------------------------------------------------------- */
+int cwt_expand_zero_compressed_f32(const uint32_t* mask, const uint32_t* word_offsets, const float* vals,
+                                   float* out, long long n_words, unsigned base_offset, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -839,6 +839,53 @@ def test_host_pipeline_slots_and_sub_batches(cuda_device):
     assert torch.equal(direct.counts.cpu(), outs[0][0])
 
 
+@pytest.mark.parametrize("case", ["relu", "dense", "zeros", "specials", "ragged"])
+def test_zero_compressed_expand_roundtrip_bit_exact(cuda_device, case):
+    """cwt_expand_zero_compressed_f32: the dense tensor comes back bit for bit (incl. -0.0, NaN, Inf, denormals), for
+    half-empty, dense and all-zero inputs and for word counts that are not a multiple of the warp's 32 words."""
+    g = torch.Generator().manual_seed(7)
+    shape = {"ragged": (3, 2, 7, 16), "zeros": (2, 4, 8, 32)}.get(case, (4, 64, 12, 12))
+    t = torch.randn(shape, generator=g)
+    if case in ("relu", "ragged", "specials"):
+        t = torch.relu(t)
+    if case == "zeros":
+        t.zero_()
+    if case == "specials":
+        flat = t.view(-1)
+        flat[0], flat[1], flat[33], flat[64], flat[100] = -0.0, float("nan"), float("inf"), 1e-42, -float("inf")
+        flat[-1] = -0.0
+    c = cwt.compress_map(t)
+    assert torch.equal(cwt.expand_map_reference(c).view(torch.int32), t.view(torch.int32))
+    out = torch.full(shape, 7.0, device=cuda_device)
+    cwt.expand_map(c.mask.to(cuda_device), c.woff.to(cuda_device), c.vals.to(cuda_device) if c.vals.numel() else
+                   torch.zeros(1, device=cuda_device), out, 0)
+    assert torch.equal(out.cpu().view(torch.int32), t.view(torch.int32))
+    # a slice of the batch expands with base_offset = its first value (what HostPipeline's sub-batches do)
+    lo, hi = 1, shape[0]
+    out2 = torch.empty((hi - lo,) + shape[1:], device=cuda_device)
+    v = c.vals[c.val_start[lo]:c.val_start[hi]]
+    cwt.expand_map(c.mask[lo:hi].to(cuda_device), c.woff[lo:hi].to(cuda_device),
+                   v.to(cuda_device) if v.numel() else torch.zeros(1, device=cuda_device), out2, c.val_start[lo])
+    assert torch.equal(out2.cpu().view(torch.int32), t[lo:hi].contiguous().view(torch.int32))
+
+
+def test_host_pipeline_zero_compressed_equals_dense(cuda_device):
+    """HostPipeline fed with zero-compressed host batches (the e2e transport of bench.py) gives the counts of the dense path
+    bit for bit — the expansion is lossless, so nothing downstream can differ — while moving fewer bytes."""
+    kw = dict(shot=1, C=64, h=12, w=12, H=89, W=89, style="unit")
+    params = syn.make_transformer_params(2, 64)
+    dense = [syn.make_batch(list(range(lo, lo + n)), **kw).pin_memory() for lo, n in ((0, 5), (5, 3), (8, 6))]
+    comp = [cwt.compress_batch(b).pin_memory() for b in dense]
+    assert all(c.nbytes() < 0.75 * c.dense_nbytes() for c in comp)
+    for sub in (0, 2, 4):
+        a = cwt.HostPipeline(cuda_device, params, 2, 0.1, 30, sub_batch=sub).run(dense)
+        pipe = cwt.HostPipeline(cuda_device, params, 2, 0.1, 30, sub_batch=sub)
+        b = pipe.run(comp)
+        assert len(a) == len(b) and all(torch.equal(x, y) for x, y in zip(a, b)), sub
+        b2 = [r.clone() for r in pipe.run(comp)]                       # staging buffers reused on the second run
+        assert all(torch.equal(x, y) for x, y in zip(a, b2)), sub
+
+
 def test_head_pipeline_equals_episode_head(cuda_device):
     """HeadPipeline (post stage of batch i on a side stream under the fit of batch i+1) gives exactly the results of the
     serial episode_head, batch by batch, and the same IoU table."""
