@@ -48,7 +48,9 @@ def parse():
     ap.add_argument("--ref-episodes", type=int, default=2, help="--impl reference: episodes per step (bounded CPU sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-sub-batch", type=int, default=32, help="HostPipeline sub-batch size (0 = whole batches)")
+    ap.add_argument("--e2e-sub-batch", type=int, default=16, help="HostPipeline sub-batch size (0 = whole batches)")
+    ap.add_argument("--e2e-sub-all", type=int, default=1, help="1: every host batch goes through in sub-batches; 0: only the first")
+    ap.add_argument("--e2e-expand-main", type=int, default=0, help="zero-compressed e2e: expansion kernel on the head's stream (1) or the copy stream (0)")
     ap.add_argument("--e2e-format", default="zc", choices=["zc", "dense"], help="host format of the e2e leg: zero-compressed "
                                                                                "features (default) or dense tensors")
     ap.add_argument("--distinct", type=int, default=64, help="distinct synthetic episodes generated per rank (tiled to E)")
@@ -405,7 +407,7 @@ def main():
     if not a.no_e2e:
         def run_e2e(host_batch, tag):
             pipe = cwt.HostPipeline(dev, params, a.heads, a.cls_lr, a.adapt_iter, fit_algo=a.fit_algo, attn_algo=a.attn_algo,
-                                    sub_batch=a.e2e_sub_batch, sub_batch_all=True)
+                                    sub_batch=a.e2e_sub_batch, sub_batch_all=bool(a.e2e_sub_all), expand_on_main=bool(a.e2e_expand_main))
             pipe.run([host_batch] * max(1, a.warmup), reduce_every_step=True)
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -56,7 +56,7 @@ SIGNATURES = {
     "cwt_feat_times_rows": (_i, [_vp, _vp, _i, _vp] + [_i] * 4 + [_vp, _sz, _vp]),
     "cwt_resize_pad_normalize_f32": (_i, [_vp, _vp] + [_i] * 5 + [_vp, _vp, _vp, _i, _vp, _vp, _i, _vp]),
     "cwt_normalize_features_f32": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _vp]),
-    "cwt_expand_zero_compressed_f32": (_i, [_vp, _vp, _vp, _vp, _ll, C.c_uint, _vp]),
+    "cwt_expand_zero_compressed_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, C.c_uint, _vp]),
 }
 
 

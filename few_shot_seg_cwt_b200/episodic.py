@@ -546,7 +546,7 @@ class HostPipeline:
 
     def __init__(self, device, params: Dict[str, torch.Tensor], n_head: int, lr: float, n_iter: int,
                  fit_algo: int = L.FIT_AUTO, attn_algo: int = L.ATTN_REASSOC, num_classes_val: int = 5, n_slots: int = 3,
-                 sub_batch: int = 32, sub_batch_all: bool = True):
+                 sub_batch: int = 16, sub_batch_all: bool = True, expand_on_main: bool = False):
         self.device = torch.device(device)
         self.params = {k: v.to(self.device) for k, v in params.items()}
         self.n_head, self.lr, self.n_iter = n_head, lr, n_iter
@@ -567,6 +567,11 @@ class HostPipeline:
         # Device-resident staging slots are reused for the whole run: no allocator traffic (a cudaMalloc of ~1 GB
         # synchronises the device). Three slots: the copy of sub-batch i+2 may start as soon as the copy of i+1 has
         # finished (its slot was released by head i-1 long ago), so the copy engine never waits for the head.
+        # Zero-compressed host batches: where the expansion kernel runs. False (default): on the copy stream, behind the copies it
+        # expands, i.e. concurrently with the previous sub-batch's fit; True: on the head's stream, right in front of the fit.
+        # Measured on B200 (bench.py e2e, 10 steps of 64 episodes, three runs each, profiles/r2b_e2e_sub_batch*.txt): 18.05-18.4 ms
+        # per step either way, sub-batches of 16 or 32 — the choice does not matter at one GPU, where the copy is hidden anyway.
+        self.expand_on_main = bool(expand_on_main)
         self.sub_batch = max(0, int(sub_batch))
         self.sub_batch_all = bool(sub_batch_all)            # sub-batch every host batch, not only the first
         self._slots: List[Optional[EpisodeBatch]] = [None] * n_slots
@@ -584,6 +589,7 @@ class HostPipeline:
         (zero-compressed features: mask / prefix / packed values are copied and the dense tensors are rebuilt on the device
         by ``cwt_expand_zero_compressed_f32``, on the copy stream too)."""
         n = hi - lo
+        pending = []                  # expansions left for the head's stream (expand_on_main)
         compressed = isinstance(hb, CompressedEpisodeBatch)
         shapes = [(tuple(hb.f_s.shape[1:]), torch.float32), (tuple(hb.s_label.shape[1:]), hb.s_label.dtype),
                   (tuple(hb.f_q.shape[1:]), torch.float32), (tuple(hb.q_label.shape[1:]), hb.q_label.dtype),
@@ -617,7 +623,7 @@ class HostPipeline:
                     if st is None or st[0].shape[0] < n or st[0].shape[1] != W or st[2].numel() < v1 - v0:
                         capn = max(n, full.f_s.shape[0])
                         st = (torch.empty((capn, W), dtype=torch.int32, device=self.device),
-                              torch.empty((capn, W), dtype=torch.int32, device=self.device),
+                              torch.empty((capn, cm.woff.shape[1]), dtype=torch.int32, device=self.device),
                               torch.empty(max(int(1.25 * (v1 - v0)) + 1024, 1), dtype=torch.float32, device=self.device))
                         cs[name] = st
                     m, o, v = st[0][:n], st[1][:n], st[2][:max(v1 - v0, 1)]
@@ -625,11 +631,14 @@ class HostPipeline:
                     o.copy_(cm.woff[lo:hi], non_blocking=True)
                     if v1 > v0:
                         v[:v1 - v0].copy_(cm.vals[v0:v1], non_blocking=True)
-                    expand_map(m, o, v, dense, v0)
+                    if self.expand_on_main:
+                        pending.append((m, o, v, dense, v0))
+                    else:
+                        expand_map(m, o, v, dense, v0)
                 self._cslots[slot] = cs
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
-        return db, ev
+        return db, ev, pending
 
     def _sub_batches(self, host_batches):
         """(batch number, first episode, end episode, is-last, host batch, E): slices of a pinned tensor along dim 0 stay pinned."""
@@ -676,8 +685,8 @@ class HostPipeline:
                 if item is None:
                     return
                 bi, lo, hi, last, hb, E = item
-                db_, ev_ = self._stage(hb, lo, hi, nslot, E)
-                queue.append((db_, ev_, nslot, bi, lo, last, E))
+                db_, ev_, pend_ = self._stage(hb, lo, hi, nslot, E)
+                queue.append((db_, ev_, pend_, nslot, bi, lo, last, E))
                 nslot = (nslot + 1) % n_slots
 
         head = HeadPipeline(self.device, self.params, self.n_head, self.lr, self.n_iter, self.fit_algo, self.attn_algo,
@@ -689,8 +698,10 @@ class HostPipeline:
 
         prefetch()
         while queue:
-            db, ev, cur, bi, lo, last, E = queue.pop(0)
+            db, ev, pend, cur, bi, lo, last, E = queue.pop(0)
             main.wait_event(ev)
+            for m_, o_, v_, dense_, v0_ in pend:              # zero-compressed features: rebuild the dense tensors in front of the fit
+                expand_map(m_, o_, v_, dense_, v0_)
             if bi == len(results):                            # first sub-batch of host batch bi: its pinned result buffers
                 r, st = self._result_buffers(bi, E)
                 results.append(r); statuses.append(st)

@@ -22,13 +22,13 @@ class CompressedMap:
     """One fp32 tensor [E, ...] compressed per episode (so that sub-batches are slices)."""
     shape: tuple                 # dense shape
     mask: torch.Tensor           # uint32 as int32 [E, W]   W = words per episode
-    woff: torch.Tensor           # uint32 as int32 [E, W]   exclusive prefix of set bits over the whole batch
+    woff: torch.Tensor           # uint32 as int32 [E, ceil(W / 32)]   set bits before each block of 32 words, over the whole batch
     vals: torch.Tensor           # float32 [nnz]
     val_start: List[int]         # [E + 1] start of every episode's values
 
     def nbytes(self, lo: int = 0, hi: int = None) -> int:
         hi = self.mask.shape[0] if hi is None else hi
-        return (hi - lo) * self.mask.shape[1] * 8 + (self.val_start[hi] - self.val_start[lo]) * 4
+        return (hi - lo) * (self.mask.shape[1] + self.woff.shape[1]) * 4 + (self.val_start[hi] - self.val_start[lo]) * 4
 
     def pin_memory(self) -> "CompressedMap":
         return CompressedMap(self.shape, self.mask.pin_memory(), self.woff.pin_memory(), self.vals.pin_memory(), self.val_start)
@@ -45,13 +45,15 @@ def compress_map(t: torch.Tensor) -> CompressedMap:
     bits = t.contiguous().view(torch.int32).reshape(-1).numpy() != 0            # the BIT PATTERN decides (keeps -0.0, NaN)
     vals = torch.from_numpy(t.contiguous().reshape(-1).numpy()[bits].copy())
     mask = np.packbits(bits.reshape(-1, 32), axis=1, bitorder="little").view(np.uint32).reshape(E, per // 32)
-    cnt = bits.reshape(-1, 32).sum(axis=1, dtype=np.int64)
-    woff = np.cumsum(cnt) - cnt
-    if woff.size and int(woff[-1]) + int(cnt[-1]) >= 2 ** 32:
+    W = per // 32
+    cnt = bits.reshape(-1, 32).sum(axis=1, dtype=np.int64).reshape(E, W)                # set bits per word
+    woff = (np.cumsum(cnt.reshape(-1)) - cnt.reshape(-1)).reshape(E, W)[:, ::32]         # ... before each block of 32 words of a row
+    total = int(cnt.sum())
+    if total >= 2 ** 32:
         raise ValueError("batch too large for 32-bit value offsets: compress fewer episodes per batch")
-    starts = [0] + [int(x) for x in np.cumsum(cnt.reshape(E, -1).sum(axis=1))] if E else [0]
+    starts = [0] + [int(x) for x in np.cumsum(cnt.sum(axis=1))] if E else [0]
     return CompressedMap(tuple(t.shape), torch.from_numpy(mask.view(np.int32).copy()),
-                         torch.from_numpy(woff.astype(np.uint32).view(np.int32).reshape(E, per // 32).copy()), vals, starts)
+                         torch.from_numpy(np.ascontiguousarray(woff).astype(np.uint32).view(np.int32).copy()), vals, starts)
 
 
 def expand_map_reference(c: CompressedMap) -> torch.Tensor:
@@ -63,13 +65,13 @@ def expand_map_reference(c: CompressedMap) -> torch.Tensor:
 
 
 def expand_map(mask: torch.Tensor, woff: torch.Tensor, vals: torch.Tensor, out: torch.Tensor, base: int) -> torch.Tensor:
-    """Device expansion of ``mask`` / ``woff`` [n, W] (device int32) + ``vals`` (device fp32) into ``out`` (dense, device)."""
+    """Device expansion of ``mask`` [n, W] / ``woff`` [n, ceil(W/32)] (device int32) + ``vals`` (device fp32) into ``out``."""
     dev = L.require_cuda(mask, woff, out)
-    n_words = mask.numel()
-    if out.numel() != 32 * n_words:
-        raise ValueError("out must hold 32 elements per mask word")
+    n_rows, W = mask.shape
+    if out.numel() != 32 * n_rows * W or tuple(woff.shape) != (n_rows, (W + 31) // 32):
+        raise ValueError("out must hold 32 elements per mask word and woff one entry per block of 32 words of a row")
     with torch.cuda.device(dev):
-        rc = L.load().cwt_expand_zero_compressed_f32(L.ptr(mask), L.ptr(woff), L.ptr(vals), L.ptr(out), n_words,
+        rc = L.load().cwt_expand_zero_compressed_f32(L.ptr(mask), L.ptr(woff), L.ptr(vals), L.ptr(out), n_rows, W,
                                                      int(base) & 0xFFFFFFFF, L.stream_ptr(dev))
     L.check(rc, "cwt_expand_zero_compressed_f32")
     return out

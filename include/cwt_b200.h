@@ -279,15 +279,17 @@ int cwt_resize_pad_normalize_f32(const float* image_hwc, const uint8_t* label_or
 
 /* ---------------------------------------------------------------------------------------
  * Zero-compressed transport of post-ReLU features (the host -> device leg in front of the path: the reference moves
- * dense tensors with .cuda(), src/test.py:153-157; ~half of the elements are zeros). Lossless:
- *   mask         [n_words] uint32   bit l of word w set <=> element 32 w + l has a non-zero BIT PATTERN
- *   word_offsets [n_words] uint32   exclusive prefix count of set bits, base_offset = the count before word 0
- *                                   (so that a slice of a larger compressed batch expands without re-basing)
- *   vals         packed fp32 values of the set bits, in element order
- *   out          [32 * n_words] fp32, 16-byte aligned: the dense tensor, bit-identical to the original
+ * dense tensors with .cuda(), src/test.py:153-157; ~half of the elements are zeros). Lossless. The tensor is a matrix of
+ * n_rows rows (episodes) of 32 * words_per_row fp32 elements:
+ *   mask          [n_rows][words_per_row] uint32   bit l of word w set <=> element 32 w + l has a non-zero BIT PATTERN
+ *   block_offsets [n_rows][ceil(words_per_row / 32)] uint32   number of set bits before each block of 32 words, counted
+ *                 over the whole compressed batch; base_offset = the count before row 0 of THIS call (so that a slice of
+ *                 a larger compressed batch expands without re-basing)
+ *   vals          packed fp32 values of the set bits, in element order
+ *   out           [n_rows][32 * words_per_row] fp32, 16-byte aligned: the dense tensor, bit-identical to the original
  * ------------------------------------------------------------------------------------- */
-int cwt_expand_zero_compressed_f32(const uint32_t* mask, const uint32_t* word_offsets, const float* vals,
-                                   float* out, long long n_words, unsigned base_offset, void* stream);
+int cwt_expand_zero_compressed_f32(const uint32_t* mask, const uint32_t* block_offsets, const float* vals,
+                                   float* out, int n_rows, int words_per_row, unsigned base_offset, void* stream);
 
 #ifdef __cplusplus
 }

@@ -427,7 +427,9 @@ def test_transformer_forward_eval(cuda_device, n_head, C, hw, algo):
     with torch.no_grad():
         kd, krd = k.to(cuda_device), kraw.to(cuda_device)
         out = m(q.to(cuda_device), kd, kd)
-        assert torch.equal(m(q.to(cuda_device), kd, kd.clone()), out)      # equal-valued v in distinct storage
+        assert torch.equal(m(q.to(cuda_device), kd, kd.view_as(kd)), out)  # the same storage through another tensor object
+        with pytest.raises(NotImplementedError):                           # distinct storage: no hidden compare + host sync
+            m(q.to(cuda_device), kd, kd.clone())
         m.normalize_k = True                         # fused F.normalize on the raw features
         out_fused = m(q.to(cuda_device), krd, krd)
     assert out.shape == (B, 2, C)
