@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("CWT_LIB_PATH") or os.path.join(_HERE, "lib", "libcwt_
 
 OK = 0
 LABEL_U8, LABEL_I64 = 0, 1
-FIT_AUTO, FIT_STREAM, FIT_RESIDENT = 0, 1, 2
+FIT_AUTO, FIT_STREAM, FIT_RESIDENT, FIT_L2 = 0, 1, 2, 3
 COSCLS_R, COSCLS_N, COSCLS_T = 1, 2, 4          # cwt_fit_coscls_f32 flags (CosCls cls_type 'r', 'n', 't')
 ATTN_REASSOC, ATTN_TCGEN05 = 0, 1
 

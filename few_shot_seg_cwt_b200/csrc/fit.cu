@@ -24,6 +24,10 @@ int pack_label_cells(const void* labels, int label_kind, int n_img, int h, int w
 size_t fit_resident_workspace_bytes(int E, int C, int h, int w);
 int fit_resident(const float* f_s, const uint4* cells, const float2* cw, float* w_io, int E, int C, int h, int w,
                  int n_iter, float lr, void* ws, size_t ws_bytes, long long* prof_out, cudaStream_t st);
+bool fit_l2_supported(int S, int C, int h, int w);
+size_t fit_l2_workspace_bytes(int E, int S, int C, int h, int w);
+int fit_l2(const float* f_s, const uint4* cells, const float2* cw, float* w_io, int E, int S, int C, int h, int w,
+           int n_iter, float lr, void* ws, size_t ws_bytes, cudaStream_t st);
 
 // one CTA per episode: W <- W0, Wd = W1 - W0
 __global__ void __launch_bounds__(256)
@@ -66,7 +70,8 @@ static size_t carve_fit(Carver& cv, FitWs& ws, int E, int S, int C, int h, int w
     ws.zd = cv.take<float>((size_t)E * S * h * w);
     ws.g60 = cv.take<float>((size_t)E * S * h * w);
     ws.loss_part = cv.take<float>((size_t)E * S * ws.nblk);
-    ws.resident_bytes = (S == 1) ? fit_resident_workspace_bytes(E, C, h, w) : 0;
+    // the persistent kernels' exchange areas: resident (1 shot) or L2-streamed (several shots, head geometry)
+    ws.resident_bytes = (S == 1) ? fit_resident_workspace_bytes(E, C, h, w) : fit_l2_workspace_bytes(E, S, C, h, w);
     ws.resident = cv.take<char>(ws.resident_bytes);
     return align_up(cv.off);
 }
@@ -97,7 +102,7 @@ static int fit_classifier_impl(const float* f_s, const void* s_label, int label_
     CWT_REQUIRE(w <= HIRES_MAXW, CWT_ERR_UNSUPPORTED, "fit: w=%d exceeds the supported width (%d)", w, HIRES_MAXW);
     CWT_REQUIRE(label_kind == CWT_LABEL_U8 || label_kind == CWT_LABEL_I64, CWT_ERR_INVALID_ARG,
                 "fit: label_kind %d", label_kind);
-    CWT_REQUIRE(algo == CWT_FIT_AUTO || algo == CWT_FIT_STREAM || algo == CWT_FIT_RESIDENT, CWT_ERR_INVALID_ARG,
+    CWT_REQUIRE(algo == CWT_FIT_AUTO || algo == CWT_FIT_STREAM || algo == CWT_FIT_RESIDENT || algo == CWT_FIT_L2, CWT_ERR_INVALID_ARG,
                 "fit: algo %d", algo);
     Carver cv(workspace, ws_bytes);
     FitWs ws;
@@ -113,8 +118,21 @@ static int fit_classifier_impl(const float* f_s, const void* s_label, int label_
     k_fit_init_weights<<<E, 256, 0, st>>>(w0, w_out, ws.wd, C);
     CWT_LAUNCHED("fit_init_weights");
 
+    // L2-streamed persistent kernel: several shots, head geometry, no loss trace (also on request for one shot)
+    if ((algo == CWT_FIT_L2 || (algo == CWT_FIT_AUTO && S > 1)) && n_iter > 0) {
+        if (!loss_trace_or_null && !prof_out && fit_l2_supported(S, C, h, w)) {
+            size_t l2_bytes = ws.resident_bytes;
+            void* l2_ws = ws.resident;
+            rc = fit_l2(f_s, ws.cells, ws.cw, w_out, E, S, C, h, w, n_iter, lr, l2_ws,
+                        S == 1 ? (fit_l2_workspace_bytes(E, S, C, h, w) <= l2_bytes ? l2_bytes : 0) : l2_bytes, st);
+            if (rc == CWT_OK) return CWT_OK;
+            if (rc != CWT_ERR_UNSUPPORTED || algo == CWT_FIT_L2) return rc;
+        } else if (algo == CWT_FIT_L2) {
+            CWT_REQUIRE(false, CWT_ERR_UNSUPPORTED, "fit: CWT_FIT_L2 needs the head geometry (C=512, 60x60) and no loss trace (C=%d %dx%d)", C, h, w);
+        }
+    }
     // resident (shared-memory) algorithm: 1-shot, no loss trace, shape must fit on chip
-    if (algo != CWT_FIT_STREAM && n_iter > 0) {
+    if (algo != CWT_FIT_STREAM && algo != CWT_FIT_L2 && n_iter > 0) {
         if (S == 1 && !loss_trace_or_null && HWl % 4 == 0) {
             rc = fit_resident(f_s, ws.cells, ws.cw, w_out, E, C, h, w, n_iter, lr, ws.resident, ws.resident_bytes,
                               prof_out, st);

@@ -45,6 +45,8 @@ extern "C" {
 #define CWT_FIT_AUTO       0
 #define CWT_FIT_STREAM     1   /* features streamed from HBM/L2 every step (any S)            */
 #define CWT_FIT_RESIDENT   2   /* features staged once into shared memory, persistent kernel  */
+#define CWT_FIT_L2         3   /* persistent kernel, features streamed from L2 every sweep (any S; C=512, 60x60): the
+                                  default for S > 1 — G episodes at a time stay L2-resident for all n_iter steps */
 
 /* transformer score algorithms */
 #define CWT_ATTN_REASSOC   0   /* scores = (Q_h A_h) X^T : skinny contraction on CUDA cores   */

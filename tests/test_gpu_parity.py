@@ -111,7 +111,7 @@ def test_fit_small_vs_oracle_and_golden(cuda_device, name):
         assert torch.equal(cwt.fit_classifier(*args), w)                   # AUTO falls back to streaming
 
 
-@pytest.mark.parametrize("algo", [L.FIT_STREAM, L.FIT_RESIDENT])
+@pytest.mark.parametrize("algo", [L.FIT_STREAM, L.FIT_RESIDENT, L.FIT_L2])
 @pytest.mark.parametrize("name", ["full_1shot_h1_yaml", "full_1shot_h4_script", "full_1shot_h4_backbone", "full_5shot_h4"])
 def test_fit_full_size_vs_golden(cuda_device, name, algo):
     """BASELINE.json shapes (60x60x512 -> 473x473, 200 steps) against the reference's recorded output."""
@@ -123,6 +123,23 @@ def test_fit_full_size_vs_golden(cuda_device, name, algo):
     w = cwt.fit_classifier(ep.f_s.to(cuda_device), ep.s_label.to(cuda_device), ep.w0.to(cuda_device),
                            case["lr"], case["n_iter"], algo=algo)
     assert rel_err(w, g["W_fit"]) < REL
+
+
+@pytest.mark.parametrize("shot,E,T", [(5, 5, 60), (2, 7, 40), (3, 3, 25), (4, 2, 25), (1, 9, 30)])
+def test_fit_l2_streamed_multi_shot(cuda_device, shot, E, T):
+    """CWT_FIT_L2, the persistent kernel that keeps G episodes' feature maps L2-resident (the default for S > 1 at the head
+    geometry; BASELINE config 2 = 5 shots): more episodes than groups, every tiles-per-CTA plan (5 shots: 3 tiles per CTA,
+    60 CTAs per episode; 2 shots: 1 tile, 72 CTAs; 3 shots: 2 tiles; ...), against the streaming algorithm; the integer
+    all-reduce makes it bit-reproducible; AUTO picks it for S > 1."""
+    b = syn.make_batch(list(range(900, 900 + E)), shot=shot, C=512, h=60, w=60, H=473, W=473).to(cuda_device)
+    ws = cwt.fit_classifier(b.f_s, b.s_label, b.w0, 0.1, T, algo=L.FIT_STREAM)
+    wl, st = cwt.fit_classifier(b.f_s, b.s_label, b.w0, 0.1, T, algo=L.FIT_L2, return_status=True)
+    assert torch.isfinite(wl).all() and int(st.abs().sum()) == 0
+    for i in range(E):
+        assert rel_err(wl[i], ws[i]) < TIGHT, i
+    assert torch.equal(cwt.fit_classifier(b.f_s, b.s_label, b.w0, 0.1, T, algo=L.FIT_L2), wl)
+    if shot > 1:
+        assert torch.equal(cwt.fit_classifier(b.f_s, b.s_label, b.w0, 0.1, T), wl)          # CWT_FIT_AUTO
 
 
 def test_fit_resident_many_episodes_per_group(cuda_device):
