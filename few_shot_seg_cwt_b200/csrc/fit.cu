@@ -71,7 +71,8 @@ static size_t carve_fit(Carver& cv, FitWs& ws, int E, int S, int C, int h, int w
     ws.g60 = cv.take<float>((size_t)E * S * h * w);
     ws.loss_part = cv.take<float>((size_t)E * S * ws.nblk);
     // the persistent kernels' exchange areas: resident (1 shot) or L2-streamed (several shots, head geometry)
-    ws.resident_bytes = (S == 1) ? fit_resident_workspace_bytes(E, C, h, w) : fit_l2_workspace_bytes(E, S, C, h, w);
+    ws.resident_bytes = fit_l2_workspace_bytes(E, S, C, h, w);
+    if (S == 1) { const size_t r = fit_resident_workspace_bytes(E, C, h, w); if (r > ws.resident_bytes) ws.resident_bytes = r; }
     ws.resident = cv.take<char>(ws.resident_bytes);
     return align_up(cv.off);
 }
@@ -121,10 +122,7 @@ static int fit_classifier_impl(const float* f_s, const void* s_label, int label_
     // L2-streamed persistent kernel: several shots, head geometry, no loss trace (also on request for one shot)
     if ((algo == CWT_FIT_L2 || (algo == CWT_FIT_AUTO && S > 1)) && n_iter > 0) {
         if (!loss_trace_or_null && !prof_out && fit_l2_supported(S, C, h, w)) {
-            size_t l2_bytes = ws.resident_bytes;
-            void* l2_ws = ws.resident;
-            rc = fit_l2(f_s, ws.cells, ws.cw, w_out, E, S, C, h, w, n_iter, lr, l2_ws,
-                        S == 1 ? (fit_l2_workspace_bytes(E, S, C, h, w) <= l2_bytes ? l2_bytes : 0) : l2_bytes, st);
+            rc = fit_l2(f_s, ws.cells, ws.cw, w_out, E, S, C, h, w, n_iter, lr, ws.resident, ws.resident_bytes, st);
             if (rc == CWT_OK) return CWT_OK;
             if (rc != CWT_ERR_UNSUPPORTED || algo == CWT_FIT_L2) return rc;
         } else if (algo == CWT_FIT_L2) {

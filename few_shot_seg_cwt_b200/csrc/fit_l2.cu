@@ -55,6 +55,7 @@ struct L2Params {
     unsigned long long* sums;  // [G][SPL][2][C]      accumulator words
     unsigned long long* fmaxw; // [G][CPG]            {max|F| bits, episode + 1}
     unsigned* abort_flag;
+    float* ftile;              // [G][NTILE][KCH][128][100]  the episode in flight, re-laid out tile by tile (see below)
     int E, S, CPG, G, T, KBITS, SPL, NTILE;
     float lr;
 };
@@ -71,7 +72,7 @@ static __host__ __device__ inline L2Smem l2_smem_layout(int NT) {
     s.scratch = take((size_t)NT * 16 * L2_NCELL * 4);           // NT x {16 x 100 P1 partials | 126 cells x 8 rows x (gl, gr)}
     s.cum = take((size_t)L2_C * 16);
     s.hrd = take((size_t)NT * 2 * L2_CT * 4);                   // HR task descriptors [NT][2][512] (static per episode)
-    s.mbar = take(8 * (2 * L2_NSTAGE + L2_KCH + 1) + 16);
+    s.mbar = take(8 * (2 * L2_NSTAGE + L2_KCH + 2) + 16);
     s.total = o;
     return s;
 }
@@ -96,7 +97,8 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_fit_l2(const __grid_constant_
     uint64_t* empty = full + L2_NSTAGE;
     uint64_t* applied = empty + L2_NSTAGE;                             // [KCH]
     uint64_t* halo_ready = applied + L2_KCH;
-    unsigned* smax = reinterpret_cast<unsigned*>(halo_ready + 1);      // [0] CTA max|F| bits, [1] episode max|F| bits
+    uint64_t* retiled = halo_ready + 1;                                 // this CTA's tiles of the episode are in p.ftile
+    unsigned* smax = reinterpret_cast<unsigned*>(retiled + 1);         // [0] CTA max|F| bits, [1] episode max|F| bits
     constexpr int ZTS = 160, GS = 128, SCS = 16 * L2_NCELL;           // per-tile strides (floats)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -117,6 +119,7 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_fit_l2(const __grid_constant_
         for (int s = 0; s < L2_NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 16); }
         for (int j = 0; j < L2_KCH; ++j) mbar_init(&applied[j], 1);
         mbar_init(halo_ready, 1);
+        mbar_init(retiled, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
@@ -208,6 +211,16 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_fit_l2(const __grid_constant_
                 unsigned mb = 0u;
                 for (int u = 0; u < units_per_sweep; ++u, ++uc) {
                     const unsigned st = wait_full(uc);
+                    if (tid == 0) {
+                        // first sweep of the episode: the unit came through the 3-D tensor map (640 rows of 80 B: slow); write it
+                        // back CONTIGUOUSLY, so that the 2 T sweeps that follow fetch it with one linear 51.2 KB bulk copy
+                        const int j = u / nta, i = u - j * nta;
+                        float* dst = p.ftile + (((size_t)group * p.NTILE + (k + i * p.CPG)) * L2_KCH + j) * (L2_STAGE_BYTES / 4);
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                     ::"l"(dst), "r"(smem_u32(ring + (size_t)st * (L2_STAGE_BYTES / 4))), "r"(L2_STAGE_BYTES) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the stage has been read: it may be refilled
+                    }
                     const uint4* F4u = reinterpret_cast<const uint4*>(ring + (size_t)st * (L2_STAGE_BYTES / 4));
                     for (int i = tid; i < L2_CCH * 25; i += L2_CT) {
                         const uint4 f = F4u[i];
@@ -217,6 +230,10 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_fit_l2(const __grid_constant_
                 }
                 mb = __reduce_max_sync(0xffffffffu, mb);
                 if (lane == 0) atomicMax(&smax[0], mb);
+                if (tid == 0) {
+                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");               // ... and written: the producer may fetch it
+                    mbar_arrive(retiled);
+                }
             }
             l2_role_sync();                                           // S3
             if (tid == 0) st_tagged(&fmaxw[k], __uint_as_float(smax[0]), (unsigned)e + 1u);
@@ -511,9 +528,19 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_fit_l2(const __grid_constant_
         // read-only, and nothing else ever writes the ring)
         if (lane == 0) {
             unsigned uc = 0;
-            for (int e = group; e < p.E; e += p.G) {
+            unsigned ep = 0;
+            for (int e = group; e < p.E; e += p.G, ++ep) {
                 const int n_sweeps = 1 + 2 * p.T;
-                for (int sw = 0; sw < n_sweeps; ++sw)
+                for (int sw = 0; sw < n_sweeps; ++sw) {
+                    if (sw == 1) {                       // the linear copy of this episode's tiles is complete
+                        unsigned it = 0;
+                        while (!mbar_try_wait(retiled, ep & 1u)) {
+                            if ((++it & 0xfffu) == 0u) {
+                                if (*reinterpret_cast<volatile unsigned*>(p.abort_flag) != 0u) return;
+                                if (it > RES_SPIN_LIMIT) { atomicExch(p.abort_flag, 1u); return; }
+                            }
+                        }
+                    }
                     for (int j = 0; j < L2_KCH; ++j)
                         for (int i = 0; i < nta; ++i, ++uc) {
                             const unsigned st = uc % L2_NSTAGE, ph = (uc / L2_NSTAGE) & 1u;
@@ -525,11 +552,17 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_fit_l2(const __grid_constant_
                                 }
                             }
                             mbar_expect_tx(&full[st], L2_STAGE_BYTES);
-                            const int z = ((e * S + tile_shot(i)) * L2_C) + j * L2_CCH;
-                            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                                         ::"r"(smem_u32(ring + (size_t)st * (L2_STAGE_BYTES / 4))), "l"(&fmap), "r"(smem_u32(&full[st])),
-                                           "r"(tile_x0(i)), "r"(tile_y0(i)), "r"(z) : "memory");
+                            if (sw == 0) {
+                                const int z = ((e * S + tile_shot(i)) * L2_C) + j * L2_CCH;
+                                asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                                             ::"r"(smem_u32(ring + (size_t)st * (L2_STAGE_BYTES / 4))), "l"(&fmap), "r"(smem_u32(&full[st])),
+                                               "r"(tile_x0(i)), "r"(tile_y0(i)), "r"(z) : "memory");
+                            } else {
+                                const float* src = p.ftile + (((size_t)group * p.NTILE + (k + i * p.CPG)) * L2_KCH + j) * (L2_STAGE_BYTES / 4);
+                                bulk_g2s(ring + (size_t)st * (L2_STAGE_BYTES / 4), src, L2_STAGE_BYTES, &full[st]);
+                            }
                         }
+                }
             }
         }
     }
@@ -578,7 +611,7 @@ size_t fit_l2_workspace_bytes(int E, int S, int C, int h, int w) {
     if (!pl.ok) return 0;
     const int nslots = (E + pl.G - 1) / pl.G;
     return align_up(sizeof(unsigned long long) * 2 * S * L2_HW * pl.G) + align_up(sizeof(unsigned long long) * (size_t)pl.G * nslots * 2 * L2_C) +
-           align_up(sizeof(unsigned long long) * 320) + 512;
+           align_up(sizeof(unsigned long long) * 320) + 512 + align_up((size_t)pl.G * S * L2_C * L2_HW * 4);
 }
 
 template <int NT>
@@ -614,6 +647,7 @@ int fit_l2(const float* f_s, const uint4* cells, const float2* cw, float* w_io, 
     p.sums = cv.take<unsigned long long>((size_t)pl.G * p.SPL * 2 * L2_C);
     p.fmaxw = cv.take<unsigned long long>(320);
     p.abort_flag = cv.take<unsigned>(64);
+    p.ftile = cv.take<float>((size_t)pl.G * S * L2_C * L2_HW);
     CWT_REQUIRE(ws && cv.ok(), CWT_ERR_WORKSPACE, "fit_l2: workspace too small");
     const size_t sync_bytes = (size_t)(reinterpret_cast<char*>(p.abort_flag + 64) - reinterpret_cast<char*>(p.zll));
     CWT_CUDA(cudaMemsetAsync(p.zll, 0, sync_bytes, st));
