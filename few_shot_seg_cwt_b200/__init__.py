@@ -10,6 +10,7 @@ wrapped with the reference's own Python call surface:
     validate_transformer           src/test.py:103-254
     meta_train_step                src/train.py:233-267
     do_epoch                       src/train.py:166-290
+    train_worker / test_worker     src/train.py:90-163, src/test.py:55-100 (checkpoints in the reference's format)
 
 Importing the package never needs a GPU; calling an op without the built library or without a CUDA
 tensor raises (there is no CPU fallback).
@@ -27,6 +28,9 @@ from .ops import (feat_times_rows, normalize_features, fit_classifier, fit_class
 from .ops import fit_status, raise_for_status  # noqa: F401
 from .hostformat import CompressedEpisodeBatch, compress_batch, compress_map, expand_map, expand_map_reference  # noqa: F401
 from .transformer import MultiHeadAttentionOne  # noqa: F401
+from .drivers import (build_transformer, freeze_backbone, get_model_dir_trans, get_optimizer, load_backbone_weights_for_test,  # noqa: F401
+                      load_backbone_weights_for_train, load_transformer_checkpoint, save_transformer_checkpoint, test_worker,
+                      train_worker)
 
 __all__ = [
     "MultiHeadAttentionOne", "fit_classifier", "fit_classifier_bias", "fit_classifier_dice", "fit_coscls", "fit_multiclass", "ValTransform", "find_new_hw", "resize_pad_normalize", "inner_loop", "increment_inner_loop", "get_classifier", "CosCls", "draw_initial_weights",
@@ -35,6 +39,8 @@ __all__ = [
     "meta_train_step", "do_epoch", "query_loss", "transformer_forward", "transformer_backward", "logits_iou",
     "upsample_argmax_iou", "intersection_union", "label_counts", "query_loss_grad",
     "rows_times_feat", "feat_times_rows", "synthetic", "fit_status", "raise_for_status",
+    "train_worker", "test_worker", "save_transformer_checkpoint", "load_transformer_checkpoint", "get_model_dir_trans",
+    "get_optimizer", "build_transformer", "freeze_backbone", "load_backbone_weights_for_test", "load_backbone_weights_for_train",
     "CompressedEpisodeBatch", "compress_batch", "compress_map", "expand_map", "expand_map_reference",
 ]
 

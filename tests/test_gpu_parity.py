@@ -6,6 +6,8 @@ measured drift is ~1e-6, so most asserts use a tighter bound; IoU counts bit-exa
 stated argmax near-tie pixels (|up(l1) - up(l0)| <= TIE_TAU * max|logit|, listed by the oracle);
 mIoU / FB-IoU within 0.05 points.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -754,6 +756,83 @@ def test_validate_transformer_dropin(cuda_device):
             batch_ce = []
     assert abs(miou - O.miou_from_counts(cI, cU)) * 100 < 0.05
     assert abs(loss - float(np.mean(losses))) < 1e-4
+
+
+def _fake_loader(n, first, kw):
+    eps = [syn.make_episode(first + i, label_dtype=torch.int64, **kw) for i in range(n)]
+    feats, items = {}, []
+    for i, ep in enumerate(eps):
+        feats[2 * i], feats[2 * i + 1] = ep.f_s[0], ep.f_q
+        simg = torch.full((1, 1, 3, 89, 89), float(2 * i))
+        qimg = torch.full((1, 3, 89, 89), float(2 * i + 1))
+        items.append((qimg, ep.q_label.unsqueeze(0), simg, ep.s_label.unsqueeze(0), [torch.tensor([ep.subcls])], None, None))
+    return eps, feats, items
+
+
+def test_validate_transformer_empty_support_mask_raises_one_batch_late(cuda_device):
+    """An episode whose support mask has no foreground raises the reference's ZeroDivisionError (src/test.py:174) — from the
+    status word read back with the counts, not from a per-episode host sync."""
+    kw = dict(shot=1, C=64, h=12, w=12, H=89, W=89, style="unit")
+    eps, feats, items = _fake_loader(4, 300, kw)
+    q, ql, si, sl, sub, a, b = items[2]
+    items[2] = (q, ql, si, torch.zeros_like(sl), sub, a, b)
+    args = _Args()
+    args.test_num, args.batch_size_val, args.image_size, args.n_runs = 4, 2, 89, 1
+    args.bottleneck_dim, args.num_classes_tr, args.cls_lr, args.adapt_iter = 64, 2, 0.1, 10
+    tr = cwt.MultiHeadAttentionOne(2, 64, 64, 64, dropout=0.5).to(cuda_device)
+    with pytest.raises(ZeroDivisionError, match="episode 2"):
+        cwt.validate_transformer(args, items, _FakeBackbone(feats), tr, verbose=False)
+
+
+def test_train_and_test_workers_reference_checkpoints(cuda_device, tmp_path):
+    """main_worker-level drivers (src/train.py:90-163, src/test.py:55-100) on fake loaders: best.pth / final.pth are written
+    in the reference's format and layout; the test driver loads a checkpoint written FROM THE REFERENCE'S OWN module and
+    reproduces the oracle's result with those weights (validate_transformer's mIoU, batched + overlapped backbone)."""
+    from few_shot_seg_cwt_b200 import drivers
+    from oracle import ref_episode as R
+    kw = dict(shot=1, C=64, h=12, w=12, H=89, W=89, style="unit")
+    _, feats_tr, items_tr = _fake_loader(3, 400, kw)
+    eps, feats, items = _fake_loader(4, 500, kw)
+    args = _Args()
+    args.model_dir, args.train_name, args.train_split, args.shot, args.arch, args.layers = str(tmp_path), "pascal", 0, 1, "resnet", 50
+    args.main_optim, args.momentum, args.weight_decay, args.nesterov = "SGD", 0.9, 1e-4, True
+    args.heads, args.bottleneck_dim, args.trans_lr, args.scale_lr = 2, 64, 0.0025, 1.0
+    args.epochs, args.iter_per_epoch, args.debug, args.save_models, args.batch_size = 2, 3, False, True, 1
+    args.image_size, args.num_classes_tr, args.cls_lr, args.adapt_iter = 89, 2, 0.1, 20
+    args.test_num, args.batch_size_val, args.n_runs, args.ckpt_used = 4, 2, 1, "best"
+
+    class Both(_FakeBackbone):
+        pass
+    torch.manual_seed(3)
+    best, tr = drivers.train_worker(args, Both({**feats_tr, **{k + 100: v for k, v in feats.items()}}), items_tr,
+                                    [(q + 100, ql, s + 100, sl, sub, a, b) for q, ql, s, sl, sub, a, b in items],
+                                    device=cuda_device, verbose=False)
+    d = cwt.get_model_dir_trans(args)
+    for name, epoch in (("best.pth", None), ("final.pth", 2)):
+        ck = torch.load(os.path.join(d, name))
+        assert set(ck) == {"epoch", "state_dict", "optimizer"} and set(ck["state_dict"]) == set(tr.state_dict())
+        assert epoch is None or ck["epoch"] == epoch
+    assert 0.0 <= best <= 1.0
+    # a checkpoint written from the REFERENCE's module, in the reference's layout -> test driver -> oracle with those weights
+    mods = R.load_reference_modules(prefer_live=False)
+    if mods is None:
+        pytest.skip("oracle/_ref not made")
+    torch.manual_seed(9)
+    ref = mods[0](2, 64, 64, 64, dropout=0.5)
+    torch.save({"epoch": 1, "state_dict": ref.state_dict()}, os.path.join(d, "best.pth"))
+    torch.manual_seed(5)
+    miou, loss = drivers.test_worker(args, _FakeBackbone(feats), items, device=cuda_device, verbose=False)
+    torch.manual_seed(5)
+    params = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+    cI, cU = {}, {}
+    for ep in eps:
+        w0 = torch.nn.Conv2d(64, 2, 1, bias=False).weight.detach().view(2, 64).clone()
+        torch.nn.Conv2d(64, 2, 1, bias=False)
+        o = R.episode_via_reference(syn.Episode(ep.f_s, ep.s_label, ep.f_q, ep.q_label, w0, ep.subcls, ep.idx), params, 2, 0.1, 20,
+                                    mods[0], mods[1])
+        cI[ep.subcls] = cI.get(ep.subcls, 0) + int(o["counts"][1, 0])
+        cU[ep.subcls] = cU.get(ep.subcls, 0) + int(o["counts"][1, 1])
+    assert abs(miou - O.miou_from_counts(cI, cU)) * 100 < 0.05
 
 
 def test_do_epoch_dropin(cuda_device):

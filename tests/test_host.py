@@ -102,6 +102,40 @@ def test_module_loads_reference_checkpoint_format():
     assert torch.equal(m.fc.weight, ref.fc.weight)
 
 
+def test_checkpoint_format_is_the_references(tmp_path):
+    """save_transformer_checkpoint writes {'epoch', 'state_dict', 'optimizer'} (src/train.py:138-163) and the reference's own
+    MultiHeadAttentionOne loads it; a checkpoint written from the reference module loads into ours (src/test.py:82-89);
+    the directory layout is src/util.py:167-179."""
+    from oracle import ref_episode as R
+    mods = R.load_reference_modules(prefer_live=False) or R.load_reference_modules(prefer_live=True)
+    if mods is None:
+        pytest.skip("reference modules not available (oracle/_ref not made)")
+    RefMHA = mods[0]
+
+    class A:
+        model_dir, train_name, train_split, shot, arch, layers = str(tmp_path), "pascal", 0, 1, "resnet", 50
+        main_optim, momentum, weight_decay, nesterov = "SGD", 0.9, 1e-4, True
+        heads, bottleneck_dim = 4, 64
+    assert cwt.get_model_dir_trans(A).endswith(os.path.join("pascal", "split=0", "model", "shot_1", "transformer_resnet50"))
+    mine = cwt.MultiHeadAttentionOne(4, 64, 64, 64, dropout=0.5)
+    opt = cwt.get_optimizer(A, [dict(params=mine.parameters(), lr=0.0025)])
+    assert isinstance(opt, torch.optim.SGD) and opt.defaults["nesterov"] and opt.defaults["momentum"] == 0.9
+    path = os.path.join(cwt.get_model_dir_trans(A), "best.pth")
+    cwt.save_transformer_checkpoint(path, 3, mine, opt)
+    ck = torch.load(path)
+    assert set(ck) == {"epoch", "state_dict", "optimizer"} and ck["epoch"] == 3
+    ref = RefMHA(4, 64, 64, 64, dropout=0.5)
+    ref.load_state_dict(ck["state_dict"])                                   # strict: same names and shapes
+    assert all(torch.equal(a, b) for a, b in zip(ref.state_dict().values(), mine.state_dict().values()))
+    # the other direction: written from the reference's module and optimizer
+    ref2 = RefMHA(4, 64, 64, 64, dropout=0.5)
+    ropt = torch.optim.SGD(ref2.parameters(), lr=0.0025, momentum=0.9, weight_decay=1e-4, nesterov=True)
+    torch.save({"epoch": 7, "state_dict": ref2.state_dict(), "optimizer": ropt.state_dict()}, str(tmp_path / "ref.pth"))
+    mine2 = cwt.MultiHeadAttentionOne(4, 64, 64, 64, dropout=0.5)
+    assert cwt.load_transformer_checkpoint(str(tmp_path / "ref.pth"), mine2, opt) == 7
+    assert torch.equal(mine2.fc.weight, ref2.fc.weight) and torch.equal(mine2.w_qkvs.weight, ref2.w_qkvs.weight)
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference checkout not present")
 def test_coscls_mirror_matches_reference_module():
     """few_shot_seg_cwt_b200.CosCls vs the reference's CosCls (src/model/pspnet.py:290-315): same state-dict keys and the
