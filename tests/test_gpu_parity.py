@@ -823,11 +823,14 @@ def test_train_and_test_workers_reference_checkpoints(cuda_device, tmp_path):
     torch.manual_seed(5)
     miou, loss = drivers.test_worker(args, _FakeBackbone(feats), items, device=cuda_device, verbose=False)
     torch.manual_seed(5)
+    cwt.MultiHeadAttentionOne(2, 64, 64, 64, dropout=0.5)      # test_worker builds (and thereby draws) the transformer first, as src/test.py:56
     params = {k: v.detach().clone() for k, v in ref.state_dict().items()}
-    cI, cU = {}, {}
-    for ep in eps:
-        w0 = torch.nn.Conv2d(64, 2, 1, bias=False).weight.detach().view(2, 64).clone()
+    w0s = []                                                   # drawn up front: the episode body below draws from the RNG itself
+    for _ in eps:
+        w0s.append(torch.nn.Conv2d(64, 2, 1, bias=False).weight.detach().view(2, 64).clone())
         torch.nn.Conv2d(64, 2, 1, bias=False)
+    cI, cU = {}, {}
+    for ep, w0 in zip(eps, w0s):
         o = R.episode_via_reference(syn.Episode(ep.f_s, ep.s_label, ep.f_q, ep.q_label, w0, ep.subcls, ep.idx), params, 2, 0.1, 20,
                                     mods[0], mods[1])
         cI[ep.subcls] = cI.get(ep.subcls, 0) + int(o["counts"][1, 0])
