@@ -528,6 +528,9 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_fit_l2(const __grid_constant_
         // read-only, and nothing else ever writes the ring)
         if (lane == 0) {
             unsigned uc = 0;
+            unsigned long long pol_first, pol_last;                // L2 eviction priorities of the two kinds of loads
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
+            asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
             unsigned ep = 0;
             for (int e = group; e < p.E; e += p.G, ++ep) {
                 const int n_sweeps = 1 + 2 * p.T;
@@ -553,13 +556,16 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_fit_l2(const __grid_constant_
                             }
                             mbar_expect_tx(&full[st], L2_STAGE_BYTES);
                             if (sw == 0) {
+                                // read once: evict-first, so that the original maps do not push the re-laid-out copies out of L2
                                 const int z = ((e * S + tile_shot(i)) * L2_C) + j * L2_CCH;
-                                asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                                asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
                                              ::"r"(smem_u32(ring + (size_t)st * (L2_STAGE_BYTES / 4))), "l"(&fmap), "r"(smem_u32(&full[st])),
-                                               "r"(tile_x0(i)), "r"(tile_y0(i)), "r"(z) : "memory");
+                                               "r"(tile_x0(i)), "r"(tile_y0(i)), "r"(z), "l"(pol_first) : "memory");
                             } else {
                                 const float* src = p.ftile + (((size_t)group * p.NTILE + (k + i * p.CPG)) * L2_KCH + j) * (L2_STAGE_BYTES / 4);
-                                bulk_g2s(ring + (size_t)st * (L2_STAGE_BYTES / 4), src, L2_STAGE_BYTES, &full[st]);
+                                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                                             ::"r"(smem_u32(ring + (size_t)st * (L2_STAGE_BYTES / 4))), "l"(src), "r"(L2_STAGE_BYTES),
+                                               "r"(smem_u32(&full[st])), "l"(pol_last) : "memory");
                             }
                         }
                 }
