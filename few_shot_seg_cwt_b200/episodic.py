@@ -215,7 +215,7 @@ def run_sweep(n_episodes: int, params: Dict[str, torch.Tensor], n_head: int, lr:
     for i in range(0, len(mine), batch):
         b = make_batch(mine[i:i + batch], **gen_kwargs).to(device)
         out = episode_head(b.f_s, b.s_label, b.f_q, b.q_label, b.w0, p, n_head, lr, n_iter)
-        table.update(out.counts, b.subcls, out.ce)
+        table.update(out.counts, b.subcls, out.ce, out.status)        # episodes with a bad fit status are counted in table.n_bad
     if reduce:
         table.all_reduce()
     return table

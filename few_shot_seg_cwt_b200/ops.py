@@ -154,26 +154,13 @@ def fit_classifier_bias(f_s: torch.Tensor, s_label: torch.Tensor, w0: torch.Tens
     CosCls with cls_type[2] == 'b', src/model/pspnet.py:294,319): logits = W . f + bias_scale * b, plain SGD on both.
     b0 [E,2] (or [2]). Returns (W [E,2,C], b [E,2]) with the leading shapes given (+ losses [n_iter,E] if requested)."""
     dev = L.require_cuda(f_s, s_label, w0, b0)
-    if f_s.dim() == 4:
-        f_s, s_label = f_s.unsqueeze(0), s_label.unsqueeze(0)
-    if f_s.dim() != 5 or s_label.dim() != 4:
-        raise ValueError(f"f_s must be [E,S,C,h,w] and s_label [E,S,H,W]; got {tuple(f_s.shape)}, {tuple(s_label.shape)}")
+    f_s, lab = _episode_inputs(f_s, s_label)
     E, S, Cc, h, w = f_s.shape
-    H, W = s_label.shape[-2:]
-    if s_label.shape[0] != E or s_label.shape[1] != S:
-        raise ValueError("f_s and s_label disagree on E or S")
+    H, W = lab.shape[-2:]
     w0_shape, b0_shape = w0.shape, b0.shape
     w0v = _f32c(w0, "w0").reshape(E, 2, Cc)
     b0v = _f32c(b0, "b0").reshape(E, 2)
-    f_s = _f32c(f_s, "f_s")
-    lab = s_label.contiguous()
-    cw = None
-    if class_weight is not None:
-        cw = _f32c(class_weight.to(dev), "class_weight").reshape(-1, 2)
-        if cw.shape[0] == 1 and E > 1:
-            cw = cw.expand(E, 2).contiguous()
-        if cw.shape[0] != E:
-            raise ValueError("class_weight must be [2] or [E,2]")
+    cw = _class_weight(class_weight, E, dev)
     w_out = torch.empty(E, 2, Cc, dtype=torch.float32, device=dev)
     b_out = torch.empty(E, 2, dtype=torch.float32, device=dev)
     losses = torch.empty(n_iter, E, dtype=torch.float32, device=dev) if return_losses else None
@@ -188,12 +175,7 @@ def fit_classifier_bias(f_s: torch.Tensor, s_label: torch.Tensor, w0: torch.Tens
                                              int(ignore_index), L.ptr(ws), ws.numel(), L.stream_ptr(dev))
     L.check(rc, "cwt_fit_classifier_bias_f32")
     if check:
-        c = counts.cpu()
-        if int(c[:, 3].sum()) > 0:
-            raise ValueError("s_label holds values outside {0, 1, ignore_index}")
-        if class_weight is None and bool((c[:, 1] == 0).any()):
-            raise ZeroDivisionError("division by zero: an episode's support mask has no foreground pixel "
-                                    "(reference: len(back_pix[0]) / len(target_pix[0]), src/test.py:174)")
+        _raise_on_label_counts(counts, cw is not None)
     out = (w_out.reshape(w0_shape), b_out.reshape(b0_shape))
     return out + (losses,) if return_losses else out
 
@@ -209,23 +191,18 @@ def fit_coscls(x_norm: torch.Tensor, s_label: torch.Tensor, weight: torch.Tensor
     ``cls.weight_v`` with flag 'r'); weight_g [E,2] (flag 'r'); bias [E,2] or None; scale [E]; flags = OR of L.COSCLS_R /
     L.COSCLS_N / L.COSCLS_T. Returns a dict of the fitted parameters (new tensors; the inputs are not modified)."""
     dev = L.require_cuda(x_norm, s_label, weight, scale)
-    if x_norm.dim() != 5 or s_label.dim() != 4:
+    if x_norm.dim() != 5:
         raise ValueError(f"x_norm must be [E,S,C,h,w] and s_label [E,S,H,W]; got {tuple(x_norm.shape)}, {tuple(s_label.shape)}")
+    x_norm, lab = _episode_inputs(x_norm, s_label, "x_norm")
     E, S, Cc, h, w = x_norm.shape
-    H, W = s_label.shape[-2:]
-    x_norm = _f32c(x_norm, "x_norm")
-    lab = s_label.contiguous()
+    H, W = lab.shape[-2:]
     wv = _f32c(weight, "weight").reshape(E, 2, Cc).clone()
     sc = _f32c(scale, "scale").reshape(E).clone()
     gv = _f32c(weight_g, "weight_g").reshape(E, 2).clone() if weight_g is not None else None
     bv = _f32c(bias, "bias").reshape(E, 2).clone() if bias is not None else None
     if (flags & L.COSCLS_R) and gv is None:
         raise ValueError("flag 'r' needs weight_g")
-    cw = None
-    if class_weight is not None:
-        cw = _f32c(class_weight.to(dev), "class_weight").reshape(-1, 2)
-        if cw.shape[0] == 1 and E > 1:
-            cw = cw.expand(E, 2).contiguous()
+    cw = _class_weight(class_weight, E, dev)
     losses = torch.empty(n_iter, E, dtype=torch.float32, device=dev) if return_losses else None
     counts = torch.empty(E, 4, dtype=torch.int32, device=dev)
     lib = L.load()
@@ -237,11 +214,7 @@ def fit_coscls(x_norm: torch.Tensor, s_label: torch.Tensor, weight: torch.Tensor
                                     int(n_iter), float(lr), int(ignore_index), L.ptr(ws), ws.numel(), L.stream_ptr(dev))
     L.check(rc, "cwt_fit_coscls_f32")
     if check:
-        c = counts.cpu()
-        if int(c[:, 3].sum()) > 0:
-            raise ValueError("s_label holds values outside {0, 1, ignore_index}")
-        if class_weight is None and bool((c[:, 1] == 0).any()):
-            raise ZeroDivisionError("division by zero: an episode's support mask has no foreground pixel")
+        _raise_on_label_counts(counts, cw is not None)
     out = {"weight": wv, "weight_g": gv, "bias": bv, "scale": sc}
     if return_losses:
         out["losses"] = losses
@@ -289,18 +262,11 @@ def fit_classifier_dice(f_s: torch.Tensor, s_label: torch.Tensor, w0: torch.Tens
     :func:`fit_classifier`; there is no class weight and an episode without foreground is legal (the dice term of an
     empty target is 1). ``check``: one host sync to raise ValueError on labels outside {0, 1, ignore_index}."""
     dev = L.require_cuda(f_s, s_label, w0)
-    if f_s.dim() == 4:
-        f_s, s_label = f_s.unsqueeze(0), s_label.unsqueeze(0)
-    if f_s.dim() != 5 or s_label.dim() != 4:
-        raise ValueError(f"f_s must be [E,S,C,h,w] and s_label [E,S,H,W]; got {tuple(f_s.shape)}, {tuple(s_label.shape)}")
+    f_s, lab = _episode_inputs(f_s, s_label)
     E, S, Cc, h, w = f_s.shape
-    H, W = s_label.shape[-2:]
-    if s_label.shape[0] != E or s_label.shape[1] != S:
-        raise ValueError("f_s and s_label disagree on E or S")
+    H, W = lab.shape[-2:]
     w0_shape = w0.shape
     w0v = _f32c(w0, "w0").reshape(E, 2, Cc)
-    f_s = _f32c(f_s, "f_s")
-    lab = s_label.contiguous()
     w_out = torch.empty(E, 2, Cc, dtype=torch.float32, device=dev)
     losses = torch.empty(n_iter, E, dtype=torch.float32, device=dev) if return_losses else None
     lib = L.load()
