@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--ref-episodes", type=int, default=2, help="--impl reference: episodes per step (bounded CPU sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-sub-batch", type=int, default=16, help="HostPipeline sub-batch size (0 = whole batches)")
+    ap.add_argument("--e2e-sub-batch", type=int, default=32, help="HostPipeline sub-batch size (0 = whole batches)")
     ap.add_argument("--e2e-sub-all", type=int, default=1, help="1: every host batch goes through in sub-batches; 0: only the first")
     ap.add_argument("--e2e-expand-main", type=int, default=0, help="zero-compressed e2e: expansion kernel on the head's stream (1) or the copy stream (0)")
     ap.add_argument("--e2e-format", default="zc", choices=["zc", "dense"], help="host format of the e2e leg: zero-compressed "

@@ -546,7 +546,7 @@ class HostPipeline:
 
     def __init__(self, device, params: Dict[str, torch.Tensor], n_head: int, lr: float, n_iter: int,
                  fit_algo: int = L.FIT_AUTO, attn_algo: int = L.ATTN_REASSOC, num_classes_val: int = 5, n_slots: int = 3,
-                 sub_batch: int = 16, sub_batch_all: bool = True, expand_on_main: bool = False):
+                 sub_batch: int = 32, sub_batch_all: bool = True, expand_on_main: bool = False):
         self.device = torch.device(device)
         self.params = {k: v.to(self.device) for k, v in params.items()}
         self.n_head, self.lr, self.n_iter = n_head, lr, n_iter
@@ -578,6 +578,7 @@ class HostPipeline:
         self._slot_free: List[Optional[torch.cuda.Event]] = [None] * n_slots
         self._results: List[Optional[Tuple[torch.Tensor, torch.Tensor]]] = []   # pinned (counts, status) per host batch
         self._cslots: List[Optional[dict]] = [None] * n_slots   # device staging of zero-compressed features (mask, prefix, values)
+        self._head: Optional[HeadPipeline] = None
 
     @staticmethod
     def _fields(b: EpisodeBatch):
@@ -689,8 +690,13 @@ class HostPipeline:
                 queue.append((db_, ev_, pend_, nslot, bi, lo, last, E))
                 nslot = (nslot + 1) % n_slots
 
-        head = HeadPipeline(self.device, self.params, self.n_head, self.lr, self.n_iter, self.fit_algo, self.attn_algo,
-                            table=self.table)
+        # ONE HeadPipeline (one side stream) for the life of this object: the library workspaces are keyed by stream, so a new
+        # side stream per run() meant a fresh cudaMalloc of every post-stage workspace inside the run (measured with
+        # tools/e2e_timeline.py: the first post stage of every run took 10 ms instead of 0.4)
+        if self._head is None:
+            self._head = HeadPipeline(self.device, self.params, self.n_head, self.lr, self.n_iter, self.fit_algo, self.attn_algo,
+                                      table=self.table)
+        head = self._head
 
         def read_back(out, dst, dst_status):
             dst.copy_(out.counts, non_blocking=True)
