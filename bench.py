@@ -53,8 +53,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-sub-batch", type=int, default=32, help="HostPipeline sub-batch size (0 = whole batches)")
-    ap.add_argument("--e2e-sub-all", type=int, default=1, help="1: every host batch goes through in sub-batches; 0: only the first")
-    ap.add_argument("--e2e-expand-main", type=int, default=0, help="zero-compressed e2e: expansion kernel on the head's stream (1) or the copy stream (0)")
+    ap.add_argument("--e2e-sub-all", type=int, default=0, help="1: every host batch goes through in sub-batches; 0: only the first")
+    ap.add_argument("--e2e-expand-main", type=int, default=1, help="zero-compressed e2e: expansion kernel on the head's stream (1) or the copy stream (0)")
+    ap.add_argument("--e2e-ramp", default="8,8,16,32", help="sub-batch sizes at the start of an e2e run (first host batch only); '' = none")
     ap.add_argument("--e2e-format", default="zc", choices=["zc", "dense"], help="host format of the e2e leg: zero-compressed "
                                                                                "features (default) or dense tensors")
     ap.add_argument("--distinct", type=int, default=64, help="distinct synthetic episodes generated per rank (tiled to E)")
@@ -434,7 +435,8 @@ def main():
     if not a.no_e2e:
         def run_e2e(host_batch, tag):
             pipe = cwt.HostPipeline(dev, params, a.heads, a.cls_lr, a.adapt_iter, fit_algo=a.fit_algo, attn_algo=a.attn_algo,
-                                    sub_batch=a.e2e_sub_batch, sub_batch_all=bool(a.e2e_sub_all), expand_on_main=bool(a.e2e_expand_main))
+                                    sub_batch=a.e2e_sub_batch, sub_batch_all=bool(a.e2e_sub_all), expand_on_main=bool(a.e2e_expand_main),
+                                    ramp=tuple(int(x) for x in a.e2e_ramp.split(",") if x))
             pipe.run([host_batch] * max(1, a.warmup), reduce_every_step=True)
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -448,8 +450,9 @@ def main():
                     "d2h_bytes_per_step": res[0].numel() * res[0].element_size() + 4 * E, "ms_per_step": ms_e / a.steps,
                     "host_format": tag,
                     "counts_equal_device_resident_run": bool(torch.equal(res[0].to(dev), last_out.counts))}
-        api = ("few_shot_seg_cwt_b200.HostPipeline.run (H2D in sub-batches of %d episodes through three device slots, "
-               "async D2H of the counts and the fit status words)" % a.e2e_sub_batch)
+        api = ("few_shot_seg_cwt_b200.HostPipeline.run (three device staging slots; first batch of the run in sub-batches of "
+               "%s episodes, %s; async D2H of the counts and the fit status words)"
+               % (a.e2e_ramp or a.e2e_sub_batch, "every batch in sub-batches of %d" % a.e2e_sub_batch if a.e2e_sub_all else "later batches whole"))
         dense = run_e2e(host, "dense fp32 tensors in pinned host memory")
         if a.e2e_format == "dense":
             e2e = dict(dense, api=api)

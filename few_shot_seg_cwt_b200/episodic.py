@@ -546,32 +546,31 @@ class HostPipeline:
 
     def __init__(self, device, params: Dict[str, torch.Tensor], n_head: int, lr: float, n_iter: int,
                  fit_algo: int = L.FIT_AUTO, attn_algo: int = L.ATTN_REASSOC, num_classes_val: int = 5, n_slots: int = 3,
-                 sub_batch: int = 32, sub_batch_all: bool = True, expand_on_main: bool = False):
+                 sub_batch: int = 32, sub_batch_all: bool = False, expand_on_main: bool = True, ramp=(8, 8, 16, 32)):
         self.device = torch.device(device)
         self.params = {k: v.to(self.device) for k, v in params.items()}
         self.n_head, self.lr, self.n_iter = n_head, lr, n_iter
         self.fit_algo, self.attn_algo = fit_algo, attn_algo
         self.copy_stream = torch.cuda.Stream(self.device)
         self.table = IoUTable(num_classes_val, self.device)
-        # Host batches go through the pipeline in SUB-BATCHES of ``sub_batch`` episodes (0 = whole batches; ``sub_batch_all`` False
-        # = only the first batch of a run). Copy (17.5 ms per 64 episodes at 55.6 GB/s) and head (17.7 ms) are balanced, so a
-        # K-batch run costs about one exposed copy plus K heads: with whole batches the exposed copy is 17.5 ms, with halves
-        # 8.8 ms, while a 32-episode head costs only ~1 % more per episode than a 64-episode one (a 16-episode head 7 %).
-        # Measured (bench.py, 10 steps of 64 episodes): whole 19.31 ms per step, sub-batches of 32: 18.87 ms, of 16: 18.99 ms.
-        # (A ramp — quarter sub-batches at the very start and end of a run — was measured too: 18.79 ms, no gain: a head can
-        # only start when everything before it has been copied, so the exposed time is one steady-state sub-batch copy
-        # whatever the first pieces are.)
-        # Re-measured with HeadPipeline (post stage hidden under the next fit), e2e episodes/s at 10 steps of 64 episodes:
-        # sub-batches of 32: 3 453 / 3 462; of 16: 3 407; of 8: 3 541, 3 541 and once 2 696 (23.7 ms per step — not
-        # investigated: no GPU time left in the round); of 4: 3 477. The default stays 32 (stable).
+        # The first host batch of a run goes through in SUB-BATCHES (``ramp`` sizes, then ``sub_batch``): the head can only start
+        # when its first piece has arrived, so the exposed copy at the start of a run is that of 8 episodes. Later batches go
+        # whole (``sub_batch_all`` False): their copy (531 MB zero-compressed = 10 ms at 53 GB/s) hides under the previous
+        # batch's fit (17 ms). ``sub_batch_all`` True sub-batches every host batch (round-1 default, for dense host tensors
+        # whose copy takes as long as the fit).
         # Device-resident staging slots are reused for the whole run: no allocator traffic (a cudaMalloc of ~1 GB
         # synchronises the device). Three slots: the copy of sub-batch i+2 may start as soon as the copy of i+1 has
         # finished (its slot was released by head i-1 long ago), so the copy engine never waits for the head.
-        # Zero-compressed host batches: where the expansion kernel runs. False (default): on the copy stream, behind the copies it
-        # expands, i.e. concurrently with the previous sub-batch's fit; True: on the head's stream, right in front of the fit.
-        # Measured on B200 (bench.py e2e, 10 steps of 64 episodes, three runs each, profiles/r2b_e2e_sub_batch*.txt): 18.05-18.4 ms
-        # per step either way, sub-batches of 16 or 32 — the choice does not matter at one GPU, where the copy is hidden anyway.
+        # Zero-compressed host batches: where the expansion kernel runs. True (default): on the head's stream, right in front of
+        # the fit (~0.25 ms per 64 episodes, exposed); False: on the copy stream, behind the copies it expands, i.e. concurrently
+        # with the previous batch's cooperative fit — whose 144 CTAs leave it one small CTA per SM: the expansion of 64 episodes
+        # then takes 5-7 ms instead of 0.25 and copy + expansion no longer fit under one fit (tools/e2e_timeline.py).
+        # Measured on B200 (bench.py e2e, 10 steps of 64 episodes, three runs each, profiles/r2d_e2e_ramp.txt): whole batches
+        # after a start-of-run ramp of 8, 8, 16, 32 episodes: 17.70 ms per step with the expansion on the head's stream, 18.22 ms
+        # on the copy stream; sub-batches of 32 throughout: 18.05-18.1 ms (two 32-episode fits cost 0.34 ms more than one
+        # 64-episode fit).
         self.expand_on_main = bool(expand_on_main)
+        self.ramp = tuple(int(x) for x in (ramp or ()))     # sub-batch sizes at the very start of a run (first host batch only)
         self.sub_batch = max(0, int(sub_batch))
         self.sub_batch_all = bool(sub_batch_all)            # sub-batch every host batch, not only the first
         self._slots: List[Optional[EpisodeBatch]] = [None] * n_slots
@@ -642,13 +641,19 @@ class HostPipeline:
         return db, ev, pending
 
     def _sub_batches(self, host_batches):
-        """(batch number, first episode, end episode, is-last, host batch, E): slices of a pinned tensor along dim 0 stay pinned."""
+        """(batch number, first episode, end episode, is-last, host batch, E): slices of a pinned tensor along dim 0 stay pinned.
+        The FIRST host batch of a run goes through in the ``ramp`` sizes (default 8, 8, 16, then ``sub_batch``): the head can
+        only start when its first piece has arrived, so the exposed copy at the start of a run is that of 8 episodes."""
         for bi, hb in enumerate(host_batches):
             E = hb.n_episodes
             step = self.sub_batch if (self.sub_batch > 0 and (bi == 0 or self.sub_batch_all)) else max(E, 1)
-            for lo in range(0, max(E, 1), step):
-                hi = min(E, lo + step)
+            sizes = list(self.ramp) if (bi == 0 and self.ramp) else []
+            lo = 0
+            while lo < max(E, 1):
+                n = sizes.pop(0) if sizes else step
+                hi = min(E, lo + max(1, n))
                 yield bi, lo, hi, hi >= E, hb, E
+                lo = max(hi, lo + 1)
 
     def _result_buffers(self, bi: int, E: int):
         """Pinned host buffers of host batch ``bi`` (counts int64 [E,2,2,3], fit status int32 [E]): owned by the pipeline and
