@@ -39,10 +39,23 @@
 // memory sweep (2 x C*NP*4 B at 128 B/clk/SM). floor(#SM / CPG) groups run concurrently
 // (4 x 36 = 144 of 148 SMs for 60x60x512), each looping over its share of the batch.
 //
-// The kernel is compiled for 512 compute threads / one CTA per SM (default) and for 256 / two CTAs per SM
+// TENSOR-MEMORY variant (default for the PSPNet head geometry, C = 512, 60 x 60, tile 20 x 5; round 2): shared memory only
+// STAGES the tile; for the 200 steps it lives in the SM's 256 KB of tensor memory (tcgen05.alloc / st / ld, no MMA involved):
+// lane = channel mod 128, column = 100 (channel / 128) + pixel, 400 of the 512 columns. tcgen05.ld streams ~380 B/clk/SM with 16
+// warps (tools/micro/tmem_bench.cu) against the 128 B/clk of the shared-memory pipe, and it leaves the LSU to the exchanges:
+//   P1  thread = lane L of its quarter, pixel block warp / 4 (25 pixels): in-thread FFMA2 over the 4 channel chunks, butterfly
+//       reduce-scatter over the 32 lanes (31 shuffles), the four lane quarters combined through shared memory;
+//   P3  thread = channel: 100 columns in 4 loads, g broadcast from shared memory, no cross-thread reduction, all chunks at once;
+//   HR  a per-episode coefficient table (it reuses the staging buffer) makes every live cell row cost the same 16 FMAs;
+//   AR  no applier warp: after its RED every compute thread waits RES_POLL_DELAY clocks, polls the accumulator word of ITS
+//       channel (one 8-byte load per lane; one warp polling all 512 words needs ~1 600 clk per round), applies the SGD step to
+//       the weights it keeps in registers and publishes Wd; the halo warp sleeps on a named barrier until z is published.
+// Measured (E = 64, 200 steps): 11.56 ms = 7 100 clk per step against 10 400 for the shared-memory kernel.
+//
+// The shared-memory kernel is compiled for 512 compute threads / one CTA per SM and for 256 / two CTAs per SM
 // (CWT_RESIDENT_BPS=2: measured slower, kept for comparison), each specialised for the PSPNet head geometry
 // (C=512, 60x60, tile 20x5 resp. 4x10: all loop bounds, divisions and predicates become compile-time) and
-// generic (run-time shapes).
+// generic (run-time shapes); CWT_RESIDENT_TMEM=0 selects it for the head geometry too.
 //
 // Launch: cooperative (all CTAs must be co-resident: they poll each other's words). Every poll loop
 // has a watchdog: on timeout the kernel raises an abort flag, stops waiting and writes NaN results
@@ -79,14 +92,27 @@ namespace cwt {
 __host__ __device__ constexpr int res_wd_pos(int c, bool permute) {
     return permute ? ((c >> 7) << 7) + ((c & 15) << 3) + ((c >> 4) & 7) : c;
 }
-constexpr int res_appliers(int CT) { return ((RES_VARIANT & 0x80) && CT == 512) ? 4 : 1; }
-constexpr int res_helper_threads(int CT) { return 32 * (res_appliers(CT) + 1); }
+constexpr int res_helper_threads(int NA) { return 32 * (NA + 1); }     // NA applier warps + the halo warp
 constexpr int RES_KCH = 4;        // channel chunks of the pipelined all-reduce
 constexpr int RES_AW = 4;         // accumulator words an applier lane keeps in flight
 constexpr int RES_HWORDS = 4;     // halo words per lane of the halo warp (ring <= 128 pixels)
 constexpr int RES_MAXTASK = 4;    // HR row-tasks per compute thread (8 * cells <= 4 * 512)
 constexpr int RES_NPROF = 12;     // profile counters per CTA
 constexpr int RES_P3_DEPTH = 4;   // pixel-quads a P3 thread keeps in flight per operand
+// polling of the accumulator words by the compute threads (tensor-memory kernel): loads in flight per thread (1 | 3), clocks
+// before the first load, clocks between loads
+#ifndef RES_HALO_GATE
+#define RES_HALO_GATE 1            // the halo warp sleeps until its CTA has published z (tensor-memory kernel)
+#endif
+#ifndef RES_POLL_INFLIGHT
+#define RES_POLL_INFLIGHT 1
+#endif
+#ifndef RES_POLL_DELAY
+#define RES_POLL_DELAY 600
+#endif
+#ifndef RES_POLL_GAP
+#define RES_POLL_GAP 0
+#endif
 
 struct ResidentParams {
     const float* f_s;          // [E][C][HW]
@@ -126,15 +152,18 @@ static __host__ __device__ inline ResSmem res_smem_layout(int C, int TW, int TH,
 }
 
 // CT: compute threads, MINB: CTAs per SM. TC / TTW / TTH / TWL / THL > 0: compile-time shape (C, tile width / height,
-// low-res width / height); 0: run-time shape.
-template <int CT, int MINB, int TC, int TTW, int TTH, int TWL, int THL, bool PROF>
-__global__ void __launch_bounds__(CT + res_helper_threads(CT), MINB) k_fit_resident(ResidentParams p) {
+// low-res width / height); 0: run-time shape. TM: the tile lives in TENSOR MEMORY for the steps (PSPNet head geometry, one CTA
+// per SM): lane = channel mod 128, column = 100 (channel / 128) + pixel — shared memory only stages it. NA: applier warps
+// (1 for the shared-memory kernels; 0 for the tensor-memory kernel, whose compute threads poll and apply their own channel).
+template <int CT, int MINB, int TC, int TTW, int TTH, int TWL, int THL, bool PROF, bool TM, int NA>
+__global__ void __launch_bounds__(CT + res_helper_threads(NA), MINB) k_fit_resident(ResidentParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int C = TC ? TC : p.C, TW = TTW ? TTW : p.TW, TH = TTH ? TTH : p.TH, wl = TWL ? TWL : p.w_lo, h = THL ? THL : p.h;
     const int NP = TW * TH, HW = wl * h, TPR = wl / TW, CPG = HW / NP;
     const int CCH = C / RES_KCH;                     // channels per chunk (C % RES_KCH == 0)
     constexpr bool kStatic = (CT == 512 && TC == 512 && TTW * TTH == 100);   // PSPNet head geometry, one CTA per SM: fully unrolled sweeps
     constexpr bool kStatic40 = (CT == 256 && TC == 512 && TTW * TTH == 40);  // ... two CTAs per SM
+    static_assert(!TM || kStatic, "the tensor-memory tile is built for C = 512, 100 pixels, 512 compute threads");
     const int NQ = NP / 4, NG = kStatic ? 16 : CT / NQ;
     const int ZW = TW + 2, ZH = TH + 2, CW = TW + 1, NCELL = CW * (TH + 1);
     const int NINT = (TW - 1) * (TH - 1);            // cells whose four corners are own pixels: need no halo
@@ -165,14 +194,20 @@ __global__ void __launch_bounds__(CT + res_helper_threads(CT), MINB) k_fit_resid
     unsigned long long* fmaxw = p.fmaxw + (size_t)group * CPG;
     const int KB = p.KBITS;                                            // arrival-count bits of an accumulator word
 
+    __shared__ uint32_t tmem_slot;
     if (tid == 0) {
         mbar_init(mbar, 1);
         for (int j = 0; j < RES_KCH; ++j) mbar_init(&applied[j], 1);
         mbar_init(halo_ready, 1);
         mbar_init(pollbar, 1);
     }
+    if (TM && warp == 0) tmem_alloc_512(&tmem_slot);       // all 512 columns: this CTA has the SM to itself
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (TM) tmem_fence_before_sync();
     __syncthreads();
+    if (TM) tmem_fence_after_sync();
+    // this warp's window of tensor memory: lane quarter 32 (warp % 4), bits 31..16 of a TMEM address are the lane
+    const uint32_t tq = TM ? tmem_slot + ((uint32_t)((warp & 3) * 32) << 16) : 0u;
 
     __shared__ long long tstore_sm[RES_KCH];          // PROF: when chunk j's partials left this CTA
 
@@ -265,7 +300,29 @@ __global__ void __launch_bounds__(CT + res_helper_threads(CT), MINB) k_fit_resid
             }
             __syncthreads();                                           // S2
             // ---------------- fixed-point unit of the episode: power of two from the group-wide max|F| ----------------
-            {
+            if constexpr (TM) {
+                // the same scan moves the tile into tensor memory: thread = channel (lane 32 (warp % 4) + lane of its quarter, chunk
+                // warp / 4), its 100 pixels = columns 100 (warp / 4) .. + 99. Rows are 400 B apart: a quarter-warp's LDS.128 is
+                // conflict-free. From here on shared memory is free of the tile until the next episode is staged.
+                unsigned mb = 0u;
+                const uint32_t row = smem_u32(F) + (uint32_t)tid * 400u, tcol = tq + 100u * (uint32_t)(warp >> 2);
+                float v[32];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+#pragma unroll
+                    for (int i = 0; i < (b < 3 ? 8 : 1); ++i) {
+                        const float4 f = lds128_v(row + (uint32_t)(b * 128 + i * 16));
+                        v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
+                        mb = max(max(mb, __float_as_uint(f.x) & 0x7fffffffu),
+                                 max(max(__float_as_uint(f.y) & 0x7fffffffu, __float_as_uint(f.z) & 0x7fffffffu), __float_as_uint(f.w) & 0x7fffffffu));
+                    }
+                    if (b < 3) tmem_st32(tcol + 32u * b, v); else tmem_st4(tcol + 96u, v);
+                }
+                tmem_wait_st();
+                mb = __reduce_max_sync(0xffffffffu, mb);
+                if (lane == 0) atomicMax(&smax[0], mb);
+                tmem_fence_before_sync();
+            } else {
                 unsigned mb = 0u;
                 const uint4* F4u = reinterpret_cast<const uint4*>(F);
                 for (int i = tid; i < C * NQ; i += CT) {
@@ -276,20 +333,103 @@ __global__ void __launch_bounds__(CT + res_helper_threads(CT), MINB) k_fit_resid
                 if (lane == 0) atomicMax(&smax[0], mb);
             }
             __syncthreads();                                           // S3
+            if (TM) tmem_fence_after_sync();
+            if constexpr (TM) {
+                // The staging buffer is free now: it takes the coefficient table of the full-resolution stage. The gradient mass a
+                // cell row sends to its left / right low-res column is linear in the 8 sigmoids p_s of the row,
+                //     gl = sum_s L_s p_s - L0,  gr = sum_s R_s p_s - R0,   L_s = A_s (1 - s/8), R_s = A_s s/8,
+                //     A_s = c0 | c1 | 0 (label 0 | 1 | ignored),  L0 / R0 = the same sums over B_s = c1 [label 1],
+                // so every live row costs the same 16 FMAs whatever its labels are (no uniform / boundary distinction, no
+                // label selects inside the step loop): 20 floats per task, rows 80 B apart (conflict-free LDS.128).
+                float* tab = F;
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    const unsigned d = hr_desc[m];
+                    if ((d >> 31) && (d & (1u << 18))) {
+                        float Ls[8], Rs[8], L0 = 0.f, R0 = 0.f;
+#pragma unroll
+                        for (int sx = 0; sx < 8; ++sx) {
+                            const unsigned code = (d >> (2 * sx)) & 3u;
+                            const float A = code == 0u ? c01.x : (code == 1u ? c01.y : 0.f), B = code == 1u ? c01.y : 0.f;
+                            const float fr = (float)sx * 0.125f;
+                            Ls[sx] = A * (1.f - fr); Rs[sx] = A * fr;
+                            L0 = fmaf(B, 1.f - fr, L0); R0 = fmaf(B, fr, R0);
+                        }
+                        float4* t4 = reinterpret_cast<float4*>(tab + (size_t)(m * CT + tid) * 20);
+                        t4[0] = make_float4(Ls[0], Ls[1], Ls[2], Ls[3]); t4[1] = make_float4(Ls[4], Ls[5], Ls[6], Ls[7]);
+                        t4[2] = make_float4(Rs[0], Rs[1], Rs[2], Rs[3]); t4[3] = make_float4(Rs[4], Rs[5], Rs[6], Rs[7]);
+                        t4[4] = make_float4(L0, R0, 0.f, 0.f);
+                    }
+                }
+            }
             if (tid == 0) st_tagged(&fmaxw[k], __uint_as_float(smax[0]), (unsigned)e + 1u);
             for (int kk = tid; kk < CPG; kk += CT)
                 atomicMax(&smax[1], __float_as_uint(poll_word(&fmaxw[kk], (unsigned)e + 1u, p.abort_flag)));
             __syncthreads();                                           // S4
             const bool ep_finite = smax[1] < 0x7f800000u;
-            float fx_inv;
-            { float unit; fixed_point_unit(smax[1], p.T, KB, unit, fx_inv); }
+            float fx_inv, fx_unit;
+            fixed_point_unit(smax[1], p.T, KB, fx_unit, fx_inv);
             unsigned long long* acc_ep = p.sums + acc_offset(e, group, p.G, p.SPL, C);
+            // NA == 0: thread c keeps W0[c] / W1[c] and the previous cumulative sums of its accumulator words in registers
+            float w0r = (TM && NA == 0) ? W0[tid & (TC ? TC - 1 : 0)] : 0.f, w1r = (TM && NA == 0) ? W1[tid & (TC ? TC - 1 : 0)] : 0.f;
+            long long cum0 = 0ll, cum1 = 0ll, tk_ar = 0ll;
+            (void)fx_unit; (void)cum0; (void)cum1; (void)tk_ar;
 
             for (int t = 0; t < p.T; ++t, ++gstep) {
                 long long tk0 = 0, tstep0 = 0;
                 if (PROF && tid == 0) { tk0 = clock64(); tstep0 = tk0; }
                 // ------------ P1 (each chunk first picks up the previous step's all-reduced dW) ------------
-                {
+                if constexpr (TM) {
+                    // Tile in tensor memory: this thread owns lane L = 32 (warp % 4) + lane, i.e. the channels 128 j + L, and the
+                    // four warps of a lane quarter split the pixels (25 each). In-thread sum over the 4 chunks, butterfly
+                    // reduce-scatter over the 32 lanes (31 shuffles: lane i ends with pixel i of the block), then the four lane
+                    // quarters are combined through shared memory in a fixed order. The loads do not depend on the all-reduce
+                    // (the features never change): a chunk's columns are on their way while the thread waits for its Wd.
+                    const uint32_t tcol = tq + 25u * (uint32_t)(warp >> 2);
+                    const float* Wl = Wd + (warp & 3) * 32 + lane;
+                    // (26 columns per chunk: the 26th belongs to the next pixel block and only fills the last packed-fp32 pair)
+                    float z[32], fj[26];
+                    f32x2 z2[13];
+#pragma unroll
+                    for (int i = 0; i < 13; ++i) z2[i] = 0ull;
+#pragma unroll
+                    for (int j = 0; j < RES_KCH; ++j) {
+                        tmem_ld16(tcol + 100u * j, fj); tmem_ld8(tcol + 100u * j + 16u, fj + 16); tmem_ld2(tcol + 100u * j + 24u, fj + 24);
+                        if (NA > 0 && t > 0) wait_applied(j, gstep - 1u);
+                        const float wd = (RES_VARIANT & 0x10) ? 0.f : Wl[j * 128];
+                        const f32x2 wd2 = pk2(wd, wd);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 26; ++i) asm volatile("" : "+f"(fj[i]));      // keeps the uses below the tcgen05.wait::ld
+#pragma unroll
+                        for (int i = 0; i < 13; ++i) z2[i] = fma2(wd2, pk2(fj[2 * i], fj[2 * i + 1]), z2[i]);     // FFMA2: two pixels per issue slot
+                    }
+#pragma unroll
+                    for (int i = 0; i < 13; ++i) upk2(z2[i], z[2 * i], z[2 * i + 1]);
+#pragma unroll
+                    for (int i = 25; i < 32; ++i) z[i] = 0.f;
+#pragma unroll
+                    for (int sft = 16; sft >= 1; sft >>= 1) {
+                        const bool hi = (lane & sft) != 0;
+#pragma unroll
+                        for (int i = 0; i < sft; ++i) {
+                            const float send = hi ? z[i] : z[i + sft], keep = hi ? z[i + sft] : z[i];
+                            z[i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+                        }
+                    }
+                    if (lane < 25) scratch[(warp & 3) * NP + 25 * (warp >> 2) + lane] = z[0];
+                    compute_sync<CT>();
+                    if (tid < NP) {
+                        const float zz = (scratch[tid] + scratch[NP + tid]) + (scratch[2 * NP + tid] + scratch[3 * NP + tid]);
+                        const int py = tid / TW, px = tid - py * TW;
+                        zt[(py + 1) * ZW + px + 1] = zz;
+                        st_tagged(&zll[(gstep & 1u) * (unsigned)HW + (y0 + py) * wl + x0 + px], zz, gstep + 1u);
+                    }
+                    // wake the halo warp (named barrier 5, non-blocking on this side): the neighbours publish about now, so every
+                    // earlier poll of the ring would only be traffic on lines that are being written
+                    if (RES_HALO_GATE) asm volatile("bar.arrive 5, %0;" ::"n"(CT + 32) : "memory");
+                    compute_sync<CT>();
+                } else {
                     float4 za = make_float4(0.f, 0.f, 0.f, 0.f);
                     const float4* F4 = reinterpret_cast<const float4*>(F) + tid;
                     const int stride = NQ * NG;
@@ -362,12 +502,29 @@ __global__ void __launch_bounds__(CT + res_helper_threads(CT), MINB) k_fit_resid
                             }
                             if (PROF && tid == 0) t_acc[1] += clock64() - tw0;
                         }
-                        const unsigned d = hr_desc[m];
+                        unsigned d = hr_desc[m];
+                        // TM: keep what is derived from the descriptor (shared-memory addresses of the four corners, ...) out of the
+                        // loop-invariant registers: they spill beside the sweeps' buffers and local-memory loads cost a long scoreboard
+                        if (TM) asm volatile("" : "+r"(d));
                         if (d >> 31) {
                             const int ci = (d >> 19) & 0xff, r = tid & 7;
                             float gl = 0.f, gr = 0.f;
                             if ((RES_VARIANT & 0x02) && (d & (1u << 18))) {
                                 gl = zt[ci + (int)((d >> 27) & 0xfu)] * 1e-6f;
+                            } else if (TM && (d & (1u << 18))) {
+                                const int zi = ci + (int)((d >> 27) & 0xfu);     // cy * ZW + cx = ci + cy
+                                const int dx = (d >> 16) & 1, dy = (d & (1u << 17)) ? ZW : 0;
+                                const float z00 = zt[zi], z01 = zt[zi + dx], z10 = zt[zi + dy], z11 = zt[zi + dy + dx];
+                                const float fr = (float)r * 0.125f;
+                                const float left = fmaf(fr, z10 - z00, z00), right = fmaf(fr, z11 - z01, z01);
+                                float pr[8];
+                                sigmoid_row(left, right, pr);
+                                const float4* t4 = reinterpret_cast<const float4*>(F + (size_t)(m * CT + tid) * 20);
+                                const float4 la = t4[0], lb = t4[1], ra = t4[2], rb4 = t4[3], k0 = t4[4];
+                                gl = (fmaf(la.x, pr[0], fmaf(la.y, pr[1], fmaf(la.z, pr[2], la.w * pr[3]))) +
+                                      fmaf(lb.x, pr[4], fmaf(lb.y, pr[5], fmaf(lb.z, pr[6], lb.w * pr[7])))) - k0.x;
+                                gr = (fmaf(ra.x, pr[0], fmaf(ra.y, pr[1], fmaf(ra.z, pr[2], ra.w * pr[3]))) +
+                                      fmaf(rb4.x, pr[4], fmaf(rb4.y, pr[5], fmaf(rb4.z, pr[6], rb4.w * pr[7])))) - k0.y;
                             } else if (d & (1u << 18)) {
                                 const int zi = ci + (int)((d >> 27) & 0xfu);     // cy * ZW + cx = ci + cy
                                 const int dx = (d >> 16) & 1, dy = (d & (1u << 17)) ? ZW : 0;
@@ -409,7 +566,95 @@ __global__ void __launch_bounds__(CT + res_helper_threads(CT), MINB) k_fit_resid
                 // ------------ P3: dW = g . F^T chunk by chunk; every partial goes straight to the channel's accumulator word,
                 // so chunk j's all-reduce runs under the rest of P3 and the next P1 ------------
                 unsigned long long* acc_t = acc_ep + (t & 1) * C;          // even / odd steps use different words (see header)
-                if constexpr (kStatic && (RES_VARIANT & 0x40) != 0) {
+                if constexpr (TM) {
+                    // Tile in tensor memory: thread = channel tid (lane L of its quarter, chunk warp / 4 = columns 100 (warp / 4) ..),
+                    // its 100 pixels come as 32 + 32 + 32 + 4 columns; g is broadcast from shared memory.
+                    // No cross-thread reduction and no hand-over between the quads: all 16 warps sweep at once (the tensor-memory
+                    // read path is ~3x the shared-memory pipe) and the four chunks leave together. Same summation order as the
+                    // shared-memory sweep (pixel p goes to accumulator p mod 4).
+                    const uint32_t tcol = tq + 100u * (uint32_t)(warp >> 2), gad = smem_u32(gsm);
+                    float f[32];
+                    float4 g[8];
+                    f32x2 da = 0ull, db = 0ull;                      // {d0, d1}, {d2, d3}
+                    if (!(RES_VARIANT & 0x08)) {
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            // the block's columns and its 8 quads of g are requested together (tensor-memory and shared-memory latencies
+                            // overlap), then 16 FFMA2
+                            if (b < 3) tmem_ld32(tcol + 32u * b, f); else tmem_ld4(tcol + 96u, f);
+#pragma unroll
+                            for (int i = 0; i < (b < 3 ? 8 : 1); ++i) g[i] = lds128_v(gad + 16u * (uint32_t)(8 * b + i));
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int i = 0; i < (b < 3 ? 32 : 4); ++i) asm volatile("" : "+f"(f[i]));   // keeps the uses below the wait
+#pragma unroll
+                            for (int i = 0; i < (b < 3 ? 8 : 1); ++i) {
+                                da = fma2(pk2(g[i].x, g[i].y), pk2(f[4 * i], f[4 * i + 1]), da);
+                                db = fma2(pk2(g[i].z, g[i].w), pk2(f[4 * i + 2], f[4 * i + 3]), db);
+                            }
+                        }
+                    } else {
+                        da = pk2(gsm[tid & 63], 0.f);
+                    }
+                    float d0, d1, d2, d3;
+                    upk2(da, d0, d1); upk2(db, d2, d3);
+                    const float d = (d0 + d1) + (d2 + d3);
+                    red_add_u64(acc_t + tid, ((unsigned long long)__float2ll_rn(d * fx_inv) << KB) + 1ull);
+                    if constexpr (NA == 0) {
+                        // No applier warp: every compute thread waits for the all-reduced sum of ITS channel (one 8-byte load per
+                        // lane and round: a poll costs the warp ~8 sectors, where one applier warp polling all 512 words needs
+                        // ~1 600 clk per round), applies the SGD step to the weights it keeps in registers and publishes Wd.
+                        if (PROF && tid == 0) tk_ar = clock64();
+                        const unsigned long long expect = (unsigned long long)CPG * (unsigned)(t / 2 + 1), cnt_mask = (1ull << KB) - 1ull;
+                        const unsigned long long* wp = acc_t + tid;
+                        unsigned long long wv = 0ull;
+                        if (!(RES_VARIANT & 0x04)) {
+                            auto done = [&](unsigned long long v) {
+                                return (RES_VARIANT & 0x1f) ? (v & cnt_mask) >= expect : (v & cnt_mask) == expect;
+                            };
+                            auto gap = [&](long long n) { const long long t0g = clock64(); while (clock64() - t0g < n) { } };
+                            if (RES_POLL_DELAY > 0) gap(RES_POLL_DELAY);      // a load issued with the RED overtakes it and is wasted
+                            unsigned it = 0;
+#if RES_POLL_INFLIGHT == 3
+                            // three loads in flight, issued RES_POLL_GAP clocks apart and re-issued as they return
+                            unsigned long long v0 = ld_relaxed_u64(wp), v1, v2;
+                            gap(RES_POLL_GAP); v1 = ld_relaxed_u64(wp);
+                            gap(RES_POLL_GAP); v2 = ld_relaxed_u64(wp);
+                            for (;;) {
+                                if (done(v0)) { wv = v0; break; }
+                                v0 = ld_relaxed_u64(wp);
+                                if (done(v1)) { wv = v1; break; }
+                                v1 = ld_relaxed_u64(wp);
+                                if (done(v2)) { wv = v2; break; }
+                                v2 = ld_relaxed_u64(wp);
+                                if ((++it & 0xffu) == 0u) {
+                                    if (*reinterpret_cast<volatile unsigned*>(p.abort_flag) != 0u) break;
+                                    if (it > (RES_SPIN_LIMIT >> 2)) { atomicExch(p.abort_flag, 1u); break; }
+                                }
+                            }
+#else
+                            for (;;) {
+                                wv = ld_relaxed_u64(wp);
+                                if (done(wv)) break;
+                                if (RES_POLL_GAP > 0) gap(RES_POLL_GAP);
+                                if ((++it & 0xffu) == 0u) {
+                                    if (*reinterpret_cast<volatile unsigned*>(p.abort_flag) != 0u) break;
+                                    if (it > (RES_SPIN_LIMIT >> 2)) { atomicExch(p.abort_flag, 1u); break; }
+                                }
+                            }
+#endif
+                        }
+                        const long long cur = (long long)wv >> KB;                       // cumulative sum over steps 0..t of this parity (exact)
+                        const long long prev = (t & 1) ? cum1 : cum0;
+                        if (t & 1) cum1 = cur; else cum0 = cur;
+                        const float dw = __ll2float_rn(cur - prev) * fx_unit;            // this step's all-reduced dW
+                        w0r = fmaf(p.lr, dw, w0r); w1r = fmaf(-p.lr, dw, w1r);
+                        Wd[tid] = w1r - w0r;
+                        if (PROF && tid == 0) { t_acc[5] += clock64() - tk_ar; t_acc[4] += 1; }
+                        compute_sync<CT>();
+                    }
+                    if (PROF && lane == 0 && (warp & 3) == 3) *reinterpret_cast<volatile long long*>(&tstore_sm[warp >> 2]) = clock64();
+                } else if constexpr (kStatic && (RES_VARIANT & 0x40) != 0) {
                     // lane = pixel quad (25 of 32 lanes), warp = 8 channels of the chunk: all 16 warps sweep chunk j together, g stays
                     // in registers, the 8 per-lane partials are summed over the lanes by a transposing butterfly (9 shuffles)
                     const float4 g4 = lane < 25 ? reinterpret_cast<const float4*>(gsm)[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -520,10 +765,11 @@ __global__ void __launch_bounds__(CT + res_helper_threads(CT), MINB) k_fit_resid
                 if (PROF && tid == 0) { long long n = clock64(); t_acc[3] += n - tk0; t_acc[6] += n - tstep0; }
             }
             // ------------ drain the last step's all-reduce ------------
-            if (p.T > 0) {
+            if (p.T > 0 && NA > 0) {
 #pragma unroll
                 for (int j = 0; j < RES_KCH; ++j) wait_applied(j, gstep - 1u);
             }
+            if (TM && NA == 0) { W0[tid] = w0r; W1[tid] = w1r; }
             __syncthreads();                                           // S5
             if (k == 0) {
                 const bool bad = *reinterpret_cast<volatile unsigned*>(p.abort_flag) != 0u || !ep_finite;   // NaN / Inf features give NaN weights
@@ -538,13 +784,14 @@ __global__ void __launch_bounds__(CT + res_helper_threads(CT), MINB) k_fit_resid
             p.prof[(size_t)blockIdx.x * RES_NPROF + 10] = t_acc[6];
         }
         if (tid == 0 && !ok) atomicExch(p.abort_flag, 1u);
-    } else if (warp < CT / 32 + res_appliers(CT)) {
+        if (TM && warp == 0) { tmem_fence_after_sync(); tmem_dealloc_512(tmem_slot); }    // every warp's last tensor-memory load precedes S5
+    } else if (NA > 0 && warp < CT / 32 + NA) {
         // =====================================================================================================
         // applier warp: accumulator words -> SGD update in shared memory -> release the compute warps
         // =====================================================================================================
         long long a_acc[4] = {0, 0, 0, 0};               // PROF: poll rounds, cycles polling, sum(done - own store), chunks
         const unsigned long long cnt_mask = (1ull << KB) - 1ull;
-        constexpr int NAPPL = res_appliers(CT);
+        constexpr int NAPPL = NA > 0 ? NA : 1;
         const int aw = warp - CT / 32;                   // applier number: owns chunks aw, aw + NAPPL, ...
         unsigned poll_parity = 0u;
         for (int e = group; e < p.E; e += p.G) {
@@ -663,6 +910,7 @@ __global__ void __launch_bounds__(CT + res_helper_threads(CT), MINB) k_fit_resid
                 const unsigned long long* zsrc = zll + (gstep & 1u) * (unsigned)HW;
                 unsigned bits[RES_HWORDS], tag[RES_HWORDS];
                 unsigned pending = 0u, it = 0u;
+                if (TM && RES_HALO_GATE) asm volatile("bar.sync 5, %0;" ::"n"(CT + 32) : "memory");     // this CTA's z of the step is out
 #pragma unroll
                 for (int m = 0; m < RES_HWORDS; ++m) { bits[m] = 0u; tag[m] = 0u; if (ring_q[m] >= 0) pending |= 1u << m; }
                 if (RES_VARIANT & 0x200) pending = 0u;
@@ -773,15 +1021,15 @@ size_t fit_resident_workspace_bytes(int E, int C, int h, int w) {
            align_up(sizeof(unsigned long long) * RES_MAXGRID) + 512 + align_up(sizeof(long long) * RES_NPROF * RES_MAXGRID);
 }
 
-template <int CT, int MINB, int TC, int TTW, int TTH, int TWL, int THL>
+template <int CT, int MINB, int TC, int TTW, int TTH, int TWL, int THL, bool TM = false, int NA = 1>
 static int launch_resident(const ResidentParams& p, const ResidentPlan& pl, bool prof, cudaStream_t st) {
     void* args[] = {const_cast<ResidentParams*>(&p)};
-    dim3 grid(pl.G * pl.CPG), block(CT + res_helper_threads(CT));
-    const void* fn = prof ? (const void*)k_fit_resident<CT, MINB, TC, TTW, TTH, TWL, THL, true>
-                          : (const void*)k_fit_resident<CT, MINB, TC, TTW, TTH, TWL, THL, false>;
+    dim3 grid(pl.G * pl.CPG), block(CT + res_helper_threads(NA));
+    const void* fn = prof ? (const void*)k_fit_resident<CT, MINB, TC, TTW, TTH, TWL, THL, true, TM, NA>
+                          : (const void*)k_fit_resident<CT, MINB, TC, TTW, TTH, TWL, THL, false, TM, NA>;
     CWT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     int resident_ctas = 0;
-    CWT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident_ctas, fn, CT + res_helper_threads(CT), pl.smem));
+    CWT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident_ctas, fn, CT + res_helper_threads(NA), pl.smem));
     CWT_REQUIRE(resident_ctas >= MINB, CWT_ERR_UNSUPPORTED, "fit_resident: only %d of %d CTAs per SM fit", resident_ctas, MINB);
     CWT_CUDA(cudaLaunchCooperativeKernel(fn, grid, block, args, pl.smem, st));
     count_launch();
@@ -822,8 +1070,14 @@ int fit_resident(const float* f_s, const uint4* cells, const float2* cw, float* 
     const bool head = (C == 512 && h == 60 && w == 60);
     int rc;
     if (pl.CT == 512) {
-        if (head && pl.TW == 20 && pl.TH == 5) rc = launch_resident<512, 1, 512, 20, 5, 60, 60>(p, pl, prof, st);
-        else rc = launch_resident<512, 1, 0, 0, 0, 0, 0>(p, pl, prof, st);
+        // PSPNet head geometry: the tile lives in tensor memory for the steps and the compute threads apply the all-reduce
+        // themselves (no applier warp). CWT_RESIDENT_TMEM=0: the shared-memory kernel of round 1 (kept for comparison).
+        int tm = 1;
+        if (const char* s = getenv("CWT_RESIDENT_TMEM")) tm = atoi(s);
+        if (head && pl.TW == 20 && pl.TH == 5) {
+            if (tm) rc = launch_resident<512, 1, 512, 20, 5, 60, 60, true, 0>(p, pl, prof, st);
+            else rc = launch_resident<512, 1, 512, 20, 5, 60, 60, false, 1>(p, pl, prof, st);
+        } else rc = launch_resident<512, 1, 0, 0, 0, 0, 0>(p, pl, prof, st);
     } else {
         if (head && pl.TW == 4 && pl.TH == 10) rc = launch_resident<256, 2, 512, 4, 10, 60, 60>(p, pl, prof, st);
         else rc = launch_resident<256, 2, 0, 0, 0, 0, 0>(p, pl, prof, st);

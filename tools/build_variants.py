@@ -15,12 +15,16 @@ def main(masks):
         extra = []
         if isinstance(m, tuple):
             m, extra = m
-        obj = os.path.join(out, f"fit_resident_v{m}.o")
+        elif ":" in m:                          # "mask:-DFOO=1,-DBAR=2" -> extra compiler flags, library named after the whole spec
+            m, fl = m.split(":", 1)
+            extra = fl.split(",")
+        tag = m + "".join("_" + e.replace("-D", "").replace("=", "") for e in extra)
+        obj = os.path.join(out, f"fit_resident_v{tag}.o")
         r = subprocess.run([B.NVCC, *B.FLAGS, f"-DRES_VARIANT={m}", *extra, "-c", os.path.join(B.CSRC, "fit_resident.cu"), "-o", obj],
                            capture_output=True, text=True)
         if r.returncode:
             raise SystemExit(r.stderr)
-        lib = os.path.join(out, f"libcwt_v{m}.so")
+        lib = os.path.join(out, f"libcwt_v{tag}.so")
         r = subprocess.run([B.NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib, obj, *others], capture_output=True, text=True)
         if r.returncode:
             raise SystemExit(r.stderr)
