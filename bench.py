@@ -354,26 +354,53 @@ def main():
     traffic_src = ({"file": counters_file, "build_fingerprint": counters["build_fingerprint"], "matches_this_build": counters_match}
                    if traffic is not None else None)
     if resident:
-        # On-chip roof: every SGD step sweeps the staged tile twice out of shared memory (P1 and P3): algorithmic
-        # shared-memory bytes = E * 2T * F; peak = 128 B/clk/SM x all SMs x the SM clock sampled in the timed region.
-        smem_bytes = E * 2 * T * S * F_bytes
-        smem_gbs = smem_bytes / (fit_ms / 1e3) / 1e9
+        # On-chip roof: every SGD step sweeps the resident tile twice (P1 and P3): algorithmic on-chip bytes = E * 2T * F.
+        # The tile lives in TENSOR MEMORY (tcgen05.st once per episode, tcgen05.ld every sweep), so the bounding resource is the
+        # tensor-memory read path: peak = the tcgen05.ld rate measured by tools/micro/tmem_bench.cu on this pool's B200s
+        # (profiles/r2g_tmem_bench.txt, 16 warps, 3 loads in flight) x all SMs x the SM clock sampled in the timed region.
+        # CWT_RESIDENT_TMEM=0 runs the round-1 kernel (tile in shared memory, 128 B/clk/SM).
+        tmem_kernel = os.environ.get("CWT_RESIDENT_TMEM", "1") != "0"
+        tmem_rate, tmem_src = 378.3, "fallback constant (profiles/r2g_tmem_bench.txt as committed)"
+        try:
+            for line in open(os.path.join(ROOT, "profiles", "r2g_tmem_bench.txt")):
+                if line.startswith("tmem only, 16 warps, 3 ld in flight"):
+                    tmem_rate = float(line.split("tmem")[2].split("B/clk")[0])
+                    tmem_src = "profiles/r2g_tmem_bench.txt (tools/micro/tmem_bench.cu: tcgen05.ld 32x32b.x32, 16 warps, 3 loads in flight)"
+        except Exception:
+            pass
+        onchip_bytes = E * 2 * T * S * F_bytes
+        onchip_gbs = onchip_bytes / (fit_ms / 1e3) / 1e9
         smem_peak = 128.0 * n_sm * sm_clk * 1e6 / 1e9
+        tmem_peak = tmem_rate * n_sm * sm_clk * 1e6 / 1e9
         steps_per_group = T * ((E + 3) // 4)
+        clk_per_step = fit_ms * 1e-3 * sm_clk * 1e6 / max(steps_per_group, 1)
+        smem_equiv = {"achieved": onchip_gbs, "peak": smem_peak, "unit": "GB/s", "frac": onchip_gbs / smem_peak,
+                      "peak_source": f"128 B/clk/SM x {n_sm} SMs x {sm_clk:.0f} MHz",
+                      "note": "the same bytes against the shared-memory pipe: the roof of a shared-memory-resident tile (the round-1 "
+                              "kernel, frac 0.30 there); kept so that the rounds compare on one denominator"}
         roofline = {
-            "kernel": ("k_fit_resident<512 compute threads, 1 CTA/SM, C=512, tile 20x5 of 60x60> (one cooperative launch: features "
-                       "staged once into shared memory by bulk-TMA, 200 SGD steps on chip, all-reduce through 64-bit L2 atomics)"),
-            "bound": "smem", "achieved": smem_gbs, "peak": smem_peak, "unit": "GB/s", "frac": smem_gbs / smem_peak,
+            "kernel": (("k_fit_resident<512 compute threads + halo warp, 1 CTA/SM, C=512, tile 20x5 of 60x60, tile in TENSOR MEMORY> (one "
+                        "cooperative launch: features staged once by bulk-TMA and moved to tensor memory with tcgen05.st, 200 SGD steps "
+                        "on chip with tcgen05.ld sweeps, all-reduce through 64-bit L2 atomics polled by the compute threads)")
+                       if tmem_kernel else
+                       ("k_fit_resident<512 compute threads, 1 CTA/SM, C=512, tile 20x5 of 60x60> (one cooperative launch: features "
+                        "staged once into shared memory by bulk-TMA, 200 SGD steps on chip, all-reduce through 64-bit L2 atomics)")),
+            "bound": "tmem" if tmem_kernel else "smem", "achieved": onchip_gbs, "peak": tmem_peak if tmem_kernel else smem_peak,
+            "unit": "GB/s", "frac": onchip_gbs / (tmem_peak if tmem_kernel else smem_peak),
             "traffic": traffic, "traffic_source": traffic_src,
-            "peak_source": f"128 B/clk/SM x {n_sm} SMs x {sm_clk:.0f} MHz (SM clock sampled during the timed region)",
-            "note": ("the step is two shared-memory sweeps of the resident tile; achieved = E*2T*F algorithmic shared-memory bytes / "
-                     "CUDA-event time of the fit call; the kernel occupies 144 of the SMs (4 groups x 36 CTAs)"),
-            "clk_per_step": fit_ms * 1e-3 * sm_clk * 1e6 / max(steps_per_group, 1),
-            "B_per_clk_per_active_SM": (2 * 512 * 100 * 4) / (fit_ms * 1e-3 * sm_clk * 1e6 / max(steps_per_group, 1)),
+            "peak_source": (f"{tmem_rate:.1f} B/clk/SM x {n_sm} SMs x {sm_clk:.0f} MHz; rate from {tmem_src}" if tmem_kernel
+                            else smem_equiv["peak_source"]),
+            "note": ("the step is two sweeps of the resident tile (P1: z = Wd.F, P3: dW = g.F^T); achieved = E*2T*F algorithmic on-chip "
+                     "bytes / CUDA-event time of the fit call; the kernel occupies 144 of the SMs (4 groups x 36 CTAs). The kernel is "
+                     "NOT bound by this bandwidth: per step ~4 700 clk are work (P1 is issue-bound: butterfly reduce over the lanes; "
+                     "full-resolution stage; gather) and ~2 400 clk are the two cross-CTA exchanges (DESIGN.md 4.4)"),
+            "clk_per_step": clk_per_step,
+            "B_per_clk_per_active_SM": (2 * 512 * 100 * 4) / clk_per_step,
+            "smem_equivalent": smem_equiv,
             "hbm_equivalent": {"achieved": fit_gbs, "peak": hbm_peak, "unit": "GB/s", "x_of_hbm_peak": fit_gbs / hbm_peak,
                                "peak_source": peak_src,
                                "note": "SURVEY §8d's (2T+1)*S*F bytes per episode / time: what an HBM-streamed fit would have to move — "
-                                       "above 1 x the HBM peak by construction, because the bytes come from shared memory"},
+                                       "above 1 x the HBM peak by construction, because the bytes never leave the chip"},
             "dram_frac": (traffic / (fit_ms / 1e3) / 1e9 / hbm_peak) if traffic else None,
             "compulsory_dram_bytes": E * S * F_bytes,
         }

@@ -635,6 +635,7 @@ __global__ void __launch_bounds__(CT + res_helper_threads(NA), MINB) k_fit_resid
 #else
                             for (;;) {
                                 wv = ld_relaxed_u64(wp);
+                                if (PROF && tid == 0) t_acc[7] += 1;
                                 if (done(wv)) break;
                                 if (RES_POLL_GAP > 0) gap(RES_POLL_GAP);
                                 if ((++it & 0xffu) == 0u) {
@@ -782,6 +783,7 @@ __global__ void __launch_bounds__(CT + res_helper_threads(NA), MINB) k_fit_resid
         if (PROF && tid == 0 && p.prof) {
             for (int i = 0; i < 6; ++i) p.prof[(size_t)blockIdx.x * RES_NPROF + i] = t_acc[i];
             p.prof[(size_t)blockIdx.x * RES_NPROF + 10] = t_acc[6];
+            p.prof[(size_t)blockIdx.x * RES_NPROF + 11] = t_acc[7];       // tensor-memory kernel: poll rounds of thread 0
         }
         if (tid == 0 && !ok) atomicExch(p.abort_flag, 1u);
         if (TM && warp == 0) { tmem_fence_after_sync(); tmem_dealloc_512(tmem_slot); }    // every warp's last tensor-memory load precedes S5

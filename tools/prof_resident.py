@@ -58,4 +58,7 @@ if a.prof:
     print(f"  total/step {c[used, 10].mean() / n_steps:8.0f} cycles (thread 0: P1 start -> its P3 store)")
     print(f"  applier lane 0: {c[used,6].sum()/c[used,9].sum():.2f} poll rounds per chunk, {c[used,7].sum()/c[used,9].sum():.0f} cycles polling per chunk "
           f"({c[used,7].sum()/c[used,6].sum():.0f} per round), own store -> chunk complete {c[used,8].sum()/c[used,9].sum():.0f} cycles")
+    if c[used, 11].sum() > 0:
+        print(f"  tensor-memory kernel, thread 0: {c[used, 11].mean() / n_steps:.2f} poll rounds per step; RED -> applied {c[used,5].sum()/c[used,4].sum():.0f} cycles "
+              f"(includes the initial delay); min / max over CTAs {(c[used,5]/c[used,4]).min():.0f} / {(c[used,5]/c[used,4]).max():.0f}")
     print(f"  all-reduce latency seen by waiting compute warps: {(c[used,5].sum()/c[used,4].sum()):.0f} cycles (waited on {c[used,4].mean()/n_steps:.2f} chunks/step)")
