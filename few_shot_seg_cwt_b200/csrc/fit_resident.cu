@@ -92,6 +92,50 @@ namespace cwt {
 __host__ __device__ constexpr int res_wd_pos(int c, bool permute) {
     return permute ? ((c >> 7) << 7) + ((c & 15) << 3) + ((c >> 4) & 7) : c;
 }
+// Tensor-memory kernel, RES_SPLIT: the step's work that does not need the halo — the full-resolution stage of the first 64
+// interior cells, the gather of the 44 pixels those cells complete and the P3 sweep over them — runs BEFORE the compute warps
+// wait for the ring, i.e. in the shadow of the halo exchange. For that the 100 pixel columns of a channel chunk are kept in
+// this order: the 45 pixels (rows 1..3, x = 1..15) whose four cells are the cells cy = 1..4, cx = 1..16 first, the others after.
+#ifndef RES_SPLIT
+#define RES_SPLIT 1
+#endif
+constexpr int TM_EARLY = 44;            // columns of the early P3 part (a multiple of 4: g is read in quads)
+__host__ __device__ constexpr int tm_col2pix(int c) {
+    if (!RES_SPLIT) return c;
+    if (c < 45) return 20 * (1 + c / 15) + 1 + c % 15;
+    if (c < 65) return c - 45;
+    if (c < 80) return 20 * (1 + (c - 65) / 5) + (((c - 65) % 5) ? 15 + (c - 65) % 5 : 0);
+    return c;
+}
+__host__ __device__ constexpr int tm_pix2col(int p) {
+    if (!RES_SPLIT) return p;
+    const int py = p / 20, px = p % 20;
+    if (py == 0) return 45 + px;
+    if (py == 4) return 80 + px;
+    if (px >= 1 && px <= 15) return 15 * (py - 1) + (px - 1);
+    return 65 + 5 * (py - 1) + (px ? px - 15 : 0);
+}
+// one block of the P3 sweep of the tensor-memory kernel: N columns of this thread's lane + N / 4 quads of g (broadcast from
+// shared memory) are requested together, then N / 2 FFMA2 into {d0, d1} / {d2, d3}
+template <int N>
+__device__ __forceinline__ void tm_p3_block(uint32_t taddr, uint32_t gaddr, f32x2& da, f32x2& db) {
+    float f[N];
+    float4 g[N / 4];
+    if constexpr (N == 32) tmem_ld32(taddr, f);
+    else if constexpr (N == 16) tmem_ld16(taddr, f);
+    else if constexpr (N == 8) tmem_ld8(taddr, f);
+    else tmem_ld4(taddr, f);
+#pragma unroll
+    for (int i = 0; i < N / 4; ++i) g[i] = lds128_v(gaddr + 16u * (uint32_t)i);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < N; ++i) asm volatile("" : "+f"(f[i]));          // keeps the uses below the tcgen05.wait::ld
+#pragma unroll
+    for (int i = 0; i < N / 4; ++i) {
+        da = fma2(pk2(g[i].x, g[i].y), pk2(f[4 * i], f[4 * i + 1]), da);
+        db = fma2(pk2(g[i].z, g[i].w), pk2(f[4 * i + 2], f[4 * i + 3]), db);
+    }
+}
 constexpr int res_helper_threads(int NA) { return 32 * (NA + 1); }     // NA applier warps + the halo warp
 constexpr int RES_KCH = 4;        // channel chunks of the pipelined all-reduce
 constexpr int RES_AW = 4;         // accumulator words an applier lane keeps in flight
@@ -99,19 +143,12 @@ constexpr int RES_HWORDS = 4;     // halo words per lane of the halo warp (ring 
 constexpr int RES_MAXTASK = 4;    // HR row-tasks per compute thread (8 * cells <= 4 * 512)
 constexpr int RES_NPROF = 12;     // profile counters per CTA
 constexpr int RES_P3_DEPTH = 4;   // pixel-quads a P3 thread keeps in flight per operand
-// polling of the accumulator words by the compute threads (tensor-memory kernel): loads in flight per thread (1 | 3), clocks
-// before the first load, clocks between loads
-#ifndef RES_HALO_GATE
-#define RES_HALO_GATE 1            // the halo warp sleeps until its CTA has published z (tensor-memory kernel)
-#endif
-#ifndef RES_POLL_INFLIGHT
-#define RES_POLL_INFLIGHT 1
-#endif
+// polling of the accumulator words by the compute threads (tensor-memory kernel): clocks between the RED and the first load
 #ifndef RES_POLL_DELAY
 #define RES_POLL_DELAY 600
 #endif
-#ifndef RES_POLL_GAP
-#define RES_POLL_GAP 0
+#ifndef RES_HALO_GATE
+#define RES_HALO_GATE 1            // the halo warp sleeps until its CTA has published z (tensor-memory kernel)
 #endif
 
 struct ResidentParams {
@@ -269,7 +306,9 @@ __global__ void __launch_bounds__(CT + res_helper_threads(NA), MINB) k_fit_resid
                 unsigned d = 0u;
                 if (o < NCELL) {
                     int cy, cx;
-                    if (o < NINT) { cy = 1 + o / (TW - 1); cx = 1 + o % (TW - 1); }
+                    if (TM && RES_SPLIT && o < 64) { cy = 1 + o / 16; cx = 1 + o % 16; }             // the cells of the early part first
+                    else if (TM && RES_SPLIT && o < NINT) { cy = 1 + (o - 64) / 3; cx = 17 + (o - 64) % 3; }
+                    else if (o < NINT) { cy = 1 + o / (TW - 1); cx = 1 + o % (TW - 1); }
                     else {
                         const int bo = o - NINT;
                         if (bo < CW) { cy = 0; cx = bo; }
@@ -302,19 +341,18 @@ __global__ void __launch_bounds__(CT + res_helper_threads(NA), MINB) k_fit_resid
             // ---------------- fixed-point unit of the episode: power of two from the group-wide max|F| ----------------
             if constexpr (TM) {
                 // the same scan moves the tile into tensor memory: thread = channel (lane 32 (warp % 4) + lane of its quarter, chunk
-                // warp / 4), its 100 pixels = columns 100 (warp / 4) .. + 99. Rows are 400 B apart: a quarter-warp's LDS.128 is
-                // conflict-free. From here on shared memory is free of the tile until the next episode is staged.
+                // warp / 4), its 100 pixels = columns 100 (warp / 4) .. + 99 in the order of tm_col2pix. From here on shared memory is
+                // free of the tile until the next episode is staged.
                 unsigned mb = 0u;
-                const uint32_t row = smem_u32(F) + (uint32_t)tid * 400u, tcol = tq + 100u * (uint32_t)(warp >> 2);
+                const float* frow = F + (size_t)tid * 100;
+                const uint32_t tcol = tq + 100u * (uint32_t)(warp >> 2);
                 float v[32];
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
 #pragma unroll
-                    for (int i = 0; i < (b < 3 ? 8 : 1); ++i) {
-                        const float4 f = lds128_v(row + (uint32_t)(b * 128 + i * 16));
-                        v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
-                        mb = max(max(mb, __float_as_uint(f.x) & 0x7fffffffu),
-                                 max(max(__float_as_uint(f.y) & 0x7fffffffu, __float_as_uint(f.z) & 0x7fffffffu), __float_as_uint(f.w) & 0x7fffffffu));
+                    for (int i = 0; i < (b < 3 ? 32 : 4); ++i) {
+                        v[i] = frow[tm_col2pix(32 * b + i)];            // column order of the tile: tm_col2pix
+                        mb = max(mb, __float_as_uint(v[i]) & 0x7fffffffu);
                     }
                     if (b < 3) tmem_st32(tcol + 32u * b, v); else tmem_st4(tcol + 96u, v);
                 }
@@ -421,7 +459,7 @@ __global__ void __launch_bounds__(CT + res_helper_threads(NA), MINB) k_fit_resid
                     compute_sync<CT>();
                     if (tid < NP) {
                         const float zz = (scratch[tid] + scratch[NP + tid]) + (scratch[2 * NP + tid] + scratch[3 * NP + tid]);
-                        const int py = tid / TW, px = tid - py * TW;
+                        const int pix = tm_col2pix(tid), py = pix / TW, px = pix - py * TW;      // column tid of the tile
                         zt[(py + 1) * ZW + px + 1] = zz;
                         st_tagged(&zll[(gstep & 1u) * (unsigned)HW + (y0 + py) * wl + x0 + px], zz, gstep + 1u);
                     }
@@ -485,11 +523,52 @@ __global__ void __launch_bounds__(CT + res_helper_threads(NA), MINB) k_fit_resid
                     compute_sync<CT>();
                 }
                 if (PROF && tid == 0) { long long n = clock64(); t_acc[0] += n - tk0; tk0 = n; }
+                // g(q) = sum_r (1-r/8) [gl(q,r) + gr(q-1,r)] + (r/8) [gl(q-w,r) + gr(q-w-1,r)]; 4 threads per own pixel, 2 rows each:
+                // the (gl, gr) pairs of rows 2k, 2k+1 of a cell are one aligned 16-byte word -> conflict-free LDS.128.
+                // Columns [c_lo, c_hi) of the tile (tensor-memory kernel: tm_col2pix; otherwise column = pixel).
+                auto gather_part = [&](int c_lo, int c_hi) {
+                    const int cc = c_lo + (tid >> 2), rq = tid & 3;
+                    const bool act = cc < c_hi;
+                    float s2 = 0.f;
+                    if (act) {
+                        const int pl = TM ? tm_col2pix(cc) : cc;
+                        const int py = pl / TW, px = pl - py * TW;
+                        const int ci = (py + 1) * CW + px + 1;             // the cell whose top-left corner is this pixel
+                        const int a = y0 + py, b = x0 + px;
+                        const float4* sc4 = reinterpret_cast<const float4*>(scratch) + rq;     // [cell][4 row pairs]
+                        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 own = sc4[ci * 4];
+                        const float4 lft = (b > 0) ? sc4[(ci - 1) * 4] : zero4;
+                        const float4 up = (a > 0) ? sc4[(ci - CW) * 4] : zero4;
+                        const float4 ul = (a > 0 && b > 0) ? sc4[(ci - CW - 1) * 4] : zero4;
+                        const float ha = (float)(2 * rq) * 0.125f, hb = (float)(2 * rq + 1) * 0.125f;
+                        s2 = fmaf(1.f - ha, own.x + lft.y, ha * (up.x + ul.y)) + fmaf(1.f - hb, own.z + lft.w, hb * (up.z + ul.w));
+                    }
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+                    if (act && rq == 0) gsm[cc] = s2;
+                };
+                constexpr bool kSplit = TM && (RES_SPLIT != 0);
+                f32x2 p3a = 0ull, p3b = 0ull;                     // tensor-memory kernel: {d0, d1}, {d2, d3} of the thread's channel
+                const uint32_t p3col = tq + 100u * (uint32_t)(warp >> 2), p3g = smem_u32(gsm);
                 // ------------ HR: one task = one row of one cell -> (gl, gr) of that row in shared memory ------------
                 // round 0 (interior cells) runs while the halo warp is still fetching the ring
 #pragma unroll
                 for (int m = 0; m < RES_MAXTASK; ++m) {
                     if (m * CT < 8 * NCELL) {                     // uniform: does this round have tasks at all
+                        if constexpr (kSplit) {
+                            if (m == 1) {
+                                // in the shadow of the halo exchange: gather + P3 over the columns round 0 has completed
+                                compute_sync<CT>();
+                                gather_part(0, TM_EARLY);
+                                compute_sync<CT>();
+                                if (!(RES_VARIANT & 0x08)) {
+                                    tm_p3_block<32>(p3col, p3g, p3a, p3b);
+                                    tm_p3_block<8>(p3col + 32u, p3g + 128u, p3a, p3b);
+                                    tm_p3_block<4>(p3col + 40u, p3g + 160u, p3a, p3b);
+                                }
+                            }
+                        }
                         if (!(RES_VARIANT & 0x01) && m == (round0_interior ? 1 : 0)) {
                             long long tw0 = 0;
                             if (PROF && tid == 0) tw0 = clock64();
@@ -539,28 +618,7 @@ __global__ void __launch_bounds__(CT + res_helper_threads(NA), MINB) k_fit_resid
                     }
                 }
                 compute_sync<CT>();
-                // g(q) = sum_r (1-r/8) [gl(q,r) + gr(q-1,r)] + (r/8) [gl(q-w,r) + gr(q-w-1,r)]; 4 threads per own pixel, 2 rows each:
-                // the (gl, gr) pairs of rows 2k, 2k+1 of a cell are one aligned 16-byte word -> conflict-free LDS.128
-                {
-                    const int pl = tid >> 2, rq = tid & 3;
-                    float s2 = 0.f;
-                    if (pl < NP) {
-                        const int py = pl / TW, px = pl - py * TW;
-                        const int ci = (py + 1) * CW + px + 1;             // the cell whose top-left corner is this pixel
-                        const int a = y0 + py, b = x0 + px;
-                        const float4* sc4 = reinterpret_cast<const float4*>(scratch) + rq;     // [cell][4 row pairs]
-                        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        const float4 own = sc4[ci * 4];
-                        const float4 lft = (b > 0) ? sc4[(ci - 1) * 4] : zero4;
-                        const float4 up = (a > 0) ? sc4[(ci - CW) * 4] : zero4;
-                        const float4 ul = (a > 0 && b > 0) ? sc4[(ci - CW - 1) * 4] : zero4;
-                        const float ha = (float)(2 * rq) * 0.125f, hb = (float)(2 * rq + 1) * 0.125f;
-                        s2 = fmaf(1.f - ha, own.x + lft.y, ha * (up.x + ul.y)) + fmaf(1.f - hb, own.z + lft.w, hb * (up.z + ul.w));
-                    }
-                    s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
-                    s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
-                    if (pl < NP && rq == 0) gsm[pl] = s2;
-                }
+                gather_part(kSplit ? TM_EARLY : 0, NP);
                 compute_sync<CT>();
                 if (PROF && tid == 0) { long long n = clock64(); t_acc[2] += n - tk0; tk0 = n; }
                 // ------------ P3: dW = g . F^T chunk by chunk; every partial goes straight to the channel's accumulator word,
@@ -568,34 +626,25 @@ __global__ void __launch_bounds__(CT + res_helper_threads(NA), MINB) k_fit_resid
                 unsigned long long* acc_t = acc_ep + (t & 1) * C;          // even / odd steps use different words (see header)
                 if constexpr (TM) {
                     // Tile in tensor memory: thread = channel tid (lane L of its quarter, chunk warp / 4 = columns 100 (warp / 4) ..),
-                    // its 100 pixels come as 32 + 32 + 32 + 4 columns; g is broadcast from shared memory.
+                    // its 100 pixels come in blocks of 32 / 16 / 8 / 4 columns; g is broadcast from shared memory.
                     // No cross-thread reduction and no hand-over between the quads: all 16 warps sweep at once (the tensor-memory
                     // read path is ~3x the shared-memory pipe) and the four chunks leave together. Same summation order as the
                     // shared-memory sweep (pixel p goes to accumulator p mod 4).
-                    const uint32_t tcol = tq + 100u * (uint32_t)(warp >> 2), gad = smem_u32(gsm);
-                    float f[32];
-                    float4 g[8];
-                    f32x2 da = 0ull, db = 0ull;                      // {d0, d1}, {d2, d3}
                     if (!(RES_VARIANT & 0x08)) {
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) {
-                            // the block's columns and its 8 quads of g are requested together (tensor-memory and shared-memory latencies
-                            // overlap), then 16 FFMA2
-                            if (b < 3) tmem_ld32(tcol + 32u * b, f); else tmem_ld4(tcol + 96u, f);
-#pragma unroll
-                            for (int i = 0; i < (b < 3 ? 8 : 1); ++i) g[i] = lds128_v(gad + 16u * (uint32_t)(8 * b + i));
-                            tmem_wait_ld();
-#pragma unroll
-                            for (int i = 0; i < (b < 3 ? 32 : 4); ++i) asm volatile("" : "+f"(f[i]));   // keeps the uses below the wait
-#pragma unroll
-                            for (int i = 0; i < (b < 3 ? 8 : 1); ++i) {
-                                da = fma2(pk2(g[i].x, g[i].y), pk2(f[4 * i], f[4 * i + 1]), da);
-                                db = fma2(pk2(g[i].z, g[i].w), pk2(f[4 * i + 2], f[4 * i + 3]), db);
-                            }
+                        if constexpr (kSplit) {                       // columns 44 .. 99 (0 .. 43 went before the halo wait)
+                            tm_p3_block<32>(p3col + 44u, p3g + 176u, p3a, p3b);
+                            tm_p3_block<16>(p3col + 76u, p3g + 304u, p3a, p3b);
+                            tm_p3_block<8>(p3col + 92u, p3g + 368u, p3a, p3b);
+                        } else {
+                            tm_p3_block<32>(p3col, p3g, p3a, p3b);
+                            tm_p3_block<32>(p3col + 32u, p3g + 128u, p3a, p3b);
+                            tm_p3_block<32>(p3col + 64u, p3g + 256u, p3a, p3b);
+                            tm_p3_block<4>(p3col + 96u, p3g + 384u, p3a, p3b);
                         }
                     } else {
-                        da = pk2(gsm[tid & 63], 0.f);
+                        p3a = pk2(gsm[tid & 63], 0.f);
                     }
+                    const f32x2 da = p3a, db = p3b;
                     float d0, d1, d2, d3;
                     upk2(da, d0, d1); upk2(db, d2, d3);
                     const float d = (d0 + d1) + (d2 + d3);
@@ -613,37 +662,19 @@ __global__ void __launch_bounds__(CT + res_helper_threads(NA), MINB) k_fit_resid
                                 return (RES_VARIANT & 0x1f) ? (v & cnt_mask) >= expect : (v & cnt_mask) == expect;
                             };
                             auto gap = [&](long long n) { const long long t0g = clock64(); while (clock64() - t0g < n) { } };
+                            // (measured and dropped: three staggered loads in flight per thread, polls on a %globaltimer grid, a returning
+                            // atomic instead of RED + delay — all 1-8 % slower: more traffic on the lines the atomics are working on)
                             if (RES_POLL_DELAY > 0) gap(RES_POLL_DELAY);      // a load issued with the RED overtakes it and is wasted
                             unsigned it = 0;
-#if RES_POLL_INFLIGHT == 3
-                            // three loads in flight, issued RES_POLL_GAP clocks apart and re-issued as they return
-                            unsigned long long v0 = ld_relaxed_u64(wp), v1, v2;
-                            gap(RES_POLL_GAP); v1 = ld_relaxed_u64(wp);
-                            gap(RES_POLL_GAP); v2 = ld_relaxed_u64(wp);
-                            for (;;) {
-                                if (done(v0)) { wv = v0; break; }
-                                v0 = ld_relaxed_u64(wp);
-                                if (done(v1)) { wv = v1; break; }
-                                v1 = ld_relaxed_u64(wp);
-                                if (done(v2)) { wv = v2; break; }
-                                v2 = ld_relaxed_u64(wp);
-                                if ((++it & 0xffu) == 0u) {
-                                    if (*reinterpret_cast<volatile unsigned*>(p.abort_flag) != 0u) break;
-                                    if (it > (RES_SPIN_LIMIT >> 2)) { atomicExch(p.abort_flag, 1u); break; }
-                                }
-                            }
-#else
                             for (;;) {
                                 wv = ld_relaxed_u64(wp);
                                 if (PROF && tid == 0) t_acc[7] += 1;
                                 if (done(wv)) break;
-                                if (RES_POLL_GAP > 0) gap(RES_POLL_GAP);
                                 if ((++it & 0xffu) == 0u) {
                                     if (*reinterpret_cast<volatile unsigned*>(p.abort_flag) != 0u) break;
                                     if (it > (RES_SPIN_LIMIT >> 2)) { atomicExch(p.abort_flag, 1u); break; }
                                 }
                             }
-#endif
                         }
                         const long long cur = (long long)wv >> KB;                       // cumulative sum over steps 0..t of this parity (exact)
                         const long long prev = (t & 1) ? cum1 : cum0;

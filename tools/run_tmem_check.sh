@@ -1,4 +1,3 @@
-# developer script: per-phase profile of the resident kernel + per-episode overhead (1-step fits)
-CWT_RESIDENT_TMEM=${1:-1} timeout 300 python tools/prof_resident.py --episodes 64 2>&1 | tail -14
-CWT_RESIDENT_TMEM=${1:-1} timeout 300 python tools/prof_resident.py --episodes 64 --iters 1 --prof 0 2>&1 | tail -2
-CWT_RESIDENT_TMEM=${1:-1} timeout 300 python tools/prof_resident.py --episodes 64 --iters 100 --prof 0 2>&1 | tail -2
+# developer script: fit parity tests + timing of the product resident kernel (and the libraries under tools/variants)
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "fit_full_size or fit_resident or fit_batch_equals or fit_status" 2>&1 | tail -3
+bash tools/run_ablation.sh ${1:-tmem_check.txt}
