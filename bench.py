@@ -53,9 +53,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-sub-batch", type=int, default=32, help="HostPipeline sub-batch size (0 = whole batches)")
-    ap.add_argument("--e2e-sub-all", type=int, default=0, help="1: every host batch goes through in sub-batches; 0: only the first")
+    ap.add_argument("--e2e-sub-all", type=int, default=1, help="1: every host batch goes through in sub-batches; 0: only the first")
     ap.add_argument("--e2e-expand-main", type=int, default=1, help="zero-compressed e2e: expansion kernel on the head's stream (1) or the copy stream (0)")
-    ap.add_argument("--e2e-ramp", default="8,8,16,32", help="sub-batch sizes at the start of an e2e run (first host batch only); '' = none")
+    ap.add_argument("--e2e-ramp", default="8,8,16", help="sub-batch sizes at the start of an e2e run (first host batch only); '' = none")
     ap.add_argument("--e2e-format", default="zc", choices=["zc", "dense"], help="host format of the e2e leg: zero-compressed "
                                                                                "features (default) or dense tensors")
     ap.add_argument("--distinct", type=int, default=64, help="distinct synthetic episodes generated per rank (tiled to E)")

@@ -546,18 +546,22 @@ class HostPipeline:
 
     def __init__(self, device, params: Dict[str, torch.Tensor], n_head: int, lr: float, n_iter: int,
                  fit_algo: int = L.FIT_AUTO, attn_algo: int = L.ATTN_REASSOC, num_classes_val: int = 5, n_slots: int = 3,
-                 sub_batch: int = 32, sub_batch_all: bool = False, expand_on_main: bool = True, ramp=(8, 8, 16, 32)):
+                 sub_batch: int = 32, sub_batch_all: bool = True, expand_on_main: bool = True, ramp=(8, 8, 16)):
         self.device = torch.device(device)
         self.params = {k: v.to(self.device) for k, v in params.items()}
         self.n_head, self.lr, self.n_iter = n_head, lr, n_iter
         self.fit_algo, self.attn_algo = fit_algo, attn_algo
         self.copy_stream = torch.cuda.Stream(self.device)
         self.table = IoUTable(num_classes_val, self.device)
-        # The first host batch of a run goes through in SUB-BATCHES (``ramp`` sizes, then ``sub_batch``): the head can only start
-        # when its first piece has arrived, so the exposed copy at the start of a run is that of 8 episodes. Later batches go
-        # whole (``sub_batch_all`` False): their copy (531 MB zero-compressed = 10 ms at 53 GB/s) hides under the previous
-        # batch's fit (17 ms). ``sub_batch_all`` True sub-batches every host batch (round-1 default, for dense host tensors
-        # whose copy takes as long as the fit).
+        # Host batches go through in SUB-BATCHES of ``sub_batch`` episodes (``sub_batch_all`` False: only the first batch of a run),
+        # the first batch starting with the ``ramp`` sizes: the head can only start when its first piece has arrived, so the
+        # exposed copy at the start of a run is that of 8 episodes. Sizing: a zero-compressed episode is 8.3 MB = 0.157 ms of
+        # H2D at 53 GB/s, its fit 0.178 ms — the copy is barely faster than the fit, so a piece's copy only hides under the
+        # previous piece's fit if the pieces stop growing: whole 64-episode batches behind a doubling ramp stall 8 ms per run
+        # (round-2 default while the fit still took 0.27 ms per episode), uniform pieces do not.
+        # Measured on B200 (bench.py e2e, 20 steps of 64 episodes, profiles/r2g_e2e_policies.txt): pieces of 32 after a ramp
+        # 8, 8, 16: 12.10 ms per step (0.957 of the device-resident rate); whole batches after 8, 8, 16, 32: 12.44; pieces of
+        # 16: 12.38; of 8: 13.05 (launch overheads); expansion on the copy stream instead of the head's: 13.4.
         # Device-resident staging slots are reused for the whole run: no allocator traffic (a cudaMalloc of ~1 GB
         # synchronises the device). Three slots: the copy of sub-batch i+2 may start as soon as the copy of i+1 has
         # finished (its slot was released by head i-1 long ago), so the copy engine never waits for the head.
@@ -565,10 +569,7 @@ class HostPipeline:
         # the fit (~0.25 ms per 64 episodes, exposed); False: on the copy stream, behind the copies it expands, i.e. concurrently
         # with the previous batch's cooperative fit — whose 144 CTAs leave it one small CTA per SM: the expansion of 64 episodes
         # then takes 5-7 ms instead of 0.25 and copy + expansion no longer fit under one fit (tools/e2e_timeline.py).
-        # Measured on B200 (bench.py e2e, 10 steps of 64 episodes, three runs each, profiles/r2d_e2e_ramp.txt): whole batches
-        # after a start-of-run ramp of 8, 8, 16, 32 episodes: 17.70 ms per step with the expansion on the head's stream, 18.22 ms
-        # on the copy stream; sub-batches of 32 throughout: 18.05-18.1 ms (two 32-episode fits cost 0.34 ms more than one
-        # 64-episode fit).
+        # Measured on B200 (profiles/r2g_e2e_policies.txt): 12.38 ms per step on the head's stream, 13.4 ms on the copy stream.
         self.expand_on_main = bool(expand_on_main)
         self.ramp = tuple(int(x) for x in (ramp or ()))     # sub-batch sizes at the very start of a run (first host batch only)
         self.sub_batch = max(0, int(sub_batch))
