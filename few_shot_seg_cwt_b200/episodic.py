@@ -225,7 +225,7 @@ def run_sweep(n_episodes: int, params: Dict[str, torch.Tensor], n_head: int, lr:
 # validate_transformer drop-in (src/test.py:103-254)
 # ----------------------------------------------------------------------------------------
 def validate_transformer(args, val_loader, model, transformer, verbose: bool = True,
-                         overlap_backbone: bool = True) -> Tuple[float, float]:
+                         overlap_backbone: bool = True, head_batch: Optional[int] = None) -> Tuple[float, float]:
     """Same arguments and return value as the reference: ``(mean mIoU over runs, mean loss over runs)``.
 
     ``args`` needs test_num, batch_size_val, image_size, n_runs, bottleneck_dim, num_classes_tr, cls_lr,
@@ -242,7 +242,14 @@ def validate_transformer(args, val_loader, model, transformer, verbose: bool = T
     and — whenever the cooperative fit leaves SMs free (post stage, launch gaps) — its kernels overlap the head; the
     head waits on an event, never on the host. Results (counts, CE, the fit's status word) are read back one batch
     late; an empty support mask still raises the reference's ``ZeroDivisionError`` (src/test.py:174), bad labels a
-    ``ValueError``, then."""
+    ``ValueError``, then.
+
+    ``head_batch`` (or ``args.head_batch``): episodes per head launch. The reference's scripts run ``batch_size_val 1``
+    (scripts/test.sh:12), and one episode occupies only 36 of the 148 SMs (0.71 ms per fit whether 1 or 4 episodes are in
+    it). Episodes are independent, so several loader batches are fused into ONE backbone call pair + ONE head launch of
+    at least ``head_batch`` episodes (default 16; never across the end of a run); the per-batch loss (the reference logs
+    the CE of each ``batch_size_val`` episodes), the per-class accumulation, the progress lines and the classifier-init RNG
+    order stay per reference batch, so the results are the same numbers."""
     if verbose:
         print('==> Start testing')
     model.eval()
@@ -255,6 +262,9 @@ def validate_transformer(args, val_loader, model, transformer, verbose: bool = T
     n_head = transformer.n_head
     C = args.bottleneck_dim
     B = int(args.batch_size_val)
+    if head_batch is None:
+        head_batch = int(getattr(args, "head_batch", 16) or 16)
+    K = max(1, -(-int(head_batch) // max(B, 1)))        # reference batches fused into one head launch
     main = torch.cuda.current_stream(device)
     bb_stream = torch.cuda.Stream(device) if overlap_backbone else main
 
@@ -272,11 +282,12 @@ def validate_transformer(args, val_loader, model, transformer, verbose: bool = T
             iter_loader = iter(val_loader)
             return next(iter_loader)
 
-    def stage_batch():
-        """Load ``B`` episodes, draw their classifier inits and queue the two backbone calls on the backbone stream."""
+    def stage_batch(n_ref: int):
+        """Load ``n_ref`` reference batches of ``B`` episodes, draw their classifier inits and queue the two backbone calls on
+        the backbone stream."""
         nonlocal iter_num
         sp, sl, qi, ql, w0_l, classes = [], [], [], [], [], []
-        for _ in range(B):
+        for _ in range(n_ref * B):
             qry_img, q_label, spprt_imgs, s_label, subcls = next_item()[:5]
             iter_num += 1
             # fresh classifier init, drawn like the reference's nn.Conv2d(...) (a-1); the reference draws a second Conv2d per
@@ -296,7 +307,7 @@ def validate_transformer(args, val_loader, model, transformer, verbose: bool = T
             with torch.no_grad():
                 f_s, _ = model.extract_features(spprt)                           # one call for all support images
                 f_q, _ = model.extract_features(qry)                             # one call for all query images
-            f_s = f_s.float().reshape(B, S, *f_s.shape[1:]).contiguous()
+            f_s = f_s.float().reshape(n_ref * B, S, *f_s.shape[1:]).contiguous()
             f_q = f_q.float().contiguous()
             ready = torch.cuda.Event()
             ready.record(bb_stream)
@@ -313,46 +324,54 @@ def validate_transformer(args, val_loader, model, transformer, verbose: bool = T
         pending = None                       # results of the previous batch, still on their way to the host
 
         def finish(p):
-            """Account one batch: the reference's per-class accumulation (src/test.py:225-234) and progress line."""
+            """Account one head launch, reference batch by reference batch: the reference's per-class accumulation
+            (src/test.py:225-234), its per-batch loss and its progress line."""
             nonlocal loss_sum, loss_cnt
             counts, ce, status, ev, classes, n_seen = p
             ev.synchronize()
-            ops.raise_for_status(status, first_episode=n_seen - len(classes))     # the reference's errors, one batch late
-            loss = float(ce[:, 0, 0].sum() / ce[:, 0, 1].sum().clamp_min(1.0))     # CE over the batch's valid pixels
-            loss_sum += loss; loss_cnt += 1
-            for i, task_classes in enumerate(classes):
-                for j, class_ in enumerate(task_classes):
-                    cls_I[class_] += int(counts[i, 0, j + 1, 0]); cls_U[class_] += int(counts[i, 0, j + 1, 1])
-                    cls_I0[class_] += int(counts[i, 1, j + 1, 0]); cls_U0[class_] += int(counts[i, 1, j + 1, 1])
-            for class_ in cls_U:
-                IoU[class_] = cls_I[class_] / (cls_U[class_] + 1e-10)
-                IoU0[class_] = cls_I0[class_] / (cls_U0[class_] + 1e-10)
-            if verbose and n_seen % 200 == 0:
-                print('Test: [{}/{}] mIoU {:.4f} mIoU0 {:.4f} Loss {:.4f} ({:.4f}) '.format(
-                    n_seen, args.test_num, np.mean(list(IoU.values())), np.mean(list(IoU0.values())),
-                    loss, loss_sum / loss_cnt))
+            n_ep = len(classes)
+            ops.raise_for_status(status[:n_ep], first_episode=n_seen - n_ep)      # the reference's errors, one launch late
+            for g0 in range(0, n_ep, B):
+                cg = ce[g0:g0 + B]
+                loss = float(cg[:, 0, 0].sum() / cg[:, 0, 1].sum().clamp_min(1.0))  # CE over the reference batch's valid pixels
+                loss_sum += loss; loss_cnt += 1
+                for i in range(g0, g0 + B):
+                    for j, class_ in enumerate(classes[i]):
+                        cls_I[class_] += int(counts[i, 0, j + 1, 0]); cls_U[class_] += int(counts[i, 0, j + 1, 1])
+                        cls_I0[class_] += int(counts[i, 1, j + 1, 0]); cls_U0[class_] += int(counts[i, 1, j + 1, 1])
+                for class_ in cls_U:
+                    IoU[class_] = cls_I[class_] / (cls_U[class_] + 1e-10)
+                    IoU0[class_] = cls_I0[class_] / (cls_U0[class_] + 1e-10)
+                seen_g = n_seen - n_ep + g0 + B
+                if verbose and seen_g % 200 == 0:
+                    print('Test: [{}/{}] mIoU {:.4f} mIoU0 {:.4f} Loss {:.4f} ({:.4f}) '.format(
+                        seen_g, args.test_num, np.mean(list(IoU.values())), np.mean(list(IoU0.values())),
+                        loss, loss_sum / loss_cnt))
 
-        # pinned result buffers, two sets (the batch being accounted and the batch in flight), allocated once per run
-        host = [(torch.empty((B, 2, 2, 3), dtype=torch.int64, pin_memory=True),
-                 torch.empty((B, 2, 2), dtype=torch.float64, pin_memory=True),
-                 torch.empty((B,), dtype=torch.int32, pin_memory=True)) for _ in range(2)]
+        # pinned result buffers, two sets (the launch being accounted and the launch in flight), allocated once per run
+        EB = K * B
+        host = [(torch.empty((EB, 2, 2, 3), dtype=torch.int64, pin_memory=True),
+                 torch.empty((EB, 2, 2), dtype=torch.float64, pin_memory=True),
+                 torch.empty((EB,), dtype=torch.int32, pin_memory=True)) for _ in range(2)]
         t0 = time.time()
-        staged = stage_batch() if nb_episodes > 0 else None
-        for e in range(nb_episodes):
+        plan = [min(K, nb_episodes - i) for i in range(0, nb_episodes, K)]       # reference batches per head launch
+        staged = stage_batch(plan[0]) if plan else None
+        for e, n_ref in enumerate(plan):
             tensors, ready, classes, n_seen = staged
-            # queue the NEXT batch's backbone before this batch's head (it runs on the backbone stream)
-            staged = stage_batch() if e + 1 < nb_episodes else None
+            # queue the NEXT launch's backbone before this launch's head (it runs on the backbone stream)
+            staged = stage_batch(plan[e + 1]) if e + 1 < len(plan) else None
             main.wait_event(ready)
             for t in tensors:
                 t.record_stream(main)
             f_s, s_lab, f_q, q_lab, w0 = tensors
             out = episode_head(f_s, s_lab, f_q, q_lab, w0, params, n_head, args.cls_lr, args.adapt_iter)
             # No device sync per batch (the reference has one per EPISODE, src/test.py:169-171): the counts travel to
-            # pinned host memory asynchronously and are accounted one batch later — the GPU never waits for Python.
+            # pinned host memory asynchronously and are accounted one launch later — the GPU never waits for Python.
+            n_ep = n_ref * B
             counts, ce, status = host[e % 2]
-            counts.copy_(out.counts, non_blocking=True)
-            ce.copy_(out.ce, non_blocking=True)
-            status.copy_(out.status, non_blocking=True)
+            counts[:n_ep].copy_(out.counts, non_blocking=True)
+            ce[:n_ep].copy_(out.ce, non_blocking=True)
+            status[:n_ep].copy_(out.status, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(main)
             if pending is not None:

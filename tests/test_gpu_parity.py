@@ -713,9 +713,12 @@ class _Args:
     pass
 
 
-def test_validate_transformer_dropin(cuda_device):
+@pytest.mark.parametrize("bsv,head_batch", [(3, None), (3, 1), (1, 4), (2, 3), (1, None)])
+def test_validate_transformer_dropin(cuda_device, bsv, head_batch):
     """The reference loop signature (src/test.py:103-106) on a fake loader/backbone; mIoU / loss against
-    the oracle run episode by episode with the same initial classifier weights."""
+    the oracle run episode by episode with the same initial classifier weights. ``head_batch``: loader batches fused into
+    one head launch (None: the default of 16 episodes; 1: one launch per reference batch; 4 with batch_size_val 1: launches
+    of 4 + 2 episodes) — the per-batch losses, the accumulation and the RNG order stay per reference batch."""
     kw = dict(shot=1, C=64, h=12, w=12, H=89, W=89, style="unit")
     n = 6
     eps = [syn.make_episode(100 + i, label_dtype=torch.int64, **kw) for i in range(n)]
@@ -726,14 +729,14 @@ def test_validate_transformer_dropin(cuda_device):
         qimg = torch.full((1, 3, 89, 89), float(2 * i + 1))
         items.append((qimg, ep.q_label.unsqueeze(0), simg, ep.s_label.unsqueeze(0), [torch.tensor([ep.subcls])], None, None))
     args = _Args()
-    args.test_num, args.batch_size_val, args.image_size, args.n_runs = n, 3, 89, 1
+    args.test_num, args.batch_size_val, args.image_size, args.n_runs = n, bsv, 89, 1
     args.bottleneck_dim, args.num_classes_tr, args.cls_lr, args.adapt_iter = 64, 2, 0.1, 50
     n_head = 2
     params = syn.make_transformer_params(n_head, 64)
     tr = cwt.MultiHeadAttentionOne(n_head, 64, 64, 64, dropout=0.5).to(cuda_device)
     tr.load_state_dict(params)
     torch.manual_seed(5)
-    miou, loss = cwt.validate_transformer(args, items, _FakeBackbone(feats), tr, verbose=False)
+    miou, loss = cwt.validate_transformer(args, items, _FakeBackbone(feats), tr, verbose=False, head_batch=head_batch)
     # oracle with the same RNG stream for the per-episode nn.Conv2d init
     torch.manual_seed(5)
     # (drawn up front: the oracle's own nn.Conv2d construction would otherwise advance the RNG in between)
@@ -751,7 +754,7 @@ def test_validate_transformer_dropin(cuda_device):
         cU[ep.subcls] = cU.get(ep.subcls, 0) + int(o["counts"][1, 1])
         nvalid = int((ep.q_label != 255).sum())
         batch_ce.append((float(o["loss"]) * nvalid, nvalid))
-        if len(batch_ce) == 3:
+        if len(batch_ce) == bsv:
             losses.append(sum(a for a, _ in batch_ce) / sum(b for _, b in batch_ce))
             batch_ce = []
     assert abs(miou - O.miou_from_counts(cI, cU)) * 100 < 0.05
