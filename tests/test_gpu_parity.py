@@ -164,6 +164,7 @@ def test_fit_resident_many_episodes_per_group(cuda_device):
     {"CWT_RESIDENT_BPS": "2"},                                   # two CTAs per SM, tile 4 x 10, 90 CTAs per episode
     {"CWT_RESIDENT_BPS": "2", "CWT_RESIDENT_TILE": "20x2"},      # ... the plan whose long runs exposed the count-overrun race
     {"CWT_RESIDENT_BPS": "1", "CWT_RESIDENT_TILE": "12x5"},      # run-time-shape kernel at the full geometry (60 CTAs per episode)
+    {"CWT_RESIDENT_TMEM": "0"},                                  # the default plan with the tile in shared memory (round-1 kernel)
 ])
 def test_fit_resident_alternative_plans_long_run(cuda_device, monkeypatch, env):
     """Every tiling of the on-chip fit gives the streaming result; long enough (many episodes x 200 steps per group) for
@@ -178,6 +179,7 @@ def test_fit_resident_alternative_plans_long_run(cuda_device, monkeypatch, env):
     wr = cwt.fit_classifier(f_s, s_label, w0, 0.1, 200, algo=L.FIT_RESIDENT)
     monkeypatch.delenv("CWT_RESIDENT_BPS", raising=False)
     monkeypatch.delenv("CWT_RESIDENT_TILE", raising=False)
+    monkeypatch.delenv("CWT_RESIDENT_TMEM", raising=False)
     ws = cwt.fit_classifier(big.f_s, big.s_label, big.w0, 0.1, 200, algo=L.FIT_STREAM)
     assert torch.isfinite(wr).all()
     for i in range(E):
@@ -186,9 +188,9 @@ def test_fit_resident_alternative_plans_long_run(cuda_device, monkeypatch, env):
 
 
 def test_fit_resident_default_plan_long_run_distinct_episodes(cuda_device):
-    """The plan behind every bench number (tile 20x5, one CTA per SM, 4 groups of 36 CTAs): 64 DISTINCT episodes x 200 steps,
-    16 episodes per group back to back — resident == streaming to rounding, bit-reproducible across two runs, and every
-    deferred status word is clean."""
+    """The plan behind every bench number (tile 20x5 held in TENSOR MEMORY, one CTA per SM, 4 groups of 36 CTAs): 64 DISTINCT
+    episodes x 200 steps, 16 episodes per group back to back — resident == streaming to rounding, bit-reproducible across two
+    runs, and every deferred status word is clean."""
     E = 64
     big = syn.make_batch(list(range(500, 500 + E)), shot=1, C=512, h=60, w=60, H=473, W=473).to(cuda_device)
     wr, st = cwt.fit_classifier(big.f_s, big.s_label, big.w0, 0.1, 200, algo=L.FIT_RESIDENT, return_status=True)
