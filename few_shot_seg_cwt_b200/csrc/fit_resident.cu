@@ -115,6 +115,20 @@ __host__ __device__ constexpr int tm_pix2col(int p) {
     if (px >= 1 && px <= 15) return 15 * (py - 1) + (px - 1);
     return 65 + 5 * (py - 1) + (px ? px - 15 : 0);
 }
+// compile-time checks of the column order: a permutation, and the early columns are exactly pixels whose four cells belong to
+// HR round 0 (cells cy = 1..4, cx = 1..16 <=> pixel rows 1..3, x = 1..15)
+constexpr bool tm_order_ok() {
+    bool seen[100] = {};
+    for (int c = 0; c < 100; ++c) {
+        const int p = tm_col2pix(c);
+        if (p < 0 || p >= 100 || seen[p] || tm_pix2col(p) != c) return false;
+        seen[p] = true;
+        const int py = p / 20, px = p % 20;
+        if (RES_SPLIT && c < TM_EARLY && !(py >= 1 && py <= 3 && px >= 1 && px <= 15)) return false;
+    }
+    return true;
+}
+static_assert(tm_order_ok(), "tm_col2pix / tm_pix2col must be inverse permutations with the round-0 pixels first");
 // one block of the P3 sweep of the tensor-memory kernel: N columns of this thread's lane + N / 4 quads of g (broadcast from
 // shared memory) are requested together, then N / 2 FFMA2 into {d0, d1} / {d2, d3}
 template <int N>

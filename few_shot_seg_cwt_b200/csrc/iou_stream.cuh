@@ -10,11 +10,12 @@
 //                      5.5 TB/s with both compute roles switched off);
 //   8 contraction      consume the ring: warp j owns the channels c = j (mod 8); a lane keeps two pixel quads x 2V
 //     warps            logit rows (+ |f_p|^2) in packed-fp32 accumulators (FFMA2: one instruction per two pixels; the
-//                      weights sit in shared memory as {m, m} pairs). After the C channels of a chunk the eight
-//                      partials are combined in a fixed order, F.normalize is applied, and the 2V logit rows of the
-//                      chunk go to one of two small logit buffers;
-//   8 up-sample        column-threaded bilinear up-sample (ATen's CPU rounding order, see iou.cu), argmax, confusion
-//     warps            counts and CE of the PREVIOUS chunk while the next one is streaming.
+//                      weights sit in shared memory as {m, m} pairs). After the C channels of a chunk a warp only dumps
+//                      its partial sums into one of two shared-memory buffers and goes on to the next chunk's stages:
+//                      the ring never waits for an epilogue;
+//   8 up-sample        combine the eight partials of the PREVIOUS chunk in a fixed order, apply F.normalize, write its 2V
+//     warps            logit rows to one of two small logit buffers, then: column-threaded bilinear up-sample (ATen's CPU
+//                      rounding order, see iou.cu), argmax, confusion counts and CE — all while the next chunk is streaming.
 //
 // Only new low-res rows are streamed: the last logit row of a chunk is carried over as the first row of the next one,
 // so f_q is read exactly once (plus one halo row per CTA range).
@@ -29,7 +30,16 @@ namespace cwt {
 constexpr int LS_CW = 8;                       // contraction warps
 constexpr int LS_UW = 8;                       // up-sample warps (measured: 8 + 8 beats 8 + 11 and 4 + 15)
 constexpr int LS_THREADS = 32 * (1 + LS_CW + LS_UW);
-constexpr int LS_CHT = 32;                     // channels per ring stage = per TMA tile copy
+#ifndef LS_CHT_N
+#define LS_CHT_N 32
+#endif
+#ifndef LS_NS_MAX
+#define LS_NS_MAX 4
+#endif
+#ifndef LS_TAPER
+#define LS_TAPER 0                             // chunks of a CTA's range: 1 = short first chunk(s) and halving last chunks
+#endif
+constexpr int LS_CHT = LS_CHT_N;               // channels per ring stage = per TMA tile copy
 constexpr int LS_MAXQ = 64;                    // pixel quads per chunk (two per lane)
 struct LsMaps { CUtensorMap m[4]; };       // m[ns - 1]: box of ns low-res rows
 
@@ -52,7 +62,7 @@ static __host__ __device__ inline LsSmem ls_smem_layout(int V, int C, int w, int
     s.stage_bytes = (unsigned)(CHT * s.row_bytes);
     size_t o = 0;
     s.ring = o; o += (size_t)NS * s.stage_bytes; o = (o + 127) / 128 * 128;
-    s.red = o;  o += (size_t)LS_CW * (R2 + 1) * LS_MAXQ * 16; o = (o + 127) / 128 * 128;
+    s.red = o;  o += (size_t)2 * LS_CW * (R2 + 1) * LS_MAXQ * 16; o = (o + 127) / 128 * 128;      // two buffers: chunk parity
     s.ms = o;   o += (size_t)C * R2 * 8; o = (o + 127) / 128 * 128;
     s.lbuf = o; o += (size_t)2 * R2 * (CB + 1) * w * 4; o = (o + 127) / 128 * 128;
     s.bars = o; o += 8 * (2 * 8 + 4);
@@ -69,6 +79,13 @@ __device__ __forceinline__ LsChunk ls_chunk(int g, int g0, int g1, int h, int CB
     c.e = g / h; c.a0 = g - c.e * h;
     c.carry = (g != g0 && c.a0 != 0) ? 1 : 0;
     int nc = c.carry ? CB : CB - 1;
+#if LS_TAPER
+    // a short first chunk gives the up-sample warps work after two low-res rows instead of five; halving chunks at the end of
+    // the range leave only one cell row to be up-sampled after the last byte has arrived
+    if (g == g0) nc = 1;
+    else if (g == g0 + 1) nc = min(nc, 2);
+    nc = min(nc, max(1, (g1 - g + 1) / 2));
+#endif
     if (c.a0 + nc >= h - 1) nc = h - c.a0;               // the last cell row (one hi-res row) needs no further low-res row
     nc = min(nc, g1 - g);
     c.nc = nc;
@@ -128,13 +145,12 @@ __global__ void __launch_bounds__(LS_THREADS, 1) k_logits_iou_stream(const __gri
         // ============================ contraction ============================
         const int cw = warp - 1, ctid = tid - 32;
         unsigned slot = 0, ph = 0;
-        int cur_e = -1, chunk = 0, prev_a0 = 0;
+        int cur_e = -1, chunk = 0;
         for (int g = g0; g < g1; ++chunk) {
             const LsChunk ck = ls_chunk(g, g0, g1, h, CB);
             g += ck.nc;
-            // everyone has left the previous chunk: its partial sums (red) and weight pairs (Ms) may be overwritten
-            asm volatile("bar.sync 1, %0;" ::"n"(32 * LS_CW) : "memory");
             if (ck.e != cur_e) {                               // new episode: its 2V weight rows as {m, m} pairs
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * LS_CW) : "memory");      // every warp is done with the previous weights
                 const float* Mg = p.wts + (size_t)ck.e * R2 * C;
                 for (int i = ctid; i < C * R2; i += 32 * LS_CW) {
                     const int r = i / C, c = i - r * C;
@@ -182,9 +198,12 @@ __global__ void __launch_bounds__(LS_THREADS, 1) k_logits_iou_stream(const __gri
                     if (++slot == (unsigned)NS) { slot = 0; ph ^= 1u; }
                 }
             }
-            // partial sums of this warp -> red[cw][r][px]
+            // partial sums of this warp -> red[chunk parity][cw][r][px]; the up-sample warps combine the eight partials, so the
+            // contraction warps go straight on to the next chunk's stages (the ring never waits for an epilogue)
             {
-                ulonglong2* rw = reinterpret_cast<ulonglong2*>(red + (size_t)cw * (R2 + 1) * LS_MAXQ * 4);
+                const int rb = chunk & 1;
+                ls_wait(&lempty[rb], ((chunk >> 1) & 1u) ^ 1u);      // the up-sample warps have read this buffer (two chunks ago)
+                ulonglong2* rw = reinterpret_cast<ulonglong2*>(red + ((size_t)rb * LS_CW + cw) * (R2 + 1) * LS_MAXQ * 4);
 #pragma unroll
                 for (int r = 0; r < R2; ++r) {
                     rw[r * LS_MAXQ + lane] = make_ulonglong2(acc[r][0], acc[r][1]);
@@ -192,45 +211,8 @@ __global__ void __launch_bounds__(LS_THREADS, 1) k_logits_iou_stream(const __gri
                 }
                 rw[R2 * LS_MAXQ + lane] = make_ulonglong2(n2[0], n2[1]);
                 rw[R2 * LS_MAXQ + lane + 32] = make_ulonglong2(n2[2], n2[3]);
+                ls_arrive(&lfull[rb]);
             }
-            const int buf = chunk & 1;
-            ls_wait(&lempty[buf], ((chunk >> 1) & 1u) ^ 1u);      // the up-sample warps are done with this logit buffer
-            asm volatile("bar.sync 1, %0;" ::"n"(32 * LS_CW) : "memory");
-            float* lb = lbuf + (size_t)buf * LBUF;
-            const int row_off = ck.sb - ck.a0;                   // 0, or 1 when row a0 is carried over
-            for (int px = ctid; px < npx; px += 32 * LS_CW) {
-                float nn = 0.f, s[R2];
-#pragma unroll
-                for (int r = 0; r < R2; ++r) s[r] = 0.f;
-#pragma unroll
-                for (int j = 0; j < LS_CW; ++j) {
-                    const float* rj = red + (size_t)j * (R2 + 1) * LS_MAXQ * 4;
-#pragma unroll
-                    for (int r = 0; r < R2; ++r) s[r] += rj[r * LS_MAXQ * 4 + px];
-                    nn += rj[R2 * LS_MAXQ * 4 + px];
-                }
-                const float den = fmaxf(sqrtf(nn), 1e-12f);
-                const int py = px / w, x = px - py * w;
-                const int grow = ck.e * h + ck.sb + py;            // global row: own rows only go to logits_out
-#pragma unroll
-                for (int r = 0; r < R2; ++r) {
-                    float v = s[r];
-                    if ((p.normalize_mask >> (r >> 1)) & 1) v = v / den;          // F.normalize(f_q, dim=1)
-                    lb[(r * LROWS + row_off + py) * w + x] = v;
-                    if (p.logits_out && grow < g1)
-                        p.logits_out[((size_t)ck.e * R2 + r) * HW + (size_t)(ck.sb + py) * w + x] = v;
-                }
-            }
-            if (ck.carry) {                                       // row a0 = a logit row of the previous chunk
-                const float* lp = lbuf + (size_t)(buf ^ 1) * LBUF;
-                const int pr = ck.a0 - prev_a0;
-                for (int i = ctid; i < R2 * w; i += 32 * LS_CW) {
-                    const int r = i / w, x = i - r * w;
-                    lb[(r * LROWS) * w + x] = lp[(r * LROWS + pr) * w + x];
-                }
-            }
-            prev_a0 = ck.a0;
-            ls_arrive(&lfull[buf]);
         }
     } else {
         // ============================ up-sample / argmax / count ============================
@@ -274,12 +256,56 @@ __global__ void __launch_bounds__(LS_THREADS, 1) k_logits_iou_stream(const __gri
                 for (int v = 0; v < V; ++v) atomicAdd(&p.ce[((size_t)e * V + v) * 2 + 1], (double)nv);
             }
         };
+        int prev_a0 = 0;
         for (int g = g0; g < g1; ++chunk) {
             const LsChunk ck = ls_chunk(g, g0, g1, h, CB);
             g += ck.nc;
             if (ck.e != cur_e) { if (cur_e >= 0) flush(cur_e); cur_e = ck.e; }
             const int buf = chunk & 1;
-            ls_wait(&lfull[buf], (chunk >> 1) & 1u);
+            ls_wait(&lfull[buf], (chunk >> 1) & 1u);               // the eight partial sums of this chunk are in red[buf]
+            {
+                // combine the partials in a fixed order, apply F.normalize, write the chunk's logit rows
+                const int npx = ck.ns * w;
+                float* lbw = lbuf + (size_t)buf * LBUF;
+                const float* rbase = red + (size_t)buf * LS_CW * (R2 + 1) * LS_MAXQ * 4;
+                const int row_off = ck.sb - ck.a0;                   // 0, or 1 when row a0 is carried over
+                for (int px = utid; px < npx; px += 32 * LS_UW) {
+                    float nn = 0.f, sv[R2];
+#pragma unroll
+                    for (int r = 0; r < R2; ++r) sv[r] = 0.f;
+#pragma unroll
+                    for (int j = 0; j < LS_CW; ++j) {
+                        const float* rj = rbase + (size_t)j * (R2 + 1) * LS_MAXQ * 4;
+#pragma unroll
+                        for (int r = 0; r < R2; ++r) sv[r] += rj[r * LS_MAXQ * 4 + px];
+                        nn += rj[R2 * LS_MAXQ * 4 + px];
+                    }
+                    const float den = fmaxf(sqrtf(nn), 1e-12f);
+                    const int py = px / w, x = px - py * w;
+                    const int grow = ck.e * h + ck.sb + py;            // global row: own rows only go to logits_out
+#pragma unroll
+                    for (int r = 0; r < R2; ++r) {
+                        float v = sv[r];
+                        if ((p.normalize_mask >> (r >> 1)) & 1) v = v / den;          // F.normalize(f_q, dim=1)
+                        lbw[(r * LROWS + row_off + py) * w + x] = v;
+                        if (p.logits_out && grow < g1)
+                            p.logits_out[((size_t)ck.e * R2 + r) * HW + (size_t)(ck.sb + py) * w + x] = v;
+                    }
+                }
+                ls_arrive(&lempty[buf]);                             // red[buf] may be overwritten (two chunks from now)
+                if (ck.carry) {                                       // row a0 = a logit row of the previous chunk
+                    const float* lp = lbuf + (size_t)(buf ^ 1) * LBUF;
+                    const int pr = ck.a0 - prev_a0;
+                    for (int i = utid; i < R2 * w; i += 32 * LS_UW) {
+                        const int r = i / w, x = i - r * w;
+                        lbw[(r * LROWS) * w + x] = lp[(r * LROWS + pr) * w + x];
+                    }
+                }
+                prev_a0 = ck.a0;
+                // the logit rows are complete; also: everyone has finished up-sampling the previous chunk, whose buffer the
+                // next chunk's combine overwrites
+                asm volatile("bar.sync 2, %0;" ::"n"(32 * LS_UW) : "memory");
+            }
             const float* lb = lbuf + (size_t)buf * LBUF;
             const LabT* labp = reinterpret_cast<const LabT*>(p.lab) + (size_t)ck.e * H * W;
             for (int X = utid; X < W; X += 32 * LS_UW) {
@@ -367,7 +393,6 @@ __global__ void __launch_bounds__(LS_THREADS, 1) k_logits_iou_stream(const __gri
                     }
                 }
             }
-            ls_arrive(&lempty[buf]);
         }
         if (cur_e >= 0) flush(cur_e);
     }
@@ -389,7 +414,7 @@ static int launch_logits_iou_stream(const float* wts, const float* f_q, const vo
     cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     LsSmem L{};
     p.CHT = LS_CHT;
-    for (p.NS = 4; p.NS >= 2; --p.NS) {
+    for (p.NS = LS_NS_MAX; p.NS >= 2; --p.NS) {
         L = ls_smem_layout(V, C, w, p.CB, p.NS, p.CHT);
         if (L.total <= (size_t)smem_cap) break;
     }

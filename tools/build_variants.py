@@ -1,6 +1,7 @@
 """Developer tool: build libcwt_b200 variants whose resident fit kernel is compiled with -DRES_VARIANT=<mask>
 (ablations / alternative phase implementations, see csrc/fit_resident.cu) into tools/variants/libcwt_v<mask>.so.
-Only fit_resident.cu is recompiled; the other objects are the product build's. Load one with CWT_LIB_PATH=..."""
+Only fit_resident.cu (or the source named by SRC=iou.cu, ...) is recompiled; the other objects are the product build's. A spec
+"mask:-DFOO=1,-DBAR=2" adds compiler flags. Load a variant with CWT_LIB_PATH=..."""
 import os, subprocess, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from few_shot_seg_cwt_b200 import build as B
@@ -8,7 +9,8 @@ from few_shot_seg_cwt_b200 import build as B
 def main(masks):
     B.build()
     objdir = os.path.join(B.LIBDIR, "obj")
-    others = [os.path.join(objdir, f) for f in sorted(os.listdir(objdir)) if f.endswith(".o") and f != "fit_resident.o"]
+    src = os.environ.get("SRC", "fit_resident.cu")
+    others = [os.path.join(objdir, f) for f in sorted(os.listdir(objdir)) if f.endswith(".o") and f != src[:-3] + ".o"]
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "variants")
     os.makedirs(out, exist_ok=True)
     for m in masks:
@@ -20,7 +22,7 @@ def main(masks):
             extra = fl.split(",")
         tag = m + "".join("_" + e.replace("-D", "").replace("=", "") for e in extra)
         obj = os.path.join(out, f"fit_resident_v{tag}.o")
-        r = subprocess.run([B.NVCC, *B.FLAGS, f"-DRES_VARIANT={m}", *extra, "-c", os.path.join(B.CSRC, "fit_resident.cu"), "-o", obj],
+        r = subprocess.run([B.NVCC, *B.FLAGS, f"-DRES_VARIANT={m}", *extra, "-c", os.path.join(B.CSRC, src), "-o", obj],
                            capture_output=True, text=True)
         if r.returncode:
             raise SystemExit(r.stderr)
