@@ -66,11 +66,12 @@
 #include <cstdio>
 #include <cstdlib>
 
-// Developer builds only (tools/build_variants.py): bit mask of ablations / alternative phase implementations that are timed
-// against the product kernel (RES_VARIANT == 0). 0x01 compute warps do not wait for the halo, 0x02 no full-resolution
-// arithmetic, 0x04 compute warps do not wait for the all-reduce, 0x08 no P3 sweep, 0x10 no P1 sweep (0x01..0x10 give wrong
-// results on purpose: they measure what a phase costs), 0x20 P3 with all quads at once, 0x40 P3 with lane = pixel quad,
-// 0x80 one applier warp per channel chunk, 0x100 / 0x200 the applier / halo warps do not poll (wrong results).
+// Developer builds only (tools/build_variants.py): bit mask of ABLATIONS that are timed against the product kernel
+// (RES_VARIANT == 0; they give wrong results on purpose: they measure what a phase costs). 0x01 compute warps do not wait for
+// the halo, 0x02 no full-resolution arithmetic, 0x04 compute warps do not wait for the all-reduce, 0x08 no P3 sweep, 0x10 no P1
+// sweep, 0x20 shared-memory kernel: P3 with all quads at once, 0x100 / 0x200 the applier / halo warps do not poll.
+// (The alternative implementations measured in round 2 — P3 with lane = pixel quad, per-chunk applier warps, bulk-copy polls,
+// Wd in consumption order: profiles/r2_resident_ablation_*.txt — lost and were removed from the source.)
 #ifndef RES_VARIANT
 #define RES_VARIANT 0
 #endif
@@ -82,16 +83,7 @@ namespace cwt {
 //   CT = 256, two CTAs per SM  (tile 4 x 10: while one CTA waits for the halo / the all-reduce or runs the ALU-bound
 //                               full-resolution stage, the other one could keep the shared-memory pipe busy — measured
 //                               25.4 ms vs 17 ms at E = 64: the exchange latencies grow with the 90 CTAs per episode)
-// helper warps: the applier warp(s) + the halo warp. With one CTA per SM every channel chunk of the all-reduce has its OWN
-// applier warp (RES_VARIANT 0x80): a chunk's words are polled from the moment the step starts, instead of only after the
-// previous chunk has been applied (one L2 round trip per chunk in series).
-// RES_VARIANT 0x400 (PSPNet head geometry only): Wd is kept in shared memory in the order the P1 threads consume it —
-// position(c) = 128 j + 8 grp + u for channel c = grp + 16 (8 j + u) — so that a thread fetches the 8 weights of a chunk with
-// two 128-bit loads instead of eight 32-bit ones (the sweeps are bound by the shared-memory pipe: 40 -> 34 wavefronts per warp
-// and chunk).
-__host__ __device__ constexpr int res_wd_pos(int c, bool permute) {
-    return permute ? ((c >> 7) << 7) + ((c & 15) << 3) + ((c >> 4) & 7) : c;
-}
+// helper warps: the applier warp (shared-memory kernels) + the halo warp.
 // Tensor-memory kernel, RES_SPLIT: the step's work that does not need the halo — the full-resolution stage of the first 64
 // interior cells, the gather of the 44 pixels those cells complete and the P3 sweep over them — runs BEFORE the compute warps
 // wait for the ring, i.e. in the shadow of the halo exchange. For that the 100 pixel columns of a channel chunk are kept in
@@ -194,7 +186,7 @@ static __host__ __device__ inline ResSmem res_smem_layout(int C, int TW, int TH,
     sz[6] = sc1 > sc2 ? sc1 : sc2;
     sz[7] = 8 * (2 + RES_KCH) + 16 + 16;                             // mbarriers + two words of the max|F| exchange + poll mbarrier
     sz[8] = (size_t)C * 16;                                          // previous cumulative dW per channel and step parity (applier warp)
-    sz[9] = (RES_VARIANT & 0x800) ? 1024 : 0;                        // landing zone of the applier's bulk-copy polls
+    sz[9] = 0;
     size_t off[10];
     for (int i = 0; i < 10; ++i) { off[i] = o; o = (o + sz[i] + 127) / 128 * 128; }
     s.F = off[0]; s.W0 = off[1]; s.W1 = off[2]; s.Wd = off[3]; s.zt = off[4]; s.g = off[5];
@@ -233,8 +225,6 @@ __global__ void __launch_bounds__(CT + res_helper_threads(NA), MINB) k_fit_resid
     uint64_t* halo_ready = mbar + 1 + RES_KCH;        // the ring of this step is in zt
     unsigned* smax = reinterpret_cast<unsigned*>(mbar + 2 + RES_KCH);   // [0] tile max|F| bits, [1] episode max|F| bits
     long long* cum = reinterpret_cast<long long*>(smem_raw + L.cum);
-    uint64_t* pollbar = mbar + 4 + RES_KCH;           // completion of the applier's bulk-copy poll (RES_VARIANT 0x800)
-    unsigned long long* pollbuf = reinterpret_cast<unsigned long long*>(smem_raw + L.poll);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int group = blockIdx.x / CPG, k = blockIdx.x - group * CPG;
@@ -250,7 +240,6 @@ __global__ void __launch_bounds__(CT + res_helper_threads(NA), MINB) k_fit_resid
         mbar_init(mbar, 1);
         for (int j = 0; j < RES_KCH; ++j) mbar_init(&applied[j], 1);
         mbar_init(halo_ready, 1);
-        mbar_init(pollbar, 1);
     }
     if (TM && warp == 0) tmem_alloc_512(&tmem_slot);       // all 512 columns: this CTA has the SM to itself
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -305,7 +294,7 @@ __global__ void __launch_bounds__(CT + res_helper_threads(NA), MINB) k_fit_resid
             }
             for (int c = tid; c < C; c += CT) {
                 const float a = p.w[((size_t)e * 2) * C + c], b = p.w[((size_t)e * 2 + 1) * C + c];
-                W0[c] = a; W1[c] = b; Wd[res_wd_pos(c, kStatic && (RES_VARIANT & 0x400))] = b - a;
+                W0[c] = a; W1[c] = b; Wd[c] = b - a;
             }
             if (tid < 2) smax[tid] = 0u;
             // HR task descriptors (static for the episode): task = (cell, row r); 8 adjacent lanes = one cell. Interior cells
@@ -496,16 +485,9 @@ __global__ void __launch_bounds__(CT + res_helper_threads(NA), MINB) k_fit_resid
                                 const float* Wj = Wd + grp + j * 128;
                                 float4 f[8];
                                 float wd[8];
-                                if constexpr ((RES_VARIANT & 0x400) != 0) {
-                                    const float4 wa = *reinterpret_cast<const float4*>(Wd + j * 128 + grp * 8);
-                                    const float4 wb = *reinterpret_cast<const float4*>(Wd + j * 128 + grp * 8 + 4);
-                                    wd[0] = wa.x; wd[1] = wa.y; wd[2] = wa.z; wd[3] = wa.w; wd[4] = wb.x; wd[5] = wb.y; wd[6] = wb.z; wd[7] = wb.w;
-#pragma unroll
-                                    for (int u = 0; u < 8; ++u) f[u] = Fj[u * 400];
-                                } else {
 #pragma unroll
                                 for (int u = 0; u < 8; ++u) { f[u] = Fj[u * 400]; wd[u] = Wj[u * 16]; }
-                                }
+
 #pragma unroll
                                 for (int u = 0; u < 8; ++u) {
                                     za.x = fmaf(wd[u], f[u].x, za.x); za.y = fmaf(wd[u], f[u].y, za.y);
@@ -700,35 +682,6 @@ __global__ void __launch_bounds__(CT + res_helper_threads(NA), MINB) k_fit_resid
                         compute_sync<CT>();
                     }
                     if (PROF && lane == 0 && (warp & 3) == 3) *reinterpret_cast<volatile long long*>(&tstore_sm[warp >> 2]) = clock64();
-                } else if constexpr (kStatic && (RES_VARIANT & 0x40) != 0) {
-                    // lane = pixel quad (25 of 32 lanes), warp = 8 channels of the chunk: all 16 warps sweep chunk j together, g stays
-                    // in registers, the 8 per-lane partials are summed over the lanes by a transposing butterfly (9 shuffles)
-                    const float4 g4 = lane < 25 ? reinterpret_cast<const float4*>(gsm)[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    const uint32_t base = smem_u32(F) + (uint32_t)(warp * 8 * 400 + lane * 16);
-#pragma unroll
-                    for (int j = 0; j < RES_KCH; ++j) {
-                        float s8[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const float4 f = lds128_v(base + (uint32_t)((j * 128 + u) * 400));
-                            s8[u] = (RES_VARIANT & 0x08) ? g4.x : fmaf(g4.x, f.x, fmaf(g4.y, f.y, fmaf(g4.z, f.z, g4.w * f.w)));
-                        }
-                        float r4[4], q2[2];
-                        const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0;
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            r4[u] = (h16 ? s8[u + 4] : s8[u]) + __shfl_xor_sync(0xffffffffu, h16 ? s8[u] : s8[u + 4], 16);
-#pragma unroll
-                        for (int u = 0; u < 2; ++u)
-                            q2[u] = (h8 ? r4[u + 2] : r4[u]) + __shfl_xor_sync(0xffffffffu, h8 ? r4[u] : r4[u + 2], 8);
-                        float d = (h4 ? q2[1] : q2[0]) + __shfl_xor_sync(0xffffffffu, h4 ? q2[0] : q2[1], 4);
-                        d += __shfl_xor_sync(0xffffffffu, d, 2);
-                        d += __shfl_xor_sync(0xffffffffu, d, 1);
-                        const int u_own = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-                        if ((lane & 3) == 0)
-                            red_add_u64(acc_t + j * 128 + warp * 8 + u_own, ((unsigned long long)__float2ll_rn(d * fx_inv) << KB) + 1ull);
-                        if (PROF && tid == 0) *reinterpret_cast<volatile long long*>(&tstore_sm[j]) = clock64();
-                    }
                 } else if constexpr (kStatic) {
                     // One thread per channel, no cross-thread reduction; g is broadcast from shared memory. The four warp
                     // quads take turns (quad j = channel chunk j, handed over through named barriers 2..4): the sweep of a
@@ -840,7 +793,6 @@ __global__ void __launch_bounds__(CT + res_helper_threads(NA), MINB) k_fit_resid
         const unsigned long long cnt_mask = (1ull << KB) - 1ull;
         constexpr int NAPPL = NA > 0 ? NA : 1;
         const int aw = warp - CT / 32;                   // applier number: owns chunks aw, aw + NAPPL, ...
-        unsigned poll_parity = 0u;
         for (int e = group; e < p.E; e += p.G) {
             __syncthreads();                                           // S1
             for (int c = aw * 32 + lane; c < 2 * C; c += 32 * NAPPL) cum[c] = 0ll;
@@ -865,37 +817,19 @@ __global__ void __launch_bounds__(CT + res_helper_threads(NA), MINB) k_fit_resid
 #pragma unroll
                         for (int m = 0; m < RES_AW; ++m) { wv[m] = 0ull; if (c0 + m * 32 + lane < CCH) pending |= 1u << m; }
                         if (RES_VARIANT & 0x100) pending = 0u;
-                        // (the bulk-copy poll is a warp-level operation: the loop condition must be warp-uniform)
-                        while ((kStatic && (RES_VARIANT & 0x800)) ? __any_sync(0xffffffffu, pending != 0u) : (pending != 0u)) {
-                            if constexpr (kStatic && (RES_VARIANT & 0x800) != 0) {
-                                // one 1 KB bulk copy (async proxy: straight from L2, not through the LSU queue the sweeps fill)
-                                if (lane == 0) { mbar_expect_tx(pollbar, 1024u); bulk_g2s(pollbuf, sw, 1024u, pollbar); }
-                                unsigned spin = 0;
-                                while (!mbar_try_wait(pollbar, poll_parity)) { if (++spin > RES_SPIN_LIMIT) break; }
-                                poll_parity ^= 1u;
-#pragma unroll
-                                for (int m = 0; m < RES_AW; ++m)
-                                    if (pending & (1u << m)) wv[m] = pollbuf[m * 32 + lane];
-                            } else {
+                        while (pending != 0u) {
 #pragma unroll
                             for (int m = 0; m < RES_AW; ++m)
                                 if (pending & (1u << m)) wv[m] = ld_relaxed_u64(&sw[c0 + m * 32 + lane]);
-                            }
 #pragma unroll
                             for (int m = 0; m < RES_AW; ++m)
                                 if ((pending & (1u << m)) && ((RES_VARIANT & 0x1f) ? (wv[m] & cnt_mask) >= expect : (wv[m] & cnt_mask) == expect))
                                     pending &= ~(1u << m);
-                            if constexpr (kStatic && (RES_VARIANT & 0x800) != 0) {
-                                if ((++it & 0xffu) == 0u) {                       // warp-uniform watchdog
-                                    if (*reinterpret_cast<volatile unsigned*>(p.abort_flag) != 0u) break;
-                                    if (it > (RES_SPIN_LIMIT >> 2)) { atomicExch(p.abort_flag, 1u); break; }
-                                }
-                            } else if (pending && (++it & 0xffu) == 0u) {
+                            if (pending && (++it & 0xffu) == 0u) {
                                 if (*reinterpret_cast<volatile unsigned*>(p.abort_flag) != 0u) break;
                                 if (it > (RES_SPIN_LIMIT >> 2)) { atomicExch(p.abort_flag, 1u); break; }
                             }
                             if (PROF) ++a_acc[0];
-                            if constexpr (kStatic && (RES_VARIANT & 0x800) != 0) __syncwarp();
                         }
                         if (PROF) {
                             __syncwarp();
@@ -913,7 +847,7 @@ __global__ void __launch_bounds__(CT + res_helper_threads(NA), MINB) k_fit_resid
                                 const float dw = __ll2float_rn(cur - cum_t[c]) * fx_unit;        // this step's all-reduced dW
                                 cum_t[c] = cur;
                                 const float n0 = fmaf(p.lr, dw, W0[c]), n1 = fmaf(-p.lr, dw, W1[c]);
-                                W0[c] = n0; W1[c] = n1; Wd[res_wd_pos(c, kStatic && (RES_VARIANT & 0x400))] = n1 - n0;
+                                W0[c] = n0; W1[c] = n1; Wd[c] = n1 - n0;
                             }
                         }
                     }
