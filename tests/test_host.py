@@ -51,6 +51,40 @@ def test_library_is_blackwell_native():
     assert arches == {"sm_100a"}, arches
 
 
+def test_hot_kernels_use_the_blackwell_units_they_claim():
+    """SASS of the shipped library: the resident fit keeps its tile in tensor memory (STTM / LDTM, no MMA), stages it with
+    bulk-TMA (UBLKCP) and reduces through 64-bit L2 atomics (REDG.E.ADD.64); the K projection runs on the 5th-gen tensor cores
+    (UTCHMMA, operands by UTMALDG, accumulator read with LDTM); the streaming kernels are TMA-fed with packed fp32 FMAs."""
+    lst = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True)
+    if lst.returncode != 0:
+        pytest.skip("cuobjdump not available")
+    kernels, cur = {}, None
+    for line in lst.stdout.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            kernels[cur] = set()
+        elif cur is not None:
+            m = re.search(r"\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]*)", line)
+            if m:
+                kernels[cur].add(m.group(1).split(".")[0] if not m.group(1).startswith("REDG") else m.group(1))
+
+    def ops_of(pattern):
+        found = [v for k, v in kernels.items() if re.search(pattern, k)]
+        assert found, pattern
+        return found
+
+    # tensor-memory resident fit: template arguments <512, 1, 512, 20, 5, 60, 60, PROF, TM = true, NA = 0>
+    for ops in ops_of(r"k_fit_residentILi512ELi1ELi512ELi20ELi5ELi60ELi60ELb[01]ELb1ELi0E"):
+        assert {"STTM", "LDTM", "UBLKCP", "FFMA2"} <= ops and any(o.startswith("REDG.E.ADD.64") for o in ops), sorted(ops)
+        assert "UTCHMMA" not in ops                         # tensor memory as a scratchpad: no MMA in this kernel
+    for ops in ops_of(r"k_kproj_scores"):
+        assert {"UTCHMMA", "UTMALDG", "LDTM"} <= ops, sorted(ops)
+    for name in ("k_logits_iou_stream", "k_rtf_stream", "k_ftr_stream"):
+        for ops in ops_of(name):
+            assert {"UTMALDG", "FFMA2"} <= ops, (name, sorted(ops))
+
+
 def test_workspace_size_queries_need_no_gpu():
     lib = _lib.load()
     # at least the packed label cells (16 B per low-res cell) and the per-step buffers of the streaming algorithm
