@@ -23,13 +23,22 @@ def _sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
+def _code_only(text: str) -> str:
+    """Source text without comments and blank lines: the fingerprint names the CODE a profile was taken on, so editing a
+    comment does not orphan the evidence under profiles/ (string literals in these sources hold no comment markers)."""
+    import re
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    return "\n".join(l.rstrip() for l in text.splitlines() if l.strip())
+
+
 def _fingerprint() -> str:
     h = hashlib.sha256()
     for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
         for f in sorted(os.listdir(root)):
             if f.endswith((".cu", ".cuh", ".h")):
                 h.update(f.encode())
-                h.update(open(os.path.join(root, f), "rb").read())
+                h.update(_code_only(open(os.path.join(root, f), encoding="utf-8").read()).encode())
     h.update(" ".join(FLAGS).encode())
     return h.hexdigest()
 
@@ -66,7 +75,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 def fingerprint() -> str:
-    """sha256 over every CUDA source, header and the compiler flags: names the build a profile was taken on."""
+    """sha256 over the code (comments stripped) of every CUDA source and header and the compiler flags: names the build a
+    profile was taken on."""
     return _fingerprint()
 
 

@@ -41,16 +41,20 @@
 //
 // TENSOR-MEMORY variant (default for the PSPNet head geometry, C = 512, 60 x 60, tile 20 x 5; round 2): shared memory only
 // STAGES the tile; for the 200 steps it lives in the SM's 256 KB of tensor memory (tcgen05.alloc / st / ld, no MMA involved):
-// lane = channel mod 128, column = 100 (channel / 128) + pixel, 400 of the 512 columns. tcgen05.ld streams ~380 B/clk/SM with 16
+// lane = channel mod 128, column = 100 (channel / 128) + pi(pixel), 400 of the 512 columns (pi: tm_col2pix below — the 44 pixels
+// that the first round of the full-resolution stage completes come first). tcgen05.ld streams ~380 B/clk/SM with 16
 // warps (tools/micro/tmem_bench.cu) against the 128 B/clk of the shared-memory pipe, and it leaves the LSU to the exchanges:
 //   P1  thread = lane L of its quarter, pixel block warp / 4 (25 pixels): in-thread FFMA2 over the 4 channel chunks, butterfly
 //       reduce-scatter over the 32 lanes (31 shuffles), the four lane quarters combined through shared memory;
-//   P3  thread = channel: 100 columns in 4 loads, g broadcast from shared memory, no cross-thread reduction, all chunks at once;
+//   P3  thread = channel: its columns in blocks of 32 / 16 / 8 / 4, g broadcast from shared memory, no cross-thread reduction,
+//       all chunks at once; the gather and the sweep over the first 44 columns run BEFORE the compute warps wait for the ring
+//       (in the shadow of the halo exchange), the other 56 after the second round of the full-resolution stage;
 //   HR  a per-episode coefficient table (it reuses the staging buffer) makes every live cell row cost the same 16 FMAs;
 //   AR  no applier warp: after its RED every compute thread waits RES_POLL_DELAY clocks, polls the accumulator word of ITS
 //       channel (one 8-byte load per lane; one warp polling all 512 words needs ~1 600 clk per round), applies the SGD step to
 //       the weights it keeps in registers and publishes Wd; the halo warp sleeps on a named barrier until z is published.
-// Measured (E = 64, 200 steps): 11.56 ms = 7 100 clk per step against 10 400 for the shared-memory kernel.
+// Measured (E = 64, 200 steps): 11.40 ms = 7 000 clk per step against 10 400 for the shared-memory kernel (DESIGN.md 4.4 lists
+// the step-by-step measurements and the variants that were slower).
 //
 // The shared-memory kernel is compiled for 512 compute threads / one CTA per SM and for 256 / two CTAs per SM
 // (CWT_RESIDENT_BPS=2: measured slower, kept for comparison), each specialised for the PSPNet head geometry
