@@ -46,6 +46,12 @@ constexpr int L2_ZW = L2_TW + 2, L2_ZH = L2_TH + 2, L2_CW = L2_TW + 1, L2_NCELL 
 constexpr int L2_NINT = (L2_TW - 1) * (L2_TH - 1);  // 76 interior cells
 constexpr int L2_NRING = 2 * L2_ZW + 2 * (L2_ZH - 2);        // 54
 constexpr int L2_MAXNT = 4;
+// L2_TM: the FIRST tile of every CTA lives in the SM's tensor memory for the steps (tcgen05.st once per episode, tcgen05.ld every
+// sweep: lane = channel mod 128, column = 100 (channel / 128) + pixel, exactly as in fit_resident.cu) and is never streamed again:
+// with 3 tiles per CTA (5 shots) a third of the per-step L2 traffic — the resource this kernel is bound by — disappears.
+#ifndef L2_TM
+#define L2_TM 1
+#endif
 
 struct L2Params {
     const uint4* cells;        // [E][S][HW]
@@ -115,16 +121,23 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_fit_l2(const __grid_constant_
     unsigned long long* zll = p.zll + (size_t)group * 2 * S * L2_HW;
     unsigned long long* fmaxw = p.fmaxw + (size_t)group * p.CPG;
 
+    __shared__ uint32_t tmem_slot;
     if (tid == 0) {
         for (int s = 0; s < L2_NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 16); }
         for (int j = 0; j < L2_KCH; ++j) mbar_init(&applied[j], 1);
         mbar_init(halo_ready, 1);
         mbar_init(retiled, 1);
     }
+    if (L2_TM && warp == 0) tmem_alloc_512(&tmem_slot);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (L2_TM) tmem_fence_before_sync();
     __syncthreads();
+    if (L2_TM) tmem_fence_after_sync();
+    const uint32_t tq = L2_TM ? tmem_slot + ((uint32_t)((warp & 3) * 32) << 16) : 0u;     // this warp's lane quarter of tensor memory
+    constexpr int I0 = L2_TM ? 1 : 0;                  // first tile that is streamed in the steps (tile 0: tensor memory)
 
-    const int units_per_sweep = L2_KCH * nta;
+    const int units_per_sweep = L2_KCH * nta;          // max|F| sweep: every tile
+    const int units_per_step_sweep = L2_KCH * (nta - I0);
     // every role walks the same unit sequence: per episode one max|F| sweep, then per step the P1 sweep and the P3 sweep,
     // each of KCH * nta units in chunk-major order (unit u of a sweep = chunk u / nta, tile u % nta)
 
@@ -211,7 +224,23 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_fit_l2(const __grid_constant_
                 unsigned mb = 0u;
                 for (int u = 0; u < units_per_sweep; ++u, ++uc) {
                     const unsigned st = wait_full(uc);
-                    if (tid == 0) {
+                    if (L2_TM && u % nta == 0 && (warp >> 2) == u / nta) {
+                        // tile 0, chunk j = u / nta: the quad of warps j moves its 128 channel rows into tensor memory (thread = channel
+                        // row, 100 columns); rows are 400 B apart: conflict-free LDS.128
+                        const uint32_t row = smem_u32(ring + (size_t)st * (L2_STAGE_BYTES / 4)) + (uint32_t)(tid & 127) * 400u;
+                        const uint32_t tcol = tq + 100u * (uint32_t)(warp >> 2);
+                        float v[32];
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+#pragma unroll
+                            for (int q4 = 0; q4 < (b < 3 ? 8 : 1); ++q4) {
+                                const float4 f = lds128_v(row + (uint32_t)(b * 128 + q4 * 16));
+                                v[4 * q4] = f.x; v[4 * q4 + 1] = f.y; v[4 * q4 + 2] = f.z; v[4 * q4 + 3] = f.w;
+                            }
+                            if (b < 3) tmem_st32(tcol + 32u * b, v); else tmem_st4(tcol + 96u, v);
+                        }
+                    }
+                    if (tid == 0 && !(L2_TM && u % nta == 0)) {
                         // first sweep of the episode: the unit came through the 3-D tensor map (640 rows of 80 B: slow); write it
                         // back CONTIGUOUSLY, so that the 2 T sweeps that follow fetch it with one linear 51.2 KB bulk copy
                         const int j = u / nta, i = u - j * nta;
@@ -234,8 +263,10 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_fit_l2(const __grid_constant_
                     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");               // ... and written: the producer may fetch it
                     mbar_arrive(retiled);
                 }
+                if (L2_TM) { tmem_wait_st(); tmem_fence_before_sync(); }
             }
             l2_role_sync();                                           // S3
+            if (L2_TM) tmem_fence_after_sync();
             if (tid == 0) st_tagged(&fmaxw[k], __uint_as_float(smax[0]), (unsigned)e + 1u);
             for (int kk = tid; kk < p.CPG; kk += L2_CT)
                 atomicMax(&smax[1], __float_as_uint(poll_word(&fmaxw[kk], (unsigned)e + 1u, p.abort_flag)));
@@ -250,16 +281,35 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_fit_l2(const __grid_constant_
                 float4 za[NT];
 #pragma unroll
                 for (int i = 0; i < NT; ++i) za[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                // tile 0 from tensor memory (L2_TM): thread = lane 32 (warp % 4) + lane of the quarter, pixel block warp / 4 (25 pixels);
+                // in-thread FFMA2 over the chunks, then a butterfly reduce-scatter over the lanes (fit_resident.cu's P1)
+                f32x2 z2[13];
+#pragma unroll
+                for (int i = 0; i < 13; ++i) z2[i] = 0ull;
 #pragma unroll
                 for (int j = 0; j < L2_KCH; ++j) {
+                    float fj[26];
+                    if (L2_TM) {                           // the columns do not depend on the all-reduce: requested before the wait
+                        const uint32_t tcol = tq + 100u * j + 25u * (uint32_t)(warp >> 2);
+                        tmem_ld16(tcol, fj); tmem_ld8(tcol + 16u, fj + 16); tmem_ld2(tcol + 24u, fj + 24);
+                    }
                     if (t > 0) wait_applied(j, gstep - 1u);
+                    if (L2_TM) {
+                        const float wl = Wd[j * 128 + (warp & 3) * 32 + lane];
+                        const f32x2 wl2 = pk2(wl, wl);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 26; ++i) asm volatile("" : "+f"(fj[i]));      // keeps the uses below the tcgen05.wait::ld
+#pragma unroll
+                        for (int i = 0; i < 13; ++i) z2[i] = fma2(wl2, pk2(fj[2 * i], fj[2 * i + 1]), z2[i]);
+                    }
                     float wd[8];
                     if (p1_active) {
 #pragma unroll
                         for (int u = 0; u < 8; ++u) wd[u] = Wd[grp + j * 128 + u * 16];
                     }
 #pragma unroll
-                    for (int i = 0; i < NT; ++i) {
+                    for (int i = I0; i < NT; ++i) {
                         if (i < nta) {
                             const unsigned st = wait_full(uc);
                             ++uc;
@@ -283,14 +333,35 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_fit_l2(const __grid_constant_
                     }
                 }
 #pragma unroll
-                for (int i = 0; i < NT; ++i)
+                for (int i = I0; i < NT; ++i)
                     if (i < nta && p1_active) *reinterpret_cast<float4*>(scratch + i * SCS + grp * L2_NP + 4 * v) = za[i];
+                if (L2_TM) {
+                    float zb[32];
+#pragma unroll
+                    for (int i = 0; i < 13; ++i) upk2(z2[i], zb[2 * i], zb[2 * i + 1]);
+#pragma unroll
+                    for (int i = 25; i < 32; ++i) zb[i] = 0.f;
+#pragma unroll
+                    for (int sft = 16; sft >= 1; sft >>= 1) {
+                        const bool hi = (lane & sft) != 0;
+#pragma unroll
+                        for (int i = 0; i < sft; ++i) {
+                            const float send = hi ? zb[i] : zb[i + sft], keep = hi ? zb[i + sft] : zb[i];
+                            zb[i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+                        }
+                    }
+                    if (lane < 25) scratch[(warp & 3) * L2_NP + 25 * (warp >> 2) + lane] = zb[0];      // tile 0: four lane-quarter partials
+                }
                 compute_sync<L2_CT>();
                 for (int q = tid; q < nta * L2_NP; q += L2_CT) {
                     const int i = q / L2_NP, pp = q - i * L2_NP;
                     float z = 0.f;
+                    if (L2_TM && i == 0) {
+                        z = (scratch[pp] + scratch[L2_NP + pp]) + (scratch[2 * L2_NP + pp] + scratch[3 * L2_NP + pp]);
+                    } else {
 #pragma unroll 4
                     for (int g2 = 0; g2 < 16; ++g2) z += scratch[i * SCS + g2 * L2_NP + pp];
+                    }
                     const int py = pp / L2_TW, px = pp - py * L2_TW;
                     zt[i * ZTS + (py + 1) * L2_ZW + px + 1] = z;
                     st_tagged(&zll[(size_t)(gstep & 1u) * S * L2_HW + (size_t)tile_shot(i) * L2_HW + (tile_y0(i) + py) * L2_WL + tile_x0(i) + px],
@@ -359,14 +430,25 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_fit_l2(const __grid_constant_
                 {
                     const int j = warp >> 2, cl = tid & 127;
                     float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+                    if (L2_TM) {
+                        // tile 0 from tensor memory: thread = channel 128 j + cl = lane (warp % 4) * 32 + lane of its quarter, columns
+                        // 100 j .. 100 j + 99; no ring unit involved, so all quads do it at once (same order of the sums as below)
+                        f32x2 da = 0ull, db = 0ull;
+                        const uint32_t tcol = tq + 100u * (uint32_t)j, gad = smem_u32(gsm);
+                        tm_p3_block<32>(tcol, gad, da, db);
+                        tm_p3_block<32>(tcol + 32u, gad + 128u, da, db);
+                        tm_p3_block<32>(tcol + 64u, gad + 256u, da, db);
+                        tm_p3_block<4>(tcol + 96u, gad + 384u, da, db);
+                        upk2(da, d0, d1); upk2(db, d2, d3);
+                    }
                     // The quads take their units in ring order. A parity wait is only meaningful for the current or the next
                     // phase of a stage's barrier, so quad j starts waiting for its first unit only when quad j - 1 has SEEN its
                     // last one (named barriers 2..4): by then every earlier phase of every stage is complete.
-                    if (j > 0) asm volatile("bar.sync %0, 256;" ::"r"(1 + j) : "memory");
+                    if (nta > I0 && j > 0) asm volatile("bar.sync %0, 256;" ::"r"(1 + j) : "memory");      // (no chain without streamed tiles)
 #pragma unroll
-                    for (int i = 0; i < NT; ++i) {
+                    for (int i = I0; i < NT; ++i) {
                         if (i < nta) {
-                            const unsigned st = wait_full(uc + (unsigned)(j * nta + i));
+                            const unsigned st = wait_full(uc + (unsigned)(j * (nta - I0) + (i - I0)));
                             if (i == nta - 1 && j < L2_KCH - 1) asm volatile("bar.arrive %0, 256;" ::"r"(2 + j) : "memory");
                             const uint32_t row = smem_u32(ring + (size_t)st * (L2_STAGE_BYTES / 4)) + (uint32_t)cl * 400u;
                             const uint32_t gad = smem_u32(gsm + i * GS);
@@ -382,7 +464,7 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_fit_l2(const __grid_constant_
                             release(st, 4u);
                         }
                     }
-                    uc += (unsigned)units_per_sweep;
+                    uc += (unsigned)units_per_step_sweep;
                     const float d = (d0 + d1) + (d2 + d3);
                     unsigned long long* acc_t = acc_ep + (t & 1) * L2_C;
                     red_add_u64(acc_t + j * 128 + cl, ((unsigned long long)__float2ll_rn(d * fx_inv) << KB) + 1ull);
@@ -404,6 +486,7 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_fit_l2(const __grid_constant_
                 }
             }
         }
+        if (L2_TM && warp == 0) { tmem_fence_after_sync(); tmem_dealloc_512(tmem_slot); }      // every warp's last tensor-memory load precedes S5
     } else if (warp == L2_CT / 32) {
         // =====================================================================================================
         // applier warp: accumulator words -> SGD update in shared memory -> release the compute warps (fit_resident.cu)
@@ -545,7 +628,7 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_fit_l2(const __grid_constant_
                         }
                     }
                     for (int j = 0; j < L2_KCH; ++j)
-                        for (int i = 0; i < nta; ++i, ++uc) {
+                        for (int i = (sw == 0 ? 0 : I0); i < nta; ++i, ++uc) {
                             const unsigned st = uc % L2_NSTAGE, ph = (uc / L2_NSTAGE) & 1u;
                             unsigned it = 0;
                             while (!mbar_try_wait(&empty[st], ph ^ 1u)) {       // first pass over the ring: returns at once
@@ -586,13 +669,19 @@ static L2Plan plan_l2(int E, int S, int n_sm) {
     if (const char* s = getenv("CWT_FIT_L2_MB")) budget_mb = atof(s);
     const int g_l2 = (int)(budget_mb * 1e6 / ((double)S * L2_C * L2_HW * 4));
     double best_score = -1.0;
+    // Score = episodes in flight / time of one SGD step of a group. Step times measured on B200 with the first tile in tensor
+    // memory (profiles/r2g_fit_l2_tmem_plans.txt, us): 6.2 / 8.9 / 13.0 / 17.5 for 1 / 2 / 3 / 4 tiles per CTA, + 0.019 per CTA of a
+    // group beyond 72 (exchange latencies), + 0.25 per group beyond 4. (The round-2f score — episodes per tile slot — tied all
+    // plans that fill the SMs and took the first: 1 615 instead of 2 255 episodes/s at 2 shots, 663 instead of 1 171 at 4.)
+    static const double step_us[L2_MAXNT + 1] = {0.0, 6.2, 8.9, 13.0, 17.5};
     for (int NT = 1; NT <= L2_MAXNT; ++NT) {
         const int CPG = (ntile + NT - 1) / NT;
         if (CPG > n_sm) continue;
         int G = n_sm / CPG;
         if (G > g_l2) G = g_l2;
         if (G < 1) G = 1;                                        // a single episode larger than the budget still runs (from HBM)
-        const double score = (double)G / NT * ((double)ntile / (NT * CPG));
+        const double t_us = step_us[NT] + 0.019 * (CPG > 72 ? CPG - 72 : 0) + 0.25 * (G > 4 ? G - 4 : 0);
+        const double score = (double)G / t_us * ((double)ntile / (NT * CPG));
         if (G > E) G = E;
         if (score > best_score + 1e-9) { best_score = score; best = L2Plan{NT, CPG, G, true}; }
     }

@@ -125,27 +125,6 @@ constexpr bool tm_order_ok() {
     return true;
 }
 static_assert(tm_order_ok(), "tm_col2pix / tm_pix2col must be inverse permutations with the round-0 pixels first");
-// one block of the P3 sweep of the tensor-memory kernel: N columns of this thread's lane + N / 4 quads of g (broadcast from
-// shared memory) are requested together, then N / 2 FFMA2 into {d0, d1} / {d2, d3}
-template <int N>
-__device__ __forceinline__ void tm_p3_block(uint32_t taddr, uint32_t gaddr, f32x2& da, f32x2& db) {
-    float f[N];
-    float4 g[N / 4];
-    if constexpr (N == 32) tmem_ld32(taddr, f);
-    else if constexpr (N == 16) tmem_ld16(taddr, f);
-    else if constexpr (N == 8) tmem_ld8(taddr, f);
-    else tmem_ld4(taddr, f);
-#pragma unroll
-    for (int i = 0; i < N / 4; ++i) g[i] = lds128_v(gaddr + 16u * (uint32_t)i);
-    tmem_wait_ld();
-#pragma unroll
-    for (int i = 0; i < N; ++i) asm volatile("" : "+f"(f[i]));          // keeps the uses below the tcgen05.wait::ld
-#pragma unroll
-    for (int i = 0; i < N / 4; ++i) {
-        da = fma2(pk2(g[i].x, g[i].y), pk2(f[4 * i], f[4 * i + 1]), da);
-        db = fma2(pk2(g[i].z, g[i].w), pk2(f[4 * i + 2], f[4 * i + 3]), db);
-    }
-}
 constexpr int res_helper_threads(int NA) { return 32 * (NA + 1); }     // NA applier warps + the halo warp
 constexpr int RES_KCH = 4;        // channel chunks of the pipelined all-reduce
 constexpr int RES_AW = 4;         // accumulator words an applier lane keeps in flight
