@@ -667,7 +667,7 @@ static L2Plan plan_l2(int E, int S, int n_sm) {
     const int ntile = L2_TPI * S;
     double budget_mb = 100.0;                                   // of the 126 MB L2 (two 5-shot episodes = 73.7 MB)
     if (const char* s = getenv("CWT_FIT_L2_MB")) budget_mb = atof(s);
-    const int g_l2 = (int)(budget_mb * 1e6 / ((double)S * L2_C * L2_HW * 4));
+    const double ep_mb = (double)S * L2_C * L2_HW * 4 / 1e6;
     double best_score = -1.0;
     // Score = episodes in flight / time of one SGD step of a group. Step times measured on B200 with the first tile in tensor
     // memory (profiles/r2g_fit_l2_tmem_plans.txt, us): 6.2 / 8.9 / 13.0 / 17.5 for 1 / 2 / 3 / 4 tiles per CTA, + 0.019 per CTA of a
@@ -678,6 +678,11 @@ static L2Plan plan_l2(int E, int S, int n_sm) {
         const int CPG = (ntile + NT - 1) / NT;
         if (CPG > n_sm) continue;
         int G = n_sm / CPG;
+        // what has to stay in L2 for the steps: with the first tile of every CTA in tensor memory only (NT - 1) / NT of an
+        // episode is ever re-read (its tile-major copy is not even written). 5 shots: 4 tiles per CTA x 3 groups = 83 MB
+        // resident, 858 episodes/s, against 3 tiles x 2 groups = 49 MB, 807 (profiles/r2i_fit_l2_5shot_plans.txt)
+        const double resident_mb = ep_mb * (L2_TM ? (double)(NT - 1) / NT : 1.0);
+        const int g_l2 = resident_mb > 0.0 ? (int)(budget_mb / resident_mb) : G;
         if (G > g_l2) G = g_l2;
         if (G < 1) G = 1;                                        // a single episode larger than the budget still runs (from HBM)
         const double t_us = step_us[NT] + 0.019 * (CPG > 72 ? CPG - 72 : 0) + 0.25 * (G > 4 ? G - 4 : 0);
@@ -690,6 +695,8 @@ static L2Plan plan_l2(int E, int S, int n_sm) {
         if (NT >= 1 && NT <= L2_MAXNT && (ntile + NT - 1) / NT <= n_sm) {
             const int CPG = (ntile + NT - 1) / NT;
             int G = n_sm / CPG;
+            const double resident_mb = ep_mb * (L2_TM ? (double)(NT - 1) / NT : 1.0);
+            const int g_l2 = resident_mb > 0.0 ? (int)(budget_mb / resident_mb) : G;
             if (G > g_l2) G = g_l2 < 1 ? 1 : g_l2;
             if (G > E) G = E;
             best = L2Plan{NT, CPG, G, true};

@@ -67,8 +67,10 @@
 #include "common.cuh"
 #include "hires.cuh"
 #include "resident_common.cuh"
+#include "tma_pipe.cuh"
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 // Developer builds only (tools/build_variants.py): bit mask of ABLATIONS that are timed against the product kernel
 // (RES_VARIANT == 0; they give wrong results on purpose: they measure what a phase costs). 0x01 compute warps do not wait for
@@ -139,6 +141,18 @@ constexpr int RES_P3_DEPTH = 4;   // pixel-quads a P3 thread keeps in flight per
 #ifndef RES_HALO_GATE
 #define RES_HALO_GATE 1            // the halo warp sleeps until its CTA has published z (tensor-memory kernel)
 #endif
+// accumulator words of the all-reduce are 8 << RES_ACC_SHIFT bytes apart (0: 16 words per 128-byte line, 2: one word per 32-byte
+// sector, 4: one word per line). Measured in round 2 (profiles/r2i_acc_stride.txt): see DESIGN.md 4.4.
+#ifndef RES_ACC_SHIFT
+#define RES_ACC_SHIFT 0
+#endif
+#define RES_ACC(i) ((size_t)(i) << RES_ACC_SHIFT)
+// Tensor-memory kernel: the tile is staged with 4 tensor-map copies (box 20 x 5 pixels x 128 channels of f_s seen as
+// [E C][60][60]; SASS UTMALDG.3D) instead of 2 560 bulk copies of 80 bytes (one per channel and tile row), whose issue rate
+// bounded the staging of an episode.
+#ifndef RES_TMA_STAGE
+#define RES_TMA_STAGE 1
+#endif
 
 struct ResidentParams {
     const float* f_s;          // [E][C][HW]
@@ -182,7 +196,8 @@ static __host__ __device__ inline ResSmem res_smem_layout(int C, int TW, int TH,
 // per SM): lane = channel mod 128, column = 100 (channel / 128) + pixel — shared memory only stages it. NA: applier warps
 // (1 for the shared-memory kernels; 0 for the tensor-memory kernel, whose compute threads poll and apply their own channel).
 template <int CT, int MINB, int TC, int TTW, int TTH, int TWL, int THL, bool PROF, bool TM, int NA>
-__global__ void __launch_bounds__(CT + res_helper_threads(NA), MINB) k_fit_resident(ResidentParams p) {
+__global__ void __launch_bounds__(CT + res_helper_threads(NA), MINB)
+k_fit_resident(const __grid_constant__ CUtensorMap fmap, ResidentParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int C = TC ? TC : p.C, TW = TTW ? TTW : p.TW, TH = TTH ? TTH : p.TH, wl = TWL ? TWL : p.w_lo, h = THL ? THL : p.h;
     const int NP = TW * TH, HW = wl * h, TPR = wl / TW, CPG = HW / NP;
@@ -270,10 +285,21 @@ __global__ void __launch_bounds__(CT + res_helper_threads(NA), MINB) k_fit_resid
             __syncthreads();                                           // S1: previous episode is done with shared memory
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads before async-proxy writes
             if (tid == 0) mbar_expect_tx(mbar, (unsigned)(C * NP * 4));
-            const float* fsrc = p.f_s + (size_t)e * C * HW + (size_t)y0 * wl + x0;
-            for (int i = tid; i < C * TH; i += CT) {         // one copy per (channel, tile row): TW * 4 bytes
-                const int c = i / TH, py = i - c * TH;
-                bulk_g2s(F + (size_t)c * NP + py * TW, fsrc + (size_t)c * HW + (size_t)py * wl, (unsigned)(TW * 4), mbar);
+            if constexpr (TM && RES_TMA_STAGE != 0) {
+                // four tensor-map copies of 128 channels x 5 rows x 20 pixels: the box arrives densely packed, i.e. as F[c][py][px]
+                if (tid == 0) {
+#pragma unroll
+                    for (int j = 0; j < RES_KCH; ++j)
+                        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                                     ::"r"(smem_u32(F + (size_t)j * 128 * NP)), "l"(&fmap), "r"(smem_u32(mbar)),
+                                       "r"(x0), "r"(y0), "r"(e * C + j * 128) : "memory");
+                }
+            } else {
+                const float* fsrc = p.f_s + (size_t)e * C * HW + (size_t)y0 * wl + x0;
+                for (int i = tid; i < C * TH; i += CT) {         // one copy per (channel, tile row): TW * 4 bytes
+                    const int c = i / TH, py = i - c * TH;
+                    bulk_g2s(F + (size_t)c * NP + py * TW, fsrc + (size_t)c * HW + (size_t)py * wl, (unsigned)(TW * 4), mbar);
+                }
             }
             for (int c = tid; c < C; c += CT) {
                 const float a = p.w[((size_t)e * 2) * C + c], b = p.w[((size_t)e * 2 + 1) * C + c];
@@ -393,7 +419,7 @@ __global__ void __launch_bounds__(CT + res_helper_threads(NA), MINB) k_fit_resid
             const bool ep_finite = smax[1] < 0x7f800000u;
             float fx_inv, fx_unit;
             fixed_point_unit(smax[1], p.T, KB, fx_unit, fx_inv);
-            unsigned long long* acc_ep = p.sums + acc_offset(e, group, p.G, p.SPL, C);
+            unsigned long long* acc_ep = p.sums + RES_ACC(acc_offset(e, group, p.G, p.SPL, C));
             // NA == 0: thread c keeps W0[c] / W1[c] and the previous cumulative sums of its accumulator words in registers
             float w0r = (TM && NA == 0) ? W0[tid & (TC ? TC - 1 : 0)] : 0.f, w1r = (TM && NA == 0) ? W1[tid & (TC ? TC - 1 : 0)] : 0.f;
             long long cum0 = 0ll, cum1 = 0ll, tk_ar = 0ll;
@@ -602,7 +628,7 @@ __global__ void __launch_bounds__(CT + res_helper_threads(NA), MINB) k_fit_resid
                 if (PROF && tid == 0) { long long n = clock64(); t_acc[2] += n - tk0; tk0 = n; }
                 // ------------ P3: dW = g . F^T chunk by chunk; every partial goes straight to the channel's accumulator word,
                 // so chunk j's all-reduce runs under the rest of P3 and the next P1 ------------
-                unsigned long long* acc_t = acc_ep + (t & 1) * C;          // even / odd steps use different words (see header)
+                unsigned long long* acc_t = acc_ep + RES_ACC((t & 1) * C);          // even / odd steps use different words (see header)
                 if constexpr (TM) {
                     // Tile in tensor memory: thread = channel tid (lane L of its quarter, chunk warp / 4 = columns 100 (warp / 4) ..),
                     // its 100 pixels come in blocks of 32 / 16 / 8 / 4 columns; g is broadcast from shared memory.
@@ -627,14 +653,14 @@ __global__ void __launch_bounds__(CT + res_helper_threads(NA), MINB) k_fit_resid
                     float d0, d1, d2, d3;
                     upk2(da, d0, d1); upk2(db, d2, d3);
                     const float d = (d0 + d1) + (d2 + d3);
-                    red_add_u64(acc_t + tid, ((unsigned long long)__float2ll_rn(d * fx_inv) << KB) + 1ull);
+                    red_add_u64(acc_t + RES_ACC(tid), ((unsigned long long)__float2ll_rn(d * fx_inv) << KB) + 1ull);
                     if constexpr (NA == 0) {
                         // No applier warp: every compute thread waits for the all-reduced sum of ITS channel (one 8-byte load per
                         // lane and round: a poll costs the warp ~8 sectors, where one applier warp polling all 512 words needs
                         // ~1 600 clk per round), applies the SGD step to the weights it keeps in registers and publishes Wd.
                         if (PROF && tid == 0) tk_ar = clock64();
                         const unsigned long long expect = (unsigned long long)CPG * (unsigned)(t / 2 + 1), cnt_mask = (1ull << KB) - 1ull;
-                        const unsigned long long* wp = acc_t + tid;
+                        const unsigned long long* wp = acc_t + RES_ACC(tid);
                         unsigned long long wv = 0ull;
                         if (!(RES_VARIANT & 0x04)) {
                             auto done = [&](unsigned long long v) {
@@ -693,7 +719,7 @@ __global__ void __launch_bounds__(CT + res_helper_threads(NA), MINB) k_fit_resid
                     if (!(RES_VARIANT & 0x20) && j < RES_KCH - 1) asm volatile("bar.arrive %0, 256;" ::"r"(2 + j) : "memory");
                     const float d = (d0 + d1) + (d2 + d3);
                     // value and arrival in ONE atomic: (fix(d) << K) + 1
-                    red_add_u64(acc_t + tid, ((unsigned long long)__float2ll_rn(d * fx_inv) << KB) + 1ull);
+                    red_add_u64(acc_t + RES_ACC(tid), ((unsigned long long)__float2ll_rn(d * fx_inv) << KB) + 1ull);
                     if (PROF && lane == 0 && (warp & 3) == 3) *reinterpret_cast<volatile long long*>(&tstore_sm[j]) = clock64();
                 } else if constexpr (kStatic40) {
                     // 2 threads per channel (adjacent lanes), part p owns quads p + 2i (i = 0..4): a quarter-warp reads 4 rows
@@ -722,7 +748,7 @@ __global__ void __launch_bounds__(CT + res_helper_threads(NA), MINB) k_fit_resid
                         float d = d0 + d1;
                         d += __shfl_xor_sync(0xffffffffu, d, 1);
                         if (p3_part == 0)                          // value and arrival in ONE atomic: (fix(d) << K) + 1
-                            red_add_u64(acc_t + j * 128 + p3_cl,
+                            red_add_u64(acc_t + RES_ACC(j * 128 + p3_cl),
                                         ((unsigned long long)__float2ll_rn(d * fx_inv) << KB) + 1ull);
                         if (PROF && tid == 0) *reinterpret_cast<volatile long long*>(&tstore_sm[j]) = clock64();
                     }
@@ -737,7 +763,7 @@ __global__ void __launch_bounds__(CT + res_helper_threads(NA), MINB) k_fit_resid
                             d0 = fmaf(g.x, f.x, d0); d1 = fmaf(g.y, f.y, d1); d2 = fmaf(g.z, f.z, d2); d3 = fmaf(g.w, f.w, d3);
                         }
                         const float d = (d0 + d1) + (d2 + d3);
-                        red_add_u64(acc_t + c, ((unsigned long long)__float2ll_rn(d * fx_inv) << KB) + 1ull);
+                        red_add_u64(acc_t + RES_ACC(c), ((unsigned long long)__float2ll_rn(d * fx_inv) << KB) + 1ull);
                     }
                     if (PROF && tid == 0) {
                         const long long n = clock64();
@@ -784,12 +810,12 @@ __global__ void __launch_bounds__(CT + res_helper_threads(NA), MINB) k_fit_resid
             __syncthreads();                                           // S4
             float fx_unit;
             { float inv; fixed_point_unit(smax[1], p.T, KB, fx_unit, inv); }
-            const unsigned long long* acc_ep = p.sums + acc_offset(e, group, p.G, p.SPL, C);
+            const unsigned long long* acc_ep = p.sums + RES_ACC(acc_offset(e, group, p.G, p.SPL, C));
             for (int t = 0; t < p.T; ++t) {
                 const unsigned long long expect = (unsigned long long)CPG * (unsigned)(t / 2 + 1);   // arrivals so far on every word of this parity
                 long long* cum_t = cum + (t & 1) * C;
                 for (int j = aw; j < RES_KCH; j += NAPPL) {
-                    const unsigned long long* sw = acc_ep + (t & 1) * C + j * CCH;
+                    const unsigned long long* sw = acc_ep + RES_ACC((t & 1) * C + j * CCH);
                     for (int c0 = 0; c0 < CCH; c0 += 32 * RES_AW) {
                         // every load of this lane is issued before any count is looked at (independent L2 round
                         // trips); words that are not complete yet are re-requested together, again as one batch
@@ -803,7 +829,7 @@ __global__ void __launch_bounds__(CT + res_helper_threads(NA), MINB) k_fit_resid
                         while (pending != 0u) {
 #pragma unroll
                             for (int m = 0; m < RES_AW; ++m)
-                                if (pending & (1u << m)) wv[m] = ld_relaxed_u64(&sw[c0 + m * 32 + lane]);
+                                if (pending & (1u << m)) wv[m] = ld_relaxed_u64(&sw[RES_ACC(c0 + m * 32 + lane)]);
 #pragma unroll
                             for (int m = 0; m < RES_AW; ++m)
                                 if ((pending & (1u << m)) && ((RES_VARIANT & 0x1f) ? (wv[m] & cnt_mask) >= expect : (wv[m] & cnt_mask) == expect))
@@ -968,7 +994,7 @@ static void resident_device_limits(int& n_sm, int& smem_cap, int& smem_sm) {
 
 static size_t resident_sum_words(const ResidentPlan& pl, int E, int C) {
     const int nslots = (E + pl.G - 1) / pl.G;
-    return (size_t)pl.G * nslots * 2 * C;
+    return RES_ACC((size_t)pl.G * nslots * 2 * C);
 }
 
 constexpr int RES_MAXGRID = 320;       // >= 2 * 148
@@ -987,7 +1013,22 @@ size_t fit_resident_workspace_bytes(int E, int C, int h, int w) {
 
 template <int CT, int MINB, int TC, int TTW, int TTH, int TWL, int THL, bool TM = false, int NA = 1>
 static int launch_resident(const ResidentParams& p, const ResidentPlan& pl, bool prof, cudaStream_t st) {
-    void* args[] = {const_cast<ResidentParams*>(&p)};
+    // tensor map over f_s as [E C][h][w] fp32, box TW x TH x 128 channels (tensor-memory kernel only; zeroed otherwise)
+    CUtensorMap map;
+    memset(&map, 0, sizeof(map));
+    if (TM && RES_TMA_STAGE) {
+        LsEncodeFn enc = ls_encode_fn();
+        CWT_REQUIRE(enc, CWT_ERR_CUDA, "fit_resident: cuTensorMapEncodeTiled is not available from this driver");
+        cuuint64_t dims[3] = {(cuuint64_t)p.w_lo, (cuuint64_t)p.h, (cuuint64_t)p.E * p.C};
+        cuuint64_t strides[2] = {(cuuint64_t)p.w_lo * 4, (cuuint64_t)p.HW * 4};
+        cuuint32_t box[3] = {(cuuint32_t)p.TW, (cuuint32_t)p.TH, 128};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.f_s), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CWT_REQUIRE(r == CUDA_SUCCESS, CWT_ERR_CUDA, "fit_resident: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    }
+    void* args[] = {&map, const_cast<ResidentParams*>(&p)};
     dim3 grid(pl.G * pl.CPG), block(CT + res_helper_threads(NA));
     const void* fn = prof ? (const void*)k_fit_resident<CT, MINB, TC, TTW, TTH, TWL, THL, true, TM, NA>
                           : (const void*)k_fit_resident<CT, MINB, TC, TTW, TTH, TWL, THL, false, TM, NA>;

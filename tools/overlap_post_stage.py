@@ -29,18 +29,23 @@ def serial(n):
     return out
 
 
-def pipelined(n, prio):
-    main = torch.cuda.current_stream(dev)
+def pipelined(n, prio, main_prio=None):
+    """main_prio: run the fits on a stream of that priority instead of the caller's stream (-1 = above the side stream's 0:
+    pending CTAs of the cooperative fit are then placed before pending CTAs of the post stage)."""
+    caller = torch.cuda.current_stream(dev)
+    main = caller if main_prio is None else torch.cuda.Stream(dev, priority=main_prio)
     side = torch.cuda.Stream(dev, priority=prio)
     out = None
-    for _ in range(n):
-        w_fit = ops.fit_classifier(b.f_s, b.s_label, b.w0, lr, T, check=False)
-        ev = torch.cuda.Event(); ev.record(main)
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            w_fit.record_stream(side)
-            out = post(w_fit)
-    main.wait_stream(side)
+    main.wait_stream(caller)
+    with torch.cuda.stream(main):
+        for _ in range(n):
+            w_fit = ops.fit_classifier(b.f_s, b.s_label, b.w0, lr, T, check=False)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                w_fit.record_stream(side)
+                out = post(w_fit)
+        main.wait_stream(side)
+    caller.wait_stream(main)
     return out
 
 
@@ -57,7 +62,8 @@ def timed(fn, *a):
 
 ms_s, c_s = timed(serial)
 print(f"serial     : {ms_s:.3f} ms per step ({E / ms_s * 1e3:.0f} episodes/s)", flush=True)
-for prio in (0, -1):
-    ms_p, c_p = timed(pipelined, steps, prio)
-    print(f"pipelined  : {ms_p:.3f} ms per step ({E / ms_p * 1e3:.0f} episodes/s), side-stream priority {prio}, "
-          f"counts identical {bool(torch.equal(c_s, c_p))}", flush=True)
+for prio, main_prio in ((0, None), (-1, None), (0, -1), (0, -2), (0, None), (0, -1)):
+    ms_p, c_p = timed(pipelined, steps, prio, main_prio)
+    print(f"pipelined  : {ms_p:.3f} ms per step ({E / ms_p * 1e3:.0f} episodes/s), side-stream priority {prio}, fit stream "
+          f"{'= caller' if main_prio is None else 'priority %d' % main_prio}, counts identical {bool(torch.equal(c_s, c_p))}", flush=True)
+print("priority range", torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else "n/a")
