@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-sub-batch", type=int, default=32, help="HostPipeline sub-batch size (0 = whole batches)")
     ap.add_argument("--e2e-sub-all", type=int, default=1, help="1: every host batch goes through in sub-batches; 0: only the first")
-    ap.add_argument("--e2e-expand-main", type=int, default=1, help="zero-compressed e2e: expansion kernel on the head's stream (1) or the copy stream (0)")
+    ap.add_argument("--e2e-expand-main", type=int, default=2, help="zero-compressed e2e: expansion kernel on the head's stream (1), the copy stream (0) or a third stream (2)")
     ap.add_argument("--e2e-ramp", default="8,8,16", help="sub-batch sizes at the start of an e2e run (first host batch only); '' = none")
     ap.add_argument("--e2e-format", default="zc", choices=["zc", "dense"], help="host format of the e2e leg: zero-compressed "
                                                                                "features (default) or dense tensors")
@@ -125,9 +125,12 @@ def load_kernel_counters():
     if not files:
         return None, None, False
     try:
-        d = json.load(open(files[-1]))
         from few_shot_seg_cwt_b200 import build as B
-        return d, os.path.relpath(files[-1], ROOT), d.get("build_fingerprint") == B.fingerprint()
+        fp = B.fingerprint()
+        loaded = [(f, json.load(open(f))) for f in files]
+        # the capture taken on THIS build if there is one, else the newest
+        f, d = next(((f, d) for f, d in reversed(loaded) if d.get("build_fingerprint") == fp), loaded[-1])
+        return d, os.path.relpath(f, ROOT), d.get("build_fingerprint") == fp
     except Exception:
         return None, None, False
 
@@ -462,7 +465,7 @@ def main():
     if not a.no_e2e:
         def run_e2e(host_batch, tag):
             pipe = cwt.HostPipeline(dev, params, a.heads, a.cls_lr, a.adapt_iter, fit_algo=a.fit_algo, attn_algo=a.attn_algo,
-                                    sub_batch=a.e2e_sub_batch, sub_batch_all=bool(a.e2e_sub_all), expand_on_main=bool(a.e2e_expand_main),
+                                    sub_batch=a.e2e_sub_batch, sub_batch_all=bool(a.e2e_sub_all), expand_on_main=int(a.e2e_expand_main),
                                     ramp=tuple(int(x) for x in a.e2e_ramp.split(",") if x))
             pipe.run([host_batch] * max(1, a.warmup), reduce_every_step=True)
             barrier()
@@ -477,9 +480,10 @@ def main():
                     "d2h_bytes_per_step": res[0].numel() * res[0].element_size() + 4 * E, "ms_per_step": ms_e / a.steps,
                     "host_format": tag,
                     "counts_equal_device_resident_run": bool(torch.equal(res[0].to(dev), last_out.counts))}
-        api = ("few_shot_seg_cwt_b200.HostPipeline.run (three device staging slots; first batch of the run in sub-batches of "
-               "%s episodes, %s; async D2H of the counts and the fit status words)"
-               % (a.e2e_ramp or a.e2e_sub_batch, "every batch in sub-batches of %d" % a.e2e_sub_batch if a.e2e_sub_all else "later batches whole"))
+        api = ("few_shot_seg_cwt_b200.HostPipeline.run (four device staging slots; first batch of the run in sub-batches of "
+               "%s episodes, %s; expansion of the zero-compressed features on %s; async D2H of the counts and the fit status words)"
+               % (a.e2e_ramp or a.e2e_sub_batch, "every batch in sub-batches of %d" % a.e2e_sub_batch if a.e2e_sub_all else "later batches whole",
+                  {0: "the copy stream", 1: "the head's stream", 2: "its own stream (under the previous piece's fit)"}.get(int(a.e2e_expand_main))))
         dense = run_e2e(host, "dense fp32 tensors in pinned host memory")
         if a.e2e_format == "dense":
             e2e = dict(dense, api=api)

@@ -564,8 +564,8 @@ class HostPipeline:
     """
 
     def __init__(self, device, params: Dict[str, torch.Tensor], n_head: int, lr: float, n_iter: int,
-                 fit_algo: int = L.FIT_AUTO, attn_algo: int = L.ATTN_REASSOC, num_classes_val: int = 5, n_slots: int = 3,
-                 sub_batch: int = 32, sub_batch_all: bool = True, expand_on_main: bool = True, ramp=(8, 8, 16)):
+                 fit_algo: int = L.FIT_AUTO, attn_algo: int = L.ATTN_REASSOC, num_classes_val: int = 5, n_slots: int = 4,
+                 sub_batch: int = 32, sub_batch_all: bool = True, expand_on_main: int = 2, ramp=(8, 8, 16)):
         self.device = torch.device(device)
         self.params = {k: v.to(self.device) for k, v in params.items()}
         self.n_head, self.lr, self.n_iter = n_head, lr, n_iter
@@ -584,12 +584,18 @@ class HostPipeline:
         # Device-resident staging slots are reused for the whole run: no allocator traffic (a cudaMalloc of ~1 GB
         # synchronises the device). Three slots: the copy of sub-batch i+2 may start as soon as the copy of i+1 has
         # finished (its slot was released by head i-1 long ago), so the copy engine never waits for the head.
-        # Zero-compressed host batches: where the expansion kernel runs. True (default): on the head's stream, right in front of
-        # the fit (~0.25 ms per 64 episodes, exposed); False: on the copy stream, behind the copies it expands, i.e. concurrently
-        # with the previous batch's cooperative fit — whose 144 CTAs leave it one small CTA per SM: the expansion of 64 episodes
-        # then takes 5-7 ms instead of 0.25 and copy + expansion no longer fit under one fit (tools/e2e_timeline.py).
-        # Measured on B200 (profiles/r2g_e2e_policies.txt): 12.38 ms per step on the head's stream, 13.4 ms on the copy stream.
-        self.expand_on_main = bool(expand_on_main)
+        # Zero-compressed host batches: where the expansion kernel runs (``expand_on_main``).
+        # 1: on the head's stream, right in front of the fit (~0.25 ms per 64 episodes, exposed).
+        # 0: on the copy stream, behind the copies it expands, i.e. concurrently with the previous piece's cooperative fit —
+        #    whose 144 CTAs leave it the four free SMs: the expansion of 64 episodes then takes 5-7 ms instead of 0.25, the next
+        #    piece's copy queues behind it and the copy engine idles (tools/e2e_timeline.py): 13.4 ms per step against 12.38.
+        # 2 (default): on a THIRD stream behind the copy it expands — the copy stream carries nothing but copies, the expansion
+        #    of piece i+1 runs on the SMs the fit of piece i leaves free, and with FOUR staging slots copy, expansion and fit of
+        #    three consecutive pieces overlap. Measured on B200 (profiles/r2i_e2e_policies.txt, 20 steps of 64 episodes,
+        #    device-resident rate 11.45 ms per step): 11.76 ms per step (0.974) against 11.98 (0.956) for mode 1 with three slots;
+        #    pieces of 16 with five slots 11.71 (0.978).
+        self.expand_on_main = int(expand_on_main)
+        self.expand_stream = torch.cuda.Stream(self.device) if self.expand_on_main == 2 else None
         self.ramp = tuple(int(x) for x in (ramp or ()))     # sub-batch sizes at the very start of a run (first host batch only)
         self.sub_batch = max(0, int(sub_batch))
         self.sub_batch_all = bool(sub_batch_all)            # sub-batch every host batch, not only the first
@@ -609,7 +615,8 @@ class HostPipeline:
         (zero-compressed features: mask / prefix / packed values are copied and the dense tensors are rebuilt on the device
         by ``cwt_expand_zero_compressed_f32``, on the copy stream too)."""
         n = hi - lo
-        pending = []                  # expansions left for the head's stream (expand_on_main)
+        pending = []                  # expansions left for the head's stream (expand_on_main == 1)
+        side_jobs = []                # expansions for the dedicated stream (expand_on_main == 2)
         compressed = isinstance(hb, CompressedEpisodeBatch)
         shapes = [(tuple(hb.f_s.shape[1:]), torch.float32), (tuple(hb.s_label.shape[1:]), hb.s_label.dtype),
                   (tuple(hb.f_q.shape[1:]), torch.float32), (tuple(hb.q_label.shape[1:]), hb.q_label.dtype),
@@ -651,13 +658,25 @@ class HostPipeline:
                     o.copy_(cm.woff[lo:hi], non_blocking=True)
                     if v1 > v0:
                         v[:v1 - v0].copy_(cm.vals[v0:v1], non_blocking=True)
-                    if self.expand_on_main:
+                    if self.expand_on_main == 1:
                         pending.append((m, o, v, dense, v0))
+                    elif self.expand_on_main == 2:
+                        side_jobs.append((m, o, v, dense, v0))
                     else:
                         expand_map(m, o, v, dense, v0)
                 self._cslots[slot] = cs
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
+        if side_jobs:
+            # the expansions on their own stream, behind this piece's copies; the head waits for THEIR event
+            self.expand_stream.wait_event(ev)
+            with torch.cuda.stream(self.expand_stream):
+                for m, o, v, dense, v0 in side_jobs:
+                    for t in (m, o, v, dense):
+                        t.record_stream(self.expand_stream)
+                    expand_map(m, o, v, dense, v0)
+                ev = torch.cuda.Event()
+                ev.record(self.expand_stream)
         return db, ev, pending
 
     def _sub_batches(self, host_batches):
@@ -668,6 +687,11 @@ class HostPipeline:
             E = hb.n_episodes
             step = self.sub_batch if (self.sub_batch > 0 and (bi == 0 or self.sub_batch_all)) else max(E, 1)
             sizes = list(self.ramp) if (bi == 0 and self.ramp) else []
+            if not sizes and 0 < step < E:
+                # equal pieces: 36 episodes in pieces of at most 32 are 18 + 18, not 32 + 4 (a 4-episode launch leaves most
+                # groups of the persistent fit idle)
+                n_pieces = (E + step - 1) // step
+                step = (E + n_pieces - 1) // n_pieces
             lo = 0
             while lo < max(E, 1):
                 n = sizes.pop(0) if sizes else step
