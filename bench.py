@@ -117,9 +117,10 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def load_kernel_counters():
-    """Latest profiles/*_kernel_counters.json (written by tools/ncu_counters_to_json.py from an ncu capture of this very
-    command) -> (dict, file name, whether its build fingerprint equals the build that is running)."""
+def load_kernel_counters(kernel=None):
+    """profiles/*_kernel_counters.json (written by tools/ncu_counters_to_json.py from an ncu capture of this very command)
+    -> (dict, file name, whether it was captured on the build that is running: the fingerprint of the whole library, or of
+    the sources ``kernel`` is compiled from, is unchanged)."""
     import glob
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_kernel_counters.json")))
     if not files:
@@ -128,9 +129,17 @@ def load_kernel_counters():
         from few_shot_seg_cwt_b200 import build as B
         fp = B.fingerprint()
         loaded = [(f, json.load(open(f))) for f in files]
+
+        def same_build(d):
+            # the whole library unchanged, or at least the sources of `kernel` (its .cu and the headers it includes)
+            if d.get("build_fingerprint") == fp:
+                return True
+            kf = d.get("kernel_source_fingerprints") or {}
+            return bool(kernel) and kernel in kf and kf[kernel] == B.kernel_fingerprint(kernel)
+
         # the capture taken on THIS build if there is one, else the newest
-        f, d = next(((f, d) for f, d in reversed(loaded) if d.get("build_fingerprint") == fp), loaded[-1])
-        return d, os.path.relpath(f, ROOT), d.get("build_fingerprint") == fp
+        f, d = next(((f, d) for f, d in reversed(loaded) if same_build(d)), loaded[-1])
+        return d, os.path.relpath(f, ROOT), same_build(d)
     except Exception:
         return None, None, False
 
@@ -348,8 +357,8 @@ def main():
     resident = (a.fit_algo in (0, 2) and S == 1)
     sm_clk = (clocks or {}).get("sm_mhz") or 1965.0
     n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-    counters, counters_file, counters_match = load_kernel_counters()
     fit_kernel = "k_fit_resident" if resident else ("k_fit_l2" if a.fit_algo in (0, 3) else None)
+    counters, counters_file, counters_match = load_kernel_counters(fit_kernel)
     kc = (counters or {}).get("kernels", {}).get(fit_kernel or "", None)
     # DRAM traffic of the dominant kernel per launch: ncu dram__bytes_read + dram__bytes_write of the SAME command
     # (tools/ncu_bench_kernels.sh -> profiles/*_kernel_counters.json, with the fingerprint of the build it was taken on)

@@ -80,8 +80,38 @@ def fingerprint() -> str:
     return _fingerprint()
 
 
+# the sources a kernel is compiled from (its .cu and every header that file includes, directly or not): a capture of that
+# kernel stays valid while THESE are unchanged, whatever happens to the rest of the library
+KERNEL_SOURCES = {
+    "k_fit_resident": ["fit_resident.cu", "resident_common.cuh", "hires.cuh", "common.cuh", "tma_pipe.cuh"],
+    "k_fit_l2": ["fit_l2.cu", "resident_common.cuh", "hires.cuh", "common.cuh", "tma_pipe.cuh"],
+    "k_logits_iou_stream": ["iou.cu", "iou_stream.cuh", "skinny.cuh", "hires.cuh", "tma_pipe.cuh", "common.cuh"],
+    "k_rtf_stream": ["transformer.cu", "skinny_stream.cuh", "skinny.cuh", "tma_pipe.cuh", "common.cuh"],
+    "k_ftr_stream": ["transformer.cu", "skinny_stream.cuh", "skinny.cuh", "tma_pipe.cuh", "common.cuh"],
+    "k_kproj_scores": ["kproj_tcgen05.cu", "common.cuh"],
+}
+
+
+def kernel_fingerprint(kernel: str) -> str:
+    """sha256 over the code (comments stripped) of the sources ``kernel`` is compiled from, the public header and the flags."""
+    h = hashlib.sha256()
+    files = [os.path.join(CSRC, f) for f in KERNEL_SOURCES[kernel]] + [os.path.join(os.path.dirname(HERE), "include", "cwt_b200.h")]
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        h.update(_code_only(open(f, encoding="utf-8").read()).encode())
+    h.update(" ".join(FLAGS).encode())
+    return h.hexdigest()
+
+
+def kernel_fingerprints() -> dict:
+    return {k: kernel_fingerprint(k) for k in KERNEL_SOURCES}
+
+
 if __name__ == "__main__":
     if "--fingerprint" in sys.argv:
         print(_fingerprint())
+    elif "--kernel-fingerprints" in sys.argv:
+        import json
+        print(json.dumps(kernel_fingerprints(), indent=1))
     else:
         print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -52,6 +52,11 @@ constexpr int L2_MAXNT = 4;
 #ifndef L2_TM
 #define L2_TM 1
 #endif
+// the halo warp sleeps on named barrier 5 until its CTA has published the step's z (fit_resident.cu's RES_HALO_GATE): the
+// neighbours publish about then, earlier polls of the ring are only traffic on lines that are being written
+#ifndef L2_HALO_GATE
+#define L2_HALO_GATE 1
+#endif
 
 struct L2Params {
     const uint4* cells;        // [E][S][HW]
@@ -367,6 +372,7 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_fit_l2(const __grid_constant_
                     st_tagged(&zll[(size_t)(gstep & 1u) * S * L2_HW + (size_t)tile_shot(i) * L2_HW + (tile_y0(i) + py) * L2_WL + tile_x0(i) + px],
                               z, gstep + 1u);
                 }
+                if (L2_HALO_GATE) asm volatile("bar.arrive 5, %0;" ::"n"(L2_CT + 32) : "memory");     // wake the halo warp (non-blocking)
                 compute_sync<L2_CT>();
                 // ------------ HR: interior cells of every tile, then (halo) the cells on the tile borders ------------
 #pragma unroll
@@ -569,6 +575,7 @@ __global__ void __launch_bounds__(L2_THREADS, 1) k_fit_l2(const __grid_constant_
                 const unsigned long long* zsrc = zll + (size_t)(gstep & 1u) * S * L2_HW;
                 unsigned bits[NT][2], tag[NT][2];
                 unsigned pending = 0u, it = 0u;
+                if (L2_HALO_GATE) asm volatile("bar.sync 5, %0;" ::"n"(L2_CT + 32) : "memory");       // this CTA's z of the step is out
 #pragma unroll
                 for (int i = 0; i < NT; ++i)
 #pragma unroll

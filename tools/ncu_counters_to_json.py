@@ -24,6 +24,12 @@ for (name, _id), m in per.items():
         k["sum"][a] = k["sum"].get(a, 0.0) + v
 out = {"tag": tag, "command": "python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --attn-both (ncu --clock-control none)",
        "build_fingerprint": open(os.path.join(ROOT, "gpurun_out", f"{tag}_build_fingerprint.txt")).read().strip(), "kernels": {}}
+# per-kernel source fingerprints (few_shot_seg_cwt_b200.build.kernel_fingerprints): recorded only while the tree still IS the
+# build the capture was taken on — a capture of one kernel stays valid when another kernel's source changes later
+sys.path.insert(0, ROOT)
+from few_shot_seg_cwt_b200 import build as B
+if B.fingerprint() == out["build_fingerprint"]:
+    out["kernel_source_fingerprints"] = B.kernel_fingerprints()
 for name, k in kernels.items():
     n = k["launches"]
     avg = {a: v / n for a, v in k["sum"].items()}
