@@ -338,3 +338,60 @@ def test_missing_library_fails_loudly(tmp_path, monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         _lib.load()
+
+
+def test_host_pipeline_pieces_are_equal_and_cover_every_episode():
+    """HostPipeline._sub_batches: the first host batch of a run goes through in the ramp sizes; every later batch in EQUAL pieces
+    of at most ``sub_batch`` episodes (36 -> 18 + 18, not 32 + 4: a 4-episode launch leaves most groups of the persistent fit
+    idle); every episode exactly once, in order; an empty batch still yields one (empty) piece so that the result list lines up."""
+    from few_shot_seg_cwt_b200.episodic import HostPipeline
+
+    class HB:
+        def __init__(self, n):
+            self.n_episodes = n
+
+    hp = HostPipeline.__new__(HostPipeline)                     # the generator needs no device
+    hp.sub_batch, hp.sub_batch_all, hp.ramp = 32, True, (8, 8, 16)
+    for E in (0, 1, 5, 32, 33, 36, 64, 100):
+        pieces = list(hp._sub_batches([HB(E), HB(E), HB(E)]))
+        for bi in range(3):
+            mine = [(lo, hi, last) for b, lo, hi, last, _, _ in pieces if b == bi]
+            assert mine[0][0] == 0 and mine[-1][1] == E and mine[-1][2] and not any(l for _, _, l in mine[:-1])
+            assert all(a[1] == b[0] for a, b in zip(mine, mine[1:]))            # contiguous, in order
+            if bi > 0 and E > 0:
+                sizes = [hi - lo for lo, hi, _ in mine]
+                assert max(sizes) <= 32 and max(sizes) - min(sizes) < len(sizes), (E, sizes)     # equal up to the rounding
+                assert len(sizes) == -(-E // 32)
+    assert [(lo, hi) for b, lo, hi, *_ in hp._sub_batches([HB(36), HB(36)]) if b == 1] == [(0, 18), (18, 36)]
+    hp.sub_batch_all = False                                     # later batches whole
+    assert [(lo, hi) for b, lo, hi, *_ in hp._sub_batches([HB(64), HB(64)]) if b == 1] == [(0, 64)]
+
+
+def test_kernel_counters_are_matched_per_kernel_source(tmp_path, monkeypatch):
+    """bench.load_kernel_counters: a capture is 'of this build' when the fingerprint of the whole library matches OR the sources
+    of the kernel the line quotes are unchanged (another kernel may have changed since); otherwise the newest file is
+    returned and flagged as not matching."""
+    import importlib
+    import json
+    from few_shot_seg_cwt_b200 import build as B
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    prof = tmp_path / "profiles"
+    prof.mkdir()
+    kf = B.kernel_fingerprints()
+    assert set(kf) >= {"k_fit_resident", "k_fit_l2", "k_logits_iou_stream", "k_kproj_scores"}
+    for k, files in B.KERNEL_SOURCES.items():                    # every listed source exists
+        for f in files:
+            assert os.path.exists(os.path.join(B.CSRC, f)), (k, f)
+    json.dump({"build_fingerprint": "stale", "kernels": {}}, open(prof / "a_kernel_counters.json", "w"))
+    json.dump({"build_fingerprint": "older build", "kernel_source_fingerprints": dict(kf, k_fit_l2="changed since"), "kernels": {}},
+              open(prof / "b_kernel_counters.json", "w"))
+    json.dump({"build_fingerprint": "stale too", "kernels": {}}, open(prof / "c_kernel_counters.json", "w"))
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    d, name, ok = bench.load_kernel_counters("k_fit_resident")
+    assert ok and name.endswith("b_kernel_counters.json")
+    d, name, ok = bench.load_kernel_counters("k_fit_l2")         # that kernel's sources changed: newest file, not matching
+    assert not ok and name.endswith("c_kernel_counters.json")
+    json.dump({"build_fingerprint": B.fingerprint(), "kernels": {}}, open(prof / "0_kernel_counters.json", "w"))
+    d, name, ok = bench.load_kernel_counters("k_fit_l2")
+    assert ok and name.endswith("0_kernel_counters.json")
