@@ -392,7 +392,7 @@ def main():
                               "kernel, frac 0.30 there); kept so that the rounds compare on one denominator"}
         roofline = {
             "kernel": (("k_fit_resident<512 compute threads + halo warp, 1 CTA/SM, C=512, tile 20x5 of 60x60, tile in TENSOR MEMORY> (one "
-                        "cooperative launch: features staged once by bulk-TMA and moved to tensor memory with tcgen05.st, 200 SGD steps "
+                        "cooperative launch: features staged once by tensor-map TMA copies and moved to tensor memory with tcgen05.st, 200 SGD steps "
                         "on chip with tcgen05.ld sweeps, all-reduce through 64-bit L2 atomics polled by the compute threads)")
                        if tmem_kernel else
                        ("k_fit_resident<512 compute threads, 1 CTA/SM, C=512, tile 20x5 of 60x60> (one cooperative launch: features "

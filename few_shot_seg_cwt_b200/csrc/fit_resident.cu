@@ -53,8 +53,10 @@
 //   AR  no applier warp: after its RED every compute thread waits RES_POLL_DELAY clocks, polls the accumulator word of ITS
 //       channel (one 8-byte load per lane; one warp polling all 512 words needs ~1 600 clk per round), applies the SGD step to
 //       the weights it keeps in registers and publishes Wd; the halo warp sleeps on a named barrier until z is published.
-// Measured (E = 64, 200 steps): 11.40 ms = 7 000 clk per step against 10 400 for the shared-memory kernel (DESIGN.md 4.4 lists
-// the step-by-step measurements and the variants that were slower).
+//   staging: four tensor-map copies per tile (cp.async.bulk.tensor.3d, box 20 x 5 pixels x 128 channels of f_s seen as
+//       [E C][60][60]) instead of one 80-byte bulk copy per channel and tile row.
+// Measured (E = 64, 200 steps): 11.28 ms = 6 820 clk per step + 17 us per episode against 10 400 clk for the shared-memory kernel
+// (DESIGN.md 4.4 lists the step-by-step measurements and the variants that were slower).
 //
 // The shared-memory kernel is compiled for 512 compute threads / one CTA per SM and for 256 / two CTAs per SM
 // (CWT_RESIDENT_BPS=2: measured slower, kept for comparison), each specialised for the PSPNet head geometry
