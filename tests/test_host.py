@@ -395,3 +395,42 @@ def test_kernel_counters_are_matched_per_kernel_source(tmp_path, monkeypatch):
     json.dump({"build_fingerprint": B.fingerprint(), "kernels": {}}, open(prof / "0_kernel_counters.json", "w"))
     d, name, ok = bench.load_kernel_counters("k_fit_l2")
     assert ok and name.endswith("0_kernel_counters.json")
+
+
+def test_zero_compressed_host_format_round_trip_on_cpu():
+    """hostformat.compress_map: lossless on the BIT PATTERN (-0.0, NaN, denormals, Inf survive; +0.0 is the only value dropped),
+    and what the device kernel consumes — bit mask + one prefix count per block of 32 mask words + packed values — rebuilds the
+    tensor when read the way cwt_expand_zero_compressed_f32 reads it (numpy restatement of csrc/expand.cu: value index of an
+    element = block prefix + set bits of the earlier words of the block + set bits below it in its word)."""
+    from few_shot_seg_cwt_b200 import hostformat as HF
+    g = torch.Generator().manual_seed(7)
+    t = torch.relu(torch.randn(3, 2, 16, 8, 8, generator=g))                  # 2048 elements per episode = 64 mask words = 2 blocks
+    flat = t.view(-1)
+    flat[5], flat[77], flat[300], flat[301] = -0.0, float("nan"), 1e-42, float("inf")
+    flat[2048:2048 + 40] = 0.0                                                  # a run of empty words at the start of episode 1
+    c = HF.compress_map(t)
+    assert c.mask.shape == (3, 64) and c.woff.shape == (3, 2) and len(c.val_start) == 4
+    assert c.val_start[-1] == c.vals.numel() == int((t.view(torch.int32) != 0).sum())
+    assert torch.equal(HF.expand_map_reference(c).view(torch.int32), t.view(torch.int32))
+    # the device algorithm, word by word
+    mask = c.mask.numpy().view(np.uint32)
+    woff = c.woff.numpy().view(np.uint32)
+    vals = c.vals.numpy()
+    out = np.zeros(t.numel(), dtype=np.float32)
+    for row in range(mask.shape[0]):
+        for wi in range(mask.shape[1]):
+            base = int(woff[row, wi // 32]) + sum(bin(int(m)).count("1") for m in mask[row, (wi // 32) * 32:wi])
+            word = int(mask[row, wi])
+            for b in range(32):
+                if (word >> b) & 1:
+                    out[(row * mask.shape[1] + wi) * 32 + b] = vals[base + bin(word & ((1 << b) - 1)).count("1")]
+    assert np.array_equal(out.view(np.int32), t.numpy().reshape(-1).view(np.int32))
+    # sub-batches are slices: the values of episodes lo..hi are vals[val_start[lo]:val_start[hi]], and nbytes counts exactly those
+    assert c.nbytes(1, 3) == 2 * (64 + 2) * 4 + (c.val_start[3] - c.val_start[1]) * 4
+    assert c.nbytes() < t.numel() * 4
+    with pytest.raises(TypeError):
+        HF.compress_map(t.double())
+    with pytest.raises(ValueError):
+        HF.compress_map(torch.zeros(2, 33))
+    e = HF.compress_map(torch.zeros(0, 64))
+    assert e.vals.numel() == 0 and e.val_start == [0]
