@@ -990,6 +990,11 @@ def test_host_pipeline_zero_compressed_equals_dense(cuda_device):
         assert len(a) == len(b) and all(torch.equal(x, y) for x, y in zip(a, b)), sub
         b2 = [r.clone() for r in pipe.run(comp)]                       # staging buffers reused on the second run
         assert all(torch.equal(x, y) for x, y in zip(a, b2)), sub
+    # where the expansion kernel runs (default 2: its own stream behind the copies; 1: the head's stream; 0: the copy stream)
+    a = cwt.HostPipeline(cuda_device, params, 2, 0.1, 30, sub_batch=2).run(dense)
+    for mode, slots in ((1, 3), (0, 3), (2, 2)):
+        b = cwt.HostPipeline(cuda_device, params, 2, 0.1, 30, sub_batch=2, expand_on_main=mode, n_slots=slots).run(comp)
+        assert len(a) == len(b) and all(torch.equal(x, y) for x, y in zip(a, b)), (mode, slots)
 
 
 def test_head_pipeline_equals_episode_head(cuda_device):
