@@ -582,7 +582,7 @@ class HostPipeline:
         # 8, 8, 16: 12.10 ms per step (0.957 of the device-resident rate); whole batches after 8, 8, 16, 32: 12.44; pieces of
         # 16: 12.38; of 8: 13.05 (launch overheads); expansion on the copy stream instead of the head's: 13.4.
         # Device-resident staging slots are reused for the whole run: no allocator traffic (a cudaMalloc of ~1 GB
-        # synchronises the device). Three slots: the copy of sub-batch i+2 may start as soon as the copy of i+1 has
+        # synchronises the device). At least three slots: the copy of sub-batch i+2 may start as soon as the copy of i+1 has
         # finished (its slot was released by head i-1 long ago), so the copy engine never waits for the head.
         # Zero-compressed host batches: where the expansion kernel runs (``expand_on_main``).
         # 1: on the head's stream, right in front of the fit (~0.25 ms per 64 episodes, exposed).
