@@ -53,7 +53,8 @@ def test_library_is_blackwell_native():
 
 def test_hot_kernels_use_the_blackwell_units_they_claim():
     """SASS of the shipped library: the resident fit keeps its tile in tensor memory (STTM / LDTM, no MMA), stages it with
-    tensor-map TMA copies (UTMALDG) and reduces through 64-bit L2 atomics (REDG.E.ADD.64); the K projection runs on the 5th-gen tensor cores
+    tensor-map TMA copies (UTMALDG) and reduces through 64-bit L2 atomics (REDG.E.ADD.64); the multi-shot fit does the same for
+    the first tile of every CTA and streams the others (UBLKCP); the K projection runs on the 5th-gen tensor cores
     (UTCHMMA, operands by UTMALDG, accumulator read with LDTM); the streaming kernels are TMA-fed with packed fp32 FMAs."""
     lst = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True)
     if lst.returncode != 0:
@@ -78,6 +79,10 @@ def test_hot_kernels_use_the_blackwell_units_they_claim():
     for ops in ops_of(r"k_fit_residentILi512ELi1ELi512ELi20ELi5ELi60ELi60ELb[01]ELb1ELi0E"):
         assert {"STTM", "LDTM", "UTMALDG", "FFMA2"} <= ops and any(o.startswith("REDG.E.ADD.64") for o in ops), sorted(ops)
         assert "UTCHMMA" not in ops                         # tensor memory as a scratchpad: no MMA in this kernel
+    # multi-shot fit: first tile of every CTA in tensor memory, the others re-laid out with bulk stores and streamed with bulk /
+    # tensor-map copies through the shared-memory ring
+    for ops in ops_of(r"k_fit_l2ILi[1-4]E"):
+        assert {"STTM", "LDTM", "UTMALDG", "UBLKCP", "FFMA2"} <= ops and any(o.startswith("REDG.E.ADD.64") for o in ops), sorted(ops)
     for ops in ops_of(r"k_kproj_scores"):
         assert {"UTCHMMA", "UTMALDG", "LDTM"} <= ops, sorted(ops)
     for name in ("k_logits_iou_stream", "k_rtf_stream", "k_ftr_stream"):
