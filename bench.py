@@ -415,6 +415,12 @@ def main():
                                        "above 1 x the HBM peak by construction, because the bytes never leave the chip"},
             "dram_frac": (traffic / (fit_ms / 1e3) / 1e9 / hbm_peak) if traffic else None,
             "compulsory_dram_bytes": E * S * F_bytes,
+            # the same figures as flat keys (a flattened view of this block keeps them): the fraction on the round-1 denominator
+            # (shared-memory pipe), the multiple of the HBM-streamed floor, and the issue-slot utilisation ncu measured for this
+            # kernel — the resource it is closest to (it is bound by exchange latencies, not by a bandwidth)
+            "frac_smem_equivalent": smem_equiv["frac"],
+            "x_of_hbm_streamed_floor": fit_gbs / hbm_peak,
+            "issue_slots_busy_frac": (kc["issue_active_pct"] / 100.0) if (kc and kc.get("issue_active_pct") is not None) else None,
         }
     elif fit_kernel == "k_fit_l2":
         # L2 roof: the episodes in flight stay L2-resident for all 2T sweeps; peak = L2 read bandwidth measured live with the
